@@ -1,0 +1,218 @@
+"""Seeded synthetic slab-electrode systems in OpenMM's CUDA array layouts.
+
+The geometry and the image-particle recipe follow the reference's only workload,
+/root/reference/example/nacl_1m_spce/nacl_constv.py:60-95 (one massless image per real atom at
+(x, y, -z) with charge -q; neutral wall atoms get their image offset by +0.001 nm, :82-85), and its
+composition (nacl_1m_eq.pdb: 38 Na+, 38 Cl-, 2046 SPC/E waters, 1280 massless neutral wall carbons
+out of 7494 real atoms, walls last; box 3.9352 x 4.2600 nm, zmax = 4.2183 nm, nacl_constv.py:28).
+Forces are *injected*: the integrator step path (BASELINE.json north_star) starts from OpenMM's
+fixed-point force buffer, so a slab carries int64 forces scaled by 2^32
+(constVLangevin.cu:10) instead of a force field.
+
+Array layouts, P = num_atoms rounded up to a multiple of 32:
+  posq   (P,4) real   x, y, z, charge
+  corr   (P,4) real   low bits of the position, "mixed" precision only
+  velm   (P,4) mixed  vx, vy, vz, 1/mass  (0 for massless)
+  force  (3,P) int64  x-plane, y-plane, z-plane, value = llround(f * 2^32)
+Slot order is the original order (identity atomIndex): reals [0,R), cell-i images [i*R,(i+1)*R).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+PRECISIONS = ("single", "mixed", "double")
+REAL = {"single": np.float32, "mixed": np.float32, "double": np.float64}
+MIXED = {"single": np.float32, "mixed": np.float64, "double": np.float64}
+
+BOLTZ = 8.31446261815324e-3  # kJ/mol/K (OpenMM >= 7.4)
+
+# example/nacl_1m_spce geometry
+EXAMPLE_LX, EXAMPLE_LY, EXAMPLE_ZMAX = 3.9352, 4.2600, 4.2183
+EXAMPLE_REAL_ATOMS = 7494
+WALL_FRACTION = 1280.0 / 7494.0
+ION_FRACTION = 76.0 / 7494.0
+
+MASS_O, MASS_H, MASS_NA, MASS_CL = 15.9994, 1.008, 22.98977, 35.45
+Q_O, Q_H = -0.8476, 0.4238
+FORCE_SCALE = 4294967296.0
+
+
+@dataclass
+class Slab:
+    precision: str
+    num_cells: int
+    num_real: int
+    num_atoms: int
+    padded: int
+    zmax: float
+    box: tuple
+    posq: np.ndarray
+    corr: np.ndarray | None
+    velm: np.ndarray
+    force: np.ndarray
+    masses: np.ndarray  # (num_atoms,) float64, original order
+    global_atom_offset: int = 0
+    meta: dict = field(default_factory=dict)
+
+    def copy(self) -> "Slab":
+        return Slab(self.precision, self.num_cells, self.num_real, self.num_atoms, self.padded,
+                    self.zmax, self.box, self.posq.copy(),
+                    None if self.corr is None else self.corr.copy(), self.velm.copy(),
+                    self.force.copy(), self.masses.copy(), self.global_atom_offset,
+                    dict(self.meta))
+
+    # -- pair classes, for the algorithmic byte count (DESIGN.md "bytes per pair") --------------
+    def pair_classes(self) -> dict:
+        w = self.velm[: self.num_real, 3] != 0
+        q = self.posq[: self.num_real, 3] != 0
+        return {
+            "massive_charged": int(np.sum(w & q)),
+            "massive_neutral": int(np.sum(w & ~q)),
+            "massless_charged": int(np.sum(~w & q)),
+            "massless_neutral": int(np.sum(~w & ~q)),
+        }
+
+
+def padded_atoms(n: int) -> int:
+    return (n + 31) // 32 * 32
+
+
+def make_slab(num_real: int, precision: str = "single", num_cells: int = 2, seed: int = 12345,
+              temperature: float = 300.0, wall_fraction: float = WALL_FRACTION,
+              ion_fraction: float = ION_FRACTION, force_sigma: float = 1000.0,
+              image_force_garbage: bool = True, zmax: float = EXAMPLE_ZMAX) -> Slab:
+    """Build a seeded slab with ``num_real`` real atoms and ``num_cells - 1`` image cells."""
+    assert precision in PRECISIONS
+    assert num_cells >= 2 and num_cells % 2 == 0
+    rng = np.random.Generator(np.random.Philox(seed))
+    R = int(num_real)
+    N = R * num_cells
+    P = padded_atoms(N)
+    real, mixed = REAL[precision], MIXED[precision]
+
+    n_wall = int(round(R * wall_fraction))
+    n_ion = int(round(R * ion_fraction))
+    n_water = (R - n_wall - n_ion) // 3 * 3
+    n_ion = R - n_wall - n_water  # absorb the remainder so the counts add up
+    scale = np.sqrt(max(R, 1) / EXAMPLE_REAL_ATOMS)  # constant number density in x, y
+    lx, ly = EXAMPLE_LX * scale, EXAMPLE_LY * scale
+
+    mass = np.zeros(R, np.float64)
+    charge = np.zeros(R, np.float64)
+    ion_sign = np.where(np.arange(n_ion) % 2 == 0, 1.0, -1.0)
+    mass[:n_ion] = np.where(ion_sign > 0, MASS_NA, MASS_CL)
+    charge[:n_ion] = ion_sign
+    wsl = slice(n_ion, n_ion + n_water)
+    mass[wsl] = np.tile([MASS_O, MASS_H, MASS_H], n_water // 3)
+    charge[wsl] = np.tile([Q_O, Q_H, Q_H], n_water // 3)
+    # walls: mass 0, charge 0 (spce.xml:28,42-44), split between z = 0 and z = zmax
+
+    pos = np.empty((R, 3), np.float64)
+    pos[:, 0] = rng.random(R) * lx
+    pos[:, 1] = rng.random(R) * ly
+    pos[:, 2] = (0.05 + 0.9 * rng.random(R)) * zmax
+    wall = slice(n_ion + n_water, R)
+    pos[wall, 2] = np.where(np.arange(n_wall) % 2 == 0, 0.0, zmax)
+
+    inv_mass = np.zeros(R, np.float64)
+    massive = mass > 0
+    inv_mass[massive] = 1.0 / mass[massive]
+    vel = rng.standard_normal((R, 3)) * np.sqrt(BOLTZ * temperature * inv_mass)[:, None]
+
+    posq64 = np.zeros((P, 4), np.float64)
+    posq64[:R, :3] = pos
+    posq64[:R, 3] = charge
+    for i in range(1, num_cells):
+        img = slice(i * R, (i + 1) * R)
+        # initial image placement as in nacl_constv.py:75-87: cell 1 at -z; further cells follow
+        # the kernel's recurrence.  The first step rewrites every charged image anyway.
+        zi = pos[:, 2].copy()
+        for j in range(1, i + 1):
+            zi = -zi + 2.0 * j * zmax if j > 1 else -zi
+        posq64[img, 0] = pos[:, 0]
+        posq64[img, 1] = pos[:, 1]
+        posq64[img, 2] = np.where(charge != 0, zi, zi + 0.001)
+        posq64[img, 3] = -charge if i % 2 == 1 else charge
+
+    posq = posq64.astype(real)
+    corr = None
+    if precision == "mixed":
+        corr = np.zeros((P, 4), real)
+        corr[:, :3] = (posq64[:, :3] - posq[:, :3].astype(np.float64)).astype(real)
+
+    velm = np.zeros((P, 4), mixed)
+    velm[:R, :3] = vel.astype(mixed)
+    velm[:R, 3] = inv_mass.astype(mixed)
+
+    force = np.zeros((3, P), np.int64)
+    f = rng.standard_normal((3, R)) * force_sigma
+    force[:, :R] = np.rint(f * FORCE_SCALE).astype(np.int64)
+    if image_force_garbage:
+        g = rng.standard_normal((3, N - R)) * force_sigma
+        force[:, R:N] = np.rint(g * FORCE_SCALE).astype(np.int64)
+
+    masses = np.zeros(N, np.float64)
+    masses[:R] = mass
+    return Slab(precision, num_cells, R, N, P, float(zmax), (lx, ly, num_cells * zmax), posq, corr,
+                velm, force, masses, 0,
+                {"seed": seed, "n_ion": n_ion, "n_water": n_water, "n_wall": n_wall,
+                 "temperature": temperature})
+
+
+def slice_slab(slab: Slab, lo: int, hi: int) -> Slab:
+    """The shard holding real atoms [lo, hi) and their images (multi-GPU range partition:
+    every image lives with its real partner)."""
+    R, nc = slab.num_real, slab.num_cells
+    r = hi - lo
+    n = r * nc
+    P = padded_atoms(n)
+    src = np.concatenate([np.arange(lo, hi) + i * R for i in range(nc)])
+    posq = np.zeros((P, 4), slab.posq.dtype)
+    posq[:n] = slab.posq[src]
+    corr = None
+    if slab.corr is not None:
+        corr = np.zeros((P, 4), slab.corr.dtype)
+        corr[:n] = slab.corr[src]
+    velm = np.zeros((P, 4), slab.velm.dtype)
+    velm[:n] = slab.velm[src]
+    force = np.zeros((3, P), np.int64)
+    force[:, :n] = slab.force[:, src]
+    return Slab(slab.precision, nc, r, n, P, slab.zmax, slab.box, posq, corr, velm, force,
+                slab.masses[src].copy(), slab.global_atom_offset + lo, dict(slab.meta))
+
+
+def new_forces(slab: Slab, step_index: int, force_sigma: float = 1000.0) -> np.ndarray:
+    """A fresh (3,P) injected force buffer for a given step (real and image slots non-zero)."""
+    rng = np.random.Generator(np.random.Philox(key=slab.meta.get("seed", 0) + 7919 * (step_index + 1)))
+    force = np.zeros((3, slab.padded), np.int64)
+    f = rng.standard_normal((3, slab.num_atoms)) * force_sigma
+    force[:, : slab.num_atoms] = np.rint(f * FORCE_SCALE).astype(np.int64)
+    return force
+
+
+def algorithmic_bytes_per_step(slab: Slab, zero_images: bool = True) -> int:
+    """Bytes the fused step must move for this slab (DESIGN.md "bytes per pair").
+
+    single precision, numCells = 2, per real/image pair:
+      always read   velm 16 + posq 16
+      massive       + read force 24, write velm 16 + posq 16
+      charged       + read image charge 4, write image posq 16
+      zeroing       + write image velm 16 + image force 24
+    => massive & charged pair = 148 B (74 B per atom-step).
+    """
+    r = np.dtype(REAL[slab.precision]).itemsize
+    m = np.dtype(MIXED[slab.precision]).itemsize
+    pos_b = 4 * r * (2 if slab.precision == "mixed" else 1)  # posq (+ correction)
+    vel_b = 4 * m
+    c = slab.pair_classes()
+    n_img = slab.num_cells - 1
+    massive = c["massive_charged"] + c["massive_neutral"]
+    charged = c["massive_charged"] + c["massless_charged"]
+    total = slab.num_real * (vel_b + pos_b)
+    total += massive * (24 + vel_b + pos_b)
+    total += charged * n_img * (r + pos_b)
+    if zero_images:
+        total += slab.num_real * n_img * (vel_b + 24)
+    return int(total)

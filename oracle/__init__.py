@@ -1,0 +1,186 @@
+"""CPU oracle for the ConstVLangevinIntegrator step path -- TEST INFRASTRUCTURE ONLY.
+
+ctypes front-end of ``oracle/libconstv_oracle.so`` (built from ``constv_oracle.c`` by
+``make -C oracle``).  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs may import this package; the product package
+``openmm_constv_b200`` never does.
+
+The functions restate /root/reference/platforms/cuda/src/kernels/constVLangevin.cu and the host
+code around it (citations are in ``constv_oracle.c``).  Parity status: integrator arithmetic pinned
+by the reference tests' analytic properties; image handling "parity unpinned" (no reference test
+touches an image particle).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libconstv_oracle.so")
+
+BOLTZ = 8.31446261815324e-3  # kJ/mol/K, OpenMM >= 7.4 SimTKOpenMMRealType.h [recalled, SURVEY 8c]
+
+PRECISIONS = ("single", "mixed", "double")
+_SUFFIX = {"single": "f32", "mixed": "mixed", "double": "f64"}
+REAL = {"single": np.float32, "mixed": np.float32, "double": np.float64}
+MIXED = {"single": np.float32, "mixed": np.float64, "double": np.float64}
+
+ERRORS = {
+    1: "Not even number of cells",
+    2: "Number of particles is not multiple of number of cells",
+    3: "Image Particle has nonzero mass",
+    4: "Unit cell dimension does not match with the provided zmax value",
+}
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with gcc (seconds).  Building the checker is not using it."""
+    if force or not os.path.exists(_LIB_PATH) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
+        for f in ("constv_oracle.c", "constv_oracle_impl.h", "Makefile")
+    ):
+        subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.oracle_kinetic_energy_f32.restype = C.c_double
+        _lib.oracle_kinetic_energy_mixed.restype = C.c_double
+        _lib.oracle_kinetic_energy_f64.restype = C.c_double
+        _lib.oracle_num_threads.restype = C.c_int
+    return _lib
+
+
+def _p(a, dtype=None):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"], "oracle arrays must be C-contiguous"
+    if dtype is not None:
+        assert a.dtype == np.dtype(dtype), (a.dtype, dtype)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _mixed_scalar(precision, v):
+    return C.c_float(v) if MIXED[precision] is np.float32 else C.c_double(v)
+
+
+def params(temperature, friction, step_size, boltz=BOLTZ):
+    out = np.zeros(3, np.float64)
+    lib().oracle_params(C.c_double(temperature), C.c_double(friction), C.c_double(step_size),
+                        C.c_double(boltz), _p(out))
+    return out
+
+
+def validate(num_atoms, num_cells, masses, box_z, cell_size):
+    """Returns zmax or raises ValueError with the reference's message."""
+    masses = np.ascontiguousarray(masses, np.float64)
+    z = C.c_double(0)
+    rc = lib().oracle_validate(C.c_int(num_atoms), C.c_int(num_cells), _p(masses),
+                               C.c_double(box_z), C.c_double(cell_size), C.byref(z))
+    if rc:
+        raise ValueError(ERRORS[rc])
+    return z.value
+
+
+def inverse_order(atom_index):
+    atom_index = np.ascontiguousarray(atom_index, np.int32)
+    inv = np.empty_like(atom_index)
+    lib().oracle_inverse_order(C.c_int(len(atom_index)), _p(atom_index), _p(inv))
+    return inv
+
+
+def part1(precision, velm, force, pos_delta, prm, step_size, random4, random_index=0,
+          num_atoms=None):
+    P = velm.shape[0]
+    n = P if num_atoms is None else num_atoms
+    m = MIXED[precision]
+    prm = np.ascontiguousarray(prm, m)
+    fn = getattr(lib(), "oracle_part1_" + _SUFFIX[precision])
+    fn(C.c_int(n), C.c_int(P), _p(velm, m), _p(force, np.int64), _p(pos_delta, m), _p(prm),
+       _mixed_scalar(precision, step_size), _p(random4, np.float32), C.c_uint(random_index))
+
+
+def part2(precision, posq, posq_corr, pos_delta, velm, step_size, num_atoms=None):
+    n = velm.shape[0] if num_atoms is None else num_atoms
+    r, m = REAL[precision], MIXED[precision]
+    fn = getattr(lib(), "oracle_part2_" + _SUFFIX[precision])
+    fn(C.c_int(n), _p(posq, r), _p(posq_corr, r) if posq_corr is not None else None,
+       _p(pos_delta, m), _p(velm, m), _mixed_scalar(precision, step_size))
+
+
+def mirror(precision, num_real, num_cells, zshift_per_cell, posq, posq_corr, inv_order):
+    r = REAL[precision]
+    fn = getattr(lib(), "oracle_mirror_" + _SUFFIX[precision])
+    fn(C.c_int(num_real), C.c_int(num_cells), C.c_double(zshift_per_cell), _p(posq, r),
+       _p(posq_corr, r) if posq_corr is not None else None, _p(inv_order, np.int32))
+
+
+def zero_images(precision, num_atoms, num_real, velm, force, inv_order, zero_velm=True,
+                zero_force=True):
+    P = velm.shape[0]
+    fn = getattr(lib(), "oracle_zero_images_" + _SUFFIX[precision])
+    fn(C.c_int(num_atoms), C.c_int(num_real), C.c_int(P), _p(velm, MIXED[precision]),
+       _p(force, np.int64), _p(inv_order, np.int32), C.c_int(zero_velm), C.c_int(zero_force))
+
+
+def kinetic_energy(precision, velm, force, time_shift, num_atoms=None):
+    P = velm.shape[0]
+    n = P if num_atoms is None else num_atoms
+    fn = getattr(lib(), "oracle_kinetic_energy_" + _SUFFIX[precision])
+    return fn(C.c_int(n), C.c_int(P), _p(velm, MIXED[precision]), _p(force, np.int64),
+              C.c_double(time_shift))
+
+
+def step(precision, num_atoms, num_cells, zshift_per_cell, posq, posq_corr, velm, force,
+         pos_delta, prm, step_size, random4, random_index, inv_order, zero_velm=True,
+         zero_force=True):
+    """One constraint-free step in the reference's launch order, all arrays updated in place."""
+    P = velm.shape[0]
+    r, m = REAL[precision], MIXED[precision]
+    prm = np.ascontiguousarray(prm, m)
+    fn = getattr(lib(), "oracle_step_" + _SUFFIX[precision])
+    fn(C.c_int(num_atoms), C.c_int(P), C.c_int(num_cells), C.c_double(zshift_per_cell),
+       _p(posq, r), _p(posq_corr, r) if posq_corr is not None else None, _p(velm, m),
+       _p(force, np.int64), _p(pos_delta, m), _p(prm), _mixed_scalar(precision, step_size),
+       _p(random4, np.float32), C.c_uint(random_index), _p(inv_order, np.int32),
+       C.c_int(zero_velm), C.c_int(zero_force))
+
+
+def philox4x32_10(counter, key):
+    counter = np.ascontiguousarray(counter, np.uint32)
+    key = np.ascontiguousarray(key, np.uint32)
+    out = np.zeros(4, np.uint32)
+    lib().oracle_philox4x32_10(_p(counter), _p(key), _p(out))
+    return out
+
+
+def gaussian4(seed, atom, step_index):
+    out = np.zeros(4, np.float32)
+    lib().oracle_gaussian4(C.c_uint64(seed), C.c_uint64(atom), C.c_uint64(step_index), _p(out))
+    return out
+
+
+def fill_noise(num_atoms, seed, step_index, atom_index=None, global_atom_offset=0):
+    out = np.zeros((num_atoms, 4), np.float32)
+    ai = None if atom_index is None else np.ascontiguousarray(atom_index, np.int32)
+    lib().oracle_fill_noise(C.c_int(num_atoms), _p(ai), C.c_uint64(seed),
+                            C.c_uint64(global_atom_offset), C.c_uint64(step_index), _p(out))
+    return out
+
+
+def num_threads():
+    return lib().oracle_num_threads()
+
+
+def set_num_threads(n):
+    lib().oracle_set_num_threads(C.c_int(n))
