@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""Benchmark of the ConstVLangevinIntegrator step path on B200 (contract: see the task brief).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one fused integrator step over one synthetic slab of ``--atoms`` particles per GPU
+(default 1,000,000 = 500k real + 500k image: BASELINE.json configs[2]).  Metric: atom-steps/s,
+whole job (sum over ranks / max-over-ranks device time).  Multi-GPU is the range partition of
+SURVEY.md 8e: every rank owns a contiguous real-atom range plus its images and there is NO
+data-path collective (weak scaling: per-GPU shard fixed, so N=8 with --atoms 2000000 is the 16M
+slab of configs[3]); the only collective is the scalar kinetic-energy all-reduce, issued once after
+the timed region as a report, never per step.
+
+L2 policy: a 1M-atom slab is 58 MB, smaller than B200's 126 MB L2, so the timed loop rotates over
+``replicas`` independent copies of the slab whose total footprint exceeds 2x L2: every step streams
+its slab from HBM.
+
+The JSON line carries, besides the base contract's keys:
+  roofline      algorithmic bytes of one launch / average launch duration (CUDA events around the
+                timed region on the launching stream / launches), against MEASURED_PEAKS.json
+  cpu_baseline  the oracle (kind "port": the reference has no CPU implementation of this path)
+                timed on this box's host cores on a bounded sample of the same workload
+  e2e           the same metric through the C ABI with HOST buffers (constv_step_host): per step
+                H2D of the real atoms' forces from pinned memory, the fused step, D2H of posq
+  clocks        SM clock / throttle reasons sampled during the timed region
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_KELVIN, FRICTION, DT = 300.0, 1.0, 0.001  # example/nacl_1m_spce/nacl_constv.py:12-16
+L2_BYTES = 126 * 1024 * 1024
+FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100_000)
+    ap.add_argument("--warmup", type=int, default=1000)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--atoms", type=int, default=1_000_000, help="particles (real+image) per GPU")
+    ap.add_argument("--precision", default="single", choices=["single", "mixed", "double"])
+    ap.add_argument("--replicas", type=int, default=0, help="slab copies rotated through (0 = auto: > 2x L2)")
+    ap.add_argument("--pairs-per-thread", type=int, default=0)
+    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cache-image-charge", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=40)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profile(atoms):
+    """dram bytes per launch from the committed ncu capture, if it was taken on this workload."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        rec = json.load(open(path))
+        if int(rec.get("atoms", -1)) == int(atoms):
+            return rec["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (NVML; nvidia-smi fallback)."""
+
+    def __init__(self, index, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._halt = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
+
+    def sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            try:
+                self.samples.append(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in (("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown),
+                                  ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                                  ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown),
+                                  ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap)):
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+        else:
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", "-i", str(self.index), "--format=csv,noheader,nounits",
+                     "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                     "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_power_cap"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(int(f[0]))
+                self.max_mhz = int(f[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+
+    def run(self):
+        while not self._halt.is_set():
+            self.sample()
+            self._halt.wait(self.period)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=5)
+        if not self.samples:
+            self.sample()
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---- CPU legs (the only place bench.py touches oracle/) ---------------------------------------------
+
+def cpu_oracle_rate(slab, seconds, steps_cap=None, window=None):
+    """Times the oracle's single-pass fused step (oracle_step_range_f32) with all host threads.
+    Returns (atom_steps_per_s, steps_done, threads, atoms_per_step)."""
+    import oracle
+    s = slab.copy()
+    prm = oracle.params(T_KELVIN, FRICTION, DT).astype(np.float32 if s.precision == "single" else np.float64)
+    dt = (np.float32 if s.precision == "single" else np.float64)(DT)
+    xi = oracle.fill_noise(s.padded, 1, 0)
+    R = s.num_real
+    w = R if window is None else max(1, min(R, window))
+    force = s.force.reshape(-1)
+    threads = oracle.num_threads()
+
+    def one(k):
+        lo = (k * w) % R
+        hi = min(R, lo + w)
+        oracle.step_range(s.precision, s.num_atoms, s.num_cells, s.zmax, s.posq, s.corr, s.velm, force,
+                          prm, dt, xi, 0, lo, hi)
+        return (hi - lo) * s.num_cells
+
+    for k in range(2):
+        one(k)
+    done, atoms = 0, 0
+    t0 = time.perf_counter()
+    while True:
+        atoms += one(done)
+        done += 1
+        el = time.perf_counter() - t0
+        if (steps_cap is not None and done >= steps_cap) or (steps_cap is None and el >= seconds):
+            break
+    el = time.perf_counter() - t0
+    return atoms / el, done, threads, atoms / done, el
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference has NO CPU implementation of this path and cannot be built
+    here, so the reference arm is the oracle port on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from openmm_constv_b200 import slab as slabmod
+    s = slabmod.make_slab(args.atoms // 2, args.precision, seed=12345)
+    # bound the run: calibrate, then size the per-step window so warmup+steps stay under ~90 s
+    rate, _, threads, _, _ = cpu_oracle_rate(s, 1.0)
+    total = max(1, args.steps + args.warmup)
+    window_atoms = min(args.atoms, max(65536, int(rate * 90.0 / total)))
+    window = max(1, window_atoms // s.num_cells)
+    cpu_oracle_rate(s, 0, steps_cap=max(1, args.warmup), window=window)
+    rate, done, threads, per_step, el = cpu_oracle_rate(s, 0, steps_cap=args.steps, window=window)
+    sample = (f"{done} steps, each the fused oracle step over a rotating window of {int(per_step)} atoms "
+              f"of the {args.atoms}-atom slab (window walks the whole slab, injected noise pool)")
+    line = {
+        "impl": "reference", "metric": "atom-steps/s", "value": rate, "unit": "atom-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * el / done, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if args.precision == "single" else "f64", "data": "synthetic",
+        "config": {"workload": f"synthetic slab, {args.atoms} atoms ({args.atoms // 2} real + images), fused ConstV Langevin step only",
+                   "atoms_per_step": int(per_step), "precision": args.precision,
+                   "note": "reference ships no CPU implementation of this path; oracle port timed"},
+        "cpu_baseline": {"value": rate, "unit": "atom-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---- the B200 arm -------------------------------------------------------------------------------------
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from openmm_constv_b200 import _capi, integrator as hostapi, slab as slabmod
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the ConstV step path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _capi.load()
+
+    # ---- workload: this rank's shard of the range-partitioned slab ------------------------------
+    R = args.atoms // 2
+    shard = slabmod.make_slab(R, args.precision, seed=12345 + rank)
+    shard.global_atom_offset = rank * R
+    alg_bytes = slabmod.algorithmic_bytes_per_step(shard)
+    rec_bytes = shard.posq.nbytes + shard.velm.nbytes + shard.force.nbytes + (shard.corr.nbytes if shard.corr is not None else 0)
+    replicas = args.replicas or max(2, int(np.ceil(2.0 * L2_BYTES / rec_bytes)) + 1)
+
+    flags = _capi.FLAGS_DEFAULT
+    if not args.no_cache_image_charge:
+        flags |= _capi.FLAG_CACHE_IMAGE_CHARGE
+
+    ctxs = []
+    for r in range(replicas):
+        sysm = hostapi.SlabSystem()
+        sysm.addParticles(shard.masses)
+        sysm.setDefaultPeriodicBoxVectors((shard.box[0], 0, 0), (0, shard.box[1], 0), (0, 0, shard.num_cells * shard.zmax))
+        it = hostapi.ConstVLangevinIntegrator(T_KELVIN, FRICTION, DT, shard.num_cells)
+        it.setRandomNumberSeed(2024)
+        ctx = hostapi.SlabContext(sysm, it, precision=args.precision, device=local_rank, flags=flags,
+                                  global_atom_offset=shard.global_atom_offset, padded=shard.padded)
+        ctx.load_slab(shard)
+        if args.pairs_per_thread or args.ctas_per_sm:
+            it._kernel.set_launch_shape(args.pairs_per_thread, args.ctas_per_sm)
+        _capi.check(lib.constv_set_parameters(it._kernel.handle, T_KELVIN, FRICTION, DT))
+        ctxs.append((ctx, it))
+    handles = [it._kernel.handle for _, it in ctxs]
+
+    stream = torch.cuda.Stream(device=dev)
+    sptr = stream.cuda_stream
+
+    def launch_steps(first, count):
+        for k in range(first, first + count):
+            _capi.check(lib.constv_step_fused(handles[k % replicas], None, 0, sptr))
+
+    # ---- optional CUDA graph: `chunk` consecutive steps per replay --------------------------------
+    K, W = args.steps, max(args.warmup, 3)
+    use_graph = (not args.no_graph) and K >= 2 * replicas
+    graph, chunk = None, 0
+    with torch.cuda.stream(stream):
+        launch_steps(0, replicas)  # first touch, refreshes image-charge snapshots outside capture
+        stream.synchronize()
+        if use_graph:
+            chunk = replicas * max(1, min(20, K // replicas))
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                launch_steps(0, chunk)
+
+        def run(nsteps):
+            done = 0
+            if graph is not None:
+                while done + chunk <= nsteps:
+                    graph.replay()
+                    done += chunk
+            launch_steps(done, nsteps - done)
+
+        run(W)
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        launches0 = _capi.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        run(K)
+        ev1.record(stream)
+        stream.synchronize()
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+        if world > 1:
+            dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    eager_launches = _capi.launch_count() - launches0
+
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_max = float(tmax.item())
+    atoms_per_step_job = shard.num_atoms * world
+    value = atoms_per_step_job * K / (ms_max * 1e-3)
+
+    # ---- kinetic energy report: the one collective of the partition (on demand, not per step) -----
+    ke_dev = torch.zeros(1, dtype=torch.float64, device=dev)
+    ctxs[0][1]._kernel.kinetic_energy_device(0.5 * DT, ke_dev)
+    if world > 1:
+        dist.all_reduce(ke_dev, op=dist.ReduceOp.SUM)
+    ke_total = float(ke_dev.item())
+    n_massive = int(np.sum(shard.velm[:R, 3] != 0)) * world
+    temperature = 2.0 * ke_total / (3 * n_massive * slabmod.BOLTZ) if n_massive else 0.0
+
+    # ---- e2e: host buffers through constv_step_host -------------------------------------------------
+    e2e = None
+    if not args.skip_e2e:
+        ctx0, it0 = ctxs[0]
+        n_e2e = max(3, args.e2e_steps)
+        host_force = [torch.from_numpy(np.ascontiguousarray(slabmod.new_forces(shard, j)[:, :R])).pin_memory() for j in range(2)]
+        esize = 4 if args.precision != "double" else 8
+        host_posq = torch.empty((shard.num_atoms, 4), dtype=torch.float32 if esize == 4 else torch.float64).pin_memory()
+        h2d = host_force[0].numel() * 8
+        d2h = host_posq.numel() * esize
+        for j in range(3):
+            _capi.check(lib.constv_step_host(it0._kernel.handle, host_force[j % 2].data_ptr(), host_posq.data_ptr(), None, sptr))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for j in range(n_e2e):
+            _capi.check(lib.constv_step_host(it0._kernel.handle, host_force[j % 2].data_ptr(), host_posq.data_ptr(), None, sptr))
+        e1.record(stream)
+        stream.synchronize()
+        ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {"value": atoms_per_step_job * n_e2e / (float(ems.item()) * 1e-3), "unit": "atom-steps/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
+               "ms_per_step": float(ems.item()) / n_e2e,
+               "what": "constv_step_host: pinned real-atom forces H2D + fused step + posq D2H, synchronous per step"}
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        rate, done, threads, per_step, el = cpu_oracle_rate(shard, args.cpu_seconds)
+        cpu = {"value": rate, "unit": "atom-steps/s", "cores": threads, "kind": "port",
+               "sample": f"{done} full fused oracle steps over the same {shard.num_atoms}-atom slab in {el:.1f} s, all host threads, injected noise pool",
+               "host_cpus": os.cpu_count()}
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        launch_ms = ms_max / K
+        achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+        line = {
+            "metric": "atom-steps/s", "value": value, "unit": "atom-steps/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": launch_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "single" else ("f32+f64" if args.precision == "mixed" else "f64"),
+            "data": "synthetic",
+            "config": {
+                "workload": f"synthetic slab, {shard.num_atoms} atoms per GPU ({R} real + {shard.num_atoms - R} image), fused ConstV Langevin step only (BASELINE configs[2]); range partition over {world} GPU(s)",
+                "atoms_per_gpu": shard.num_atoms, "total_atoms": atoms_per_step_job, "precision": args.precision,
+                "pair_classes": shard.pair_classes(), "rng": "in-kernel Philox4x32-10",
+                "l2": f"rotating {replicas} slab replicas ({replicas * rec_bytes / 1e6:.0f} MB) > 126 MB L2: every step streams from HBM",
+                "launch": ("CUDA graph of %d steps, PDL" % chunk) if graph is not None else "eager, PDL",
+                "image_charge": "re-read from posq" if args.no_cache_image_charge else "side array",
+                "T_K": T_KELVIN, "friction_per_ps": FRICTION, "dt_ps": DT,
+            },
+            "steps_per_s": K / (ms_max * 1e-3),
+            "atom_steps_per_s_per_gpu": value / world,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic_from_profile(shard.num_atoms), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "frac_of_8TBs_nominal": achieved / 8000.0,
+                         "kernel": "constv_fused_step_kernel"},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": int(K),
+            "eager_launches_in_region": int(eager_launches),
+            "clocks": clocks,
+            "kinetic_energy_kj_mol": ke_total, "temperature_K": temperature,
+        }
+        print(json.dumps(line), flush=True)
+    for ctx, _ in ctxs:
+        ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,220 @@
+/*
+ * constv_b200.h -- C ABI of the B200-native ConstVLangevinIntegrator step path.
+ *
+ * This is the drop-in boundary under the reference's OpenMM plugin classes: the C++ kernel class
+ * (openmm_constv_b200/plugin/platforms/cuda) and the Python host mirror (openmm_constv_b200/) both
+ * call ONLY these entry points.  Plain pointers, sizes and scalars; no C++ or torch types.
+ * Every function cites the reference interface it replaces; paths are relative to the reference
+ * repository root (scychon/openmm_constV), "Kernels.cpp" = platforms/cuda/src/CudaConstVKernels.cpp,
+ * "Langevin.cu" = platforms/cuda/src/kernels/constVLangevin.cu.
+ *
+ * Conventions
+ *   - All functions return CONSTV_OK (0) or an error code; constv_last_error() gives the message of
+ *     the calling thread's last failure.  A CONSTV_ERR_SYSTEM message is verbatim the text of the
+ *     OpenMMException the reference throws for the same condition.
+ *   - `stream` is a cudaStream_t / CUstream passed as void* (NULL = legacy default stream, which is
+ *     what OpenMM 7.x launches on).  All launches are asynchronous unless stated.
+ *   - Device arrays use OpenMM's CUDA layouts, P = padded_num_atoms:
+ *       posq            real4[P]   x, y, z, charge
+ *       posq_correction real4[P]   mixed precision only, else NULL
+ *       velm            mixed4[P]  vx, vy, vz, inverse mass (0 = massless)
+ *       force           int64[3*P] x-plane, y-plane, z-plane, fixed point scaled by 2^32
+ *       pos_delta       mixed4[P]  only for the split (constraint) path
+ *       atom_index      int32[P]   slot -> original atom index, NULL = identity order
+ *     real/mixed = float/float (single), float/double (mixed), double/double (double).
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     CONSTV_ERR_CUDA.
+ */
+#ifndef CONSTV_B200_H_
+#define CONSTV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CONSTV_API __attribute__((visibility("default")))
+
+#define CONSTV_VERSION 100 /* 0.1.0 */
+
+typedef struct constv_slab constv_slab; /* one Context's worth of integrator state (opaque) */
+
+enum {
+    CONSTV_OK = 0,
+    CONSTV_ERR_INVALID = 1, /* bad argument */
+    CONSTV_ERR_CUDA = 2,    /* CUDA runtime failure (message carries cudaGetErrorString) */
+    CONSTV_ERR_STATE = 3,   /* call sequence error: arrays not bound, parameters not set, ... */
+    CONSTV_ERR_SYSTEM = 4   /* the System violates the integrator's requirements (reference text) */
+};
+
+enum { CONSTV_PRECISION_SINGLE = 0, CONSTV_PRECISION_MIXED = 1, CONSTV_PRECISION_DOUBLE = 2 };
+
+enum {
+    /* z_img = -z + 2*i*zmax, evaluated in double, as the shipped kernel does (Langevin.cu:151-152) */
+    CONSTV_MIRROR_REFERENCE = 0,
+    /* z_img = -z exactly (BASELINE.json north_star); numCells must be 2 */
+    CONSTV_MIRROR_NEGATE = 1
+};
+
+enum {
+    CONSTV_FLAG_ZERO_IMAGE_VELM = 1u << 0,   /* rewrite every image's velm to (0,0,0,0) each step */
+    CONSTV_FLAG_ZERO_IMAGE_FORCE = 1u << 1,  /* rewrite every image's three force entries to 0   */
+    /* read image charges from a side array snapshotted by constv_refresh_image_charges() instead of
+     * re-reading posq[image].w every step (Langevin.cu:153).  Charges are constant during a run
+     * unless the caller edits them (then call constv_refresh_image_charges again). */
+    CONSTV_FLAG_CACHE_IMAGE_CHARGE = 1u << 2,
+    /* launch with programmatic dependent launch so back-to-back steps overlap launch latency */
+    CONSTV_FLAG_PDL = 1u << 3
+};
+#define CONSTV_FLAGS_DEFAULT (CONSTV_FLAG_ZERO_IMAGE_VELM | CONSTV_FLAG_ZERO_IMAGE_FORCE | CONSTV_FLAG_PDL)
+
+typedef struct constv_config {
+    uint32_t struct_size;      /* = sizeof(constv_config), for ABI evolution */
+    int32_t device;            /* CUDA device ordinal; -1 = current device */
+    int32_t num_atoms;         /* N = all particles, real + image (cu.getNumAtoms()) */
+    int32_t padded_num_atoms;  /* P >= N, force plane stride (cu.getPaddedNumAtoms()) */
+    int32_t num_cells;         /* integrator.getNumCells(): even, N % num_cells == 0 */
+    int32_t precision;         /* CONSTV_PRECISION_* */
+    int32_t mirror_mode;       /* CONSTV_MIRROR_* */
+    uint32_t flags;            /* CONSTV_FLAG_* */
+    double zmax;               /* resolved cell size (> 0), see constv_validate_system */
+    uint64_t seed;             /* Philox key; integrator.getRandomNumberSeed() (0 = caller picks) */
+    uint64_t global_atom_offset; /* original index of this slab's atom 0 in the whole system
+                                    (multi-GPU range partition); keys the Philox stream */
+    double boltz;              /* Boltzmann constant in kJ/mol/K; 0 = OpenMM's BOLTZ (8.31446261815324e-3) */
+} constv_config;
+
+/* ---- life cycle ------------------------------------------------------------------------------- */
+
+/* Replaces the checks in CudaIntegrateConstVLangevinStepKernel::initialize, Kernels.cpp:76-96:
+ * numCells even, N % numCells == 0, every particle with index >= N/numCells massless, and
+ * zmax = (cell_size < 0 ? box_z/numCells : cell_size) with zmax*numCells == box_z exactly.
+ * masses: N doubles in original particle order (system.getParticleMass).  Writes *zmax_out.
+ * Failure: CONSTV_ERR_SYSTEM with the reference's message.  Pure host code (no device needed). */
+CONSTV_API int constv_validate_system(int32_t num_atoms, int32_t num_cells, const double* masses,
+                                      double box_z, double cell_size, double* zmax_out);
+
+/* Replaces the allocation half of initialize (params + invAtomOrder, Kernels.cpp:71,99) and the
+ * RNG seeding (:64).  invAtomOrder starts as the identity (the reference leaves it uninitialised). */
+CONSTV_API int constv_create(const constv_config* config, constv_slab** out);
+
+/* Replaces ~CudaIntegrateConstVLangevinStepKernel, Kernels.cpp:53-59. */
+CONSTV_API int constv_destroy(constv_slab* slab);
+
+/* Hands the library the device arrays the reference fetches from CudaContext /
+ * CudaIntegrationUtilities on every execute (Kernels.cpp:147-166: getVelm, getForce, getPosDelta,
+ * getPosq, getPosqCorrection, getAtomIndexArray).  The arrays stay owned by the caller.
+ * posq_correction is required for mixed precision; pos_delta only for the split path;
+ * atom_index NULL means identity order. */
+CONSTV_API int constv_bind_arrays(constv_slab* slab, void* posq, void* posq_correction, void* velm,
+                                  void* force, void* pos_delta, const int32_t* atom_index);
+
+/* Alternative to constv_bind_arrays for hosts without device arrays of their own: the library
+ * allocates posq/(posq_correction)/velm/force/pos_delta in HBM and binds them. */
+CONSTV_API int constv_alloc_arrays(constv_slab* slab);
+
+/* Device addresses of the bound arrays (any output pointer may be NULL). */
+CONSTV_API int constv_get_arrays(constv_slab* slab, void** posq, void** posq_correction, void** velm,
+                                 void** force, void** pos_delta);
+
+/* ---- per-step entry points -------------------------------------------------------------------- */
+
+/* Replaces the parameter block of execute, Kernels.cpp:113-137: kT = BOLTZ*T,
+ * vscale = exp(-dt*friction), fscale = friction == 0 ? dt : (1-vscale)/friction,
+ * noisescale = sqrt(kT*(1-vscale^2)), cached on (T, friction, dt), rounded to float for single
+ * precision (:98-103).  Also covers setNextStepSize (:112). */
+CONSTV_API int constv_set_parameters(constv_slab* slab, double temperature, double friction,
+                                     double step_size);
+
+/* out[0..3] = vscale, fscale, noisescale, dt as the kernels see them (after rounding to `mixed`). */
+CONSTV_API int constv_get_parameters(const constv_slab* slab, double out[4]);
+
+/* Replaces the reorderInverseAtomOrderIndexes launch, Kernels.cpp:139-142 / Langevin.cu:170-177:
+ * invAtomOrder[atom_index[slot]] = slot.  Call when cu.getAtomsWereReordered(). */
+CONSTV_API int constv_update_inverse_order(constv_slab* slab, void* stream);
+
+/* Snapshot posq[image slot].w of every image into the side array used with
+ * CONSTV_FLAG_CACHE_IMAGE_CHARGE (the value Langevin.cu:153 re-reads every step). */
+CONSTV_API int constv_refresh_image_charges(constv_slab* slab, void* stream);
+
+/* Replaces the integrateConstVLangevinPart1 launch, Kernels.cpp:146-149 / Langevin.cu:7-28.
+ * random4 != NULL: consume the caller's float4 Gaussian pool at random4[random_index + slot]
+ * (exactly the reference's addressing; OpenMM's integration.getRandom()).  random4 == NULL: draw
+ * from the built-in counter-based Philox4x32-10 stream keyed (seed; original atom index, step). */
+CONSTV_API int constv_step_part1(constv_slab* slab, const void* random4, uint32_t random_index,
+                                 void* stream);
+
+/* Replaces the integrateConstVLangevinPart2 + updateImageParticlePositions launches,
+ * Kernels.cpp:158-166 / Langevin.cu:34-75,138-164, plus the image zeroing, and advances time and
+ * step count (Kernels.cpp:170-171).  The caller applies constraints to pos_delta between
+ * constv_step_part1 and this call (integration.applyConstraints, Kernels.cpp:153). */
+CONSTV_API int constv_step_part2_mirror(constv_slab* slab, void* stream);
+
+/* The whole of execute (Kernels.cpp:139-172) for a system without constraints in ONE kernel:
+ * part 1, part 2, the image rewrite and the image zeroing, each atom record crossing HBM once;
+ * pos_delta never leaves registers.  Same random4 / Philox convention as constv_step_part1. */
+CONSTV_API int constv_step_fused(constv_slab* slab, const void* random4, uint32_t random_index,
+                                 void* stream);
+
+/* One launch that advances n independent slabs (an ensemble of Contexts) by one fused step each;
+ * all slabs must share device, precision and identity order.  Philox noise only. */
+CONSTV_API int constv_step_fused_batched(constv_slab* const* slabs, int32_t n, void* stream);
+
+/* Replaces computeKineticEnergy, Kernels.cpp:175-177 (OpenMM's
+ * integration.computeKineticEnergy(0.5*dt)): KE = 0.5*sum m|v + time_shift*F/m|^2 over massive
+ * atoms, accumulated in double.  Synchronises `stream` and writes *ke_out on the host. */
+CONSTV_API int constv_kinetic_energy(constv_slab* slab, double time_shift, double* ke_out,
+                                     void* stream);
+
+/* Same, asynchronous: the double lands in device memory at ke_device (e.g. the buffer a scalar
+ * NCCL all-reduce then sums across the range partition). */
+CONSTV_API int constv_kinetic_energy_device(constv_slab* slab, double time_shift, double* ke_device,
+                                            void* stream);
+
+/* Writes the float4 Gaussians the Philox path would consume at `step` for slots [0, N) to the
+ * device array out4 (the stream that stands in for integration.prepareRandomNumbers/getRandom,
+ * Kernels.cpp:146,148).  For parity tests and for checkpoint verification. */
+CONSTV_API int constv_generate_noise(constv_slab* slab, uint64_t step, void* out4, void* stream);
+
+/* ---- bookkeeping (cu.getTime/setTime, getStepCount/setStepCount, Kernels.cpp:170-171) -------- */
+
+/* The step counter lives in device memory so that CUDA-graph replays advance the Philox stream;
+ * reading it synchronises the device.  It is the only persistent state to checkpoint besides the
+ * seed. */
+CONSTV_API int constv_get_step_count(constv_slab* slab, uint64_t* count);
+CONSTV_API int constv_set_step_count(constv_slab* slab, uint64_t count);
+CONSTV_API int constv_get_time(const constv_slab* slab, double* time);
+CONSTV_API int constv_set_time(constv_slab* slab, double time);
+
+/* ---- host-buffer convenience (the reference-facing call with HOST memory) -------------------- */
+
+/* Copy whole arrays between host buffers (layouts above, any may be NULL to skip) and the bound
+ * device arrays.  Synchronous with respect to `stream`. */
+CONSTV_API int constv_upload_state(constv_slab* slab, const void* posq, const void* posq_correction,
+                                   const void* velm, const int64_t* force, void* stream);
+CONSTV_API int constv_download_state(constv_slab* slab, void* posq, void* posq_correction,
+                                     void* velm, int64_t* force, void* stream);
+
+/* One step driven from host memory: uploads this step's forces for the real atoms
+ * (host_force_real: 3 planes of num_real int64, plane stride num_real), runs the fused step and
+ * downloads the updated posq (all N atoms, real4) and, if non-NULL, velm.  Pinned host memory
+ * makes the copies asynchronous; the call returns after the download has completed. */
+CONSTV_API int constv_step_host(constv_slab* slab, const int64_t* host_force_real, void* host_posq_out,
+                                void* host_velm_out, void* stream);
+
+/* ---- diagnostics ------------------------------------------------------------------------------ */
+
+CONSTV_API const char* constv_last_error(void);
+CONSTV_API int constv_version(void);
+/* Kernels launched by this library in this process so far (bench.py's gpu_launches). */
+CONSTV_API uint64_t constv_launch_count(void);
+/* Tuning knobs of the fused kernel: real/image pairs per thread (1, 2 or 4) and resident CTAs per
+ * SM that size the persistent grid (1..16); 0 keeps the current value. */
+CONSTV_API int constv_set_launch_shape(constv_slab* slab, int32_t pairs_per_thread, int32_t ctas_per_sm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONSTV_B200_H_ */

@@ -1,0 +1,644 @@
+// Host side of the C ABI declared in include/constv_b200.h: argument checking, parameter
+// computation, launch configuration and the CUDA runtime calls.  The reference code this replaces
+// is platforms/cuda/src/CudaConstVKernels.cpp:53-177 (scychon/openmm_constV); every entry point
+// cites its lines in the header.  No CPU fallback exists: without a device the calls fail.
+#include "constv_b200.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "constv_kernels.cuh"
+
+using namespace constv;
+
+namespace {
+
+thread_local std::string g_lastError;
+std::atomic<uint64_t> g_launchCount{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_lastError = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t err__ = (expr);                                                            \
+        if (err__ != cudaSuccess)                                                              \
+            return fail(CONSTV_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(err__));    \
+    } while (0)
+
+constexpr double kBoltzDefault = 8.31446261815324e-3;  // OpenMM SimTKOpenMMRealType.h BOLTZ (>= 7.4)
+constexpr int kBlock = 256;
+
+size_t realSize(int prec) { return prec == CONSTV_PRECISION_DOUBLE ? 8 : 4; }
+size_t mixedSize(int prec) { return prec == CONSTV_PRECISION_SINGLE ? 4 : 8; }
+
+}  // namespace
+
+struct constv_slab {
+    constv_config cfg{};
+    int numReal = 0;
+    int numSMs = 0;
+    // bound arrays
+    void* posq = nullptr;
+    void* corr = nullptr;
+    void* velm = nullptr;
+    void* force = nullptr;
+    void* posDelta = nullptr;
+    const int32_t* atomIndex = nullptr;
+    bool owned = false;
+    // library-owned device state
+    int* invAtomOrder = nullptr;
+    void* imageCharge = nullptr;
+    bool imageChargeValid = false;
+    DevCounters* counters = nullptr;
+    double* kePartials = nullptr;
+    double* keOut = nullptr;
+    double* keHost = nullptr;  // pinned
+    SlabDev* batchTable = nullptr;  // device table for the ensemble launch led by this slab
+    int batchCapacity = 0;
+    std::vector<SlabDev> batchHost;
+    // parameters
+    bool paramsSet = false;
+    double temperature = 0, friction = 0, stepSize = -1;
+    double vscale = 0, fscaleFixed = 0, noisescale = 0, dt = 0, invDt = 0;
+    double time = 0;
+    // launch shape
+    int ilp = 2;
+    int ctasPerSM = 4;
+    int blockSize = kBlock;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    int rc = CONSTV_OK;
+    explicit DeviceGuard(int device) {
+        if (device < 0) return;  // caller's current context (OpenMM interop): never switch
+        if (cudaGetDevice(&prev) != cudaSuccess) { rc = fail(CONSTV_ERR_CUDA, "cudaGetDevice failed: no CUDA device"); return; }
+        if (prev != device) {
+            cudaError_t e = cudaSetDevice(device);
+            if (e != cudaSuccess) { rc = fail(CONSTV_ERR_CUDA, "cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(e)); return; }
+            switched = true;
+        }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
+#define GUARD(slab)                              \
+    if (!(slab)) return fail(CONSTV_ERR_INVALID, "null slab"); \
+    DeviceGuard guard__((slab)->cfg.device);     \
+    if (guard__.rc) return guard__.rc
+
+SlabDev makeDev(const constv_slab* s) {
+    SlabDev d{};
+    d.posq = s->posq;
+    d.corr = s->corr;
+    d.velm = s->velm;
+    d.force = static_cast<long long*>(s->force);
+    d.posDelta = s->posDelta;
+    d.atomIndex = s->atomIndex;
+    d.invAtomOrder = s->invAtomOrder;
+    d.imageCharge = ((s->cfg.flags & CONSTV_FLAG_CACHE_IMAGE_CHARGE) && s->imageChargeValid) ? s->imageCharge : nullptr;
+    d.counters = s->counters;
+    d.numAtoms = s->cfg.num_atoms;
+    d.numReal = s->numReal;
+    d.padded = s->cfg.padded_num_atoms;
+    d.numCells = s->cfg.num_cells;
+    d.zshift = s->cfg.mirror_mode == CONSTV_MIRROR_NEGATE ? 0.0 : s->cfg.zmax;
+    d.invDt = s->invDt;
+    d.vscale = s->vscale;
+    d.fscaleFixed = s->fscaleFixed;
+    d.noisescale = s->noisescale;
+    d.dt = s->dt;
+    d.seed = s->cfg.seed;
+    d.globalAtomOffset = s->cfg.global_atom_offset;
+    d.zeroVelm = (s->cfg.flags & CONSTV_FLAG_ZERO_IMAGE_VELM) ? 1u : 0u;
+    d.zeroForce = (s->cfg.flags & CONSTV_FLAG_ZERO_IMAGE_FORCE) ? 1u : 0u;
+    d.tileBase = 0;
+    return d;
+}
+
+int checkReady(const constv_slab* s, bool needDelta) {
+    if (!s->posq || !s->velm || !s->force) return fail(CONSTV_ERR_STATE, "device arrays are not bound (constv_bind_arrays / constv_alloc_arrays)");
+    if (s->cfg.precision == CONSTV_PRECISION_MIXED && !s->corr) return fail(CONSTV_ERR_STATE, "mixed precision needs posq_correction");
+    if (needDelta && !s->posDelta) return fail(CONSTV_ERR_STATE, "the split path needs pos_delta");
+    if (!s->paramsSet) return fail(CONSTV_ERR_STATE, "constv_set_parameters has not been called");
+    return CONSTV_OK;
+}
+
+template <typename K, typename... Args>
+int launch(K kernel, int grid, int block, bool pdl, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned) grid);
+    cfg.blockDim = dim3((unsigned) block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, args...));
+    g_launchCount.fetch_add(1, std::memory_order_relaxed);
+    return CONSTV_OK;
+}
+
+int gridFor(const constv_slab* s, long long work, int perBlock, int ctasPerSM) {
+    long long blocks = (work + perBlock - 1) / perBlock;
+    long long cap = (long long) s->numSMs * ctasPerSM;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int) blocks;
+}
+
+// ---- dispatch over (precision, ILP) --------------------------------------------------------------
+
+template <int PREC>
+int launchFused(constv_slab* s, const SlabDev& d, const float4* random, unsigned randomIndex, cudaStream_t st) {
+    const bool pdl = s->cfg.flags & CONSTV_FLAG_PDL;
+    switch (s->ilp) {
+        case 1: return launch(constv_fused_step_kernel<PREC, kBlock, 1>, gridFor(s, s->numReal, kBlock * 1, s->ctasPerSM), kBlock, pdl, st, d, random, randomIndex);
+        case 4: return launch(constv_fused_step_kernel<PREC, kBlock, 4>, gridFor(s, s->numReal, kBlock * 4, s->ctasPerSM), kBlock, pdl, st, d, random, randomIndex);
+        default: return launch(constv_fused_step_kernel<PREC, kBlock, 2>, gridFor(s, s->numReal, kBlock * 2, s->ctasPerSM), kBlock, pdl, st, d, random, randomIndex);
+    }
+}
+
+template <int PREC>
+int launchFusedIndexed(constv_slab* s, const SlabDev& d, const float4* random, unsigned randomIndex, cudaStream_t st) {
+    return launch(constv_fused_step_indexed_kernel<PREC, kBlock>, gridFor(s, s->cfg.num_atoms, kBlock, 8), kBlock,
+                  (bool) (s->cfg.flags & CONSTV_FLAG_PDL), st, d, random, randomIndex);
+}
+
+template <int PREC>
+int launchPart1(constv_slab* s, const SlabDev& d, const float4* random, unsigned randomIndex, cudaStream_t st) {
+    return launch(constv_part1_kernel<PREC, kBlock>, gridFor(s, s->cfg.num_atoms, kBlock, 8), kBlock,
+                  (bool) (s->cfg.flags & CONSTV_FLAG_PDL), st, d, random, randomIndex);
+}
+
+template <int PREC>
+int launchPart2(constv_slab* s, const SlabDev& d, cudaStream_t st) {
+    if (!s->atomIndex)
+        return launch(constv_part2_mirror_kernel<PREC, kBlock>, gridFor(s, s->numReal, kBlock, 8), kBlock,
+                      (bool) (s->cfg.flags & CONSTV_FLAG_PDL), st, d);
+    int rc = launch(constv_part2_indexed_kernel<PREC, kBlock>, gridFor(s, s->cfg.num_atoms, kBlock, 8), kBlock, false, st, d);
+    if (rc) return rc;
+    return launch(constv_mirror_indexed_kernel<PREC, kBlock>, gridFor(s, s->numReal, kBlock, 8), kBlock, false, st, d);
+}
+
+template <int PREC>
+int launchKE(constv_slab* s, const SlabDev& d, double scale, double* out, cudaStream_t st) {
+    const int grid = gridFor(s, s->cfg.num_atoms, kBlock, 4);
+    return launch(constv_kinetic_energy_kernel<PREC, kBlock>, grid, kBlock, false, st, d, scale, s->kePartials, out);
+}
+
+template <int PREC>
+int launchBatched(constv_slab* lead, int n, int totalTiles, int ilp, cudaStream_t st) {
+    const bool pdl = lead->cfg.flags & CONSTV_FLAG_PDL;
+    long long cap = (long long) lead->numSMs * lead->ctasPerSM;
+    const int grid = (int) (totalTiles < cap ? totalTiles : cap);
+    const SlabDev* table = lead->batchTable;
+    switch (ilp) {
+        case 1: return launch(constv_fused_step_batched_kernel<PREC, kBlock, 1>, grid, kBlock, pdl, st, table, n, totalTiles);
+        case 4: return launch(constv_fused_step_batched_kernel<PREC, kBlock, 4>, grid, kBlock, pdl, st, table, n, totalTiles);
+        default: return launch(constv_fused_step_batched_kernel<PREC, kBlock, 2>, grid, kBlock, pdl, st, table, n, totalTiles);
+    }
+}
+
+#define DISPATCH_PREC(prec, call)                                       \
+    switch (prec) {                                                     \
+        case CONSTV_PRECISION_SINGLE: { constexpr int PR = PREC_SINGLE; rc = call; break; } \
+        case CONSTV_PRECISION_MIXED:  { constexpr int PR = PREC_MIXED;  rc = call; break; } \
+        default:                      { constexpr int PR = PREC_DOUBLE; rc = call; break; } \
+    }
+
+void advanceTime(constv_slab* s) { s->time += s->stepSize; }
+
+}  // namespace
+
+// =================================================================================================
+
+extern "C" {
+
+const char* constv_last_error(void) { return g_lastError.c_str(); }
+int constv_version(void) { return CONSTV_VERSION; }
+uint64_t constv_launch_count(void) { return g_launchCount.load(std::memory_order_relaxed); }
+
+int constv_validate_system(int32_t num_atoms, int32_t num_cells, const double* masses, double box_z,
+                           double cell_size, double* zmax_out) {
+    if (num_atoms < 0 || num_cells <= 0 || (!masses && num_atoms > 0))
+        return fail(CONSTV_ERR_INVALID, "constv_validate_system: bad arguments");
+    if (num_cells % 2 != 0) return fail(CONSTV_ERR_SYSTEM, "Not even number of cells");
+    if (num_atoms % num_cells != 0) return fail(CONSTV_ERR_SYSTEM, "Number of particles is not multiple of number of cells");
+    for (int i = num_atoms / num_cells; i < num_atoms; i++)
+        if (masses[i] != 0.0) return fail(CONSTV_ERR_SYSTEM, "Image Particle has nonzero mass");
+    double zmax = cell_size;
+    if (zmax < 0)
+        zmax = box_z / num_cells;
+    else if (zmax * num_cells != box_z)
+        return fail(CONSTV_ERR_SYSTEM, "Unit cell dimension does not match with the provided zmax value");
+    if (zmax_out) *zmax_out = zmax;
+    return CONSTV_OK;
+}
+
+int constv_create(const constv_config* config, constv_slab** out) {
+    if (!config || !out) return fail(CONSTV_ERR_INVALID, "constv_create: null argument");
+    if (config->struct_size != sizeof(constv_config)) return fail(CONSTV_ERR_INVALID, "constv_create: struct_size %u != %zu", config->struct_size, sizeof(constv_config));
+    if (config->num_cells < 2 || config->num_cells % 2 != 0) return fail(CONSTV_ERR_SYSTEM, "Not even number of cells");
+    if (config->num_atoms <= 0 || config->num_atoms % config->num_cells != 0) return fail(CONSTV_ERR_SYSTEM, "Number of particles is not multiple of number of cells");
+    if (config->padded_num_atoms < config->num_atoms) return fail(CONSTV_ERR_INVALID, "padded_num_atoms < num_atoms");
+    if (config->precision < 0 || config->precision > 2) return fail(CONSTV_ERR_INVALID, "unknown precision %d", config->precision);
+    if (config->mirror_mode != CONSTV_MIRROR_REFERENCE && config->mirror_mode != CONSTV_MIRROR_NEGATE) return fail(CONSTV_ERR_INVALID, "unknown mirror mode %d", config->mirror_mode);
+    if (config->mirror_mode == CONSTV_MIRROR_NEGATE && config->num_cells != 2) return fail(CONSTV_ERR_INVALID, "CONSTV_MIRROR_NEGATE requires num_cells == 2");
+    if (!(config->zmax > 0)) return fail(CONSTV_ERR_INVALID, "zmax must be resolved (> 0); see constv_validate_system");
+
+    constv_slab* s = new (std::nothrow) constv_slab();
+    if (!s) return fail(CONSTV_ERR_INVALID, "out of host memory");
+    s->cfg = *config;
+    if (s->cfg.boltz == 0) s->cfg.boltz = kBoltzDefault;
+    s->numReal = config->num_atoms / config->num_cells;
+    DeviceGuard guard(config->device);
+    if (guard.rc) { delete s; return guard.rc; }
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->numSMs, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) { delete s; return fail(CONSTV_ERR_CUDA, "no usable CUDA device: %s", cudaGetErrorString(e)); }
+
+    const int P = config->padded_num_atoms;
+    auto cleanup = [&](cudaError_t err, const char* what) {
+        constv_destroy(s);
+        return fail(CONSTV_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(err));
+    };
+    if ((e = cudaMalloc(&s->invAtomOrder, sizeof(int) * (size_t) P)) != cudaSuccess) return cleanup(e, "cudaMalloc(invAtomOrder)");
+    if ((e = cudaMalloc(&s->imageCharge, realSize(config->precision) * (size_t) (config->num_atoms - s->numReal))) != cudaSuccess) return cleanup(e, "cudaMalloc(imageCharge)");
+    if ((e = cudaMalloc(&s->counters, sizeof(DevCounters))) != cudaSuccess) return cleanup(e, "cudaMalloc(counters)");
+    if ((e = cudaMemset(s->counters, 0, sizeof(DevCounters))) != cudaSuccess) return cleanup(e, "cudaMemset(counters)");
+    const int maxBlocks = s->numSMs * 16;
+    if ((e = cudaMalloc(&s->kePartials, sizeof(double) * (size_t) maxBlocks)) != cudaSuccess) return cleanup(e, "cudaMalloc(kePartials)");
+    if ((e = cudaMalloc(&s->keOut, sizeof(double))) != cudaSuccess) return cleanup(e, "cudaMalloc(keOut)");
+    if ((e = cudaMallocHost(&s->keHost, sizeof(double))) != cudaSuccess) return cleanup(e, "cudaMallocHost(keHost)");
+    // identity inverse order (the reference leaves this array uninitialised until the first reorder)
+    {
+        std::vector<int> ident((size_t) P);
+        for (int i = 0; i < P; i++) ident[(size_t) i] = i;
+        if ((e = cudaMemcpy(s->invAtomOrder, ident.data(), sizeof(int) * (size_t) P, cudaMemcpyHostToDevice)) != cudaSuccess) return cleanup(e, "cudaMemcpy(invAtomOrder)");
+    }
+    *out = s;
+    return CONSTV_OK;
+}
+
+int constv_destroy(constv_slab* s) {
+    if (!s) return CONSTV_OK;
+    DeviceGuard guard(s->cfg.device);
+    if (s->owned) {
+        cudaFree(s->posq); cudaFree(s->corr); cudaFree(s->velm); cudaFree(s->force); cudaFree(s->posDelta);
+    }
+    cudaFree(s->invAtomOrder);
+    cudaFree(s->imageCharge);
+    cudaFree(s->counters);
+    cudaFree(s->kePartials);
+    cudaFree(s->keOut);
+    cudaFree(s->batchTable);
+    if (s->keHost) cudaFreeHost(s->keHost);
+    delete s;
+    return CONSTV_OK;
+}
+
+int constv_bind_arrays(constv_slab* s, void* posq, void* posq_correction, void* velm, void* force,
+                       void* pos_delta, const int32_t* atom_index) {
+    if (!s) return fail(CONSTV_ERR_INVALID, "null slab");
+    if (!posq || !velm || !force) return fail(CONSTV_ERR_INVALID, "posq, velm and force are required");
+    if (s->cfg.precision == CONSTV_PRECISION_MIXED && !posq_correction) return fail(CONSTV_ERR_INVALID, "mixed precision needs posq_correction");
+    if (((uintptr_t) posq | (uintptr_t) posq_correction | (uintptr_t) velm | (uintptr_t) force | (uintptr_t) pos_delta) & 15u)
+        return fail(CONSTV_ERR_INVALID, "device arrays must be 16-byte aligned");
+    if (s->owned) {
+        DeviceGuard guard(s->cfg.device);
+        cudaFree(s->posq); cudaFree(s->corr); cudaFree(s->velm); cudaFree(s->force); cudaFree(s->posDelta);
+        s->owned = false;
+    }
+    s->posq = posq;
+    s->corr = s->cfg.precision == CONSTV_PRECISION_MIXED ? posq_correction : nullptr;
+    s->velm = velm;
+    s->force = force;
+    s->posDelta = pos_delta;
+    s->atomIndex = atom_index;
+    s->imageChargeValid = false;
+    return CONSTV_OK;
+}
+
+int constv_alloc_arrays(constv_slab* s) {
+    GUARD(s);
+    if (s->owned) return CONSTV_OK;
+    const size_t P = (size_t) s->cfg.padded_num_atoms;
+    const size_t rb = 4 * realSize(s->cfg.precision) * P, mb = 4 * mixedSize(s->cfg.precision) * P;
+    void *posq = nullptr, *corr = nullptr, *velm = nullptr, *force = nullptr, *delta = nullptr;
+    CUDA_TRY(cudaMalloc(&posq, rb));
+    CUDA_TRY(cudaMemset(posq, 0, rb));
+    if (s->cfg.precision == CONSTV_PRECISION_MIXED) {
+        CUDA_TRY(cudaMalloc(&corr, rb));
+        CUDA_TRY(cudaMemset(corr, 0, rb));
+    }
+    CUDA_TRY(cudaMalloc(&velm, mb));
+    CUDA_TRY(cudaMemset(velm, 0, mb));
+    CUDA_TRY(cudaMalloc(&force, 24 * P));
+    CUDA_TRY(cudaMemset(force, 0, 24 * P));
+    CUDA_TRY(cudaMalloc(&delta, mb));
+    CUDA_TRY(cudaMemset(delta, 0, mb));
+    s->posq = posq; s->corr = corr; s->velm = velm; s->force = force; s->posDelta = delta;
+    s->atomIndex = nullptr;
+    s->owned = true;
+    s->imageChargeValid = false;
+    return CONSTV_OK;
+}
+
+int constv_get_arrays(constv_slab* s, void** posq, void** posq_correction, void** velm, void** force, void** pos_delta) {
+    if (!s) return fail(CONSTV_ERR_INVALID, "null slab");
+    if (posq) *posq = s->posq;
+    if (posq_correction) *posq_correction = s->corr;
+    if (velm) *velm = s->velm;
+    if (force) *force = s->force;
+    if (pos_delta) *pos_delta = s->posDelta;
+    return CONSTV_OK;
+}
+
+int constv_set_parameters(constv_slab* s, double temperature, double friction, double step_size) {
+    if (!s) return fail(CONSTV_ERR_INVALID, "null slab");
+    if (!(step_size > 0)) return fail(CONSTV_ERR_INVALID, "step size must be positive");
+    if (s->paramsSet && temperature == s->temperature && friction == s->friction && step_size == s->stepSize)
+        return CONSTV_OK;  // Kernels.cpp:113: recompute only on change
+    const double kT = s->cfg.boltz * temperature;
+    const double vscale = std::exp(-step_size * friction);
+    const double fscale = (friction == 0 ? step_size : (1 - vscale) / friction);
+    const double noisescale = std::sqrt(kT * (1 - vscale * vscale));
+    if (s->cfg.precision == CONSTV_PRECISION_SINGLE) {
+        const float dtf = (float) step_size;
+        s->vscale = (double) (float) vscale;
+        s->fscaleFixed = (double) ((float) fscale / (float) 4294967296.0);  // Langevin.cu:10
+        s->noisescale = (double) (float) noisescale;
+        s->dt = (double) dtf;
+        s->invDt = 1.0 / (double) dtf;  // Langevin.cu:36
+    } else {
+        s->vscale = vscale;
+        s->fscaleFixed = fscale / 4294967296.0;
+        s->noisescale = noisescale;
+        s->dt = step_size;
+        s->invDt = 1.0 / step_size;
+    }
+    s->temperature = temperature;
+    s->friction = friction;
+    s->stepSize = step_size;
+    s->paramsSet = true;
+    return CONSTV_OK;
+}
+
+int constv_get_parameters(const constv_slab* s, double out[4]) {
+    if (!s || !out) return fail(CONSTV_ERR_INVALID, "null argument");
+    if (!s->paramsSet) return fail(CONSTV_ERR_STATE, "constv_set_parameters has not been called");
+    out[0] = s->vscale;
+    out[1] = s->fscaleFixed * 4294967296.0;
+    out[2] = s->noisescale;
+    out[3] = s->dt;
+    return CONSTV_OK;
+}
+
+int constv_update_inverse_order(constv_slab* s, void* stream) {
+    GUARD(s);
+    if (!s->atomIndex) return fail(CONSTV_ERR_STATE, "no atom_index array is bound (identity order)");
+    const int n = s->cfg.num_atoms;
+    int rc = launch(constv_inverse_order_kernel, gridFor(s, n, 256, 8), 256, false, (cudaStream_t) stream, n,
+                    (const int*) s->atomIndex, s->invAtomOrder);
+    return rc;
+}
+
+int constv_refresh_image_charges(constv_slab* s, void* stream) {
+    GUARD(s);
+    if (!s->posq) return fail(CONSTV_ERR_STATE, "device arrays are not bound");
+    const int n = s->cfg.num_atoms - s->numReal;
+    int rc;
+    if (s->cfg.precision == CONSTV_PRECISION_DOUBLE)
+        rc = launch(constv_image_charge_kernel<double>, gridFor(s, n, 256, 8), 256, false, (cudaStream_t) stream,
+                    s->numReal, s->cfg.num_cells, (const double*) s->posq, (const int*) s->invAtomOrder, (double*) s->imageCharge);
+    else
+        rc = launch(constv_image_charge_kernel<float>, gridFor(s, n, 256, 8), 256, false, (cudaStream_t) stream,
+                    s->numReal, s->cfg.num_cells, (const float*) s->posq, (const int*) s->invAtomOrder, (float*) s->imageCharge);
+    if (rc == CONSTV_OK) s->imageChargeValid = true;
+    return rc;
+}
+
+int constv_step_fused(constv_slab* s, const void* random4, uint32_t random_index, void* stream) {
+    GUARD(s);
+    int rc = checkReady(s, false);
+    if (rc) return rc;
+    if ((s->cfg.flags & CONSTV_FLAG_CACHE_IMAGE_CHARGE) && !s->imageChargeValid) {
+        rc = constv_refresh_image_charges(s, stream);
+        if (rc) return rc;
+    }
+    const SlabDev d = makeDev(s);
+    const float4* rnd = static_cast<const float4*>(random4);
+    cudaStream_t st = (cudaStream_t) stream;
+    if (s->atomIndex) {
+        DISPATCH_PREC(s->cfg.precision, launchFusedIndexed<PR>(s, d, rnd, random_index, st));
+    } else {
+        DISPATCH_PREC(s->cfg.precision, launchFused<PR>(s, d, rnd, random_index, st));
+    }
+    if (rc == CONSTV_OK) advanceTime(s);
+    return rc;
+}
+
+int constv_step_part1(constv_slab* s, const void* random4, uint32_t random_index, void* stream) {
+    GUARD(s);
+    int rc = checkReady(s, true);
+    if (rc) return rc;
+    const SlabDev d = makeDev(s);
+    DISPATCH_PREC(s->cfg.precision, launchPart1<PR>(s, d, static_cast<const float4*>(random4), random_index, (cudaStream_t) stream));
+    return rc;
+}
+
+int constv_step_part2_mirror(constv_slab* s, void* stream) {
+    GUARD(s);
+    int rc = checkReady(s, true);
+    if (rc) return rc;
+    if ((s->cfg.flags & CONSTV_FLAG_CACHE_IMAGE_CHARGE) && !s->imageChargeValid) {
+        rc = constv_refresh_image_charges(s, stream);
+        if (rc) return rc;
+    }
+    const SlabDev d = makeDev(s);
+    DISPATCH_PREC(s->cfg.precision, launchPart2<PR>(s, d, (cudaStream_t) stream));
+    if (rc == CONSTV_OK) advanceTime(s);
+    return rc;
+}
+
+int constv_step_fused_batched(constv_slab* const* slabs, int32_t n, void* stream) {
+    if (!slabs || n <= 0) return fail(CONSTV_ERR_INVALID, "constv_step_fused_batched: empty batch");
+    constv_slab* lead = slabs[0];
+    GUARD(lead);
+    int rc;
+    lead->batchHost.resize((size_t) n);
+    const int tile = kBlock * lead->ilp;
+    int totalTiles = 0;
+    for (int k = 0; k < n; k++) {
+        constv_slab* s = slabs[k];
+        if (!s) return fail(CONSTV_ERR_INVALID, "null slab in batch");
+        if (s->cfg.precision != lead->cfg.precision || s->cfg.device != lead->cfg.device)
+            return fail(CONSTV_ERR_INVALID, "batched slabs must share device and precision");
+        if (s->atomIndex) return fail(CONSTV_ERR_INVALID, "batched launch needs identity slot order");
+        if ((rc = checkReady(s, false))) return rc;
+        if ((s->cfg.flags & CONSTV_FLAG_CACHE_IMAGE_CHARGE) && !s->imageChargeValid)
+            if ((rc = constv_refresh_image_charges(s, stream))) return rc;
+        SlabDev d = makeDev(s);
+        d.tileBase = totalTiles;
+        totalTiles += (s->numReal + tile - 1) / tile;
+        lead->batchHost[(size_t) k] = d;
+    }
+    if (lead->batchCapacity < n) {
+        cudaFree(lead->batchTable);
+        lead->batchTable = nullptr;
+        lead->batchCapacity = 0;
+        CUDA_TRY(cudaMalloc(&lead->batchTable, sizeof(SlabDev) * (size_t) n));
+        lead->batchCapacity = n;
+    }
+    CUDA_TRY(cudaMemcpyAsync(lead->batchTable, lead->batchHost.data(), sizeof(SlabDev) * (size_t) n, cudaMemcpyHostToDevice, (cudaStream_t) stream));
+    DISPATCH_PREC(lead->cfg.precision, launchBatched<PR>(lead, n, totalTiles, lead->ilp, (cudaStream_t) stream));
+    if (rc == CONSTV_OK)
+        for (int k = 0; k < n; k++) advanceTime(slabs[k]);
+    return rc;
+}
+
+int constv_kinetic_energy_device(constv_slab* s, double time_shift, double* ke_device, void* stream) {
+    GUARD(s);
+    if (!s->velm || !s->force) return fail(CONSTV_ERR_STATE, "device arrays are not bound");
+    if (!ke_device) return fail(CONSTV_ERR_INVALID, "null output");
+    const SlabDev d = makeDev(s);
+    const double scale = time_shift / 4294967296.0;
+    int rc;
+    DISPATCH_PREC(s->cfg.precision, launchKE<PR>(s, d, scale, ke_device, (cudaStream_t) stream));
+    return rc;
+}
+
+int constv_kinetic_energy(constv_slab* s, double time_shift, double* ke_out, void* stream) {
+    if (!ke_out) return fail(CONSTV_ERR_INVALID, "null output");
+    int rc = constv_kinetic_energy_device(s, time_shift, s ? s->keOut : nullptr, stream);
+    if (rc) return rc;
+    GUARD(s);
+    CUDA_TRY(cudaMemcpyAsync(s->keHost, s->keOut, sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t) stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t) stream));
+    *ke_out = *s->keHost;
+    return CONSTV_OK;
+}
+
+int constv_generate_noise(constv_slab* s, uint64_t step, void* out4, void* stream) {
+    GUARD(s);
+    if (!out4) return fail(CONSTV_ERR_INVALID, "null output");
+    const int n = s->cfg.num_atoms;
+    return launch(constv_noise_kernel, gridFor(s, n, 256, 8), 256, false, (cudaStream_t) stream, n,
+                  (const int*) s->atomIndex, (unsigned long long) s->cfg.seed,
+                  (unsigned long long) s->cfg.global_atom_offset, (unsigned long long) step, static_cast<float4*>(out4));
+}
+
+int constv_get_step_count(constv_slab* s, uint64_t* count) {
+    GUARD(s);
+    if (!count) return fail(CONSTV_ERR_INVALID, "null output");
+    unsigned long long v = 0;
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(&v, &s->counters->step, sizeof v, cudaMemcpyDeviceToHost));
+    *count = v;
+    return CONSTV_OK;
+}
+
+int constv_set_step_count(constv_slab* s, uint64_t count) {
+    GUARD(s);
+    const unsigned long long v = count;
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(&s->counters->step, &v, sizeof v, cudaMemcpyHostToDevice));
+    return CONSTV_OK;
+}
+
+int constv_get_time(const constv_slab* s, double* time) {
+    if (!s || !time) return fail(CONSTV_ERR_INVALID, "null argument");
+    *time = s->time;
+    return CONSTV_OK;
+}
+
+int constv_set_time(constv_slab* s, double time) {
+    if (!s) return fail(CONSTV_ERR_INVALID, "null slab");
+    s->time = time;
+    return CONSTV_OK;
+}
+
+int constv_upload_state(constv_slab* s, const void* posq, const void* posq_correction, const void* velm,
+                        const int64_t* force, void* stream) {
+    GUARD(s);
+    if (!s->posq) return fail(CONSTV_ERR_STATE, "device arrays are not bound");
+    const size_t P = (size_t) s->cfg.padded_num_atoms;
+    const size_t rb = 4 * realSize(s->cfg.precision) * P, mb = 4 * mixedSize(s->cfg.precision) * P;
+    cudaStream_t st = (cudaStream_t) stream;
+    if (posq) { CUDA_TRY(cudaMemcpyAsync(s->posq, posq, rb, cudaMemcpyHostToDevice, st)); s->imageChargeValid = false; }
+    if (posq_correction && s->corr) CUDA_TRY(cudaMemcpyAsync(s->corr, posq_correction, rb, cudaMemcpyHostToDevice, st));
+    if (velm) CUDA_TRY(cudaMemcpyAsync(s->velm, velm, mb, cudaMemcpyHostToDevice, st));
+    if (force) CUDA_TRY(cudaMemcpyAsync(s->force, force, 24 * P, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return CONSTV_OK;
+}
+
+int constv_download_state(constv_slab* s, void* posq, void* posq_correction, void* velm, int64_t* force, void* stream) {
+    GUARD(s);
+    if (!s->posq) return fail(CONSTV_ERR_STATE, "device arrays are not bound");
+    const size_t P = (size_t) s->cfg.padded_num_atoms;
+    const size_t rb = 4 * realSize(s->cfg.precision) * P, mb = 4 * mixedSize(s->cfg.precision) * P;
+    cudaStream_t st = (cudaStream_t) stream;
+    if (posq) CUDA_TRY(cudaMemcpyAsync(posq, s->posq, rb, cudaMemcpyDeviceToHost, st));
+    if (posq_correction && s->corr) CUDA_TRY(cudaMemcpyAsync(posq_correction, s->corr, rb, cudaMemcpyDeviceToHost, st));
+    if (velm) CUDA_TRY(cudaMemcpyAsync(velm, s->velm, mb, cudaMemcpyDeviceToHost, st));
+    if (force) CUDA_TRY(cudaMemcpyAsync(force, s->force, 24 * P, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return CONSTV_OK;
+}
+
+int constv_step_host(constv_slab* s, const int64_t* host_force_real, void* host_posq_out, void* host_velm_out, void* stream) {
+    GUARD(s);
+    int rc = checkReady(s, false);
+    if (rc) return rc;
+    if (s->atomIndex) return fail(CONSTV_ERR_STATE, "constv_step_host needs identity slot order");
+    cudaStream_t st = (cudaStream_t) stream;
+    const size_t P = (size_t) s->cfg.padded_num_atoms, R = (size_t) s->numReal, N = (size_t) s->cfg.num_atoms;
+    if (host_force_real)
+        CUDA_TRY(cudaMemcpy2DAsync(s->force, 8 * P, host_force_real, 8 * R, 8 * R, 3, cudaMemcpyHostToDevice, st));
+    rc = constv_step_fused(s, nullptr, 0, stream);
+    if (rc) return rc;
+    if (host_posq_out)
+        CUDA_TRY(cudaMemcpyAsync(host_posq_out, s->posq, 4 * realSize(s->cfg.precision) * N, cudaMemcpyDeviceToHost, st));
+    if (host_velm_out)
+        CUDA_TRY(cudaMemcpyAsync(host_velm_out, s->velm, 4 * mixedSize(s->cfg.precision) * N, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return CONSTV_OK;
+}
+
+int constv_set_launch_shape(constv_slab* s, int32_t pairs_per_thread, int32_t ctas_per_sm) {
+    if (!s) return fail(CONSTV_ERR_INVALID, "null slab");
+    if (pairs_per_thread != 0) {
+        if (pairs_per_thread != 1 && pairs_per_thread != 2 && pairs_per_thread != 4)
+            return fail(CONSTV_ERR_INVALID, "pairs_per_thread must be 1, 2 or 4");
+        s->ilp = pairs_per_thread;
+    }
+    if (ctas_per_sm != 0) {
+        if (ctas_per_sm < 1 || ctas_per_sm > 16) return fail(CONSTV_ERR_INVALID, "ctas_per_sm must be in 1..16");
+        s->ctasPerSM = ctas_per_sm;
+    }
+    return CONSTV_OK;
+}
+
+}  // extern "C"

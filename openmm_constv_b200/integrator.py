@@ -1,0 +1,392 @@
+"""Python host mirror of the reference's plugin interface for the ConstV Langevin step path.
+
+Same names, argument meaning and error behaviour as the reference (scychon/openmm_constV):
+
+  ConstVLangevinIntegrator            openmmapi/include/openmm/ConstVLangevinIntegrator.h:46-176,
+                                      openmmapi/src/ConstVLangevinIntegrator.cpp:44-85,
+                                      python/constvplugin.i:65-80
+  IntegrateConstVLangevinStepKernel   openmmapi/include/openmm/ConstVKernels.h:49-77 (interface),
+                                      platforms/cuda/src/CudaConstVKernels.cpp:53-177 (CUDA impl)
+  SlabSystem / SlabContext            the small part of OpenMM's System / Context / CudaContext the
+                                      path touches, standing in for OpenMM, which is
+                                      not available here.  Forces are injected: the context's
+                                      ``force_fn`` plays the role of context.calcForcesAndEnergy.
+
+All compute goes through the C ABI (``_capi``); torch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _capi
+from ._capi import ConstVError, check
+
+_TORCH_REAL = {"single": "float32", "mixed": "float32", "double": "float64"}
+_TORCH_MIXED = {"single": "float32", "mixed": "float64", "double": "float64"}
+
+
+class OpenMMException(Exception):
+    """Stands in for OpenMM::OpenMMException (same messages as the reference)."""
+
+
+def _raise_openmm(err: ConstVError):
+    if err.code == _capi.ERR_SYSTEM:
+        raise OpenMMException(str(err)) from None
+    raise err
+
+
+class SlabSystem:
+    """The slice of OpenMM::System the integrator reads: particle masses and the periodic box
+    (CudaConstVKernels.cpp:79-89)."""
+
+    def __init__(self):
+        self._masses: list[float] = []
+        self._box = ((1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0))
+
+    def addParticle(self, mass: float) -> int:
+        self._masses.append(float(mass))
+        return len(self._masses) - 1
+
+    def addParticles(self, masses) -> None:
+        self._masses.extend(np.asarray(masses, np.float64).tolist())
+
+    def getParticleMasses(self) -> np.ndarray:
+        return np.asarray(self._masses, np.float64)
+
+    def getNumParticles(self) -> int:
+        return len(self._masses)
+
+    def getParticleMass(self, index: int) -> float:
+        return self._masses[index]
+
+    def setParticleMass(self, index: int, mass: float) -> None:
+        self._masses[index] = float(mass)
+
+    def setDefaultPeriodicBoxVectors(self, a, b, c) -> None:
+        self._box = (tuple(a), tuple(b), tuple(c))
+
+    def getDefaultPeriodicBoxVectors(self):
+        return self._box
+
+
+class ConstVLangevinIntegrator:
+    """Langevin dynamics with exact image charges between slab electrodes.
+
+    ``ConstVLangevinIntegrator(temperature, frictionCoeff, stepSize, numCells=2, zmax=-1)``:
+    kelvin, 1/ps, ps; ``numCells`` counts real + image cells; ``zmax`` < 0 derives the cell size
+    from the periodic box (ConstVLangevinIntegrator.h:57).  Constraint tolerance defaults to 1e-5
+    and the random seed to 0 (ConstVLangevinIntegrator.cpp:50-51).
+    """
+
+    def __init__(self, temperature, frictionCoeff, stepSize, numCells=2, zmax=-1):
+        self._context = None
+        self._kernel = None
+        self.setTemperature(temperature)
+        self.setFriction(frictionCoeff)
+        self.setStepSize(stepSize)
+        self.setNumCells(numCells)
+        self.setCellSize(zmax)
+        self.setConstraintTolerance(1e-5)
+        self.setRandomNumberSeed(0)
+
+    # -- accessors (ConstVLangevinIntegrator.h:63-144 and OpenMM::Integrator) ------------------
+    def getNumCells(self): return self._num_cells
+    def setNumCells(self, cells): self._num_cells = int(cells)
+    def getCellSize(self): return self._cell_size
+    def setCellSize(self, zmax): self._cell_size = float(zmax)
+    def getTemperature(self): return self._temperature
+    def setTemperature(self, temp): self._temperature = float(temp)
+    def getFriction(self): return self._friction
+    def setFriction(self, coeff): self._friction = float(coeff)
+    def getRandomNumberSeed(self): return self._seed
+    def setRandomNumberSeed(self, seed): self._seed = int(seed)
+    def getStepSize(self): return self._step_size
+    def setStepSize(self, size): self._step_size = float(size)
+    def getConstraintTolerance(self): return self._constraint_tol
+    def setConstraintTolerance(self, tol): self._constraint_tol = float(tol)
+
+    # -- Integrator protocol (ConstVLangevinIntegrator.cpp:54-85) ------------------------------
+    def _initialize(self, context: "SlabContext") -> None:
+        if self._context is not None and self._context is not context:
+            raise OpenMMException("This Integrator is already bound to a context")
+        self._context = context
+        self._kernel = IntegrateConstVLangevinStepKernel(IntegrateConstVLangevinStepKernel.Name(),
+                                                         context)
+        self._kernel.initialize(context.getSystem(), self)
+
+    def _cleanup(self) -> None:
+        if self._kernel is not None:
+            self._kernel.close()
+        self._kernel = None
+        self._context = None
+
+    def getKernelNames(self):
+        return [IntegrateConstVLangevinStepKernel.Name()]
+
+    def computeKineticEnergy(self) -> float:
+        if self._context is None:
+            raise OpenMMException("This Integrator is not bound to a context!")
+        return self._kernel.computeKineticEnergy(self._context, self)
+
+    def step(self, steps: int) -> None:
+        if self._context is None:
+            raise OpenMMException("This Integrator is not bound to a context!")
+        for _ in range(int(steps)):
+            self._context.updateContextState()
+            self._context.calcForcesAndEnergy(True, False)
+            self._kernel.execute(self._context, self)
+
+
+class IntegrateConstVLangevinStepKernel:
+    """B200 implementation of the kernel interface ConstVKernels.h:49-77, the analogue of
+    CudaIntegrateConstVLangevinStepKernel (CudaConstVKernels.h:46-79): ``initialize``,
+    ``execute``, ``computeKineticEnergy``; owns the C-ABI slab handle."""
+
+    @staticmethod
+    def Name() -> str:
+        return "IntegrateConstVLangevinStep"
+
+    def __init__(self, name: str, context: "SlabContext"):
+        if name != self.Name():
+            raise OpenMMException(f"Tried to create kernel with illegal kernel name '{name}'")
+        self._lib = _capi.load()
+        self._ctx = context
+        self._slab = C.c_void_p(None)
+
+    def initialize(self, system: SlabSystem, integrator: ConstVLangevinIntegrator) -> None:
+        ctx = self._ctx
+        n = system.getNumParticles()
+        masses = system.getParticleMasses()
+        box_z = system.getDefaultPeriodicBoxVectors()[2][2]
+        try:  # CudaConstVKernels.cpp:76-96
+            zmax = _capi.validate_system(masses, integrator.getNumCells(), box_z,
+                                         integrator.getCellSize())
+        except ConstVError as err:
+            _raise_openmm(err)
+        seed = integrator.getRandomNumberSeed()
+        if seed == 0:  # ConstVLangevinIntegrator.h:138-140: a unique seed per Context
+            seed = int.from_bytes(os.urandom(8), "little") | 1
+        cfg = _capi.Config()
+        cfg.struct_size = C.sizeof(_capi.Config)
+        cfg.device = ctx.device_index
+        cfg.num_atoms = n
+        cfg.padded_num_atoms = ctx.padded
+        cfg.num_cells = integrator.getNumCells()
+        cfg.precision = _capi.PRECISION[ctx.precision]
+        cfg.mirror_mode = ctx.mirror_mode
+        cfg.flags = ctx.flags
+        cfg.zmax = zmax
+        cfg.seed = seed & 0xFFFFFFFFFFFFFFFF
+        cfg.global_atom_offset = ctx.global_atom_offset
+        cfg.boltz = 0.0
+        check(self._lib.constv_create(C.byref(cfg), C.byref(self._slab)))
+        self.zmax = zmax
+        self.seed = cfg.seed
+        self.rebind()
+
+    def rebind(self) -> None:
+        ctx = self._ctx
+        check(self._lib.constv_bind_arrays(
+            self._slab, ctx.posq.data_ptr(), ctx.corr.data_ptr() if ctx.corr is not None else None,
+            ctx.velm.data_ptr(), ctx.force.data_ptr(), ctx.pos_delta.data_ptr(),
+            ctx.atom_index.data_ptr() if ctx.atom_index is not None else None))
+        if ctx.atom_index is not None:
+            check(self._lib.constv_update_inverse_order(self._slab, ctx.stream_ptr()))
+
+    def execute(self, context: "SlabContext", integrator: ConstVLangevinIntegrator) -> None:
+        lib, slab, st = self._lib, self._slab, context.stream_ptr()
+        check(lib.constv_set_parameters(slab, integrator.getTemperature(), integrator.getFriction(),
+                                        integrator.getStepSize()))
+        if context.atoms_were_reordered:  # CudaConstVKernels.cpp:139-142
+            check(lib.constv_update_inverse_order(slab, st))
+            context.atoms_were_reordered = False
+        rnd, idx = context.prepare_random_numbers()
+        if context.apply_constraints is None:
+            check(lib.constv_step_fused(slab, rnd, idx, st))
+        else:  # CudaConstVKernels.cpp:146-166 with the constraint hand-off at :153
+            check(lib.constv_step_part1(slab, rnd, idx, st))
+            context.apply_constraints(context, integrator.getConstraintTolerance())
+            check(lib.constv_step_part2_mirror(slab, st))
+        context.time += integrator.getStepSize()
+        context.step_count += 1
+
+    def computeKineticEnergy(self, context: "SlabContext", integrator: ConstVLangevinIntegrator) -> float:
+        ke = C.c_double(0.0)
+        check(self._lib.constv_kinetic_energy(self._slab, 0.5 * integrator.getStepSize(),
+                                              C.byref(ke), context.stream_ptr()))
+        return ke.value
+
+    # -- extras of the B200 path -----------------------------------------------------------------
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._slab
+
+    def kinetic_energy_device(self, time_shift: float, out_tensor) -> None:
+        check(self._lib.constv_kinetic_energy_device(self._slab, time_shift, out_tensor.data_ptr(),
+                                                     self._ctx.stream_ptr()))
+
+    def get_step_count(self) -> int:
+        v = C.c_uint64(0)
+        check(self._lib.constv_get_step_count(self._slab, C.byref(v)))
+        return v.value
+
+    def set_step_count(self, count: int) -> None:
+        check(self._lib.constv_set_step_count(self._slab, count))
+
+    def set_launch_shape(self, pairs_per_thread: int = 0, ctas_per_sm: int = 0) -> None:
+        check(self._lib.constv_set_launch_shape(self._slab, pairs_per_thread, ctas_per_sm))
+
+    def close(self) -> None:
+        if self._slab:
+            self._lib.constv_destroy(self._slab)
+            self._slab = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SlabContext:
+    """Device-resident state in OpenMM's CUDA layouts plus the Context calls the integrator makes
+    (updateContextState, calcForcesAndEnergy, getState-like accessors).
+
+    ``force_fn(context)`` must fill ``context.force`` ((3,P) int64 fixed point) on the device each
+    step; None keeps the current buffer (injected forces).  ``apply_constraints(context, tol)``,
+    when given, is called between part 1 and part 2 on ``context.pos_delta``.
+    """
+
+    def __init__(self, system: SlabSystem, integrator: ConstVLangevinIntegrator, precision="single",
+                 device=0, mirror_mode=_capi.MIRROR_REFERENCE, flags=_capi.FLAGS_DEFAULT,
+                 force_fn=None, apply_constraints=None, random_pool=None, global_atom_offset=0,
+                 padded=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("SlabContext needs a CUDA device: the ConstV step path has no CPU fallback")
+        _capi.load()
+        self.torch = torch
+        self._system = system
+        self._integrator = integrator
+        self.precision = precision
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.mirror_mode = mirror_mode
+        self.flags = flags
+        self.force_fn = force_fn
+        self.apply_constraints = apply_constraints
+        self.random_pool = random_pool       # optional (M,4) float32 device tensor of injected noise
+        self.random_index = 0
+        self.global_atom_offset = int(global_atom_offset)
+        n = system.getNumParticles()
+        self.num_atoms = n
+        self.padded = int(padded) if padded is not None else (n + 31) // 32 * 32
+        rt = getattr(torch, _TORCH_REAL[precision])
+        mt = getattr(torch, _TORCH_MIXED[precision])
+        P = self.padded
+        self.posq = torch.zeros((P, 4), dtype=rt, device=self.device)
+        self.corr = torch.zeros((P, 4), dtype=rt, device=self.device) if precision == "mixed" else None
+        self.velm = torch.zeros((P, 4), dtype=mt, device=self.device)
+        self.force = torch.zeros((3, P), dtype=torch.int64, device=self.device)
+        self.pos_delta = torch.zeros((P, 4), dtype=mt, device=self.device)
+        self.atom_index = None
+        self.atoms_were_reordered = False
+        self.time = 0.0
+        self.step_count = 0
+        masses = system.getParticleMasses()
+        inv = np.zeros(P, np.float64)
+        inv[:n][masses != 0] = 1.0 / masses[masses != 0]
+        self.velm[:, 3] = torch.as_tensor(inv, dtype=mt, device=self.device)
+        integrator._initialize(self)
+
+    # -- what the integrator calls ---------------------------------------------------------------
+    def getSystem(self): return self._system
+    def getIntegrator(self): return self._integrator
+    def updateContextState(self): pass
+
+    def calcForcesAndEnergy(self, include_forces=True, include_energy=False):
+        if self.force_fn is not None:
+            self.force_fn(self)
+
+    def stream_ptr(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def prepare_random_numbers(self):
+        """Mirrors integration.prepareRandomNumbers / getRandom (CudaConstVKernels.cpp:146,148)
+        when a pool of injected Gaussians is attached; (None, 0) selects the Philox stream."""
+        if self.random_pool is None:
+            return None, 0
+        idx = self.random_index
+        if idx + self.padded > self.random_pool.shape[0]:
+            raise RuntimeError("injected random pool exhausted")
+        self.random_index += self.padded
+        return self.random_pool.data_ptr(), idx
+
+    # -- state I/O -------------------------------------------------------------------------------
+    def load_slab(self, slab) -> None:
+        """Upload a ``slab.Slab`` (host arrays in the same layouts)."""
+        t = self.torch
+        assert slab.padded == self.padded and slab.precision == self.precision
+        self.posq.copy_(t.from_numpy(slab.posq))
+        if self.corr is not None:
+            self.corr.copy_(t.from_numpy(slab.corr))
+        self.velm.copy_(t.from_numpy(slab.velm))
+        self.force.copy_(t.from_numpy(slab.force))
+
+    def setPositions(self, positions, charges=None):
+        t = self.torch
+        p = np.asarray(positions, np.float64)
+        n = len(p)
+        lo = p.astype(self.posq.cpu().numpy().dtype)
+        self.posq[:n, :3] = t.as_tensor(lo, device=self.device)
+        if self.corr is not None:
+            self.corr[:n, :3] = t.as_tensor((p - lo.astype(np.float64)).astype(np.float32), device=self.device)
+        if charges is not None:
+            self.posq[:n, 3] = t.as_tensor(np.asarray(charges), dtype=self.posq.dtype, device=self.device)
+
+    def setVelocities(self, velocities):
+        v = np.asarray(velocities, np.float64)
+        self.velm[: len(v), :3] = self.torch.as_tensor(v, dtype=self.velm.dtype, device=self.device)
+
+    def setForces(self, forces_kj_mol_nm):
+        """Inject forces (N,3) in kJ/mol/nm as OpenMM's fixed-point buffer."""
+        f = np.rint(np.asarray(forces_kj_mol_nm, np.float64).T * 4294967296.0).astype(np.int64)
+        self.force[:, : f.shape[1]] = self.torch.as_tensor(f, device=self.device)
+
+    def getPositions(self):
+        p = self.posq[: self.num_atoms, :3].double()
+        if self.corr is not None:
+            p = p + self.corr[: self.num_atoms, :3].double()
+        return p.cpu().numpy()
+
+    def getVelocities(self):
+        return self.velm[: self.num_atoms, :3].double().cpu().numpy()
+
+    def getKineticEnergy(self):
+        return self._integrator.computeKineticEnergy()
+
+    def getTime(self): return self.time
+    def getStepCount(self): return self.step_count
+
+    def set_atom_order(self, atom_index) -> None:
+        """Install a slot permutation (what cu.reorderAtoms() leaves behind): ``atom_index[slot]``
+        is the original atom held by ``slot``.  The caller permutes the state arrays itself."""
+        t = self.torch
+        ai = np.arange(self.padded, dtype=np.int32)
+        ai[: len(atom_index)] = atom_index
+        self.atom_index = t.as_tensor(ai, device=self.device)
+        self.atoms_were_reordered = True
+        self._integrator._kernel.rebind()
+
+    def reinitialize(self):
+        self._integrator._cleanup()
+        self.time = 0.0
+        self.step_count = 0
+        self.random_index = 0
+        self._integrator._initialize(self)
+
+    def close(self):
+        self._integrator._cleanup()

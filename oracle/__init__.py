@@ -156,6 +156,21 @@ def step(precision, num_atoms, num_cells, zshift_per_cell, posq, posq_corr, velm
        C.c_int(zero_velm), C.c_int(zero_force))
 
 
+def step_range(precision, num_atoms, num_cells, zshift_per_cell, posq, posq_corr, velm, force, prm,
+               step_size, random4, random_index, lo, hi, zero_velm=True, zero_force=True):
+    """The step restricted to real atoms [lo, hi) and their images, identity order, single pass
+    (the loop a CPU port of the fused step would run; used for the timed CPU baseline)."""
+    P = velm.shape[0]
+    r, m = REAL[precision], MIXED[precision]
+    prm = np.ascontiguousarray(prm, m)
+    fn = getattr(lib(), "oracle_step_range_" + _SUFFIX[precision])
+    fn(C.c_int(num_atoms), C.c_int(P), C.c_int(num_cells), C.c_double(zshift_per_cell),
+       _p(posq, r), _p(posq_corr, r) if posq_corr is not None else None, _p(velm, m),
+       _p(force, np.int64), _p(prm), _mixed_scalar(precision, step_size),
+       _p(random4, np.float32), C.c_uint(random_index), C.c_int(zero_velm), C.c_int(zero_force),
+       C.c_int(lo), C.c_int(hi))
+
+
 def philox4x32_10(counter, key):
     counter = np.ascontiguousarray(counter, np.uint32)
     key = np.ascontiguousarray(key, np.uint32)

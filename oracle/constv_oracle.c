@@ -153,7 +153,7 @@ void oracle_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint
  * The Gaussian stream of the B200 path (DESIGN.md "RNG"): one Philox block per (atom, step),
  * counter = (atom_lo, atom_hi, step_lo, step_hi), key = (seed_lo, seed_hi), atom = GLOBAL ORIGINAL
  * atom index (independent of slot order and of the multi-GPU partition).  Each 32-bit word gives a
- * 24-bit uniform u = ((w >> 8) + 0.5) * 2^-24 in (0,1); two Box-Muller pairs:
+ * uniform u = ((w >> 9) + 0.5) * 2^-23 in (0,1), exact in float; two Box-Muller pairs:
  *   xi.x = r1*cos(2 pi u2), xi.y = r1*sin(2 pi u2), r1 = sqrt(-2 ln u1)
  *   xi.z = r2*cos(2 pi u4), xi.w = r2*sin(2 pi u4), r2 = sqrt(-2 ln u3)
  * Evaluated here in double and rounded to float; the device evaluates in float, so the comparison
@@ -167,7 +167,7 @@ void oracle_gaussian4(uint64_t seed, uint64_t atom, uint64_t step, float out[4])
     oracle_philox4x32_10(ctr, key, w);
     double u[4];
     for (int i = 0; i < 4; i++)
-        u[i] = ((double) (w[i] >> 8) + 0.5) * (1.0 / 16777216.0);
+        u[i] = ((double) (w[i] >> 9) + 0.5) * (1.0 / 8388608.0);
     const double twoPi = 6.283185307179586476925286766559;
     const double r1 = sqrt(-2.0 * log(u[0]));
     const double r2 = sqrt(-2.0 * log(u[2]));

@@ -220,6 +220,90 @@ void FN(oracle_step)(int numAtoms, int paddedNumAtoms, int numCells, double zshi
                            zeroVelm, zeroForce);
 }
 
+
+/*
+ * The same step restricted to the real atoms [lo, hi) and their images (identity slot order only).
+ * Used by bench.py's CPU legs to time a bounded window of a large slab; a full step is
+ * lo = 0, hi = numAtoms/numCells and gives exactly what oracle_step gives.
+ */
+void FN(oracle_step_range)(int numAtoms, int paddedNumAtoms, int numCells, double zshiftPerCell,
+                           REAL* posq, REAL* posqCorrection, MIXED* velm, long long* force,
+                           const MIXED* params, MIXED stepSize, const float* random4,
+                           unsigned int randomIndex, int zeroVelm, int zeroForce, int lo, int hi) {
+    const int R = numAtoms / numCells;
+    const MIXED vscale = params[0];
+    const MIXED fscale = params[1] / (MIXED) 4294967296.0;
+    const MIXED noisescale = params[2];
+    const double invStepSize = 1.0 / (double) stepSize;
+    const size_t P = (size_t) paddedNumAtoms;
+#pragma omp parallel for schedule(static)
+    for (int index = lo; index < hi; index++) {
+        MIXED* vel = velm + 4 * (size_t) index;
+        REAL* p = posq + 4 * (size_t) index;
+        const MIXED w = vel[3];
+        if (w != 0) {
+            const float* xi = random4 + 4 * ((size_t) randomIndex + (size_t) index);
+            const MIXED fw = fscale * w;
+            const MIXED ns = noisescale * M_SQRT(w);
+            MIXED d[3];
+            for (int k = 0; k < 3; k++) {
+                const MIXED f = (MIXED) force[(size_t) index + P * k];
+                vel[k] = M_FMA(ns, (MIXED) xi[k], M_FMA(fw, f, vscale * vel[k]));
+                d[k] = stepSize * vel[k];
+            }
+#if MIXED_POS
+            REAL* c = posqCorrection + 4 * (size_t) index;
+            for (int k = 0; k < 3; k++) {
+                MIXED pos = (MIXED) p[k] + (MIXED) c[k];
+                pos += d[k];
+                p[k] = (REAL) pos;
+                c[k] = (REAL) (pos - (MIXED) p[k]);
+            }
+            c[3] = 0;
+#else
+            for (int k = 0; k < 3; k++)
+                p[k] = (REAL) (p[k] + d[k]);
+#endif
+            for (int k = 0; k < 3; k++)
+                vel[k] = (MIXED) (invStepSize * (double) d[k]);
+        }
+        if (p[3] != -p[3]) {
+#if MIXED_POS
+            const REAL* c0 = posqCorrection + 4 * (size_t) index;
+            MIXED x = (MIXED) p[0] + (MIXED) c0[0], y = (MIXED) p[1] + (MIXED) c0[1],
+                  z = (MIXED) p[2] + (MIXED) c0[2];
+#else
+            REAL x = p[0], y = p[1], z = p[2];
+#endif
+            for (int i = 1; i < numCells; i++) {
+                REAL* pi = posq + 4 * ((size_t) index + (size_t) R * i);
+#if MIXED_POS
+                z = fma(zshiftPerCell, (double) (2 * i), -z);
+                REAL* ci = posqCorrection + 4 * ((size_t) index + (size_t) R * i);
+                pi[0] = (REAL) x; pi[1] = (REAL) y; pi[2] = (REAL) z;
+                ci[0] = (REAL) (x - (MIXED) pi[0]);
+                ci[1] = (REAL) (y - (MIXED) pi[1]);
+                ci[2] = (REAL) (z - (MIXED) pi[2]);
+                ci[3] = 0;
+#else
+                z = (REAL) fma(zshiftPerCell, (double) (2 * i), -(double) z);
+                pi[0] = x; pi[1] = y; pi[2] = z;
+#endif
+            }
+        }
+        for (int i = 1; i < numCells; i++) {
+            const size_t slot = (size_t) index + (size_t) R * i;
+            if (zeroVelm) {
+                MIXED* v = velm + 4 * slot;
+                v[0] = 0; v[1] = 0; v[2] = 0; v[3] = 0;
+            }
+            if (zeroForce) {
+                force[slot] = 0; force[slot + P] = 0; force[slot + 2 * P] = 0;
+            }
+        }
+    }
+}
+
 #undef M_FMA
 #undef M_SQRT
 #undef FN

@@ -1,0 +1,456 @@
+"""Parity of the CUDA path against the CPU oracle, through the C ABI (via the Python host mirror,
+which only forwards to include/constv_b200.h entry points).
+
+Bars (BASELINE.json north_star): image positions bit-exact; positions and velocities within fp32
+relative 1e-6 per step and over 1000-step friction-0 trajectories.  The CUDA path is written to the
+oracle's canonical operation order, so with injected noise the tests below demand BIT-EXACT
+equality of every array; the Philox Gaussians are compared within 4e-6 absolute (device float
+log/sincospi against the oracle's double evaluation), the underlying stream being exact.
+"""
+import numpy as np
+import pytest
+
+from openmm_constv_b200 import slab as slabmod
+from tests.helpers import (assert_bits_equal, identity_order, oracle_params_for, oracle_step,
+                           permute_slab)
+
+pytestmark = pytest.mark.gpu
+
+T, GAMMA, DT = 300.0, 1.0, 0.001
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    from openmm_constv_b200 import _capi, integrator
+    _capi.load()  # raises if libconstv_b200.so is missing: no fallback
+    return integrator
+
+
+def make_context(gpu, s, T_=T, gamma=GAMMA, dt=DT, seed=77, mirror_mode=0, flags=None, pool=None,
+                 **kw):
+    from openmm_constv_b200 import _capi
+    import torch
+    sysm = gpu.SlabSystem()
+    sysm.addParticles(s.masses)
+    sysm.setDefaultPeriodicBoxVectors((s.box[0], 0, 0), (0, s.box[1], 0), (0, 0, s.num_cells * s.zmax))
+    it = gpu.ConstVLangevinIntegrator(T_, gamma, dt, s.num_cells)
+    it.setRandomNumberSeed(seed)
+    ctx = gpu.SlabContext(sysm, it, precision=s.precision, mirror_mode=mirror_mode,
+                          flags=_capi.FLAGS_DEFAULT if flags is None else flags,
+                          random_pool=None if pool is None else torch.as_tensor(pool).cuda(),
+                          global_atom_offset=s.global_atom_offset, padded=s.padded, **kw)
+    ctx.load_slab(s)
+    return ctx, it
+
+
+def download(ctx, s):
+    out = s.copy()
+    out.posq = ctx.posq.cpu().numpy()
+    out.velm = ctx.velm.cpu().numpy()
+    out.force = ctx.force.cpu().numpy()
+    if ctx.corr is not None:
+        out.corr = ctx.corr.cpu().numpy()
+    return out
+
+
+def assert_slab_bits_equal(a, b):
+    assert_bits_equal(a.posq, b.posq, "posq")
+    assert_bits_equal(a.velm, b.velm, "velm")
+    if a.corr is not None:
+        assert_bits_equal(a.corr, b.corr, "posqCorrection")
+    assert np.array_equal(a.force, b.force), "force"
+
+
+# ---- injected noise: everything bit-exact ---------------------------------------------------------
+
+@pytest.mark.parametrize("precision", slabmod.PRECISIONS)
+@pytest.mark.parametrize("num_cells,mirror_mode", [(2, 0), (2, 1), (4, 0)])
+@pytest.mark.parametrize("num_real", [1, 33, 4999])
+def test_fused_step_bit_exact(gpu, oracle, precision, num_cells, mirror_mode, num_real):
+    import torch
+    s0 = slabmod.make_slab(num_real, precision, num_cells=num_cells, seed=5)
+    nsteps = 4
+    pool = np.concatenate([oracle.fill_noise(s0.padded, 21, k) for k in range(nsteps)])
+    ctx, it = make_context(gpu, s0, mirror_mode=mirror_mode, pool=pool)
+    ref = s0.copy()
+    prm, dt = oracle_params_for(oracle, precision, T, GAMMA, DT)
+    for k in range(nsteps):
+        f = slabmod.new_forces(s0, k)
+        ctx.force.copy_(torch.from_numpy(f))
+        ref.force[:] = f
+        it.step(1)
+        oracle_step(oracle, ref, prm, dt, pool, zshift=(0.0 if mirror_mode else s0.zmax),
+                    random_index=k * s0.padded)
+        assert_slab_bits_equal(download(ctx, s0), ref)
+    assert ctx.getStepCount() == nsteps and it._kernel.get_step_count() == nsteps
+    assert ctx.getTime() == pytest.approx(nsteps * DT)
+    ctx.close()
+
+
+@pytest.mark.parametrize("precision", slabmod.PRECISIONS)
+@pytest.mark.parametrize("ilp,ctas", [(1, 1), (2, 3), (4, 16)])
+def test_launch_shapes_give_identical_results(gpu, oracle, precision, ilp, ctas):
+    s0 = slabmod.make_slab(70001, precision, seed=8)
+    pool = oracle.fill_noise(s0.padded, 3, 0)
+    ctx, it = make_context(gpu, s0, pool=pool)
+    it._kernel.set_launch_shape(ilp, ctas)
+    it.step(1)
+    ref = s0.copy()
+    prm, dt = oracle_params_for(oracle, precision, T, GAMMA, DT)
+    oracle_step(oracle, ref, prm, dt, pool)
+    assert_slab_bits_equal(download(ctx, s0), ref)
+    ctx.close()
+
+
+@pytest.mark.parametrize("precision", slabmod.PRECISIONS)
+def test_split_path_equals_fused_and_oracle(gpu, oracle, precision):
+    """part 1 | constraint hand-off (a no-op callback here) | part 2 + mirror."""
+    s0 = slabmod.make_slab(3001, precision, num_cells=4, seed=6)
+    pool = oracle.fill_noise(s0.padded, 9, 0)
+    seen = {}
+
+    def constraints(ctx, tol):
+        seen["tol"] = tol
+        seen["delta"] = ctx.pos_delta.cpu().numpy()
+
+    ctx, it = make_context(gpu, s0, pool=pool, apply_constraints=constraints)
+    it.step(1)
+    ref = s0.copy()
+    prm, dt = oracle_params_for(oracle, precision, T, GAMMA, DT)
+    delta = oracle_step(oracle, ref, prm, dt, pool)
+    assert seen["tol"] == 1e-5
+    massive = s0.velm[:, 3] != 0
+    assert_bits_equal(seen["delta"][massive], delta[massive], "posDelta")
+    assert_slab_bits_equal(download(ctx, s0), ref)
+    assert it._kernel.get_step_count() == 1
+    ctx.close()
+
+
+@pytest.mark.parametrize("precision", slabmod.PRECISIONS)
+@pytest.mark.parametrize("split", [False, True])
+def test_reordered_slots(gpu, oracle, precision, split):
+    """Behind OpenMM the slots are permuted (atomIndex); invAtomOrder is rebuilt on the device."""
+    s0 = slabmod.make_slab(2501, precision, num_cells=2, seed=10)
+    perm = np.random.default_rng(3).permutation(s0.num_atoms).astype(np.int32)
+    sp, atom_index = permute_slab(s0, perm)
+    pool = oracle.fill_noise(s0.padded, 4, 0, atom_index=atom_index)
+    ctx, it = make_context(gpu, sp, pool=pool, apply_constraints=(lambda c, t: None) if split else None)
+    ctx.set_atom_order(perm)
+    it.step(1)
+    ref = sp.copy()
+    prm, dt = oracle_params_for(oracle, precision, T, GAMMA, DT)
+    oracle_step(oracle, ref, prm, dt, pool, inv=oracle.inverse_order(atom_index))
+    assert_slab_bits_equal(download(ctx, sp), ref)
+    ctx.close()
+
+
+def test_trajectory_1000_steps_friction_zero(gpu, oracle):
+    """north_star: reference-matching 1000-step trajectory with friction 0 (fp32).  Static injected
+    forces; every 100 steps all arrays must still be bit-identical to the oracle's."""
+    s0 = slabmod.make_slab(2000, "single", seed=12, force_sigma=50.0, image_force_garbage=False)
+    from openmm_constv_b200 import _capi
+    flags = _capi.FLAG_ZERO_IMAGE_VELM | _capi.FLAG_PDL      # keep the force buffer constant
+    ctx, it = make_context(gpu, s0, T_=300.0, gamma=0.0, dt=0.001, flags=flags)
+    ref = s0.copy()
+    prm, dt = oracle_params_for(oracle, "single", 300.0, 0.0, 0.001)
+    assert prm[2] == 0.0
+    zero_noise = np.zeros((s0.padded, 4), np.float32)
+    inv = identity_order(s0.padded)
+    delta = np.zeros((s0.padded, 4), np.float32)
+    for k in range(1000):
+        it.step(1)
+        oracle.step("single", ref.num_atoms, 2, ref.zmax, ref.posq, None, ref.velm,
+                    ref.force.reshape(-1), delta, prm, dt, zero_noise, 0, inv, True, False)
+        if (k + 1) % 100 == 0:
+            got = download(ctx, s0)
+            assert_slab_bits_equal(got, ref)
+            rel = np.abs(got.posq[:, :3] - ref.posq[:, :3]).max() / np.abs(ref.posq[:, :3]).max()
+            assert rel <= 1e-6
+    ctx.close()
+
+
+# ---- Philox stream ---------------------------------------------------------------------------------
+
+def test_philox_gaussians_match_oracle(gpu, oracle):
+    import ctypes as C
+    import torch
+    from openmm_constv_b200 import _capi
+    s0 = slabmod.make_slab(40000, "single", seed=1)
+    ctx, it = make_context(gpu, s0, seed=0xDEADBEEFCAFE)
+    out = torch.zeros((s0.padded, 4), dtype=torch.float32, device="cuda")
+    for step in (0, 1, 2**33 + 5):
+        _capi.check(_capi.load().constv_generate_noise(it._kernel.handle, step, out.data_ptr(), ctx.stream_ptr()))
+        got = out.cpu().numpy()[: s0.num_atoms]
+        want = oracle.fill_noise(s0.num_atoms, 0xDEADBEEFCAFE, step)
+        assert np.max(np.abs(got - want)) < 4e-6
+    assert abs(got.mean()) < 0.02 and abs(got.std() - 1) < 0.02
+    ctx.close()
+
+
+@pytest.mark.parametrize("precision", slabmod.PRECISIONS)
+def test_philox_step_consumes_exactly_the_published_stream(gpu, oracle, precision):
+    """A Philox-driven fused step equals the oracle fed with the noise constv_generate_noise
+    publishes for the same (seed, step) -- bit for bit -- and advances the device step counter;
+    the global atom offset shifts the stream (multi-GPU range partition)."""
+    import torch
+    from openmm_constv_b200 import _capi
+    full = slabmod.make_slab(6000, precision, seed=14)
+    shard = slabmod.slice_slab(full, 2000, 4500)
+    ctx, it = make_context(gpu, shard, seed=99)
+    ref = shard.copy()
+    prm, dt = oracle_params_for(oracle, precision, T, GAMMA, DT)
+    noise = torch.zeros((shard.padded, 4), dtype=torch.float32, device="cuda")
+    for k in range(3):
+        _capi.check(_capi.load().constv_generate_noise(it._kernel.handle, k, noise.data_ptr(), ctx.stream_ptr()))
+        xi = noise.cpu().numpy()
+        want = oracle.fill_noise(shard.num_atoms, 99, k, global_atom_offset=2000)
+        assert np.max(np.abs(xi[: shard.num_atoms] - want)) < 4e-6
+        it.step(1)
+        oracle_step(oracle, ref, prm, dt, xi)
+        assert_slab_bits_equal(download(ctx, shard), ref)
+    ctx.close()
+
+
+def test_seed_determinism(gpu):
+    """TestCudaConstVLangevinIntegrator.cpp:212-268: same seed -> same trajectory, different seed
+    -> different; seed 0 -> a fresh seed per context."""
+    s0 = slabmod.make_slab(1000, "single", seed=2)
+
+    def run(seed):
+        ctx, it = make_context(gpu, s0, seed=seed)
+        it.step(10)
+        p = ctx.posq.cpu().numpy()
+        ctx.close()
+        return p
+
+    a, b, c = run(5), run(5), run(10)
+    assert_bits_equal(a, b)
+    assert not np.array_equal(a, c)
+    assert not np.array_equal(run(0), run(0))
+
+
+def test_cuda_graph_replay_advances_the_stream(gpu):
+    """The step counter lives on the device, so replaying a captured graph keeps advancing the
+    Philox stream: 2 replays of a 4-step graph == 8 eager steps."""
+    import torch
+    s0 = slabmod.make_slab(5000, "single", seed=3)
+    ctx_a, it_a = make_context(gpu, s0, seed=42)
+    it_a.step(8)
+    want = download(ctx_a, s0)
+    ctx_a.close()
+    ctx_b, it_b = make_context(gpu, s0, seed=42)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        it_b.step(0)
+        g = torch.cuda.CUDAGraph()
+        # parameters must be set before capture; warm nothing else
+        from openmm_constv_b200 import _capi
+        _capi.check(_capi.load().constv_set_parameters(it_b._kernel.handle, T, GAMMA, DT))
+        with torch.cuda.graph(g, stream=stream):
+            for _ in range(4):
+                _capi.check(_capi.load().constv_step_fused(it_b._kernel.handle, None, 0, ctx_b.stream_ptr()))
+        g.replay()
+        g.replay()
+    torch.cuda.synchronize()
+    assert it_b._kernel.get_step_count() == 8
+    assert_slab_bits_equal(download(ctx_b, s0), want)
+    ctx_b.close()
+
+
+# ---- kinetic energy ----------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("precision", slabmod.PRECISIONS)
+@pytest.mark.parametrize("num_real", [7, 100003])
+def test_kinetic_energy(gpu, oracle, precision, num_real):
+    s0 = slabmod.make_slab(num_real, precision, seed=15)
+    ctx, it = make_context(gpu, s0)
+    want = oracle.kinetic_energy(precision, s0.velm, s0.force.reshape(-1), 0.5 * DT, s0.num_atoms)
+    got = it.computeKineticEnergy()
+    assert got == pytest.approx(want, rel=1e-12)
+    assert ctx.getKineticEnergy() == got     # deterministic reduction order
+    # equipartition sanity on the Maxwell-Boltzmann slab (forces shift it slightly)
+    dof = 3 * int(np.sum(s0.velm[: s0.num_real, 3] != 0))
+    if num_real > 1000:
+        assert got == pytest.approx(0.5 * dof * slabmod.BOLTZ * 300.0, rel=0.05)
+    ctx.close()
+
+
+# ---- ensemble launch -----------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("precision", ["single", "mixed"])
+def test_batched_ensemble_equals_individual_steps(gpu, oracle, precision):
+    import ctypes as C
+    from openmm_constv_b200 import _capi
+    sizes = [1000, 777, 2048, 1, 5000]
+    slabs = [slabmod.make_slab(r, precision, seed=30 + i) for i, r in enumerate(sizes)]
+    temps = [250.0 + 25 * i for i in range(len(sizes))]
+    singles, batch = [], []
+    for s, t in zip(slabs, temps):
+        singles.append(make_context(gpu, s, T_=t, seed=1234))
+        batch.append(make_context(gpu, s, T_=t, seed=1234))
+    lib = _capi.load()
+    handles = (C.c_void_p * len(batch))(*[it._kernel.handle for _, it in batch])
+    for _, it in batch:
+        _capi.check(lib.constv_set_parameters(it._kernel.handle, it.getTemperature(), GAMMA, DT))
+    for k in range(3):
+        for ctx, it in singles:
+            it.step(1)
+        _capi.check(lib.constv_step_fused_batched(handles, len(batch), batch[0][0].stream_ptr()))
+    for (ca, ia), (cb, ib), s in zip(singles, batch, slabs):
+        assert_slab_bits_equal(download(cb, s), download(ca, s))
+        assert ib._kernel.get_step_count() == 3
+        ca.close()
+        cb.close()
+
+
+# ---- host-buffer entry point ---------------------------------------------------------------------------
+
+def test_step_host_roundtrip(gpu, oracle):
+    import ctypes as C
+    import torch
+    from openmm_constv_b200 import _capi
+    s0 = slabmod.make_slab(3000, "single", seed=17)
+    ctx, it = make_context(gpu, s0, seed=5)
+    lib = _capi.load()
+    _capi.check(lib.constv_set_parameters(it._kernel.handle, T, GAMMA, DT))
+    f = slabmod.new_forces(s0, 3)
+    host_force = torch.from_numpy(np.ascontiguousarray(f[:, : s0.num_real])).pin_memory()
+    host_posq = torch.zeros((s0.num_atoms, 4), dtype=torch.float32).pin_memory()
+    host_velm = torch.zeros((s0.num_atoms, 4), dtype=torch.float32).pin_memory()
+    noise = torch.zeros((s0.padded, 4), dtype=torch.float32, device="cuda")
+    _capi.check(lib.constv_generate_noise(it._kernel.handle, 0, noise.data_ptr(), ctx.stream_ptr()))
+    _capi.check(lib.constv_step_host(it._kernel.handle, host_force.data_ptr(), host_posq.data_ptr(),
+                                     host_velm.data_ptr(), ctx.stream_ptr()))
+    ref = s0.copy()
+    ref.force[:, : s0.num_real] = f[:, : s0.num_real]
+    prm, dt = oracle_params_for(oracle, "single", T, GAMMA, DT)
+    oracle_step(oracle, ref, prm, dt, noise.cpu().numpy())
+    assert_bits_equal(host_posq.numpy(), ref.posq[: s0.num_atoms])
+    assert_bits_equal(host_velm.numpy(), ref.velm[: s0.num_atoms])
+    ctx.close()
+
+
+# ---- full-size, size-independent properties ------------------------------------------------------------
+
+def test_full_size_slab_properties_and_oracle(gpu, oracle):
+    """BASELINE config: 1M-atom slab (500k real + 500k image).  Checked against the oracle (the C
+    oracle handles 1M atoms in milliseconds) and through properties evaluated on the device:
+    image z == float(-double(z) + 2*zmax) bit for bit, x/y/charge carried, image velm and force
+    zero, massless atoms untouched, neutral atoms' images untouched."""
+    import torch
+    s0 = slabmod.make_slab(500_000, "single", seed=12345)
+    R = s0.num_real
+    ctx, it = make_context(gpu, s0, seed=2024)
+    before_posq = ctx.posq.clone()
+    before_velm = ctx.velm.clone()
+    noise = torch.zeros((s0.padded, 4), dtype=torch.float32, device="cuda")
+    from openmm_constv_b200 import _capi
+    _capi.check(_capi.load().constv_generate_noise(it._kernel.handle, 0, noise.data_ptr(), ctx.stream_ptr()))
+    it.step(1)
+    posq, velm, force = ctx.posq, ctx.velm, ctx.force
+    charged = before_posq[:R, 3] != 0
+    massless = before_velm[:R, 3] == 0
+    expect_z = (-posq[:R, 2].double() + 2.0 * s0.zmax).float()
+    assert torch.equal(posq[R:2 * R, 2][charged].view(torch.int32), expect_z[charged].view(torch.int32))
+    assert torch.equal(posq[R:2 * R, :2][charged], posq[:R, :2][charged])
+    assert torch.equal(posq[R:2 * R, 3], before_posq[R:2 * R, 3])
+    assert torch.equal(posq[R:2 * R][~charged], before_posq[R:2 * R][~charged])
+    assert not velm[R:2 * R].any() and not force[:, R:2 * R].any()
+    assert torch.equal(posq[:R][massless], before_posq[:R][massless])
+    assert torch.equal(velm[:R][massless], before_velm[:R][massless])
+    assert not torch.equal(posq[:R][~massless], before_posq[:R][~massless])
+    ref = s0.copy()
+    prm, dt = oracle_params_for(oracle, "single", T, GAMMA, DT)
+    oracle_step(oracle, ref, prm, dt, noise.cpu().numpy())
+    assert_slab_bits_equal(download(ctx, s0), ref)
+    ctx.close()
+
+
+# ---- error behaviour and the reference tests' physics -----------------------------------------------------
+
+def test_error_messages_through_the_plugin_interface(gpu):
+    sysm = gpu.SlabSystem()
+    sysm.addParticles([1.0, 1.0, 0.0, 0.0])
+    sysm.setDefaultPeriodicBoxVectors((3, 0, 0), (0, 3, 0), (0, 0, 8.0))
+    for args, masses, msg in [
+        ((300, 1, 0.001, 3), None, "Not even number of cells"),
+        ((300, 1, 0.001, 4), [1.0, 0, 0, 0, 0, 0], "Number of particles is not multiple of number of cells"),
+        ((300, 1, 0.001, 2), [1.0, 1.0, 0.0, 2.0], "Image Particle has nonzero mass"),
+        ((300, 1, 0.001, 2, 3.9), None, "Unit cell dimension does not match with the provided zmax value"),
+    ]:
+        sy = sysm
+        if masses is not None:
+            sy = gpu.SlabSystem()
+            sy.addParticles(masses)
+            sy.setDefaultPeriodicBoxVectors((3, 0, 0), (0, 3, 0), (0, 0, 8.0))
+        with pytest.raises(gpu.OpenMMException, match=msg):
+            gpu.SlabContext(sy, gpu.ConstVLangevinIntegrator(*args))
+    it = gpu.ConstVLangevinIntegrator(300, 1, 0.001)
+    c1 = gpu.SlabContext(sysm, it)
+    with pytest.raises(gpu.OpenMMException, match="already bound to a context"):
+        gpu.SlabContext(sysm, it)
+    c1.close()
+
+
+def test_single_bond_damped_oscillator_on_gpu(gpu):
+    """TestCudaConstVLangevinIntegrator.cpp:52-94 with the bond force evaluated on the device
+    by a torch expression standing in for context.calcForcesAndEnergy."""
+    import torch
+    sysm = gpu.SlabSystem()
+    sysm.addParticles([2.0, 2.0, 0.0, 0.0])
+    sysm.setDefaultPeriodicBoxVectors((10, 0, 0), (0, 10, 0), (0, 0, 100.0))
+
+    def bond(ctx):
+        p = ctx.posq[:2, :3].double()
+        d = p[1] - p[0]
+        r = d.norm()
+        g = 1.0 * (r - 1.5) * d / r
+        f = torch.stack([g, -g])                      # (2,3)
+        ctx.force[:, :2] = torch.round(f.T * 4294967296.0).to(torch.int64)
+
+    for precision in ("single", "mixed", "double"):
+        it = gpu.ConstVLangevinIntegrator(0, 0.1, 0.01)
+        ctx = gpu.SlabContext(sysm, it, precision=precision, force_fn=bond)
+        ctx.setPositions([[-1, 0, 10], [1, 0, 10], [-1, 0, -10], [1, 0, -10]], charges=[0, 0, 0, 0])
+        freq = np.sqrt(1 - 0.05 * 0.05)
+        for _ in range(1000):
+            t = ctx.getTime()
+            dist = 1.5 + 0.5 * np.exp(-0.05 * t) * np.cos(freq * t)
+            if _ % 50 == 0:
+                p = ctx.getPositions()
+                assert abs(p[0, 0] + 0.5 * dist) < 0.02 and abs(p[1, 0] - 0.5 * dist) < 0.02
+            it.step(1)
+        # friction 0: energy conservation within 1 %
+        it.setFriction(0.0)
+        ctx.setPositions([[-1, 0, 10], [1, 0, 10]])
+        ctx.setVelocities([[0, 0, 0], [0, 0, 0]])
+
+        def energy():
+            bond(ctx)
+            p = ctx.getPositions()
+            return it.computeKineticEnergy() + 0.5 * (np.linalg.norm(p[1] - p[0]) - 1.5) ** 2
+
+        e0 = energy()
+        for _ in range(200):
+            it.step(5)
+            assert energy() == pytest.approx(e0, rel=0.01)
+        ctx.close()
+
+
+def test_massless_particles_keep_zero_velocity(gpu):
+    """TestCudaConstVLangevinIntegrator.cpp:196-209."""
+    sysm = gpu.SlabSystem()
+    sysm.addParticles([0.0, 1.0, 0.0, 0.0])
+    sysm.setDefaultPeriodicBoxVectors((10, 0, 0), (0, 10, 0), (0, 0, 20.0))
+    it = gpu.ConstVLangevinIntegrator(300.0, 2.0, 0.01)
+    ctx = gpu.SlabContext(sysm, it)
+    ctx.setPositions([[-1, 0, 3], [1, 0, 3], [-1, 0, -3], [1, 0, -3]], charges=[0.5, -0.5, -0.5, 0.5])
+    ctx.setForces([[100, 100, 100]] * 4)
+    p0 = ctx.getPositions()
+    it.step(5)
+    v = ctx.getVelocities()
+    assert v[0, 0] == 0.0 and not v[0].any() and v[1].any()
+    assert np.array_equal(ctx.getPositions()[0], p0[0])
+    ctx.close()

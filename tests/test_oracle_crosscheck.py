@@ -131,3 +131,22 @@ def test_parameters(oracle):
         assert np.array_equal(p, onp.params(T_, g, dt, oracle.BOLTZ))
     assert oracle.params(100.0, 0.0, 0.002)[1] == 0.002      # friction == 0 -> fscale = dt
     assert oracle.params(100.0, 0.0, 0.002)[2] == 0.0
+
+
+@pytest.mark.parametrize("precision", slabmod.PRECISIONS)
+def test_single_pass_range_step_equals_three_kernel_step(oracle, precision):
+    """oracle_step_range (the fused single-pass loop timed as the CPU baseline) is the same
+    function as the reference's three-kernel sequence, also when applied window by window."""
+    s0 = slabmod.make_slab(1000, precision, num_cells=4, seed=21)
+    prm, dt = oracle_params_for(oracle, precision, T, GAMMA, DT)
+    xi = oracle.fill_noise(s0.padded, 8, 0)
+    a, b = s0.copy(), s0.copy()
+    oracle_step(oracle, a, prm, dt, xi)
+    for lo, hi in [(0, 100), (100, 101), (101, 1000)]:
+        oracle.step_range(precision, b.num_atoms, b.num_cells, b.zmax, b.posq, b.corr, b.velm,
+                          b.force.reshape(-1), prm, dt, xi, 0, lo, hi)
+    assert_bits_equal(a.posq, b.posq)
+    assert_bits_equal(a.velm, b.velm)
+    if precision == "mixed":
+        assert_bits_equal(a.corr, b.corr)
+    assert np.array_equal(a.force, b.force)
