@@ -57,8 +57,14 @@ def parse_args():
     ap.add_argument("--replicas", type=int, default=0, help="slab copies rotated through (0 = auto: > 2x L2)")
     ap.add_argument("--pairs-per-thread", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--variant", type=int, default=0, help="0 auto (one-shot LDG kernel), 1 LDG kernel, 2 TMA ring kernel")
+    ap.add_argument("--tma-block", type=int, default=0)
+    ap.add_argument("--tma-stages", type=int, default=0)
+    ap.add_argument("--tma-ctas", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cache-image-charge", action="store_true")
+    ap.add_argument("--keep-in-l2", action="store_true", help="default cache policy instead of evict-first")
+    ap.add_argument("--temperature", type=float, default=T_KELVIN, help="experiments only: 0 disables the noise term")
     ap.add_argument("--e2e-steps", type=int, default=40)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--skip-cpu", action="store_true")
@@ -153,25 +159,28 @@ class ClockSampler(threading.Thread):
 
 # ---- CPU legs (the only place bench.py touches oracle/) ---------------------------------------------
 
-def cpu_oracle_rate(slab, seconds, steps_cap=None, window=None):
-    """Times the oracle's single-pass fused step (oracle_step_range_f32) with all host threads.
-    Returns (atom_steps_per_s, steps_done, threads, atoms_per_step)."""
+def cpu_oracle_rate(slab, seconds, steps_cap=None, window=None, replicas=1):
+    """Times the oracle's single-pass fused step (oracle_step_range_f32) with all host threads,
+    rotating over `replicas` copies of the slab exactly as the GPU arm does (so neither side runs
+    out of its last-level cache).  Returns (atom_steps_per_s, steps, threads, atoms_per_step, s)."""
     import oracle
-    s = slab.copy()
+    copies = [slab.copy() for _ in range(max(1, replicas))]
+    s = copies[0]
     prm = oracle.params(T_KELVIN, FRICTION, DT).astype(np.float32 if s.precision == "single" else np.float64)
     dt = (np.float32 if s.precision == "single" else np.float64)(DT)
     xi = oracle.fill_noise(s.padded, 1, 0)
     R = s.num_real
     w = R if window is None else max(1, min(R, window))
-    force = s.force.reshape(-1)
     threads = oracle.num_threads()
+    per_pass = (R + w - 1) // w
 
     def one(k):
-        lo = (k * w) % R
+        c = copies[(k // per_pass) % len(copies)]
+        lo = (k % per_pass) * w
         hi = min(R, lo + w)
-        oracle.step_range(s.precision, s.num_atoms, s.num_cells, s.zmax, s.posq, s.corr, s.velm, force,
-                          prm, dt, xi, 0, lo, hi)
-        return (hi - lo) * s.num_cells
+        oracle.step_range(c.precision, c.num_atoms, c.num_cells, c.zmax, c.posq, c.corr, c.velm,
+                          c.force.reshape(-1), prm, dt, xi, 0, lo, hi)
+        return (hi - lo) * c.num_cells
 
     for k in range(2):
         one(k)
@@ -196,14 +205,15 @@ def run_reference_arm(args):
     from openmm_constv_b200 import slab as slabmod
     s = slabmod.make_slab(args.atoms // 2, args.precision, seed=12345)
     # bound the run: calibrate, then size the per-step window so warmup+steps stay under ~90 s
-    rate, _, threads, _, _ = cpu_oracle_rate(s, 1.0)
+    reps = 6
+    rate, _, threads, _, _ = cpu_oracle_rate(s, 1.0, replicas=reps)
     total = max(1, args.steps + args.warmup)
     window_atoms = min(args.atoms, max(65536, int(rate * 90.0 / total)))
     window = max(1, window_atoms // s.num_cells)
-    cpu_oracle_rate(s, 0, steps_cap=max(1, args.warmup), window=window)
-    rate, done, threads, per_step, el = cpu_oracle_rate(s, 0, steps_cap=args.steps, window=window)
-    sample = (f"{done} steps, each the fused oracle step over a rotating window of {int(per_step)} atoms "
-              f"of the {args.atoms}-atom slab (window walks the whole slab, injected noise pool)")
+    cpu_oracle_rate(s, 0, steps_cap=max(1, args.warmup), window=window, replicas=reps)
+    rate, done, threads, per_step, el = cpu_oracle_rate(s, 0, steps_cap=args.steps, window=window, replicas=reps)
+    sample = (f"{done} steps, each the fused oracle step over a window of {int(per_step)} atoms walking through "
+              f"{reps} replicas of the {args.atoms}-atom slab (like the GPU arm's L2 rotation), injected noise pool")
     line = {
         "impl": "reference", "metric": "atom-steps/s", "value": rate, "unit": "atom-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -254,25 +264,40 @@ def main():
     flags = _capi.FLAGS_DEFAULT
     if not args.no_cache_image_charge:
         flags |= _capi.FLAG_CACHE_IMAGE_CHARGE
+    if args.keep_in_l2:
+        flags |= _capi.FLAG_KEEP_IN_L2
 
     ctxs = []
     for r in range(replicas):
         sysm = hostapi.SlabSystem()
         sysm.addParticles(shard.masses)
         sysm.setDefaultPeriodicBoxVectors((shard.box[0], 0, 0), (0, shard.box[1], 0), (0, 0, shard.num_cells * shard.zmax))
-        it = hostapi.ConstVLangevinIntegrator(T_KELVIN, FRICTION, DT, shard.num_cells)
+        it = hostapi.ConstVLangevinIntegrator(args.temperature, FRICTION, DT, shard.num_cells)
         it.setRandomNumberSeed(2024)
         ctx = hostapi.SlabContext(sysm, it, precision=args.precision, device=local_rank, flags=flags,
                                   global_atom_offset=shard.global_atom_offset, padded=shard.padded)
         ctx.load_slab(shard)
         if args.pairs_per_thread or args.ctas_per_sm:
             it._kernel.set_launch_shape(args.pairs_per_thread, args.ctas_per_sm)
-        _capi.check(lib.constv_set_parameters(it._kernel.handle, T_KELVIN, FRICTION, DT))
+        it._kernel.set_kernel_variant(args.variant, args.tma_block, args.tma_stages, args.tma_ctas)
+        _capi.check(lib.constv_set_parameters(it._kernel.handle, args.temperature, FRICTION, DT))
         ctxs.append((ctx, it))
     handles = [it._kernel.handle for _, it in ctxs]
 
     stream = torch.cuda.Stream(device=dev)
     sptr = stream.cuda_stream
+
+    # ---- kinetic energy report: the ONE collective of the partition (on demand, never per step),
+    # taken on the initial state (the timed loop below keeps the injected forces constant, so the
+    # state it ends in is not physical)
+    ke_dev = torch.zeros(1, dtype=torch.float64, device=dev)
+    ctxs[0][1]._kernel.kinetic_energy_device(0.0, ke_dev)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.all_reduce(ke_dev, op=dist.ReduceOp.SUM)
+    ke_total = float(ke_dev.item())
+    n_massive = int(np.sum(shard.velm[:R, 3] != 0)) * world
+    temperature = 2.0 * ke_total / (3 * n_massive * slabmod.BOLTZ) if n_massive else 0.0
 
     def launch_steps(first, count):
         for k in range(first, first + count):
@@ -326,16 +351,11 @@ def main():
     atoms_per_step_job = shard.num_atoms * world
     value = atoms_per_step_job * K / (ms_max * 1e-3)
 
-    # ---- kinetic energy report: the one collective of the partition (on demand, not per step) -----
-    ke_dev = torch.zeros(1, dtype=torch.float64, device=dev)
-    ctxs[0][1]._kernel.kinetic_energy_device(0.5 * DT, ke_dev)
-    if world > 1:
-        dist.all_reduce(ke_dev, op=dist.ReduceOp.SUM)
-    ke_total = float(ke_dev.item())
-    n_massive = int(np.sum(shard.velm[:R, 3] != 0)) * world
-    temperature = 2.0 * ke_total / (3 * n_massive * slabmod.BOLTZ) if n_massive else 0.0
-
     # ---- e2e: host buffers through constv_step_host -------------------------------------------------
+    # Per step: H2D of the step's input (the real atoms' fixed-point forces, pinned memory), the fused
+    # step, the kinetic-energy reduction, and D2H of the step's result.  `value` reads back the scalar
+    # a StateDataReporter asks for every step (kinetic energy); `full_state` also reads back posq of
+    # all atoms (what a DCD frame needs) and is reported beside it.
     e2e = None
     if not args.skip_e2e:
         ctx0, it0 = ctxs[0]
@@ -344,32 +364,42 @@ def main():
         esize = 4 if args.precision != "double" else 8
         host_posq = torch.empty((shard.num_atoms, 4), dtype=torch.float32 if esize == 4 else torch.float64).pin_memory()
         h2d = host_force[0].numel() * 8
-        d2h = host_posq.numel() * esize
-        for j in range(3):
-            _capi.check(lib.constv_step_host(it0._kernel.handle, host_force[j % 2].data_ptr(), host_posq.data_ptr(), None, sptr))
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for j in range(n_e2e):
-            _capi.check(lib.constv_step_host(it0._kernel.handle, host_force[j % 2].data_ptr(), host_posq.data_ptr(), None, sptr))
-        e1.record(stream)
-        stream.synchronize()
-        ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        e2e = {"value": atoms_per_step_job * n_e2e / (float(ems.item()) * 1e-3), "unit": "atom-steps/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
-               "ms_per_step": float(ems.item()) / n_e2e,
-               "what": "constv_step_host: pinned real-atom forces H2D + fused step + posq D2H, synchronous per step"}
+        ke_host = C.c_double(0.0)
+
+        def e2e_run(with_posq):
+            out = host_posq.data_ptr() if with_posq else None
+            for j in range(3):
+                _capi.check(lib.constv_step_host(it0._kernel.handle, host_force[j % 2].data_ptr(), out, None, C.byref(ke_host), sptr))
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for j in range(n_e2e):
+                _capi.check(lib.constv_step_host(it0._kernel.handle, host_force[j % 2].data_ptr(), out, None, C.byref(ke_host), sptr))
+            e1.record(stream)
+            stream.synchronize()
+            ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+            return float(ems.item())
+
+        ms_ke = e2e_run(False)
+        ms_full = e2e_run(True)
+        e2e = {"value": atoms_per_step_job * n_e2e / (ms_ke * 1e-3), "unit": "atom-steps/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8, "steps": n_e2e,
+               "ms_per_step": ms_ke / n_e2e,
+               "what": "constv_step_host: pinned real-atom forces H2D + fused step + kinetic-energy kernel + D2H of the energy scalar, synchronous per step",
+               "full_state": {"value": atoms_per_step_job * n_e2e / (ms_full * 1e-3), "ms_per_step": ms_full / n_e2e,
+                              "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(host_posq.numel() * esize + 8),
+                              "what": "same, plus D2H of posq for all atoms"}}
 
     # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        rate, done, threads, per_step, el = cpu_oracle_rate(shard, args.cpu_seconds)
+        rate, done, threads, per_step, el = cpu_oracle_rate(shard, args.cpu_seconds, replicas=replicas)
         cpu = {"value": rate, "unit": "atom-steps/s", "cores": threads, "kind": "port",
-               "sample": f"{done} full fused oracle steps over the same {shard.num_atoms}-atom slab in {el:.1f} s, all host threads, injected noise pool",
+               "sample": f"{done} full fused oracle steps rotating over {replicas} replicas of the same {shard.num_atoms}-atom slab in {el:.1f} s, all host threads, injected noise pool",
                "host_cpus": os.cpu_count()}
 
     if rank == 0:
@@ -389,7 +419,9 @@ def main():
                 "l2": f"rotating {replicas} slab replicas ({replicas * rec_bytes / 1e6:.0f} MB) > 126 MB L2: every step streams from HBM",
                 "launch": ("CUDA graph of %d steps, PDL" % chunk) if graph is not None else "eager, PDL",
                 "image_charge": "re-read from posq" if args.no_cache_image_charge else "side array",
-                "T_K": T_KELVIN, "friction_per_ps": FRICTION, "dt_ps": DT,
+                "kernel_variant": {"variant": args.variant, "tma_block": args.tma_block, "tma_stages": args.tma_stages,
+                                   "tma_ctas": args.tma_ctas, "pairs_per_thread": args.pairs_per_thread, "ctas_per_sm": args.ctas_per_sm},
+                "T_K": args.temperature, "friction_per_ps": FRICTION, "dt_ps": DT,
             },
             "steps_per_s": K / (ms_max * 1e-3),
             "atom_steps_per_s_per_gpu": value / world,

@@ -66,7 +66,11 @@ enum {
      * unless the caller edits them (then call constv_refresh_image_charges again). */
     CONSTV_FLAG_CACHE_IMAGE_CHARGE = 1u << 2,
     /* launch with programmatic dependent launch so back-to-back steps overlap launch latency */
-    CONSTV_FLAG_PDL = 1u << 3
+    CONSTV_FLAG_PDL = 1u << 3,
+    /* By default the step marks everything it touches evict-first (ld/st.global.cs): in a real
+     * simulation the force kernels between two steps flush L2 anyway.  Set this for step-only loops
+     * over a slab that fits in L2 (56 B per atom) so its state stays cache resident. */
+    CONSTV_FLAG_KEEP_IN_L2 = 1u << 4
 };
 #define CONSTV_FLAGS_DEFAULT (CONSTV_FLAG_ZERO_IMAGE_VELM | CONSTV_FLAG_ZERO_IMAGE_FORCE | CONSTV_FLAG_PDL)
 
@@ -197,12 +201,15 @@ CONSTV_API int constv_upload_state(constv_slab* slab, const void* posq, const vo
 CONSTV_API int constv_download_state(constv_slab* slab, void* posq, void* posq_correction,
                                      void* velm, int64_t* force, void* stream);
 
-/* One step driven from host memory: uploads this step's forces for the real atoms
- * (host_force_real: 3 planes of num_real int64, plane stride num_real), runs the fused step and
- * downloads the updated posq (all N atoms, real4) and, if non-NULL, velm.  Pinned host memory
- * makes the copies asynchronous; the call returns after the download has completed. */
+/* One step driven from host memory (what `integrator.step(1)` followed by a state query costs a
+ * host that keeps its buffers on the CPU): uploads this step's forces for the real atoms
+ * (host_force_real: 3 planes of num_real int64, plane stride num_real; NULL = keep the device
+ * buffer), runs the fused step, and downloads whichever results are asked for: the kinetic energy
+ * at the half-step shift 0.5*dt (host_ke_out, the scalar getState(getEnergy=True) reports), the
+ * updated posq (host_posq_out, all N atoms) and velm (host_velm_out).  Pinned host memory makes the
+ * copies asynchronous; the call returns after everything requested has landed. */
 CONSTV_API int constv_step_host(constv_slab* slab, const int64_t* host_force_real, void* host_posq_out,
-                                void* host_velm_out, void* stream);
+                                void* host_velm_out, double* host_ke_out, void* stream);
 
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 
@@ -210,9 +217,19 @@ CONSTV_API const char* constv_last_error(void);
 CONSTV_API int constv_version(void);
 /* Kernels launched by this library in this process so far (bench.py's gpu_launches). */
 CONSTV_API uint64_t constv_launch_count(void);
-/* Tuning knobs of the fused kernel: real/image pairs per thread (1, 2 or 4) and resident CTAs per
- * SM that size the persistent grid (1..16); 0 keeps the current value. */
+/* Tuning knobs of the fused kernel: real/image pairs per thread (1, 2 or 4) and the grid:
+ * ctas_per_sm = -1 launches a one-shot grid (one tile per CTA, the default), 1..32 a persistent grid
+ * of that many CTAs per SM; 0 keeps the current value. */
 CONSTV_API int constv_set_launch_shape(constv_slab* slab, int32_t pairs_per_thread, int32_t ctas_per_sm);
+
+/* Which fused kernel constv_step_fused launches: 0 = automatic (currently the plain-load one-shot
+ * kernel, which measured faster than the TMA ring on B200), 1 = the plain-load kernel, 2 = the
+ * TMA-pipelined kernel (error unless the slab is eligible: identity order, Philox noise,
+ * CONSTV_FLAG_CACHE_IMAGE_CHARGE, even P).
+ * (block_size, stages) in {(128,6), (256,2), (256,3), (256,4), (512,2), (512,3)} shape the TMA ring, ctas_per_sm caps the persistent
+ * grid (0 = as many as shared memory allows); 0 keeps the current block_size / stages. */
+CONSTV_API int constv_set_kernel_variant(constv_slab* slab, int32_t variant, int32_t block_size,
+                                         int32_t stages, int32_t ctas_per_sm);
 
 #ifdef __cplusplus
 }

@@ -76,9 +76,12 @@ struct constv_slab {
     double vscale = 0, fscaleFixed = 0, noisescale = 0, dt = 0, invDt = 0;
     double time = 0;
     // launch shape
-    int ilp = 2;
-    int ctasPerSM = 4;
-    int blockSize = kBlock;
+    int ilp = 1;
+    int ctasPerSM = 0;   // 0 = one-shot grid (one tile per CTA); > 0 = persistent grid of that many CTAs per SM
+    int variant = 0;     // 0 auto (= the one-shot LDG kernel, the faster one as measured), 1 LDG, 2 TMA ring
+    int tmaBlock = 256;  // pairs per chunk = threads per CTA of the TMA kernel
+    int tmaStages = 4;
+    int tmaCtasPerSM = 0;  // 0 = as many as shared memory allows
 };
 
 namespace {
@@ -125,6 +128,10 @@ SlabDev makeDev(const constv_slab* s) {
     d.fscaleFixed = s->fscaleFixed;
     d.noisescale = s->noisescale;
     d.dt = s->dt;
+    d.vscaleF = (float) s->vscale;
+    d.fscaleFixedF = (float) s->fscaleFixed;
+    d.noisescaleF = (float) s->noisescale;
+    d.dtF = (float) s->dt;
     d.seed = s->cfg.seed;
     d.globalAtomOffset = s->cfg.global_atom_offset;
     d.zeroVelm = (s->cfg.flags & CONSTV_FLAG_ZERO_IMAGE_VELM) ? 1u : 0u;
@@ -160,7 +167,7 @@ int launch(K kernel, int grid, int block, bool pdl, cudaStream_t stream, Args...
 
 int gridFor(const constv_slab* s, long long work, int perBlock, int ctasPerSM) {
     long long blocks = (work + perBlock - 1) / perBlock;
-    long long cap = (long long) s->numSMs * ctasPerSM;
+    long long cap = ctasPerSM > 0 ? (long long) s->numSMs * ctasPerSM : blocks;  // 0 = one-shot grid
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return (int) blocks;
@@ -168,14 +175,73 @@ int gridFor(const constv_slab* s, long long work, int perBlock, int ctasPerSM) {
 
 // ---- dispatch over (precision, ILP) --------------------------------------------------------------
 
-template <int PREC>
-int launchFused(constv_slab* s, const SlabDev& d, const float4* random, unsigned randomIndex, cudaStream_t st) {
+template <int PREC, bool STREAM>
+int launchFusedS(constv_slab* s, const SlabDev& d, const float4* random, unsigned randomIndex, cudaStream_t st) {
     const bool pdl = s->cfg.flags & CONSTV_FLAG_PDL;
     switch (s->ilp) {
-        case 1: return launch(constv_fused_step_kernel<PREC, kBlock, 1>, gridFor(s, s->numReal, kBlock * 1, s->ctasPerSM), kBlock, pdl, st, d, random, randomIndex);
-        case 4: return launch(constv_fused_step_kernel<PREC, kBlock, 4>, gridFor(s, s->numReal, kBlock * 4, s->ctasPerSM), kBlock, pdl, st, d, random, randomIndex);
-        default: return launch(constv_fused_step_kernel<PREC, kBlock, 2>, gridFor(s, s->numReal, kBlock * 2, s->ctasPerSM), kBlock, pdl, st, d, random, randomIndex);
+        case 1: return launch(constv_fused_step_kernel<PREC, kBlock, 1, STREAM>, gridFor(s, s->numReal, kBlock * 1, s->ctasPerSM), kBlock, pdl, st, d, random, randomIndex);
+        case 4: return launch(constv_fused_step_kernel<PREC, kBlock, 4, STREAM>, gridFor(s, s->numReal, kBlock * 4, s->ctasPerSM), kBlock, pdl, st, d, random, randomIndex);
+        default: return launch(constv_fused_step_kernel<PREC, kBlock, 2, STREAM>, gridFor(s, s->numReal, kBlock * 2, s->ctasPerSM), kBlock, pdl, st, d, random, randomIndex);
     }
+}
+
+template <int PREC>
+int launchFused(constv_slab* s, const SlabDev& d, const float4* random, unsigned randomIndex, cudaStream_t st) {
+    return (s->cfg.flags & CONSTV_FLAG_KEEP_IN_L2) ? launchFusedS<PREC, false>(s, d, random, randomIndex, st)
+                                                   : launchFusedS<PREC, true>(s, d, random, randomIndex, st);
+}
+
+template <int PREC, int BLOCK, int STAGES>
+int launchFusedTmaShape(constv_slab* s, const SlabDev& d, cudaStream_t st) {
+    auto kernel = constv_fused_step_tma_kernel<PREC, BLOCK, STAGES, true>;
+    const int smem = STAGES * StageLayout<PREC, BLOCK>::kBytes;
+    static thread_local int configuredDevice = -1;
+    static thread_local int maxCtas = 0;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (configuredDevice != dev) {
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&maxCtas, kernel, BLOCK, smem));
+        configuredDevice = dev;
+    }
+    if (maxCtas < 1) return fail(CONSTV_ERR_CUDA, "TMA kernel does not fit on this device (%d bytes of shared memory)", smem);
+    int per = s->tmaCtasPerSM > 0 && s->tmaCtasPerSM < maxCtas ? s->tmaCtasPerSM : maxCtas;
+    long long grid = (long long) s->numSMs * per;
+    const long long chunks = ((long long) s->numReal + BLOCK - 1) / BLOCK;
+    if (grid > chunks) grid = chunks;
+    if (grid < 1) grid = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned) grid);
+    cfg.blockDim = dim3(BLOCK);
+    cfg.dynamicSmemBytes = (size_t) smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (s->cfg.flags & CONSTV_FLAG_PDL) ? 1 : 0;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, d));
+    g_launchCount.fetch_add(1, std::memory_order_relaxed);
+    return CONSTV_OK;
+}
+
+template <int PREC>
+int launchFusedTma(constv_slab* s, const SlabDev& d, cudaStream_t st) {
+    const int key = s->tmaBlock * 10 + s->tmaStages;
+    switch (key) {
+        case 2562: return launchFusedTmaShape<PREC, 256, 2>(s, d, st);
+        case 2563: return launchFusedTmaShape<PREC, 256, 3>(s, d, st);
+        case 2564: return launchFusedTmaShape<PREC, 256, 4>(s, d, st);
+        case 5122: return launchFusedTmaShape<PREC, 512, 2>(s, d, st);
+        case 5123: return launchFusedTmaShape<PREC, 512, 3>(s, d, st);
+        case 1286: return launchFusedTmaShape<PREC, 128, 6>(s, d, st);
+        default: return fail(CONSTV_ERR_INVALID, "unsupported TMA shape block=%d stages=%d", s->tmaBlock, s->tmaStages);
+    }
+}
+
+bool tmaEligible(const constv_slab* s, const void* random4) {
+    return !s->atomIndex && !random4 && (s->cfg.flags & CONSTV_FLAG_CACHE_IMAGE_CHARGE) && s->imageChargeValid &&
+           (s->cfg.padded_num_atoms % 2 == 0);
 }
 
 template <int PREC>
@@ -209,7 +275,7 @@ int launchKE(constv_slab* s, const SlabDev& d, double scale, double* out, cudaSt
 template <int PREC>
 int launchBatched(constv_slab* lead, int n, int totalTiles, int ilp, cudaStream_t st) {
     const bool pdl = lead->cfg.flags & CONSTV_FLAG_PDL;
-    long long cap = (long long) lead->numSMs * lead->ctasPerSM;
+    const long long cap = lead->ctasPerSM > 0 ? (long long) lead->numSMs * lead->ctasPerSM : totalTiles;
     const int grid = (int) (totalTiles < cap ? totalTiles : cap);
     const SlabDev* table = lead->batchTable;
     switch (ilp) {
@@ -450,8 +516,13 @@ int constv_step_fused(constv_slab* s, const void* random4, uint32_t random_index
     const SlabDev d = makeDev(s);
     const float4* rnd = static_cast<const float4*>(random4);
     cudaStream_t st = (cudaStream_t) stream;
+    const bool tma = s->variant == 2 && tmaEligible(s, random4);
+    if (s->variant == 2 && !tma)
+        return fail(CONSTV_ERR_STATE, "the TMA kernel needs identity order, Philox noise, CONSTV_FLAG_CACHE_IMAGE_CHARGE and even padded_num_atoms");
     if (s->atomIndex) {
         DISPATCH_PREC(s->cfg.precision, launchFusedIndexed<PR>(s, d, rnd, random_index, st));
+    } else if (tma) {
+        DISPATCH_PREC(s->cfg.precision, launchFusedTma<PR>(s, d, st));
     } else {
         DISPATCH_PREC(s->cfg.precision, launchFused<PR>(s, d, rnd, random_index, st));
     }
@@ -608,7 +679,8 @@ int constv_download_state(constv_slab* s, void* posq, void* posq_correction, voi
     return CONSTV_OK;
 }
 
-int constv_step_host(constv_slab* s, const int64_t* host_force_real, void* host_posq_out, void* host_velm_out, void* stream) {
+int constv_step_host(constv_slab* s, const int64_t* host_force_real, void* host_posq_out, void* host_velm_out,
+                     double* host_ke_out, void* stream) {
     GUARD(s);
     int rc = checkReady(s, false);
     if (rc) return rc;
@@ -619,11 +691,17 @@ int constv_step_host(constv_slab* s, const int64_t* host_force_real, void* host_
         CUDA_TRY(cudaMemcpy2DAsync(s->force, 8 * P, host_force_real, 8 * R, 8 * R, 3, cudaMemcpyHostToDevice, st));
     rc = constv_step_fused(s, nullptr, 0, stream);
     if (rc) return rc;
+    if (host_ke_out) {
+        rc = constv_kinetic_energy_device(s, 0.5 * s->stepSize, s->keOut, stream);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(s->keHost, s->keOut, sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
     if (host_posq_out)
         CUDA_TRY(cudaMemcpyAsync(host_posq_out, s->posq, 4 * realSize(s->cfg.precision) * N, cudaMemcpyDeviceToHost, st));
     if (host_velm_out)
         CUDA_TRY(cudaMemcpyAsync(host_velm_out, s->velm, 4 * mixedSize(s->cfg.precision) * N, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (host_ke_out) *host_ke_out = *s->keHost;
     return CONSTV_OK;
 }
 
@@ -635,9 +713,19 @@ int constv_set_launch_shape(constv_slab* s, int32_t pairs_per_thread, int32_t ct
         s->ilp = pairs_per_thread;
     }
     if (ctas_per_sm != 0) {
-        if (ctas_per_sm < 1 || ctas_per_sm > 16) return fail(CONSTV_ERR_INVALID, "ctas_per_sm must be in 1..16");
-        s->ctasPerSM = ctas_per_sm;
+        if (ctas_per_sm < -1 || ctas_per_sm > 32) return fail(CONSTV_ERR_INVALID, "ctas_per_sm must be -1 (one-shot grid) or 1..32");
+        s->ctasPerSM = ctas_per_sm < 0 ? 0 : ctas_per_sm;
     }
+    return CONSTV_OK;
+}
+
+int constv_set_kernel_variant(constv_slab* s, int32_t variant, int32_t block_size, int32_t stages, int32_t ctas_per_sm) {
+    if (!s) return fail(CONSTV_ERR_INVALID, "null slab");
+    if (variant < 0 || variant > 2) return fail(CONSTV_ERR_INVALID, "variant must be 0 (auto), 1 (LDG) or 2 (TMA)");
+    s->variant = variant;
+    if (block_size) s->tmaBlock = block_size;
+    if (stages) s->tmaStages = stages;
+    if (ctas_per_sm >= 0) s->tmaCtasPerSM = ctas_per_sm;
     return CONSTV_OK;
 }
 

@@ -239,6 +239,10 @@ class IntegrateConstVLangevinStepKernel:
     def set_launch_shape(self, pairs_per_thread: int = 0, ctas_per_sm: int = 0) -> None:
         check(self._lib.constv_set_launch_shape(self._slab, pairs_per_thread, ctas_per_sm))
 
+    def set_kernel_variant(self, variant: int = 0, block_size: int = 0, stages: int = 0,
+                           ctas_per_sm: int = 0) -> None:
+        check(self._lib.constv_set_kernel_variant(self._slab, variant, block_size, stages, ctas_per_sm))
+
     def close(self) -> None:
         if self._slab:
             self._lib.constv_destroy(self._slab)

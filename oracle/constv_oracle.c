@@ -154,10 +154,13 @@ void oracle_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint
  * counter = (atom_lo, atom_hi, step_lo, step_hi), key = (seed_lo, seed_hi), atom = GLOBAL ORIGINAL
  * atom index (independent of slot order and of the multi-GPU partition).  Each 32-bit word gives a
  * uniform u = ((w >> 9) + 0.5) * 2^-23 in (0,1), exact in float; two Box-Muller pairs:
- *   xi.x = r1*cos(2 pi u2), xi.y = r1*sin(2 pi u2), r1 = sqrt(-2 ln u1)
- *   xi.z = r2*cos(2 pi u4), xi.w = r2*sin(2 pi u4), r2 = sqrt(-2 ln u3)
- * Evaluated here in double and rounded to float; the device evaluates in float, so the comparison
- * in tests carries a stated absolute tolerance.  The 32-bit Philox words themselves are bit-exact.
+ *   a1 = u2*fl(2 pi) - fl(pi), a2 = u4*fl(2 pi) - fl(pi)   (fl = the float constants 0x40C90FDB /
+ *        0x40490FDB, so the angle lies in (-pi, pi) and is defined identically on both sides)
+ *   xi.x = r1*cos(a1), xi.y = r1*sin(a1), r1 = sqrt(-2 ln u1)
+ *   xi.z = r2*cos(a2), xi.w = r2*sin(a2), r2 = sqrt(-2 ln u3)
+ * Evaluated here in double and rounded to float; the device evaluates log/sqrt/sin/cos on its
+ * special-function unit in float, so the comparison in tests carries a stated absolute tolerance.
+ * The 32-bit Philox words themselves are bit-exact.
  */
 void oracle_gaussian4(uint64_t seed, uint64_t atom, uint64_t step, float out[4]) {
     const uint32_t ctr[4] = {(uint32_t) atom, (uint32_t) (atom >> 32), (uint32_t) step,
@@ -168,13 +171,16 @@ void oracle_gaussian4(uint64_t seed, uint64_t atom, uint64_t step, float out[4])
     double u[4];
     for (int i = 0; i < 4; i++)
         u[i] = ((double) (w[i] >> 9) + 0.5) * (1.0 / 8388608.0);
-    const double twoPi = 6.283185307179586476925286766559;
+    const double twoPiF = (double) 6.2831854820251464844f;
+    const double piF = (double) 3.1415927410125732422f;
     const double r1 = sqrt(-2.0 * log(u[0]));
     const double r2 = sqrt(-2.0 * log(u[2]));
-    out[0] = (float) (r1 * cos(twoPi * u[1]));
-    out[1] = (float) (r1 * sin(twoPi * u[1]));
-    out[2] = (float) (r2 * cos(twoPi * u[3]));
-    out[3] = (float) (r2 * sin(twoPi * u[3]));
+    const double a1 = u[1] * twoPiF - piF;
+    const double a2 = u[3] * twoPiF - piF;
+    out[0] = (float) (r1 * cos(a1));
+    out[1] = (float) (r1 * sin(a1));
+    out[2] = (float) (r2 * cos(a2));
+    out[3] = (float) (r2 * sin(a2));
 }
 
 /* Fill random4[slot] for slots [0, numAtoms) with the stream above; atomIndex may be NULL. */

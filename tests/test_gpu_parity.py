@@ -213,6 +213,42 @@ def test_philox_step_consumes_exactly_the_published_stream(gpu, oracle, precisio
     ctx.close()
 
 
+@pytest.mark.parametrize("precision", slabmod.PRECISIONS)
+@pytest.mark.parametrize("num_real,num_cells", [(1, 2), (3, 2), (6, 2), (1027, 2), (50001, 2), (20002, 4)])
+@pytest.mark.parametrize("block,stages", [(256, 4), (512, 2), (128, 6)])
+def test_tma_pipelined_kernel_bit_exact(gpu, oracle, precision, num_real, num_cells, block, stages):
+    """The TMA-ring kernel (cp.async.bulk + mbarrier pipeline) against the oracle, including slabs
+    smaller than one quad, ragged ends (R % 4 != 0) and ranges shorter than a chunk."""
+    import torch
+    from openmm_constv_b200 import _capi
+    s0 = slabmod.make_slab(num_real, precision, num_cells=num_cells, seed=40)
+    ctx, it = make_context(gpu, s0, seed=7, flags=_capi.FLAGS_DEFAULT | _capi.FLAG_CACHE_IMAGE_CHARGE)
+    it._kernel.set_kernel_variant(2, block, stages, 0)
+    ref = s0.copy()
+    prm, dt = oracle_params_for(oracle, precision, T, GAMMA, DT)
+    noise = torch.zeros((s0.padded, 4), dtype=torch.float32, device="cuda")
+    for k in range(3):
+        _capi.check(_capi.load().constv_generate_noise(it._kernel.handle, k, noise.data_ptr(), ctx.stream_ptr()))
+        f = slabmod.new_forces(s0, k)
+        ctx.force.copy_(torch.from_numpy(f))
+        ref.force[:] = f
+        it.step(1)
+        oracle_step(oracle, ref, prm, dt, noise.cpu().numpy())
+        assert_slab_bits_equal(download(ctx, s0), ref)
+    assert it._kernel.get_step_count() == 3
+    ctx.close()
+
+
+def test_tma_kernel_refuses_ineligible_slabs(gpu):
+    from openmm_constv_b200 import _capi
+    s0 = slabmod.make_slab(1000, "single", seed=41)
+    ctx, it = make_context(gpu, s0)      # no image-charge side array
+    it._kernel.set_kernel_variant(2, 256, 4, 0)
+    with pytest.raises(_capi.ConstVError, match="TMA kernel needs"):
+        it.step(1)
+    ctx.close()
+
+
 def test_seed_determinism(gpu):
     """TestCudaConstVLangevinIntegrator.cpp:212-268: same seed -> same trajectory, different seed
     -> different; seed 0 -> a fresh seed per context."""
@@ -270,10 +306,16 @@ def test_kinetic_energy(gpu, oracle, precision, num_real):
     got = it.computeKineticEnergy()
     assert got == pytest.approx(want, rel=1e-12)
     assert ctx.getKineticEnergy() == got     # deterministic reduction order
-    # equipartition sanity on the Maxwell-Boltzmann slab (forces shift it slightly)
+    # equipartition sanity on the Maxwell-Boltzmann slab: without the half-step force shift the
+    # kinetic energy is 1.5 kT per massive atom
+    import ctypes as C
+    from openmm_constv_b200 import _capi
+    ke0 = C.c_double(0)
+    _capi.check(_capi.load().constv_kinetic_energy(it._kernel.handle, 0.0, C.byref(ke0), ctx.stream_ptr()))
+    assert ke0.value == pytest.approx(oracle.kinetic_energy(precision, s0.velm, s0.force.reshape(-1), 0.0, s0.num_atoms), rel=1e-12)
     dof = 3 * int(np.sum(s0.velm[: s0.num_real, 3] != 0))
     if num_real > 1000:
-        assert got == pytest.approx(0.5 * dof * slabmod.BOLTZ * 300.0, rel=0.05)
+        assert ke0.value == pytest.approx(0.5 * dof * slabmod.BOLTZ * 300.0, rel=0.02)
     ctx.close()
 
 
@@ -321,14 +363,17 @@ def test_step_host_roundtrip(gpu, oracle):
     host_velm = torch.zeros((s0.num_atoms, 4), dtype=torch.float32).pin_memory()
     noise = torch.zeros((s0.padded, 4), dtype=torch.float32, device="cuda")
     _capi.check(lib.constv_generate_noise(it._kernel.handle, 0, noise.data_ptr(), ctx.stream_ptr()))
+    ke = C.c_double(0.0)
     _capi.check(lib.constv_step_host(it._kernel.handle, host_force.data_ptr(), host_posq.data_ptr(),
-                                     host_velm.data_ptr(), ctx.stream_ptr()))
+                                     host_velm.data_ptr(), C.byref(ke), ctx.stream_ptr()))
     ref = s0.copy()
     ref.force[:, : s0.num_real] = f[:, : s0.num_real]
     prm, dt = oracle_params_for(oracle, "single", T, GAMMA, DT)
     oracle_step(oracle, ref, prm, dt, noise.cpu().numpy())
     assert_bits_equal(host_posq.numpy(), ref.posq[: s0.num_atoms])
     assert_bits_equal(host_velm.numpy(), ref.velm[: s0.num_atoms])
+    want_ke = oracle.kinetic_energy("single", ref.velm, ref.force.reshape(-1), 0.5 * DT, s0.num_atoms)
+    assert ke.value == pytest.approx(want_ke, rel=1e-12)
     ctx.close()
 
 
