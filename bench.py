@@ -202,24 +202,32 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    import oracle
     from openmm_constv_b200 import slab as slabmod
-    s = slabmod.make_slab(args.atoms // 2, args.precision, seed=12345)
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use every host thread
+    try:
+        host_threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        host_threads = os.cpu_count() or 1
+    oracle.set_num_threads(host_threads)
+    total_atoms = args.atoms * max(1, args.gpus)  # the whole job's slab, as the GPU arm partitions it
+    s = slabmod.make_slab(total_atoms // 2, args.precision, seed=12345)
     # bound the run: calibrate, then size the per-step window so warmup+steps stay under ~90 s
-    reps = 6
+    reps = 6 if total_atoms <= 2_000_000 else 2
     rate, _, threads, _, _ = cpu_oracle_rate(s, 1.0, replicas=reps)
     total = max(1, args.steps + args.warmup)
-    window_atoms = min(args.atoms, max(65536, int(rate * 90.0 / total)))
+    window_atoms = min(total_atoms, max(65536, int(rate * 90.0 / total)))
     window = max(1, window_atoms // s.num_cells)
     cpu_oracle_rate(s, 0, steps_cap=max(1, args.warmup), window=window, replicas=reps)
     rate, done, threads, per_step, el = cpu_oracle_rate(s, 0, steps_cap=args.steps, window=window, replicas=reps)
     sample = (f"{done} steps, each the fused oracle step over a window of {int(per_step)} atoms walking through "
-              f"{reps} replicas of the {args.atoms}-atom slab (like the GPU arm's L2 rotation), injected noise pool")
+              f"{reps} replicas of the {total_atoms}-atom slab (like the GPU arm's L2 rotation), injected noise pool")
     line = {
         "impl": "reference", "metric": "atom-steps/s", "value": rate, "unit": "atom-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * el / done, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if args.precision == "single" else "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic slab, {args.atoms} atoms ({args.atoms // 2} real + images), fused ConstV Langevin step only",
+        "config": {"workload": f"synthetic slab, {total_atoms} atoms ({total_atoms // 2} real + images), fused ConstV Langevin step only",
                    "atoms_per_step": int(per_step), "precision": args.precision,
                    "note": "reference ships no CPU implementation of this path; oracle port timed"},
         "cpu_baseline": {"value": rate, "unit": "atom-steps/s", "cores": threads, "kind": "port", "sample": sample},
@@ -239,7 +247,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from openmm_constv_b200 import _capi, integrator as hostapi, slab as slabmod
+    from openmm_constv_b200 import _capi, integrator as hostapi, partition, slab as slabmod
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -256,7 +264,7 @@ def main():
     # ---- workload: this rank's shard of the range-partitioned slab ------------------------------
     R = args.atoms // 2
     shard = slabmod.make_slab(R, args.precision, seed=12345 + rank)
-    shard.global_atom_offset = rank * R
+    shard.global_atom_offset = partition.shard_range(R * world, rank, world)[0]
     alg_bytes = slabmod.algorithmic_bytes_per_step(shard)
     rec_bytes = shard.posq.nbytes + shard.velm.nbytes + shard.force.nbytes + (shard.corr.nbytes if shard.corr is not None else 0)
     replicas = args.replicas or max(2, int(np.ceil(2.0 * L2_BYTES / rec_bytes)) + 1)
@@ -293,11 +301,10 @@ def main():
     ke_dev = torch.zeros(1, dtype=torch.float64, device=dev)
     ctxs[0][1]._kernel.kinetic_energy_device(0.0, ke_dev)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.all_reduce(ke_dev, op=dist.ReduceOp.SUM)
+    partition.allreduce_scalar_sum(ke_dev)  # NCCL over NVLink when world > 1
     ke_total = float(ke_dev.item())
     n_massive = int(np.sum(shard.velm[:R, 3] != 0)) * world
-    temperature = 2.0 * ke_total / (3 * n_massive * slabmod.BOLTZ) if n_massive else 0.0
+    temperature = partition.temperature_from_kinetic_energy(ke_total, n_massive, slabmod.BOLTZ)
 
     def launch_steps(first, count):
         for k in range(first, first + count):
@@ -397,6 +404,11 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
+        import oracle
+        try:
+            oracle.set_num_threads(len(os.sched_getaffinity(0)))
+        except AttributeError:
+            oracle.set_num_threads(os.cpu_count() or 1)
         rate, done, threads, per_step, el = cpu_oracle_rate(shard, args.cpu_seconds, replicas=replicas)
         cpu = {"value": rate, "unit": "atom-steps/s", "cores": threads, "kind": "port",
                "sample": f"{done} full fused oracle steps rotating over {replicas} replicas of the same {shard.num_atoms}-atom slab in {el:.1f} s, all host threads, injected noise pool",

@@ -1,0 +1,6 @@
+#ifndef OPENMM_CONSTV_H_
+#define OPENMM_CONSTV_H_
+// Umbrella header (as openmmapi/include/OpenMMConstV.h of the reference; Langevin integrator only).
+#include "openmm/Integrator.h"
+#include "openmm/ConstVLangevinIntegrator.h"
+#endif /* OPENMM_CONSTV_H_ */

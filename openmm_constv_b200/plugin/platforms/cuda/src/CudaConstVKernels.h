@@ -1,0 +1,41 @@
+#ifndef CUDA_CONSTV_KERNELS_H_
+#define CUDA_CONSTV_KERNELS_H_
+
+// CUDA-platform implementation of IntegrateConstVLangevinStepKernel on top of the B200 C ABI
+// (include/constv_b200.h).  Replaces the reference's class of the same name
+// (platforms/cuda/src/CudaConstVKernels.h:46-79, CudaConstVKernels.cpp:53-177): instead of four
+// runtime-compiled kernels it binds OpenMM's device arrays to a constv_slab and calls the
+// precompiled sm_100a kernels.
+
+#include "CudaArray.h"
+#include "CudaContext.h"
+#include "constv_b200.h"
+#include "openmm/ConstVKernels.h"
+
+namespace OpenMM {
+
+class CudaIntegrateConstVLangevinStepKernel : public IntegrateConstVLangevinStepKernel {
+public:
+    CudaIntegrateConstVLangevinStepKernel(std::string name, const Platform& platform, CudaContext& cu)
+        : IntegrateConstVLangevinStepKernel(name, platform), cu(cu), slab(NULL), zmax(0), hasConstraints(false), slotsPermuted(false) {
+    }
+    ~CudaIntegrateConstVLangevinStepKernel();
+    void initialize(const System& system, const ConstVLangevinIntegrator& integrator);
+    void execute(ContextImpl& context, const ConstVLangevinIntegrator& integrator);
+    double computeKineticEnergy(ContextImpl& context, const ConstVLangevinIntegrator& integrator);
+    /** The C-ABI handle (tests and tools). */
+    constv_slab* getSlab() { return slab; }
+    double getCellSize() const { return zmax; }
+
+private:
+    void bindArrays();
+    CudaContext& cu;
+    constv_slab* slab;
+    double zmax;
+    bool hasConstraints;
+    bool slotsPermuted;  // true once OpenMM has re-sorted the atoms at least once
+};
+
+}  // namespace OpenMM
+
+#endif /* CUDA_CONSTV_KERNELS_H_ */
