@@ -4,6 +4,8 @@
 
 Outputs (git-ignored, shipped to the GPU box by gpurun):
     openmm_constv_b200/libconstv_b200.so   the C-ABI library (include/constv_b200.h)
+    openmm_constv_b200/plugin/lib/...      the OpenMM plugin libraries over it (plugin/Makefile)
+    openmm_constv_b200/plugin/bin/Test*    their C++ tests
 """
 from __future__ import annotations
 
@@ -59,8 +61,28 @@ def build_capi(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+PLUGIN_DIR = os.path.join(HERE, "plugin")
+
+
+def build_plugin(force: bool = False, verbose: bool = False) -> str:
+    """The OpenMM-facing C++ libraries (libOpenMMConstV, lib/plugins/libConstVPluginCUDA) and their
+    C++ tests, via plugin/Makefile: against the OpenMM shim, or a real OpenMM when OPENMM_DIR is
+    set in the environment."""
+    cmd = ["make", "-C", PLUGIN_DIR, "-j8"]
+    if force:
+        subprocess.run(["make", "-C", PLUGIN_DIR, "clean"], capture_output=True, text=True)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("building the plugin libraries failed")
+    if verbose:
+        print(res.stdout)
+    return os.path.join(PLUGIN_DIR, "lib")
+
+
 def build_all(force: bool = False, verbose: bool = False) -> None:
     build_capi(force, verbose)
+    build_plugin(force, verbose)
 
 
 if __name__ == "__main__":

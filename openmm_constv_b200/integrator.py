@@ -198,7 +198,8 @@ class IntegrateConstVLangevinStepKernel:
 
     def execute(self, context: "SlabContext", integrator: ConstVLangevinIntegrator) -> None:
         lib, slab, st = self._lib, self._slab, context.stream_ptr()
-        check(lib.constv_set_parameters(slab, integrator.getTemperature(), integrator.getFriction(),
+        # the raw numbers (kelvin, 1/ps): subclasses may decorate the getters with units
+        check(lib.constv_set_parameters(slab, integrator._temperature, integrator._friction,
                                         integrator.getStepSize()))
         if context.atoms_were_reordered:  # CudaConstVKernels.cpp:139-142
             check(lib.constv_update_inverse_order(slab, st))

@@ -22,7 +22,13 @@ void ConstVLangevinIntegrator::initialize(ContextImpl& contextRef) {
     context = &contextRef;
     owner = &contextRef.getOwner();
     kernel = context->getPlatform().createKernel(IntegrateConstVLangevinStepKernel::Name(), contextRef);
-    kernel.getAs<IntegrateConstVLangevinStepKernel>().initialize(contextRef.getSystem(), *this);
+    try {
+        kernel.getAs<IntegrateConstVLangevinStepKernel>().initialize(contextRef.getSystem(), *this);
+    } catch (...) {
+        // the Context is about to be torn down: release the kernel while its platform data is alive
+        kernel = Kernel();
+        throw;
+    }
 }
 
 void ConstVLangevinIntegrator::cleanup() {

@@ -1,0 +1,75 @@
+"""The OpenMM-facing C++ plugin (openmm_constv_b200/plugin): builds against the OpenMM shim and runs
+its C++ tests, which are modelled on the reference's own
+(serialization/tests/TestSerializeConstVIntegrator.cpp, platforms/cuda/tests/
+TestCudaConstVLangevinIntegrator.cpp, run once per precision as tests/CMakeLists.txt:22-24 does)."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PLUGIN = os.path.join(ROOT, "openmm_constv_b200", "plugin")
+
+
+@pytest.fixture(scope="module")
+def plugin_built():
+    from openmm_constv_b200 import build
+    build.build_all()
+    return PLUGIN
+
+
+def run(binary, *args, timeout=600):
+    res = subprocess.run([os.path.join(PLUGIN, "bin", binary), *args], capture_output=True, text=True, timeout=timeout)
+    assert res.returncode == 0, f"{binary} {' '.join(args)} failed:\n{res.stdout}\n{res.stderr}"
+    assert "Done" in res.stdout
+    return res.stdout
+
+
+def test_serialization_round_trip(plugin_built):
+    run("TestSerializeConstVIntegrator")
+
+
+def test_plugin_surface_without_gpu(plugin_built):
+    run("TestConstVPluginSurface")
+
+
+def test_plugin_exports_the_reference_symbols(plugin_built):
+    """CudaConstVKernelFactory.cpp:38-61 and ConstVSerializationProxyRegistration.cpp:63-65."""
+    ctypes.CDLL(os.path.join(PLUGIN, "lib", "libOpenMMShim.so"), mode=ctypes.RTLD_GLOBAL)
+    api = ctypes.CDLL(os.path.join(PLUGIN, "lib", "libOpenMMConstV.so"), mode=ctypes.RTLD_GLOBAL)
+    assert hasattr(api, "registerConstVSerializationProxies")
+    plugin = ctypes.CDLL(os.path.join(PLUGIN, "lib", "plugins", "libConstVPluginCUDA.so"))
+    for name in ("registerPlatforms", "registerKernelFactories", "registerConstVCudaKernelFactories"):
+        assert hasattr(plugin, name), name
+
+
+def test_constvplugin_python_module():
+    """python/constvplugin.i:65-80: module name, class, constructor defaults, accessors."""
+    sys.path.insert(0, os.path.join(PLUGIN, "python"))
+    try:
+        import constvplugin
+    finally:
+        sys.path.pop(0)
+    integ = constvplugin.ConstVLangevinIntegrator(300.0, 1.0, 0.001)
+    assert integ.getNumCells() == 2 and integ.getCellSize() == -1
+    assert integ.getRandomNumberSeed() == 0 and integ.getConstraintTolerance() == 1e-5
+    for setter, getter, value in (("setNumCells", "getNumCells", 4), ("setCellSize", "getCellSize", 4.2183),
+                                  ("setTemperature", "getTemperature", 310.0), ("setFriction", "getFriction", 0.5),
+                                  ("setRandomNumberSeed", "getRandomNumberSeed", 42)):
+        getattr(integ, setter)(value)
+        got = getattr(integ, getter)()
+        got = getattr(got, "_value", got)  # Quantity when an OpenMM unit package exists
+        assert got == value
+    with pytest.raises(constvplugin.OpenMMException, match="not bound to a context"):
+        integ.step(1)
+    text = open(os.path.join(PLUGIN, "python", "constvplugin.i")).read()
+    assert "%module constvplugin" in text and "class ConstVLangevinIntegrator : public Integrator" in text
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["single", "mixed", "double"])
+def test_cuda_integrator_through_the_plugin(plugin_built, precision):
+    out = run("TestCudaConstVLangevinIntegrator", precision, timeout=900)
+    assert f"Done ({precision})" in out
