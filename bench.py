@@ -69,6 +69,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-ref-gpu", action="store_true", help="do not time the reference's own CUDA kernels beside ours")
     return ap.parse_args()
 
 
@@ -196,32 +197,99 @@ def cpu_oracle_rate(slab, seconds, steps_cap=None, window=None, replicas=1):
     return atoms / el, done, threads, atoms / done, el
 
 
+def cpu_reference_rate(slab, seconds, steps_cap=None, window=None, replicas=1):
+    """Times the REFERENCE'S OWN kernel source compiled for the host (oracle/_ref/
+    libconstv_ref_host.so: constVLangevin.cu unmodified, CUDA execution model emulated, one OpenMP
+    thread per contiguous range of atoms; part 1, part 2 and the image rewrite as three passes,
+    the launch sequence of CudaConstVKernels.cpp:146-166) on all host threads, rotating over
+    `replicas` copies of the slab like the GPU arm.  Same return value as cpu_oracle_rate."""
+    import oracle
+    from oracle import ref
+    copies = [slab.copy() for _ in range(max(1, replicas))]
+    s = copies[0]
+    m = np.float32 if s.precision == "single" else np.float64
+    prm = oracle.params(T_KELVIN, FRICTION, DT).astype(m)
+    dt = m(DT)
+    xi = oracle.fill_noise(s.padded, 1, 0)
+    inv = np.arange(s.padded, dtype=np.int32)
+    deltas = [np.zeros((s.padded, 4), m) for _ in copies]
+    R = s.num_real
+    w = R if window is None else max(1, min(R, window))
+    threads = ref.host_num_threads()
+    per_pass = (R + w - 1) // w
+
+    def one(k):
+        j = (k // per_pass) % len(copies)
+        c = copies[j]
+        lo = (k % per_pass) * w
+        hi = min(R, lo + w)
+        ref.host_step_range(c.precision, c.num_atoms, c.num_cells, c.zmax, c.posq, c.corr, c.velm,
+                            c.force.reshape(-1), deltas[j], prm, dt, xi, 0, inv, lo, hi)
+        return (hi - lo) * c.num_cells
+
+    for k in range(2):
+        one(k)
+    done, atoms = 0, 0
+    t0 = time.perf_counter()
+    while True:
+        atoms += one(done)
+        done += 1
+        el = time.perf_counter() - t0
+        if (steps_cap is not None and done >= steps_cap) or (steps_cap is None and el >= seconds):
+            break
+    el = time.perf_counter() - t0
+    return atoms / el, done, threads, atoms / done, el
+
+
+def host_thread_count():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_leg():
+    """(rate function, kind): the reference's own source when oracle/_ref travelled with the tree,
+    else the oracle port."""
+    import oracle
+    from oracle import ref
+    n = host_thread_count()
+    oracle.set_num_threads(n)  # torchrun exports OMP_NUM_THREADS=1; the CPU legs use every host thread
+    if ref.available("host"):
+        ref.host_set_num_threads(n)
+        return cpu_reference_rate, "reference"
+    return cpu_oracle_rate, "port"
+
+
 def run_reference_arm(args):
-    """--impl reference: the reference has NO CPU implementation of this path and cannot be built
-    here, so the reference arm is the oracle port on all host threads."""
+    """--impl reference: the reference's C++ host code needs OpenMM and ships no CPU platform for
+    this path, but its kernel source is self-contained: the reference arm times
+    that source compiled for the host (oracle/_ref, kind "reference") on all host threads, and
+    reports the faster single-pass oracle port beside it.  Without oracle/_ref the port is timed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import oracle
     from openmm_constv_b200 import slab as slabmod
-    # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use every host thread
-    try:
-        host_threads = len(os.sched_getaffinity(0))
-    except AttributeError:
-        host_threads = os.cpu_count() or 1
-    oracle.set_num_threads(host_threads)
+    rate_fn, kind = cpu_leg()
     total_atoms = args.atoms * max(1, args.gpus)  # the whole job's slab, as the GPU arm partitions it
     s = slabmod.make_slab(total_atoms // 2, args.precision, seed=12345)
     # bound the run: calibrate, then size the per-step window so warmup+steps stay under ~90 s
     reps = 6 if total_atoms <= 2_000_000 else 2
-    rate, _, threads, _, _ = cpu_oracle_rate(s, 1.0, replicas=reps)
+    rate, _, threads, _, _ = rate_fn(s, 1.0, replicas=reps)
     total = max(1, args.steps + args.warmup)
     window_atoms = min(total_atoms, max(65536, int(rate * 90.0 / total)))
     window = max(1, window_atoms // s.num_cells)
-    cpu_oracle_rate(s, 0, steps_cap=max(1, args.warmup), window=window, replicas=reps)
-    rate, done, threads, per_step, el = cpu_oracle_rate(s, 0, steps_cap=args.steps, window=window, replicas=reps)
-    sample = (f"{done} steps, each the fused oracle step over a window of {int(per_step)} atoms walking through "
+    rate_fn(s, 0, steps_cap=max(1, args.warmup), window=window, replicas=reps)
+    rate, done, threads, per_step, el = rate_fn(s, 0, steps_cap=args.steps, window=window, replicas=reps)
+    what = ("the reference's constVLangevin.cu compiled for the host (part 1, part 2, image rewrite)" if kind == "reference"
+            else "the fused oracle step")
+    sample = (f"{done} steps, each {what} over a window of {int(per_step)} atoms walking through "
               f"{reps} replicas of the {total_atoms}-atom slab (like the GPU arm's L2 rotation), injected noise pool")
+    port = None
+    if kind == "reference":
+        prate, pdone, _, _, pel = cpu_oracle_rate(s, min(10.0, args.cpu_seconds), window=window, replicas=reps)
+        port = {"value": prate, "unit": "atom-steps/s", "kind": "port", "cores": threads,
+                "sample": f"{pdone} single-pass oracle steps over the same windows in {pel:.1f} s"}
     line = {
         "impl": "reference", "metric": "atom-steps/s", "value": rate, "unit": "atom-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -229,13 +297,65 @@ def run_reference_arm(args):
         "vs_baseline": None, "dtype": "f32" if args.precision == "single" else "f64", "data": "synthetic",
         "config": {"workload": f"synthetic slab, {total_atoms} atoms ({total_atoms // 2} real + images), fused ConstV Langevin step only",
                    "atoms_per_step": int(per_step), "precision": args.precision,
-                   "note": "reference ships no CPU implementation of this path; oracle port timed"},
-        "cpu_baseline": {"value": rate, "unit": "atom-steps/s", "cores": threads, "kind": "port", "sample": sample},
+                   "note": "the reference ships no CPU platform for this path; its kernel source compiled for the host is timed"
+                           if kind == "reference" else "oracle/_ref absent: oracle port timed"},
+        "cpu_baseline": {"value": rate, "unit": "atom-steps/s", "cores": threads, "kind": kind, "sample": sample, "port": port},
         "e2e": {"value": rate, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+def time_reference_gpu(torch, ctxs, shard, stream, steps, max_blocks, use_graph):
+    """The reference's own kernels (constVLangevin.cu compiled by nvcc for sm_100a, oracle/_ref)
+    on the same rotating slab replicas: per step the three launches of CudaConstVKernels.cpp:146-166
+    (part 1 reading a pre-filled float4 Gaussian pool, part 2, image rewrite), 128-thread blocks,
+    grid capped at `max_blocks` (0 = uncapped).  The pool refill (OpenMM's RNG kernel) and the
+    reordering kernel are NOT charged to the reference.  Returns ms per step."""
+    import oracle
+    from oracle import ref
+    dev = ctxs[0][0].device
+    m = np.float32 if shard.precision == "single" else np.float64
+    prm = oracle.params(T_KELVIN, FRICTION, DT).astype(m)
+    r = ref.CudaReference(shard.precision, prm, m(DT), dev, max_blocks=max_blocks)
+    pool = torch.randn((shard.padded, 4), dtype=torch.float32, device=dev)
+    inv = torch.arange(shard.padded, dtype=torch.int32, device=dev)
+    sptr = stream.cuda_stream
+    n = len(ctxs)
+
+    def launch(first, count):
+        for k in range(first, first + count):
+            c = ctxs[k % n][0]
+            r.step(shard.num_atoms, shard.num_cells, shard.zmax, c.posq, c.corr, c.velm, c.force, c.pos_delta, pool, 0,
+                   inv, stream=sptr)
+
+    with torch.cuda.stream(stream):
+        launch(0, n)
+        stream.synchronize()
+        graph, chunk = None, 0
+        if use_graph and steps >= 2 * n:
+            chunk = n * max(1, min(20, steps // n))
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                launch(0, chunk)
+
+        def run(nsteps):
+            done = 0
+            if graph is not None:
+                while done + chunk <= nsteps:
+                    graph.replay()
+                    done += chunk
+            launch(done, nsteps - done)
+
+        run(max(3, steps // 10))
+        stream.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run(steps)
+        e1.record(stream)
+        stream.synchronize()
+    return e0.elapsed_time(e1) / steps
 
 
 # ---- the B200 arm -------------------------------------------------------------------------------------
@@ -355,6 +475,7 @@ def main():
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_max = float(tmax.item())
+    launch_ms_for_ref = ms_max / K
     atoms_per_step_job = shard.num_atoms * world
     value = atoms_per_step_job * K / (ms_max * 1e-3)
 
@@ -401,18 +522,41 @@ def main():
                               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(host_posq.numel() * esize + 8),
                               "what": "same, plus D2H of posq for all atoms"}}
 
+    # ---- the reference's own CUDA kernels on this GPU (information beside the headline) ---------------
+    ref_gpu = None
+    if rank == 0 and world == 1 and not args.skip_ref_gpu:
+        from oracle import ref as refmod
+        if refmod.available("cuda"):
+            for ctx, _ in ctxs:
+                ctx.load_slab(shard)
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            n_ref = max(60, min(K, 6000))
+            ms_cap = time_reference_gpu(torch, ctxs, shard, stream, n_ref, 6 * sms, graph is not None)
+            ms_unc = time_reference_gpu(torch, ctxs, shard, stream, n_ref, 0, graph is not None)
+            best = min(ms_cap, ms_unc)
+            ref_gpu = {"value": shard.num_atoms / (best * 1e-3), "unit": "atom-steps/s", "ms_per_step": best,
+                       "ms_per_step_grid_6_blocks_per_sm": ms_cap, "ms_per_step_grid_uncapped": ms_unc, "steps": n_ref,
+                       "launches_per_step": 3,
+                       "what": "the reference's constVLangevin.cu compiled by nvcc for sm_100a (oracle/_ref): part 1 (reads a "
+                               "pre-filled Gaussian pool; refill not charged), part 2, image rewrite; 128-thread blocks; same "
+                               "rotating replicas, same CUDA-graph launch; value = the faster of OpenMM's capped grid "
+                               "(6 blocks/SM, recalled) and an uncapped grid",
+                       "speedup_of_fused_step": best / launch_ms_for_ref}
+
     # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        import oracle
-        try:
-            oracle.set_num_threads(len(os.sched_getaffinity(0)))
-        except AttributeError:
-            oracle.set_num_threads(os.cpu_count() or 1)
-        rate, done, threads, per_step, el = cpu_oracle_rate(shard, args.cpu_seconds, replicas=replicas)
-        cpu = {"value": rate, "unit": "atom-steps/s", "cores": threads, "kind": "port",
-               "sample": f"{done} full fused oracle steps rotating over {replicas} replicas of the same {shard.num_atoms}-atom slab in {el:.1f} s, all host threads, injected noise pool",
+        rate_fn, kind = cpu_leg()
+        rate, done, threads, per_step, el = rate_fn(shard, args.cpu_seconds, replicas=replicas)
+        what = ("steps of the reference's constVLangevin.cu compiled for the host (part 1, part 2, image rewrite; oracle/_ref)"
+                if kind == "reference" else "fused oracle steps")
+        cpu = {"value": rate, "unit": "atom-steps/s", "cores": threads, "kind": kind,
+               "sample": f"{done} full {what} rotating over {replicas} replicas of the same {shard.num_atoms}-atom slab in {el:.1f} s, all host threads, injected noise pool",
                "host_cpus": os.cpu_count()}
+        if kind == "reference":
+            prate, pdone, _, _, pel = cpu_oracle_rate(shard, args.cpu_seconds / 2, replicas=replicas)
+            cpu["port"] = {"value": prate, "unit": "atom-steps/s", "kind": "port", "cores": threads,
+                           "sample": f"{pdone} single-pass oracle steps in {pel:.1f} s (a tuned CPU port, for scale)"}
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -443,6 +587,7 @@ def main():
                          "frac_of_8TBs_nominal": achieved / 8000.0,
                          "kernel": "constv_fused_step_kernel"},
             "cpu_baseline": cpu,
+            "reference_gpu": ref_gpu,
             "e2e": e2e,
             "gpu_launches": int(K),
             "eager_launches_in_region": int(eager_launches),

@@ -224,7 +224,10 @@ template <> __device__ __forceinline__ StepScalars<double> scalars_of<double>(co
     return {d.vscale, d.fscaleFixed, d.noisescale, d.dt, d.invDt, d.zshift};
 }
 
-// Langevin.cu:17-23.  v <- fma(ns, xi, fma(fw, F, vscale*v)); delta <- dt*v.
+// Langevin.cu:17-23.  v <- fma(ns, xi, fma(vscale, v, fw*F)); delta <- dt*v.  This is the contraction
+// nvcc applies to the reference's expression vscale*v + fscale*w*F + noisescale*sqrtInvMass*xi
+// (SASS of the reference kernel: FMUL t = fw*F; FFMA(vscale, v, t); FFMA(ns, xi, .)), so the
+// result equals the reference kernel's bit for bit (tests/test_gpu_reference.py).
 template <typename M>
 __device__ __forceinline__ void part1_update(Vec4<M>& v, Vec4<M>& delta, long long fx, long long fy,
                                              long long fz, float xix, float xiy, float xiz,
@@ -233,9 +236,9 @@ __device__ __forceinline__ void part1_update(Vec4<M>& v, Vec4<M>& delta, long lo
     const M sqrtInvMass = sqrt_rn(w);
     const M fw = mul_rn(s.fs, w);
     const M ns = mul_rn(s.noisescale, sqrtInvMass);
-    v.x = fma_rn(ns, (M) xix, fma_rn(fw, from_fixed(fx, M()), mul_rn(s.vscale, v.x)));
-    v.y = fma_rn(ns, (M) xiy, fma_rn(fw, from_fixed(fy, M()), mul_rn(s.vscale, v.y)));
-    v.z = fma_rn(ns, (M) xiz, fma_rn(fw, from_fixed(fz, M()), mul_rn(s.vscale, v.z)));
+    v.x = fma_rn(ns, (M) xix, fma_rn(s.vscale, v.x, mul_rn(fw, from_fixed(fx, M()))));
+    v.y = fma_rn(ns, (M) xiy, fma_rn(s.vscale, v.y, mul_rn(fw, from_fixed(fy, M()))));
+    v.z = fma_rn(ns, (M) xiz, fma_rn(s.vscale, v.z, mul_rn(fw, from_fixed(fz, M()))));
     delta.x = mul_rn(s.dt, v.x);
     delta.y = mul_rn(s.dt, v.y);
     delta.z = mul_rn(s.dt, v.z);

@@ -20,6 +20,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libconstv_oracle.so")
+_LIB_PATH_NOFMA = os.path.join(_HERE, "libconstv_oracle_nofma.so")
 
 BOLTZ = 8.31446261815324e-3  # kJ/mol/K, OpenMM >= 7.4 SimTKOpenMMRealType.h [recalled, SURVEY 8c]
 
@@ -38,27 +39,66 @@ ERRORS = {
 
 def build(force: bool = False) -> str:
     """Compile the oracle with gcc (seconds).  Building the checker is not using it."""
-    if force or not os.path.exists(_LIB_PATH) or any(
-        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
-        for f in ("constv_oracle.c", "constv_oracle_impl.h", "Makefile")
+    if force or any(
+        not os.path.exists(t) or any(
+            os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(t)
+            for f in ("constv_oracle.c", "constv_oracle_impl.h", "Makefile"))
+        for t in (_LIB_PATH, _LIB_PATH_NOFMA)
     ):
-        subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
+        subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True, capture_output=True)
     return _LIB_PATH
 
 
-_lib = None
+def build_ref(force: bool = False, reference_root: str = "/root/reference"):
+    """Compile the reference's own kernel source into oracle/_ref/ (host emulation + nvcc sm_100a),
+    see oracle/Makefile `ref`.  Only possible where the reference tree exists (the build
+    container); elsewhere the prebuilt files that travelled with the tree are used.  Returns the
+    _ref directory, or None if neither the sources nor prebuilt libraries are there."""
+    ref_dir = os.path.join(_HERE, "_ref")
+    src = os.path.join(reference_root, "platforms", "cuda", "src", "kernels", "constVLangevin.cu")
+    if os.path.exists(src):
+        cmd = ["make", "-C", _HERE, "ref", "REF_ROOT=" + reference_root] + (["-B"] if force else [])
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("building oracle/_ref failed:\n" + res.stdout + res.stderr)
+    return ref_dir if os.path.exists(os.path.join(ref_dir, "libconstv_ref_host.so")) else None
+
+
+_libs = {}
+_variant = "fma"
+
+
+def _load(path):
+    so = C.CDLL(path)
+    so.oracle_kinetic_energy_f32.restype = C.c_double
+    so.oracle_kinetic_energy_mixed.restype = C.c_double
+    so.oracle_kinetic_energy_f64.restype = C.c_double
+    so.oracle_num_threads.restype = C.c_int
+    return so
 
 
 def lib() -> C.CDLL:
-    global _lib
-    if _lib is None:
+    if _variant not in _libs:
         build()
-        _lib = C.CDLL(_LIB_PATH)
-        _lib.oracle_kinetic_energy_f32.restype = C.c_double
-        _lib.oracle_kinetic_energy_mixed.restype = C.c_double
-        _lib.oracle_kinetic_energy_f64.restype = C.c_double
-        _lib.oracle_num_threads.restype = C.c_int
-    return _lib
+        _libs[_variant] = _load(_LIB_PATH if _variant == "fma" else _LIB_PATH_NOFMA)
+    return _libs[_variant]
+
+
+class uncontracted:
+    """Context manager: inside it every oracle function runs the ORACLE_NO_CONTRACT build (each
+    operation rounded separately), which is what a host compilation of the reference's kernel
+    source without FMA contraction computes (oracle/ref_host.cpp)."""
+
+    def __enter__(self):
+        global _variant
+        self._saved = _variant
+        _variant = "nofma"
+        return self
+
+    def __exit__(self, *exc):
+        global _variant
+        _variant = self._saved
+        return False
 
 
 def _p(a, dtype=None):

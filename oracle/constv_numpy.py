@@ -73,8 +73,8 @@ def part1(mixed, velm, force, pos_delta, prm, step_size, random4, random_index, 
     for k in range(3):
         f = force[k, idx].astype(m)
         xi = random4[random_index + idx, k].astype(m)
-        t = (vscale * velm[idx, k]).astype(m)
-        velm[idx, k] = fma(ns, xi, fma(fw, f, t))
+        t = (fw * f).astype(m)  # nvcc: FMUL t = (fscale*w)*F; FFMA(vscale, v, t); FFMA(ns, xi, .)
+        velm[idx, k] = fma(ns, xi, fma(vscale, velm[idx, k], t))
         pos_delta[idx, k] = (dt * velm[idx, k]).astype(m)
     pos_delta[idx, 3] = 0
 

@@ -16,11 +16,23 @@
 #define CAT(a, b) CAT_(a, b)
 #define FN(name) CAT(name, SUFFIX)
 
-#if MIXED_IS_DOUBLE
+/* ORACLE_NO_CONTRACT builds the variant in which every operation is rounded separately: what an
+ * uncontracted host compilation of the reference's kernel source computes (oracle/ref_host.cpp).
+ * The default variant fuses exactly the operations nvcc fuses in that source (checked in the SASS
+ * of oracle/_ref/libconstv_ref_cuda.so and, bit for bit, on the GPU by tests/test_gpu_reference.py). */
+#if ORACLE_NO_CONTRACT
+#define M_FMA(a, b, c) ((a) * (b) + (c))
+#define D_FMA(a, b, c) ((a) * (b) + (c))
+#elif MIXED_IS_DOUBLE
 #define M_FMA(a, b, c) fma((a), (b), (c))
-#define M_SQRT(a) sqrt(a)
+#define D_FMA(a, b, c) fma((a), (b), (c))
 #else
 #define M_FMA(a, b, c) fmaf((a), (b), (c))
+#define D_FMA(a, b, c) fma((a), (b), (c))
+#endif
+#if MIXED_IS_DOUBLE
+#define M_SQRT(a) sqrt(a)
+#else
 #define M_SQRT(a) sqrtf(a)
 #endif
 
@@ -32,8 +44,10 @@
  *   :17    slots whose inverse mass is zero are skipped entirely
  *   :18-21 v <- vscale*v + fscale*invMass*F + noisescale*sqrt(invMass)*xi
  *   :23    posDelta <- dt*v, w = 0
- * Canonical operation order (what nvcc's default fmad contraction makes of the left-associated
- * source expression): v = fma(ns, xi, fma(fw, F, vscale*v)), fw = fs*w, ns = noisescale*sqrt(w).
+ * Canonical operation order = what nvcc's default fmad contraction makes of the left-associated
+ * source expression vscale*v + fscale*w*F + noisescale*sqrtInvMass*xi (SASS of the reference
+ * kernel: FMUL t = (fscale*w)*F; FFMA(vscale, v, t); FFMA(ns, xi, .)):
+ *   v = fma(ns, xi, fma(vscale, v, fw*F)), fw = fscale*w, ns = noisescale*sqrt(w).
  */
 void FN(oracle_part1)(int numAtoms, int paddedNumAtoms, MIXED* velm, const long long* force,
                       MIXED* posDelta, const MIXED* params, MIXED stepSize, const float* random4,
@@ -52,8 +66,8 @@ void FN(oracle_part1)(int numAtoms, int paddedNumAtoms, MIXED* velm, const long 
             const MIXED ns = noisescale * sqrtInvMass;
             for (int k = 0; k < 3; k++) {
                 const MIXED f = (MIXED) force[(size_t) index + (size_t) paddedNumAtoms * k];
-                const MIXED t = vscale * vel[k];
-                vel[k] = M_FMA(ns, (MIXED) xi[k], M_FMA(fw, f, t));
+                const MIXED t = fw * f;
+                vel[k] = M_FMA(ns, (MIXED) xi[k], M_FMA(vscale, vel[k], t));
             }
             MIXED* d = posDelta + 4 * (size_t) index;
             d[0] = stepSize * vel[0];
@@ -132,7 +146,7 @@ void FN(oracle_mirror)(int numRealAtoms, int numCells, double zshiftPerCell, REA
                 const size_t slot = (size_t) invAtomOrder[(size_t) index + (size_t) numRealAtoms * i];
                 REAL* pi = posq + 4 * slot;
 #if MIXED_POS
-                z = fma(zshiftPerCell, (double) (2 * i), -z);
+                z = D_FMA(zshiftPerCell, (double) (2 * i), -z);
                 REAL* ci = posqCorrection + 4 * slot;
                 const REAL qi = pi[3];
                 pi[0] = (REAL) x; pi[1] = (REAL) y; pi[2] = (REAL) z; pi[3] = qi;
@@ -141,7 +155,7 @@ void FN(oracle_mirror)(int numRealAtoms, int numCells, double zshiftPerCell, REA
                 ci[2] = (REAL) (z - (MIXED) pi[2]);
                 ci[3] = 0;
 #else
-                z = (REAL) fma(zshiftPerCell, (double) (2 * i), -(double) z);
+                z = (REAL) D_FMA(zshiftPerCell, (double) (2 * i), -(double) z);
                 pi[0] = x; pi[1] = y; pi[2] = z;
 #endif
             }
@@ -248,7 +262,7 @@ void FN(oracle_step_range)(int numAtoms, int paddedNumAtoms, int numCells, doubl
             MIXED d[3];
             for (int k = 0; k < 3; k++) {
                 const MIXED f = (MIXED) force[(size_t) index + P * k];
-                vel[k] = M_FMA(ns, (MIXED) xi[k], M_FMA(fw, f, vscale * vel[k]));
+                vel[k] = M_FMA(ns, (MIXED) xi[k], M_FMA(vscale, vel[k], fw * f));
                 d[k] = stepSize * vel[k];
             }
 #if MIXED_POS
@@ -278,7 +292,7 @@ void FN(oracle_step_range)(int numAtoms, int paddedNumAtoms, int numCells, doubl
             for (int i = 1; i < numCells; i++) {
                 REAL* pi = posq + 4 * ((size_t) index + (size_t) R * i);
 #if MIXED_POS
-                z = fma(zshiftPerCell, (double) (2 * i), -z);
+                z = D_FMA(zshiftPerCell, (double) (2 * i), -z);
                 REAL* ci = posqCorrection + 4 * ((size_t) index + (size_t) R * i);
                 pi[0] = (REAL) x; pi[1] = (REAL) y; pi[2] = (REAL) z;
                 ci[0] = (REAL) (x - (MIXED) pi[0]);
@@ -286,7 +300,7 @@ void FN(oracle_step_range)(int numAtoms, int paddedNumAtoms, int numCells, doubl
                 ci[2] = (REAL) (z - (MIXED) pi[2]);
                 ci[3] = 0;
 #else
-                z = (REAL) fma(zshiftPerCell, (double) (2 * i), -(double) z);
+                z = (REAL) D_FMA(zshiftPerCell, (double) (2 * i), -(double) z);
                 pi[0] = x; pi[1] = y; pi[2] = z;
 #endif
             }
@@ -305,6 +319,7 @@ void FN(oracle_step_range)(int numAtoms, int paddedNumAtoms, int numCells, doubl
 }
 
 #undef M_FMA
+#undef D_FMA
 #undef M_SQRT
 #undef FN
 #undef CAT
