@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--atoms", type=int, default=1_000_000, help="particles (real+image) per GPU")
     ap.add_argument("--precision", default="single", choices=["single", "mixed", "double"])
+    ap.add_argument("--ensemble", type=int, default=0,
+                    help="BASELINE configs[4]: M independent slabs of --atoms particles per GPU advanced by ONE batched "
+                         "launch per step (64 slabs of 100k atoms over 8 GPUs = --ensemble 8 --atoms 100000)")
     ap.add_argument("--replicas", type=int, default=0, help="slab copies rotated through (0 = auto: > 2x L2)")
     ap.add_argument("--pairs-per-thread", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
@@ -387,7 +390,8 @@ def main():
     shard.global_atom_offset = partition.shard_range(R * world, rank, world)[0]
     alg_bytes = slabmod.algorithmic_bytes_per_step(shard)
     rec_bytes = shard.posq.nbytes + shard.velm.nbytes + shard.force.nbytes + (shard.corr.nbytes if shard.corr is not None else 0)
-    replicas = args.replicas or max(2, int(np.ceil(2.0 * L2_BYTES / rec_bytes)) + 1)
+    M = max(1, args.ensemble)  # slabs advanced per step on this GPU (1 = the plain slab configs)
+    replicas = args.replicas or max(2, int(np.ceil(2.0 * L2_BYTES / (rec_bytes * M))) + 1)
 
     flags = _capi.FLAGS_DEFAULT
     if not args.no_cache_image_charge:
@@ -396,12 +400,12 @@ def main():
         flags |= _capi.FLAG_KEEP_IN_L2
 
     ctxs = []
-    for r in range(replicas):
+    for r in range(replicas * M):
         sysm = hostapi.SlabSystem()
         sysm.addParticles(shard.masses)
         sysm.setDefaultPeriodicBoxVectors((shard.box[0], 0, 0), (0, shard.box[1], 0), (0, 0, shard.num_cells * shard.zmax))
         it = hostapi.ConstVLangevinIntegrator(args.temperature, FRICTION, DT, shard.num_cells)
-        it.setRandomNumberSeed(2024)
+        it.setRandomNumberSeed(2024 + (r % M))
         ctx = hostapi.SlabContext(sysm, it, precision=args.precision, device=local_rank, flags=flags,
                                   global_atom_offset=shard.global_atom_offset, padded=shard.padded)
         ctx.load_slab(shard)
@@ -426,9 +430,14 @@ def main():
     n_massive = int(np.sum(shard.velm[:R, 3] != 0)) * world
     temperature = partition.temperature_from_kinetic_energy(ke_total, n_massive, slabmod.BOLTZ)
 
+    groups = [(C.c_void_p * M)(*handles[g * M:(g + 1) * M]) for g in range(replicas)]
+
     def launch_steps(first, count):
         for k in range(first, first + count):
-            _capi.check(lib.constv_step_fused(handles[k % replicas], None, 0, sptr))
+            if args.ensemble:
+                _capi.check(lib.constv_step_fused_batched(groups[k % replicas], M, sptr))
+            else:
+                _capi.check(lib.constv_step_fused(handles[k % replicas], None, 0, sptr))
 
     # ---- optional CUDA graph: `chunk` consecutive steps per replay --------------------------------
     K, W = args.steps, max(args.warmup, 3)
@@ -476,7 +485,7 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_max = float(tmax.item())
     launch_ms_for_ref = ms_max / K
-    atoms_per_step_job = shard.num_atoms * world
+    atoms_per_step_job = shard.num_atoms * M * world
     value = atoms_per_step_job * K / (ms_max * 1e-3)
 
     # ---- e2e: host buffers through constv_step_host -------------------------------------------------
@@ -485,7 +494,7 @@ def main():
     # a StateDataReporter asks for every step (kinetic energy); `full_state` also reads back posq of
     # all atoms (what a DCD frame needs) and is reported beside it.
     e2e = None
-    if not args.skip_e2e:
+    if not args.skip_e2e and not args.ensemble:
         ctx0, it0 = ctxs[0]
         n_e2e = max(3, args.e2e_steps)
         host_force = [torch.from_numpy(np.ascontiguousarray(slabmod.new_forces(shard, j)[:, :R])).pin_memory() for j in range(2)]
@@ -512,19 +521,60 @@ def main():
                 dist.all_reduce(ems, op=dist.ReduceOp.MAX)
             return float(ems.item())
 
+        def e2e_pipelined(buffers, code, nsteps):
+            """submit step k+1, then collect step k: the upload of k+1 overlaps the kernels and the
+            read-back of k.  Every step still uploads its own forces and returns its own energy."""
+            h = it0._kernel.handle
+            ticket = C.c_uint64(0)
+
+            def loop(n):
+                prev = None
+                for j in range(n):
+                    _capi.check(lib.constv_step_host_submit(h, buffers[j % 2].data_ptr(), code, C.byref(ticket), sptr))
+                    if prev is not None:
+                        _capi.check(lib.constv_step_host_collect(h, prev, C.byref(ke_host)))
+                    prev = ticket.value
+                _capi.check(lib.constv_step_host_collect(h, prev, C.byref(ke_host)))
+
+            loop(4)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            loop(nsteps)
+            e1.record(stream)
+            stream.synchronize()
+            ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+            return float(ems.item())
+
         ms_ke = e2e_run(False)
         ms_full = e2e_run(True)
-        e2e = {"value": atoms_per_step_job * n_e2e / (ms_ke * 1e-3), "unit": "atom-steps/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8, "steps": n_e2e,
-               "ms_per_step": ms_ke / n_e2e,
-               "what": "constv_step_host: pinned real-atom forces H2D + fused step + kinetic-energy kernel + D2H of the energy scalar, synchronous per step",
+        n_pipe = 4 * n_e2e
+        ms_pipe = e2e_pipelined(host_force, _capi.FORCE_FIXED64, n_pipe)
+        host_force32 = [(torch.randn((3, R), dtype=torch.float32) * 1000.0).pin_memory() for _ in range(2)]
+        ms_pipe32 = e2e_pipelined(host_force32, _capi.FORCE_FLOAT32, n_pipe)
+        e2e = {"value": atoms_per_step_job * n_pipe / (ms_pipe * 1e-3), "unit": "atom-steps/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8, "steps": n_pipe,
+               "ms_per_step": ms_pipe / n_pipe,
+               "what": "constv_step_host_submit/_collect, two tickets in flight: every step uploads its real-atom forces "
+                       "(int64 fixed point, OpenMM's buffer format, pinned memory) and reads back its kinetic energy; the "
+                       "upload of step k+1 overlaps the kernels of step k; PCIe-bound",
+               "float32_forces": {"value": atoms_per_step_job * n_pipe / (ms_pipe32 * 1e-3), "ms_per_step": ms_pipe32 / n_pipe,
+                                  "h2d_bytes_per_step": int(h2d // 2), "d2h_bytes_per_step": 8,
+                                  "what": "same with float32 host forces converted to fixed point on the device"},
+               "synchronous": {"value": atoms_per_step_job * n_e2e / (ms_ke * 1e-3), "ms_per_step": ms_ke / n_e2e,
+                               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
+                               "what": "constv_step_host: upload, fused step, kinetic energy, read-back, one step at a time"},
                "full_state": {"value": atoms_per_step_job * n_e2e / (ms_full * 1e-3), "ms_per_step": ms_full / n_e2e,
                               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(host_posq.numel() * esize + 8),
-                              "what": "same, plus D2H of posq for all atoms"}}
+                              "what": "synchronous, plus D2H of posq for all atoms"}}
 
     # ---- the reference's own CUDA kernels on this GPU (information beside the headline) ---------------
     ref_gpu = None
-    if rank == 0 and world == 1 and not args.skip_ref_gpu:
+    if rank == 0 and world == 1 and not args.skip_ref_gpu and not args.ensemble:
         from oracle import ref as refmod
         if refmod.available("cuda"):
             for ctx, _ in ctxs:
@@ -545,7 +595,7 @@ def main():
 
     # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.skip_cpu:
+    if rank == 0 and world == 1 and not args.skip_cpu and not args.ensemble:
         rate_fn, kind = cpu_leg()
         rate, done, threads, per_step, el = rate_fn(shard, args.cpu_seconds, replicas=replicas)
         what = ("steps of the reference's constVLangevin.cu compiled for the host (part 1, part 2, image rewrite; oracle/_ref)"
@@ -561,6 +611,7 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         launch_ms = ms_max / K
+        alg_bytes *= M
         achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
         line = {
             "metric": "atom-steps/s", "value": value, "unit": "atom-steps/s", "n_gpus": world,
@@ -569,10 +620,12 @@ def main():
             "dtype": "f32" if args.precision == "single" else ("f32+f64" if args.precision == "mixed" else "f64"),
             "data": "synthetic",
             "config": {
-                "workload": f"synthetic slab, {shard.num_atoms} atoms per GPU ({R} real + {shard.num_atoms - R} image), fused ConstV Langevin step only (BASELINE configs[2]); range partition over {world} GPU(s)",
+                "workload": (f"ensemble of {M * world} independent synthetic slabs of {shard.num_atoms} atoms, {M} per GPU advanced by one batched launch per step (BASELINE configs[4])"
+                             if args.ensemble else
+                             f"synthetic slab, {shard.num_atoms} atoms per GPU ({R} real + {shard.num_atoms - R} image), fused ConstV Langevin step only (BASELINE configs[2]); range partition over {world} GPU(s)"),
                 "atoms_per_gpu": shard.num_atoms, "total_atoms": atoms_per_step_job, "precision": args.precision,
                 "pair_classes": shard.pair_classes(), "rng": "in-kernel Philox4x32-10",
-                "l2": f"rotating {replicas} slab replicas ({replicas * rec_bytes / 1e6:.0f} MB) > 126 MB L2: every step streams from HBM",
+                "l2": f"rotating {replicas} replicas of the per-step working set ({replicas * M * rec_bytes / 1e6:.0f} MB) > 126 MB L2: every step streams from HBM",
                 "launch": ("CUDA graph of %d steps, PDL" % chunk) if graph is not None else "eager, PDL",
                 "image_charge": "re-read from posq" if args.no_cache_image_charge else "side array",
                 "kernel_variant": {"variant": args.variant, "tma_block": args.tma_block, "tma_stages": args.tma_stages,
@@ -582,10 +635,10 @@ def main():
             "steps_per_s": K / (ms_max * 1e-3),
             "atom_steps_per_s_per_gpu": value / world,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic_from_profile(shard.num_atoms), "peak_source": peak_src,
+                         "traffic": None if args.ensemble else traffic_from_profile(shard.num_atoms), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "frac_of_8TBs_nominal": achieved / 8000.0,
-                         "kernel": "constv_fused_step_kernel"},
+                         "kernel": "constv_fused_step_batched_kernel" if args.ensemble else "constv_fused_step_kernel"},
             "cpu_baseline": cpu,
             "reference_gpu": ref_gpu,
             "e2e": e2e,

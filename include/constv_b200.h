@@ -211,6 +211,20 @@ CONSTV_API int constv_download_state(constv_slab* slab, void* posq, void* posq_c
 CONSTV_API int constv_step_host(constv_slab* slab, const int64_t* host_force_real, void* host_posq_out,
                                 void* host_velm_out, double* host_ke_out, void* stream);
 
+/* Pipelined form of constv_step_host for hosts that produce forces on the CPU every step: submit
+ * step k+1 before collecting step k, and the PCIe upload of step k+1's forces (on an internal copy
+ * stream, into a double-buffered staging area) overlaps step k's kernels and read-back.  At most two
+ * tickets may be outstanding.  host_force_real: 3 planes of num_real values (plane stride num_real),
+ * pinned memory, either OpenMM's int64 fixed point (CONSTV_FORCE_FIXED64) or float32 in kJ/mol/nm
+ * (CONSTV_FORCE_FLOAT32, half the PCIe bytes), which the device converts exactly as OpenMM's force
+ * kernels fill the buffer: (long long)(f * 2^32), truncating.  The buffer must stay valid until the
+ * ticket is collected.  collect() blocks until that step's kinetic energy (half-step shift, as
+ * constv_step_host) has landed and returns it. */
+enum { CONSTV_FORCE_FIXED64 = 0, CONSTV_FORCE_FLOAT32 = 1 };
+CONSTV_API int constv_step_host_submit(constv_slab* slab, const void* host_force_real, int32_t force_format,
+                                       uint64_t* ticket_out, void* stream);
+CONSTV_API int constv_step_host_collect(constv_slab* slab, uint64_t ticket, double* host_ke_out);
+
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 
 CONSTV_API const char* constv_last_error(void);

@@ -20,6 +20,7 @@ FLAG_ZERO_IMAGE_FORCE = 1 << 1
 FLAG_CACHE_IMAGE_CHARGE = 1 << 2
 FLAG_PDL = 1 << 3
 FLAG_KEEP_IN_L2 = 1 << 4
+FORCE_FIXED64, FORCE_FLOAT32 = 0, 1
 FLAGS_DEFAULT = FLAG_ZERO_IMAGE_VELM | FLAG_ZERO_IMAGE_FORCE | FLAG_PDL
 
 # every symbol include/constv_b200.h declares (tests check the library exports exactly these)
@@ -30,7 +31,8 @@ SYMBOLS = [
     "constv_step_part2_mirror", "constv_step_fused", "constv_step_fused_batched",
     "constv_kinetic_energy", "constv_kinetic_energy_device", "constv_generate_noise",
     "constv_get_step_count", "constv_set_step_count", "constv_get_time", "constv_set_time",
-    "constv_upload_state", "constv_download_state", "constv_step_host", "constv_last_error",
+    "constv_upload_state", "constv_download_state", "constv_step_host", "constv_step_host_submit",
+    "constv_step_host_collect", "constv_last_error",
     "constv_version", "constv_launch_count", "constv_set_launch_shape", "constv_set_kernel_variant",
 ]
 
@@ -89,6 +91,8 @@ def load() -> C.CDLL:
         "constv_upload_state": [vp, vp, vp, vp, vp, vp],
         "constv_download_state": [vp, vp, vp, vp, vp, vp],
         "constv_step_host": [vp, vp, vp, vp, C.POINTER(dbl), vp],
+        "constv_step_host_submit": [vp, vp, i32, C.POINTER(u64), vp],
+        "constv_step_host_collect": [vp, u64, C.POINTER(dbl)],
         "constv_set_launch_shape": [vp, i32, i32],
         "constv_set_kernel_variant": [vp, i32, i32, i32, i32],
     }

@@ -41,6 +41,7 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr double kBoltzDefault = 8.31446261815324e-3;  // OpenMM SimTKOpenMMRealType.h BOLTZ (>= 7.4)
 constexpr int kBlock = 256;
+constexpr int kBatchMax = 128;  // slabs per batched launch (descriptors travel as kernel parameters)
 
 size_t realSize(int prec) { return prec == CONSTV_PRECISION_DOUBLE ? 8 : 4; }
 size_t mixedSize(int prec) { return prec == CONSTV_PRECISION_SINGLE ? 4 : 8; }
@@ -67,9 +68,7 @@ struct constv_slab {
     double* kePartials = nullptr;
     double* keOut = nullptr;
     double* keHost = nullptr;  // pinned
-    SlabDev* batchTable = nullptr;  // device table for the ensemble launch led by this slab
-    int batchCapacity = 0;
-    std::vector<SlabDev> batchHost;
+    std::vector<SlabDev> batchScratch;  // descriptor table of the ensemble launch led by this slab
     // parameters
     bool paramsSet = false;
     double temperature = 0, friction = 0, stepSize = -1;
@@ -82,6 +81,16 @@ struct constv_slab {
     int tmaBlock = 256;  // pairs per chunk = threads per CTA of the TMA kernel
     int tmaStages = 4;
     int tmaCtasPerSM = 0;  // 0 = as many as shared memory allows
+    // pipelined host stepping (constv_step_host_submit / _collect): two slots
+    struct HostPipe {
+        bool ready = false;
+        cudaStream_t copyStream = nullptr;
+        void* stage[2] = {nullptr, nullptr};
+        cudaEvent_t h2dDone[2] = {nullptr, nullptr}, stageFree[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+        double* keDev = nullptr;   // 2 doubles
+        double* keHost = nullptr;  // 2 doubles, pinned
+        uint64_t submitted = 0, collected = 0;
+    } pipe;
 };
 
 namespace {
@@ -272,17 +281,23 @@ int launchKE(constv_slab* s, const SlabDev& d, double scale, double* out, cudaSt
     return launch(constv_kinetic_energy_kernel<PREC, kBlock>, grid, kBlock, false, st, d, scale, s->kePartials, out);
 }
 
-template <int PREC>
-int launchBatched(constv_slab* lead, int n, int totalTiles, int ilp, cudaStream_t st) {
+template <int PREC, int CAP>
+int launchBatchedCap(constv_slab* lead, const SlabDev* table, int n, int totalTiles, cudaStream_t st) {
+    static thread_local BatchParams<CAP> b;  // up to 24 KB: kept off the stack
+    b.numSlabs = n;
+    b.totalTiles = totalTiles;
+    for (int k = 0; k < n; k++) b.slab[k] = table[k];
     const bool pdl = lead->cfg.flags & CONSTV_FLAG_PDL;
     const long long cap = lead->ctasPerSM > 0 ? (long long) lead->numSMs * lead->ctasPerSM : totalTiles;
     const int grid = (int) (totalTiles < cap ? totalTiles : cap);
-    const SlabDev* table = lead->batchTable;
-    switch (ilp) {
-        case 1: return launch(constv_fused_step_batched_kernel<PREC, kBlock, 1>, grid, kBlock, pdl, st, table, n, totalTiles);
-        case 4: return launch(constv_fused_step_batched_kernel<PREC, kBlock, 4>, grid, kBlock, pdl, st, table, n, totalTiles);
-        default: return launch(constv_fused_step_batched_kernel<PREC, kBlock, 2>, grid, kBlock, pdl, st, table, n, totalTiles);
-    }
+    return launch(constv_fused_step_batched_kernel<PREC, kBlock, CAP>, grid, kBlock, pdl, st, b);
+}
+
+template <int PREC>
+int launchBatched(constv_slab* lead, const SlabDev* table, int n, int totalTiles, cudaStream_t st) {
+    if (n <= 8) return launchBatchedCap<PREC, 8>(lead, table, n, totalTiles, st);
+    if (n <= 32) return launchBatchedCap<PREC, 32>(lead, table, n, totalTiles, st);
+    return launchBatchedCap<PREC, kBatchMax>(lead, table, n, totalTiles, st);
 }
 
 #define DISPATCH_PREC(prec, call)                                       \
@@ -378,7 +393,18 @@ int constv_destroy(constv_slab* s) {
     cudaFree(s->counters);
     cudaFree(s->kePartials);
     cudaFree(s->keOut);
-    cudaFree(s->batchTable);
+    if (s->pipe.ready) {
+        cudaStreamSynchronize(s->pipe.copyStream);
+        for (int k = 0; k < 2; k++) {
+            cudaFree(s->pipe.stage[k]);
+            cudaEventDestroy(s->pipe.h2dDone[k]);
+            cudaEventDestroy(s->pipe.stageFree[k]);
+            cudaEventDestroy(s->pipe.done[k]);
+        }
+        cudaFree(s->pipe.keDev);
+        cudaFreeHost(s->pipe.keHost);
+        cudaStreamDestroy(s->pipe.copyStream);
+    }
     if (s->keHost) cudaFreeHost(s->keHost);
     delete s;
     return CONSTV_OK;
@@ -558,9 +584,6 @@ int constv_step_fused_batched(constv_slab* const* slabs, int32_t n, void* stream
     constv_slab* lead = slabs[0];
     GUARD(lead);
     int rc;
-    lead->batchHost.resize((size_t) n);
-    const int tile = kBlock * lead->ilp;
-    int totalTiles = 0;
     for (int k = 0; k < n; k++) {
         constv_slab* s = slabs[k];
         if (!s) return fail(CONSTV_ERR_INVALID, "null slab in batch");
@@ -570,23 +593,24 @@ int constv_step_fused_batched(constv_slab* const* slabs, int32_t n, void* stream
         if ((rc = checkReady(s, false))) return rc;
         if ((s->cfg.flags & CONSTV_FLAG_CACHE_IMAGE_CHARGE) && !s->imageChargeValid)
             if ((rc = constv_refresh_image_charges(s, stream))) return rc;
-        SlabDev d = makeDev(s);
-        d.tileBase = totalTiles;
-        totalTiles += (s->numReal + tile - 1) / tile;
-        lead->batchHost[(size_t) k] = d;
     }
-    if (lead->batchCapacity < n) {
-        cudaFree(lead->batchTable);
-        lead->batchTable = nullptr;
-        lead->batchCapacity = 0;
-        CUDA_TRY(cudaMalloc(&lead->batchTable, sizeof(SlabDev) * (size_t) n));
-        lead->batchCapacity = n;
+    // one launch per group of up to kBatchMax slabs; each group's ticket lives on its first slab
+    std::vector<SlabDev>& table = lead->batchScratch;
+    for (int first = 0; first < n; first += kBatchMax) {
+        const int m = n - first < kBatchMax ? n - first : kBatchMax;
+        table.resize((size_t) m);
+        int totalTiles = 0;
+        for (int k = 0; k < m; k++) {
+            SlabDev d = makeDev(slabs[first + k]);
+            d.tileBase = totalTiles;
+            totalTiles += (slabs[first + k]->numReal + kBlock - 1) / kBlock;
+            table[(size_t) k] = d;
+        }
+        DISPATCH_PREC(lead->cfg.precision, launchBatched<PR>(slabs[first], table.data(), m, totalTiles, (cudaStream_t) stream));
+        if (rc) return rc;
     }
-    CUDA_TRY(cudaMemcpyAsync(lead->batchTable, lead->batchHost.data(), sizeof(SlabDev) * (size_t) n, cudaMemcpyHostToDevice, (cudaStream_t) stream));
-    DISPATCH_PREC(lead->cfg.precision, launchBatched<PR>(lead, n, totalTiles, lead->ilp, (cudaStream_t) stream));
-    if (rc == CONSTV_OK)
-        for (int k = 0; k < n; k++) advanceTime(slabs[k]);
-    return rc;
+    for (int k = 0; k < n; k++) advanceTime(slabs[k]);
+    return CONSTV_OK;
 }
 
 int constv_kinetic_energy_device(constv_slab* s, double time_shift, double* ke_device, void* stream) {
@@ -702,6 +726,67 @@ int constv_step_host(constv_slab* s, const int64_t* host_force_real, void* host_
         CUDA_TRY(cudaMemcpyAsync(host_velm_out, s->velm, 4 * mixedSize(s->cfg.precision) * N, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (host_ke_out) *host_ke_out = *s->keHost;
+    return CONSTV_OK;
+}
+
+int constv_step_host_submit(constv_slab* s, const void* host_force_real, int32_t force_format, uint64_t* ticket_out,
+                            void* stream) {
+    GUARD(s);
+    int rc = checkReady(s, false);
+    if (rc) return rc;
+    if (s->atomIndex) return fail(CONSTV_ERR_STATE, "constv_step_host_submit needs identity slot order");
+    if (!host_force_real || !ticket_out) return fail(CONSTV_ERR_INVALID, "null argument");
+    if (force_format != CONSTV_FORCE_FIXED64 && force_format != CONSTV_FORCE_FLOAT32) return fail(CONSTV_ERR_INVALID, "unknown force format %d", force_format);
+    constv_slab::HostPipe& p = s->pipe;
+    if (p.submitted - p.collected >= 2) return fail(CONSTV_ERR_STATE, "two tickets are outstanding: collect one first");
+    const size_t R = (size_t) s->numReal;
+    if (!p.ready) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&p.copyStream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; k++) {
+            CUDA_TRY(cudaMalloc(&p.stage[k], 24 * R));
+            CUDA_TRY(cudaEventCreateWithFlags(&p.h2dDone[k], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&p.stageFree[k], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&p.done[k], cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaMalloc(&p.keDev, 2 * sizeof(double)));
+        CUDA_TRY(cudaMallocHost(&p.keHost, 2 * sizeof(double)));
+        p.ready = true;
+    }
+    const int slot = (int) (p.submitted & 1);
+    cudaStream_t st = (cudaStream_t) stream;
+    const size_t bytes = (force_format == CONSTV_FORCE_FLOAT32 ? 12 : 24) * R;
+    // upload on the copy stream as soon as the staging slot's previous contents have been consumed
+    if (p.submitted >= 2) CUDA_TRY(cudaStreamWaitEvent(p.copyStream, p.stageFree[slot], 0));
+    CUDA_TRY(cudaMemcpyAsync(p.stage[slot], host_force_real, bytes, cudaMemcpyHostToDevice, p.copyStream));
+    CUDA_TRY(cudaEventRecord(p.h2dDone[slot], p.copyStream));
+    // compute stream: staging -> force planes, fused step, kinetic energy, read-back
+    CUDA_TRY(cudaStreamWaitEvent(st, p.h2dDone[slot], 0));
+    const int grid = gridFor(s, (long long) (3 * R), 256, 16);
+    if (force_format == CONSTV_FORCE_FLOAT32)
+        rc = launch(constv_stage_forces_kernel<true>, grid, 256, false, st, s->numReal, s->cfg.padded_num_atoms, (const void*) p.stage[slot], (long long*) s->force);
+    else
+        rc = launch(constv_stage_forces_kernel<false>, grid, 256, false, st, s->numReal, s->cfg.padded_num_atoms, (const void*) p.stage[slot], (long long*) s->force);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(p.stageFree[slot], st));
+    rc = constv_step_fused(s, nullptr, 0, stream);
+    if (rc) return rc;
+    rc = constv_kinetic_energy_device(s, 0.5 * s->stepSize, p.keDev + slot, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(p.keHost + slot, p.keDev + slot, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(p.done[slot], st));
+    *ticket_out = p.submitted++;
+    return CONSTV_OK;
+}
+
+int constv_step_host_collect(constv_slab* s, uint64_t ticket, double* host_ke_out) {
+    GUARD(s);
+    constv_slab::HostPipe& p = s->pipe;
+    if (!p.ready || ticket != p.collected || ticket >= p.submitted)
+        return fail(CONSTV_ERR_STATE, "tickets are collected in submission order (next: %llu)", (unsigned long long) p.collected);
+    const int slot = (int) (ticket & 1);
+    CUDA_TRY(cudaEventSynchronize(p.done[slot]));
+    if (host_ke_out) *host_ke_out = p.keHost[slot];
+    p.collected++;
     return CONSTV_OK;
 }
 

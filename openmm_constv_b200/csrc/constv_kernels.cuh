@@ -300,18 +300,29 @@ template <int PREC> struct ImageCursor {
     }
 };
 
-// Every step kernel takes a ticket when a CTA is done; the last CTA advances the device-resident
-// step counter (so that CUDA-graph replays advance the Philox stream without host involvement).
-// All threads of the CTA have read counters->step before the __syncthreads() that precedes their
-// first tile, hence before this CTA's ticket.
-__device__ __forceinline__ void finish_step(DevCounters* counters) {
-    if (threadIdx.x == 0) {
-        const unsigned int ticket = atomicInc(&counters->done, gridDim.x - 1);
-        if (ticket == gridDim.x - 1) {
-            counters->step += 1;
-            __threadfence();
-        }
-    }
+// The step counter lives in device memory (so that CUDA-graph replays advance the Philox stream
+// without host involvement) and is advanced by the step kernel itself.  Protocol, per unit of work
+// ("ticket holder": a tile, or a CTA of a persistent kernel):
+//   1. thread 0 reads the counter and publishes it to the CTA through shared memory (StepBox);
+//   2. after the barrier that makes it visible -- i.e. once the value has arrived -- thread 0 takes
+//      one ticket (atomicInc wrapping at holders-1, so the ticket counter is back at 0 for the next
+//      launch); the atomic's round trip overlaps the unit's arithmetic and stores;
+//   3. when its work is done, the holder of the LAST ticket stores step+1.  Every other holder took
+//      its ticket after it had read the counter, so nobody can observe the new value early, and
+//      no CTA ever waits for an atomic or re-reads the counter before it exits.
+struct StepBox {
+    unsigned long long step;
+};
+
+__device__ __forceinline__ void publish_step(StepBox& box, const DevCounters* counters) {
+    if (threadIdx.x == 0) box.step = __ldcg(&counters->step);
+}
+__device__ __forceinline__ unsigned int take_ticket(DevCounters* counters, unsigned int holders) {
+    return threadIdx.x == 0 ? atomicInc(&counters->done, holders - 1) : 0u;
+}
+__device__ __forceinline__ void close_step(DevCounters* counters, unsigned int ticket, unsigned int holders,
+                                           unsigned long long step) {
+    if (threadIdx.x == 0 && ticket == holders - 1) counters->step = step + 1;
 }
 
 // ---- the fused step, identity slot order -------------------------------------------------------
@@ -386,8 +397,10 @@ __device__ __forceinline__ void process_pair(const SlabDev& d, const StepScalars
 
 // LDG variant: all loads of a tile (ILP pairs per thread) are issued before the first use so that
 // each thread keeps ILP*(60..100) bytes in flight.
-template <int PREC, int BLOCK, int ILP, bool STREAM>
-__device__ __forceinline__ void fused_tile(const SlabDev& d, const int base, const int end, const unsigned long long step,
+// `stepOf()` is called once, after the tile's loads have been issued: it returns the step index (the
+// Philox counter) and is where the caller synchronises the CTA on the published counter.
+template <int PREC, int BLOCK, int ILP, bool STREAM, typename StepFn>
+__device__ __forceinline__ void fused_tile(const SlabDev& d, const int base, const int end, StepFn stepOf,
                                            const float4* __restrict__ random, const unsigned int randomIndex) {
     using Real = typename Prec<PREC>::Real;
     using Mixed = typename Prec<PREC>::Mixed;
@@ -424,6 +437,7 @@ __device__ __forceinline__ void fused_tile(const SlabDev& d, const int base, con
             if (random) xi[j] = __ldcs(random + (size_t) randomIndex + i);
         }
     }
+    const unsigned long long step = stepOf();
 #pragma unroll
     for (int j = 0; j < ILP; j++) {
         if (!valid[j]) continue;
@@ -435,17 +449,27 @@ template <int PREC, int BLOCK, int ILP, bool STREAM>
 __global__ void __launch_bounds__(BLOCK)
 constv_fused_step_kernel(const __grid_constant__ SlabDev d, const float4* __restrict__ random,
                          const unsigned int randomIndex) {
+    __shared__ StepBox box;
     pdl_wait();
-    const unsigned long long step = d.counters->step;
-    __syncthreads();
     pdl_launch();
     // One tile per CTA when the host launches a one-shot grid (the default: the hardware CTA
     // scheduler then keeps the memory access front sequential and balances the tail, which measured
     // 10-15 % faster than a persistent grid for this 11-stream pattern); grid-stride otherwise.
     constexpr int kTile = BLOCK * ILP;
-    for (long long base = (long long) blockIdx.x * kTile; base < d.numReal; base += (long long) gridDim.x * kTile)
-        fused_tile<PREC, BLOCK, ILP, STREAM>(d, (int) base, d.numReal, step, random, randomIndex);
-    finish_step(d.counters);
+    const unsigned int holders = (unsigned int) ((d.numReal + kTile - 1) / kTile);  // one ticket per tile
+    for (long long base = (long long) blockIdx.x * kTile; base < d.numReal; base += (long long) gridDim.x * kTile) {
+        unsigned int ticket = 0;
+        unsigned long long step = 0;
+        fused_tile<PREC, BLOCK, ILP, STREAM>(d, (int) base, d.numReal, [&]() {
+            publish_step(box, d.counters);
+            __syncthreads();
+            step = box.step;
+            ticket = take_ticket(d.counters, holders);
+            return step;
+        }, random, randomIndex);
+        close_step(d.counters, ticket, holders, step);
+        if (base + (long long) gridDim.x * kTile < d.numReal) __syncthreads();  // box is rewritten by the next tile
+    }
 }
 
 // ---- the fused step, TMA-pipelined (the B200 fast path) -----------------------------------------
@@ -509,8 +533,9 @@ constv_fused_step_tma_kernel(const __grid_constant__ SlabDev d) {
     const int hi = min(R, (int) (((long long) quads * (blockIdx.x + 1) / gridDim.x) << 2));
     const int numChunks = (hi - lo + BLOCK - 1) / BLOCK;
 
+    __shared__ StepBox box;
     pdl_wait();
-    const unsigned long long step = d.counters->step;
+    publish_step(box, d.counters);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; s++) mbar_init(smem_u32(&fullBar[s]), 1);
@@ -519,6 +544,8 @@ constv_fused_step_tma_kernel(const __grid_constant__ SlabDev d) {
     }
     __syncthreads();
     pdl_launch();
+    const unsigned long long step = box.step;
+    const unsigned int ticket = take_ticket(d.counters, gridDim.x);  // one ticket per persistent CTA
 
     const Real* __restrict__ posq = static_cast<const Real*>(d.posq);
     const Real* __restrict__ corrA = static_cast<const Real*>(d.corr);
@@ -582,46 +609,44 @@ constv_fused_step_tma_kernel(const __grid_constant__ SlabDev d) {
         __syncthreads();  // every thread has consumed its slice of this stage
         if (threadIdx.x == 0 && chunk + STAGES < numChunks) issue(chunk + STAGES);
     }
-    finish_step(d.counters);
+    close_step(d.counters, ticket, gridDim.x, step);
 }
 
-// Ensemble launch: `table` holds one SlabDev per slab, tileBase = exclusive prefix of the per-slab
-// tile counts.  One grid covers every slab; blocks find their slab by binary search.
-template <int PREC, int BLOCK, int ILP>
+// Ensemble launch: one grid advances up to CAP independent slabs by one step each.  The per-slab
+// descriptors travel in the kernel parameters (constant bank: no dependent global loads before a
+// CTA can issue its data loads, nothing to upload per step, capturable in a CUDA graph);
+// tileBase = exclusive prefix of the per-slab tile counts, blocks find their slab by binary search.
+template <int CAP> struct BatchParams {
+    int numSlabs, totalTiles;
+    SlabDev slab[CAP];
+};
+
+template <int PREC, int BLOCK, int CAP>
 __global__ void __launch_bounds__(BLOCK)
-constv_fused_step_batched_kernel(const SlabDev* __restrict__ table, const int numSlabs, const int totalTiles) {
+constv_fused_step_batched_kernel(const __grid_constant__ BatchParams<CAP> b) {
+    __shared__ StepBox box;
     pdl_wait();
-    __shared__ SlabDev d;
-    __shared__ unsigned long long stepOfSlab;
-    constexpr int kTile = BLOCK * ILP;
-    int current = -1;
-    for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
-        int lo = 0, hi = numSlabs - 1;
+    pdl_launch();
+    for (int tile = blockIdx.x; tile < b.totalTiles; tile += gridDim.x) {
+        int lo = 0, hi = b.numSlabs - 1;
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
-            if (table[mid].tileBase <= tile) lo = mid; else hi = mid - 1;
+            if (b.slab[mid].tileBase <= tile) lo = mid; else hi = mid - 1;
         }
-        if (lo != current) {
+        const SlabDev& d = b.slab[lo];
+        // one ticket per tile, on the tile's own slab: every slab's counter advances exactly once
+        const unsigned int holders = (unsigned int) ((d.numReal + BLOCK - 1) / BLOCK);
+        unsigned int ticket = 0;
+        unsigned long long step = 0;
+        fused_tile<PREC, BLOCK, 1, true>(d, (tile - d.tileBase) * BLOCK, d.numReal, [&]() {
+            publish_step(box, d.counters);
             __syncthreads();
-            if (threadIdx.x == 0) {
-                d = table[lo];
-                stepOfSlab = table[lo].counters->step;
-            }
-            __syncthreads();
-            current = lo;
-        }
-        fused_tile<PREC, BLOCK, ILP, true>(d, (tile - d.tileBase) * kTile, d.numReal, stepOfSlab, nullptr, 0u);
-    }
-    // every slab's counter advances once per launch: slab k is closed by the CTAs' shared ticket
-    // on slab 0's counters; the last CTA bumps all step counters.
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        DevCounters* c0 = table[0].counters;
-        const unsigned int ticket = atomicInc(&c0->done, gridDim.x - 1);
-        if (ticket == gridDim.x - 1) {
-            for (int k = 0; k < numSlabs; k++) table[k].counters->step += 1;
-            __threadfence();
-        }
+            step = box.step;
+            ticket = take_ticket(d.counters, holders);
+            return step;
+        }, nullptr, 0u);
+        close_step(d.counters, ticket, holders, step);
+        if (tile + (int) gridDim.x < b.totalTiles) __syncthreads();
     }
 }
 
@@ -636,10 +661,13 @@ constv_fused_step_indexed_kernel(const __grid_constant__ SlabDev d, const float4
     using Real = typename Prec<PREC>::Real;
     using Mixed = typename Prec<PREC>::Mixed;
     constexpr bool kSplit = Prec<PREC>::kSplitPos;
+    __shared__ StepBox box;
     pdl_wait();
-    const unsigned long long step = d.counters->step;
+    publish_step(box, d.counters);
     __syncthreads();
     pdl_launch();
+    const unsigned long long step = box.step;
+    const unsigned int ticket = take_ticket(d.counters, gridDim.x);  // one ticket per CTA
     const int R = d.numReal;
     const size_t P = (size_t) d.padded;
     Real* __restrict__ posq = static_cast<Real*>(d.posq);
@@ -689,7 +717,7 @@ constv_fused_step_indexed_kernel(const __grid_constant__ SlabDev d, const float4
             }
         }
     }
-    finish_step(d.counters);
+    close_step(d.counters, ticket, gridDim.x, step);
 }
 
 // ---- split path: part 1 | constraints (caller) | part 2 + mirror -------------------------------
@@ -780,7 +808,8 @@ constv_part2_mirror_kernel(const __grid_constant__ SlabDev d) {
             }
         }
     }
-    finish_step(d.counters);
+    // no thread of this launch reads the counter (part 1 did): one thread advances it
+    if (blockIdx.x == 0 && threadIdx.x == 0) d.counters->step = __ldcg(&d.counters->step) + 1;
 }
 
 // reordered slots: part 2 per slot (+ zeroing of image slots) ...
@@ -845,7 +874,8 @@ constv_mirror_indexed_kernel(const __grid_constant__ SlabDev d) {
             }
         }
     }
-    finish_step(d.counters);
+    // no thread of this launch reads the counter (part 1 did): one thread advances it
+    if (blockIdx.x == 0 && threadIdx.x == 0) d.counters->step = __ldcg(&d.counters->step) + 1;
 }
 
 // ---- small kernels -----------------------------------------------------------------------------
@@ -863,6 +893,21 @@ __global__ void constv_image_charge_kernel(const int numReal, const int numCells
     const int n = numReal * (numCells - 1);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
         imageCharge[k] = posq[4 * (size_t) invAtomOrder[numReal + k] + 3];
+}
+
+// Host-force staging -> OpenMM's force planes (constv_step_host_submit).  FROM_FLOAT converts as
+// OpenMM's force kernels do when they accumulate: (long long)(f * 0x100000000), truncating.
+template <bool FROM_FLOAT>
+__global__ void constv_stage_forces_kernel(const int numReal, const int padded, const void* __restrict__ staged,
+                                           long long* __restrict__ force) {
+    const int total = 3 * numReal;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+        const int plane = k / numReal, i = k - plane * numReal;
+        long long v;
+        if (FROM_FLOAT) v = __float2ll_rz(__fmul_rn(__ldcs(static_cast<const float*>(staged) + k), 4294967296.0f));
+        else v = __ldcs(static_cast<const long long*>(staged) + k);
+        force[(size_t) plane * padded + i] = v;
+    }
 }
 
 __global__ void constv_noise_kernel(const int numAtoms, const int* __restrict__ atomIndex,

@@ -377,6 +377,64 @@ def test_step_host_roundtrip(gpu, oracle):
     ctx.close()
 
 
+@pytest.mark.parametrize("fmt", ["fixed64", "float32"])
+def test_pipelined_host_stepping_equals_synchronous(gpu, oracle, fmt):
+    """constv_step_host_submit/_collect (upload of step k+1 overlapping step k) must give exactly what
+    the synchronous constv_step_host gives; float32 host forces are converted on the device as
+    OpenMM's force kernels fill the buffer: (long long)(f * 2^32), truncating."""
+    import ctypes as C
+    import torch
+    from openmm_constv_b200 import _capi
+    lib = _capi.load()
+    s0 = slabmod.make_slab(5003, "single", seed=23)
+    R, nsteps = s0.num_real, 7
+    rng = np.random.default_rng(4)
+    f32 = [(rng.standard_normal((3, R)) * 1000.0).astype(np.float32) for _ in range(nsteps)]
+    fixed = [np.trunc(f.astype(np.float64) * 4294967296.0).astype(np.int64) for f in f32]  # float*2^32 is exact
+    assert all(np.array_equal(np.trunc(f * np.float32(4294967296.0)).astype(np.int64), g) for f, g in zip(f32, fixed))
+    # synchronous path with int64 forces
+    ctx_a, it_a = make_context(gpu, s0, seed=5)
+    _capi.check(lib.constv_set_parameters(it_a._kernel.handle, T, GAMMA, DT))
+    ke_a = []
+    for g in fixed:
+        hf = torch.from_numpy(np.ascontiguousarray(g)).pin_memory()
+        ke = C.c_double(0.0)
+        _capi.check(lib.constv_step_host(it_a._kernel.handle, hf.data_ptr(), None, None, C.byref(ke), ctx_a.stream_ptr()))
+        ke_a.append(ke.value)
+    # pipelined path, two tickets in flight
+    ctx_b, it_b = make_context(gpu, s0, seed=5)
+    _capi.check(lib.constv_set_parameters(it_b._kernel.handle, T, GAMMA, DT))
+    src = fixed if fmt == "fixed64" else f32
+    code = _capi.FORCE_FIXED64 if fmt == "fixed64" else _capi.FORCE_FLOAT32
+    pinned = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in src]
+    ke_b, tickets = [], []
+    for k in range(nsteps):
+        t = C.c_uint64(0)
+        _capi.check(lib.constv_step_host_submit(it_b._kernel.handle, pinned[k].data_ptr(), code, C.byref(t), ctx_b.stream_ptr()))
+        tickets.append(t.value)
+        if k >= 1:
+            ke = C.c_double(0.0)
+            _capi.check(lib.constv_step_host_collect(it_b._kernel.handle, tickets[k - 1], C.byref(ke)))
+            ke_b.append(ke.value)
+    ke = C.c_double(0.0)
+    _capi.check(lib.constv_step_host_collect(it_b._kernel.handle, tickets[-1], C.byref(ke)))
+    ke_b.append(ke.value)
+    assert tickets == list(range(nsteps))
+    assert ke_a == ke_b
+    torch.cuda.synchronize()
+    assert_slab_bits_equal(download(ctx_b, s0), download(ctx_a, s0))
+    # discipline: a third outstanding ticket and out-of-order collection are refused
+    t = C.c_uint64(0)
+    for _ in range(2):
+        _capi.check(lib.constv_step_host_submit(it_b._kernel.handle, pinned[0].data_ptr(), code, C.byref(t), ctx_b.stream_ptr()))
+    assert lib.constv_step_host_submit(it_b._kernel.handle, pinned[0].data_ptr(), code, C.byref(t), ctx_b.stream_ptr()) == _capi.ERR_STATE
+    assert lib.constv_step_host_collect(it_b._kernel.handle, t.value, None) == _capi.ERR_STATE
+    _capi.check(lib.constv_step_host_collect(it_b._kernel.handle, t.value - 1, None))
+    _capi.check(lib.constv_step_host_collect(it_b._kernel.handle, t.value, None))
+    ctx_a.close()
+    ctx_b.close()
+
+
 # ---- full-size, size-independent properties ------------------------------------------------------------
 
 def test_full_size_slab_properties_and_oracle(gpu, oracle):
