@@ -3,7 +3,7 @@
 # the identical command that exited 0 (B200_PROFILING.md).
 set -u
 mkdir -p gpurun_out
-CMD="python bench.py --steps 18 --warmup 6 --no-graph --skip-cpu --skip-e2e"
+CMD="python bench.py --steps 18 --warmup 6 --no-graph --skip-cpu --skip-e2e --skip-ref-gpu"
 $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 $CMD > gpurun_out/plain2.log 2>&1 &&
