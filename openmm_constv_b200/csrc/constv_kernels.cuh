@@ -338,11 +338,13 @@ template <int PREC> struct PairIn {
     typename Prec<PREC>::Real q1;                // charge of the cell-1 image
 };
 
-// Part 1 + part 2 + image rewrite + image zeroing for pair i; all stores go straight to global.
+// What one real atom leaves in HBM at the end of a step (identity slot order): its own record (when
+// it moved), the rewritten images (charged atoms only, Langevin.cu:143) and the zeroed image
+// velocities / forces.  i = slot of the real atom, q1 = charge of its cell-1 image.
 template <int PREC, bool STREAM>
-__device__ __forceinline__ void process_pair(const SlabDev& d, const StepScalars<typename Prec<PREC>::Mixed>& s,
-                                             const int i, PairIn<PREC>& in, const bool havePool, float4 xi,
-                                             const unsigned long long step) {
+__device__ __forceinline__ void emit_atom(const SlabDev& d, const double zshift, const int i, const bool moved,
+                                          const Vec4<typename Prec<PREC>::Mixed>& v, const Vec4<typename Prec<PREC>::Real>& p,
+                                          const Vec4<typename Prec<PREC>::Real>& c, const typename Prec<PREC>::Real q1) {
     using Real = typename Prec<PREC>::Real;
     using Mixed = typename Prec<PREC>::Mixed;
     constexpr bool kSplit = Prec<PREC>::kSplitPos;
@@ -352,23 +354,16 @@ __device__ __forceinline__ void process_pair(const SlabDev& d, const StepScalars
     Real* __restrict__ corrA = static_cast<Real*>(d.corr);
     Mixed* __restrict__ velm = static_cast<Mixed*>(d.velm);
     long long* __restrict__ force = d.force;
-    if (in.v.w != 0) {
-        if (!havePool) {
-            xi = (s.noisescale != 0) ? gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) i, step)
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        Vec4<Mixed> delta;
-        part1_update(in.v, delta, in.fx, in.fy, in.fz, xi.x, xi.y, xi.z, s);
-        part2_update<PREC>(in.p, in.c, in.v, delta, s.invDt);
-        store4x<STREAM>(velm, (size_t) i, in.v);
-        store4x<STREAM>(posq, (size_t) i, in.p);
-        if (kSplit) store4x<STREAM>(corrA, (size_t) i, in.c);
+    if (moved) {
+        store4x<STREAM>(velm, (size_t) i, v);
+        store4x<STREAM>(posq, (size_t) i, p);
+        if (kSplit) store4x<STREAM>(corrA, (size_t) i, c);
     }
     // image rewrite (Langevin.cu:143: neutral atoms are skipped)
-    if (in.p.w != -in.p.w) {
-        ImageCursor<PREC> cur(in.p, in.c);
-        cur.advance(1, s.zshift);
-        store4x<STREAM>(posq, (size_t) i + R, cur.posq(in.q1));
+    if (p.w != -p.w) {
+        ImageCursor<PREC> cur(p, c);
+        cur.advance(1, zshift);
+        store4x<STREAM>(posq, (size_t) i + R, cur.posq(q1));
         if (kSplit) store4x<STREAM>(corrA, (size_t) i + R, cur.corr());
         if (d.numCells > 2) {
 #pragma unroll 1
@@ -376,7 +371,7 @@ __device__ __forceinline__ void process_pair(const SlabDev& d, const StepScalars
                 const size_t slot = (size_t) i + (size_t) R * cell;
                 const Real qc = d.imageCharge ? static_cast<const Real*>(d.imageCharge)[(size_t) (cell - 1) * R + i]
                                               : posq[4 * slot + 3];
-                cur.advance(cell, s.zshift);
+                cur.advance(cell, zshift);
                 store4x<STREAM>(posq, slot, cur.posq(qc));
                 if (kSplit) store4x<STREAM>(corrA, slot, cur.corr());
             }
@@ -393,6 +388,25 @@ __device__ __forceinline__ void process_pair(const SlabDev& d, const StepScalars
             __stcs(force + 2 * P + slot, 0LL);
         }
     }
+}
+
+// Part 1 + part 2 + image rewrite + image zeroing for pair i; all stores go straight to global.
+template <int PREC, bool STREAM>
+__device__ __forceinline__ void process_pair(const SlabDev& d, const StepScalars<typename Prec<PREC>::Mixed>& s,
+                                             const int i, PairIn<PREC>& in, const bool havePool, float4 xi,
+                                             const unsigned long long step) {
+    using Mixed = typename Prec<PREC>::Mixed;
+    const bool moved = in.v.w != 0;
+    if (moved) {
+        if (!havePool) {
+            xi = (s.noisescale != 0) ? gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) i, step)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        Vec4<Mixed> delta;
+        part1_update(in.v, delta, in.fx, in.fy, in.fz, xi.x, xi.y, xi.z, s);
+        part2_update<PREC>(in.p, in.c, in.v, delta, s.invDt);
+    }
+    emit_atom<PREC, STREAM>(d, s.zshift, i, moved, in.v, in.p, in.c, in.q1);
 }
 
 // LDG variant: all loads of a tile (ILP pairs per thread) are issued before the first use so that
@@ -837,7 +851,7 @@ constv_part2_indexed_kernel(const __grid_constant__ SlabDev d) {
             store4(posq, (size_t) slot, p);
             if (kSplit) store4(corrA, (size_t) slot, c);
         }
-        if (d.atomIndex[slot] >= d.numReal) {
+        if ((d.atomIndex ? d.atomIndex[slot] : slot) >= d.numReal) {
             if (d.zeroVelm) store4(velm, (size_t) slot, Vec4<Mixed>{0, 0, 0, 0});
             if (d.zeroForce) {
                 __stcs(force + slot, 0LL);

@@ -161,6 +161,72 @@ def make_slab(num_real: int, precision: str = "single", num_cells: int = 2, seed
                  "temperature": temperature})
 
 
+MASS_DRUDE = 0.4  # amu, the usual Drude particle mass
+
+
+def make_drude_slab(num_real: int, precision: str = "single", num_cells: int = 2, seed: int = 12345,
+                    drude_sigma: float = 0.012, **kw):
+    """A slab for ConstVDrudeLangevinIntegrator: ``make_slab`` whose "water" atoms are regrouped as
+    polarizable 4-site molecules (parent O carrying a Drude particle on a spring, two H).
+
+    Returns ``(slab, normal_particles, pair_particles)`` as the reference's kernel builds them from the
+    DrudeForce (CudaConstVKernels.cpp:213-230): ``pair_particles`` is an (n, 2) int32 array of
+    (Drude particle, parent) ORIGINAL indices, ``normal_particles`` the sorted indices of every other
+    real atom (ions, hydrogens, massless walls).  The Drude particle sits ``drude_sigma`` nm (rms per
+    component) from its parent, so with a hard wall at ~0.02 nm a good fraction of the pairs bounce.
+    """
+    s = make_slab(num_real, precision, num_cells=num_cells, seed=seed, **kw)
+    rng = np.random.Generator(np.random.Philox(seed + 99))
+    R = s.num_real
+    n_ion, n_water = s.meta["n_ion"], s.meta["n_water"]
+    n_mol = n_water // 4
+    first = n_ion
+    real, mixed = REAL[precision], MIXED[precision]
+    parents = first + 4 * np.arange(n_mol)
+    drudes = parents + 1
+    mass = s.masses[:R].copy()
+    charge = s.posq[:R, 3].astype(np.float64)
+    pos = s.posq[:R, :3].astype(np.float64)
+    if s.corr is not None:
+        pos += s.corr[:R, :3].astype(np.float64)
+    for k, (m, q) in enumerate(((MASS_O - MASS_DRUDE, 1.0), (MASS_DRUDE, -1.8476), (MASS_H, Q_H), (MASS_H, Q_H))):
+        mass[first + k: first + 4 * n_mol: 4] = m
+        charge[first + k: first + 4 * n_mol: 4] = q
+    # atoms of the former 3-site waters left over after regrouping become neutral, massless fillers
+    mass[first + 4 * n_mol: first + n_water] = 0.0
+    charge[first + 4 * n_mol: first + n_water] = 0.0
+    pos[drudes] = pos[parents] + rng.standard_normal((n_mol, 3)) * drude_sigma
+    inv_mass = np.where(mass > 0, 1.0 / np.where(mass > 0, mass, 1.0), 0.0)
+    vel = rng.standard_normal((R, 3)) * np.sqrt(BOLTZ * s.meta["temperature"] * inv_mass)[:, None]
+    s.masses[:R] = mass
+    p64 = np.zeros((s.padded, 4), np.float64)
+    p64[:, :3] = s.posq[:, :3]
+    if s.corr is not None:
+        p64[:, :3] += s.corr[:, :3]
+    p64[:, 3] = s.posq[:, 3]
+    p64[:R, :3] = pos
+    p64[:R, 3] = charge
+    for i in range(1, num_cells):
+        img = slice(i * R, (i + 1) * R)
+        zi = pos[:, 2].copy()
+        for j in range(1, i + 1):
+            zi = -zi + 2.0 * j * s.zmax if j > 1 else -zi
+        p64[img, 0], p64[img, 1] = pos[:, 0], pos[:, 1]
+        p64[img, 2] = np.where(charge != 0, zi, zi + 0.001)
+        p64[img, 3] = -charge if i % 2 == 1 else charge
+    s.posq = p64.astype(real)
+    if s.corr is not None:
+        s.corr[:, :3] = (p64[:, :3] - s.posq[:, :3].astype(np.float64)).astype(real)
+    s.velm[:R, :3] = vel.astype(mixed)
+    s.velm[:R, 3] = inv_mass.astype(mixed)
+    pairs = np.stack([drudes, parents], axis=1).astype(np.int32)
+    in_pair = np.zeros(R, bool)
+    in_pair[pairs.reshape(-1)] = True
+    normal = np.nonzero(~in_pair)[0].astype(np.int32)
+    s.meta.update(n_pairs=int(n_mol), n_normal=int(len(normal)))
+    return s, normal, np.ascontiguousarray(pairs)
+
+
 def slice_slab(slab: Slab, lo: int, hi: int) -> Slab:
     """The shard holding real atoms [lo, hi) and their images (multi-GPU range partition:
     every image lives with its real partner)."""

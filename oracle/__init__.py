@@ -42,7 +42,7 @@ def build(force: bool = False) -> str:
     if force or any(
         not os.path.exists(t) or any(
             os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(t)
-            for f in ("constv_oracle.c", "constv_oracle_impl.h", "Makefile"))
+            for f in ("constv_oracle.c", "constv_oracle_impl.h", "constv_oracle_drude_impl.h", "Makefile"))
         for t in (_LIB_PATH, _LIB_PATH_NOFMA)
     ):
         subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True, capture_output=True)
@@ -209,6 +209,50 @@ def step_range(precision, num_atoms, num_cells, zshift_per_cell, posq, posq_corr
        _p(force, np.int64), _p(prm), _mixed_scalar(precision, step_size),
        _p(random4, np.float32), C.c_uint(random_index), C.c_int(zero_velm), C.c_int(zero_force),
        C.c_int(lo), C.c_int(hi))
+
+
+# ---- ConstVDrudeLangevinIntegrator (constVDrudeLangevin.cu, CudaConstVKernels.cpp:252-349) ----------
+
+def drude_params(temperature, friction, drude_temperature, drude_friction, max_drude_distance, step_size,
+                 boltz=BOLTZ):
+    """[vscale, fscale/2^32, noisescale, vscaleDrude, fscaleDrude/2^32, noisescaleDrude,
+    maxDrudeDistance, hardwallscaleDrude] in double."""
+    out = np.zeros(8, np.float64)
+    lib().oracle_drude_params(C.c_double(temperature), C.c_double(friction), C.c_double(drude_temperature),
+                              C.c_double(drude_friction), C.c_double(max_drude_distance), C.c_double(step_size),
+                              C.c_double(boltz), _p(out))
+    return out
+
+
+def drude_part1(precision, velm, force, pos_delta, normal, pairs, scalars, step_size, random4, random_index=0):
+    m = MIXED[precision]
+    s = np.ascontiguousarray(scalars, m)
+    fn = getattr(lib(), "oracle_drude_part1_" + _SUFFIX[precision])
+    fn(C.c_int(len(normal)), C.c_int(len(pairs)), C.c_int(velm.shape[0]), _p(velm, m), _p(force, np.int64),
+       _p(pos_delta, m), _p(normal, np.int32), _p(pairs, np.int32), _mixed_scalar(precision, step_size), _p(s),
+       _p(random4, np.float32), C.c_uint(random_index))
+
+
+def drude_hardwall(precision, posq, posq_corr, velm, pairs, step_size, max_drude_distance, hardwall_scale):
+    r, m = REAL[precision], MIXED[precision]
+    fn = getattr(lib(), "oracle_drude_hardwall_" + _SUFFIX[precision])
+    fn(C.c_int(len(pairs)), _p(posq, r), _p(posq_corr, r) if posq_corr is not None else None, _p(velm, m),
+       _p(pairs, np.int32), _mixed_scalar(precision, step_size), _mixed_scalar(precision, max_drude_distance),
+       _mixed_scalar(precision, hardwall_scale))
+
+
+def drude_step(precision, num_atoms, num_cells, zshift_per_cell, posq, posq_corr, velm, force, pos_delta,
+               normal, pairs, scalars, step_size, random4, random_index, inv_order, zero_velm=True,
+               zero_force=True):
+    """One constraint-free Drude step in the reference's launch order (+ the explicit image zeroing)."""
+    r, m = REAL[precision], MIXED[precision]
+    s = np.ascontiguousarray(scalars, m)
+    fn = getattr(lib(), "oracle_drude_step_" + _SUFFIX[precision])
+    fn(C.c_int(num_atoms), C.c_int(velm.shape[0]), C.c_int(num_cells), C.c_double(zshift_per_cell), _p(posq, r),
+       _p(posq_corr, r) if posq_corr is not None else None, _p(velm, m), _p(force, np.int64), _p(pos_delta, m),
+       C.c_int(len(normal)), _p(normal, np.int32), C.c_int(len(pairs)), _p(pairs, np.int32), _p(s),
+       _mixed_scalar(precision, step_size), _p(random4, np.float32), C.c_uint(random_index),
+       _p(inv_order, np.int32), C.c_int(zero_velm), C.c_int(zero_force))
 
 
 def philox4x32_10(counter, key):

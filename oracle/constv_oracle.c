@@ -46,6 +46,7 @@
 #define MIXED_POS 0
 #define MIXED_IS_DOUBLE 0
 #include "constv_oracle_impl.h"
+#include "constv_oracle_drude_impl.h"
 #undef REAL
 #undef MIXED
 #undef SUFFIX
@@ -58,6 +59,7 @@
 #define MIXED_POS 1
 #define MIXED_IS_DOUBLE 1
 #include "constv_oracle_impl.h"
+#include "constv_oracle_drude_impl.h"
 #undef REAL
 #undef MIXED
 #undef SUFFIX
@@ -70,6 +72,7 @@
 #define MIXED_POS 0
 #define MIXED_IS_DOUBLE 1
 #include "constv_oracle_impl.h"
+#include "constv_oracle_drude_impl.h"
 #undef REAL
 #undef MIXED
 #undef SUFFIX
@@ -92,6 +95,28 @@ void oracle_params(double temperature, double friction, double stepSize, double 
     out[0] = vscale;
     out[1] = fscale;
     out[2] = noisescale;
+}
+
+/*
+ * Parameters of the Drude integrator, CudaConstVKernels.cpp:262-270, in double (the caller narrows
+ * them to float for single precision as :284-312 does).  NOTE: unlike the plain integrator there
+ * is no friction == 0 special case in the reference: fscale = (1-vscale)/friction/2^32.
+ * out[8] = vscale, fscale/2^32, noisescale, vscaleDrude, fscaleDrude/2^32, noisescaleDrude,
+ *          maxDrudeDistance, hardwallscaleDrude = sqrt(kB*T_drude).
+ */
+void oracle_drude_params(double temperature, double friction, double drudeTemperature, double drudeFriction,
+                         double maxDrudeDistance, double stepSize, double boltz, double out[8]) {
+    const double vscale = exp(-stepSize * friction);
+    const double fscale = (1 - vscale) / friction / (double) 0x100000000;
+    const double noisescale = sqrt(2 * boltz * temperature * friction) * sqrt(0.5 * (1 - vscale * vscale) / friction);
+    const double vscaleDrude = exp(-stepSize * drudeFriction);
+    const double fscaleDrude = (1 - vscaleDrude) / drudeFriction / (double) 0x100000000;
+    const double noisescaleDrude = sqrt(2 * boltz * drudeTemperature * drudeFriction) *
+                                   sqrt(0.5 * (1 - vscaleDrude * vscaleDrude) / drudeFriction);
+    out[0] = vscale; out[1] = fscale; out[2] = noisescale;
+    out[3] = vscaleDrude; out[4] = fscaleDrude; out[5] = noisescaleDrude;
+    out[6] = maxDrudeDistance;
+    out[7] = sqrt(boltz * drudeTemperature);
 }
 
 /*

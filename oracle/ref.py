@@ -114,6 +114,30 @@ def host_inverse_order(atom_index):
     return inv
 
 
+def host_drude_step(precision, num_atoms, num_cells, zmax, posq, corr, velm, force, pos_delta, normal, pairs,
+                    scalars, step_size, random4, random_index, inv_order):
+    """One constraint-free step of the reference's Drude integrator on the host, in its launch order
+    (CudaConstVKernels.cpp:317-349): Drude part 1, part 2, hard wall (if maxDrudeDistance > 0),
+    image rewrite.  scalars = oracle.drude_params(...) (doubles; narrowed to `mixed` by the launcher
+    as CudaConstVKernels.cpp:284-312 does)."""
+    h = host()
+    sfx = SUFFIX[precision]
+    P = velm.shape[0]
+    num_real = num_atoms // num_cells
+    _, dt = host_arrays(precision, np.zeros(3), step_size)
+    if corr is None:
+        corr = np.zeros((1, 4), REAL[precision])
+    sc = [C.c_double(float(x)) for x in scalars]
+    getattr(h, "constv_ref_drude_host_configure_" + sfx)(C.c_int(num_real), C.c_int(P), C.c_int(len(normal)),
+                                                          C.c_int(len(pairs)))
+    getattr(h, "constv_ref_drude_host_part1_" + sfx)(_p(velm), _p(force), _p(pos_delta), _p(normal), _p(pairs), _p(dt),
+                                                      *sc[:6], _p(random4), C.c_uint(random_index))
+    getattr(h, "constv_ref_drude_host_part2_" + sfx)(_p(posq), _p(corr), _p(pos_delta), _p(velm), _p(dt))
+    if scalars[6] > 0:
+        getattr(h, "constv_ref_drude_host_hardwall_" + sfx)(_p(posq), _p(corr), _p(velm), _p(pairs), _p(dt), sc[6], sc[7])
+    host_mirror(precision, num_real, num_cells, zmax, posq, corr, inv_order)
+
+
 def host_num_threads() -> int:
     return host().constv_ref_host_num_threads()
 
@@ -176,4 +200,42 @@ class CudaReference:
         """CudaConstVKernels.cpp:146-166 without constraints: three launches."""
         self.part1(num_atoms, velm, force, pos_delta, random4, random_index, stream)
         self.part2(num_atoms, posq, corr, pos_delta, velm, stream)
+        self.mirror(num_atoms // num_cells, num_cells, zmax, posq, corr, inv_order, stream)
+
+
+class CudaDrudeReference(CudaReference):
+    """The reference's Drude kernels on the GPU (oracle/ref_drude_cuda.cu) plus the shared image
+    rewrite: the launch sequence of CudaConstVKernels.cpp:317-349 without constraints."""
+
+    def __init__(self, precision, scalars, step_size, device, normal, pairs, num_real, padded, max_blocks=0):
+        super().__init__(precision, np.zeros(3), step_size, device, max_blocks=max_blocks)
+        torch = self.torch
+        self.scalars = [float(x) for x in scalars]
+        self.normal = torch.as_tensor(np.ascontiguousarray(normal, np.int32), device=device)
+        self.pairs = torch.as_tensor(np.ascontiguousarray(pairs, np.int32).reshape(-1, 2), device=device)
+        self.num_real, self.num_normal, self.num_pairs = int(num_real), len(normal), len(pairs)
+        sfx = SUFFIX[precision]
+        vp, i32, u32, dbl = C.c_void_p, C.c_int, C.c_uint, C.c_double
+        self._configure = getattr(self.lib, "constv_ref_drude_cuda_configure_" + sfx)
+        self._dpart1 = getattr(self.lib, "constv_ref_drude_cuda_part1_" + sfx)
+        self._dpart2 = getattr(self.lib, "constv_ref_drude_cuda_part2_" + sfx)
+        self._hardwall = getattr(self.lib, "constv_ref_drude_cuda_hardwall_" + sfx)
+        self._configure.argtypes = [i32, i32, i32, i32]
+        self._dpart1.argtypes = [i32, vp, vp, vp, vp, vp, vp, dbl, dbl, dbl, dbl, dbl, dbl, vp, u32, i32, vp]
+        self._dpart2.argtypes = [i32, vp, vp, vp, vp, vp, i32, vp]
+        self._hardwall.argtypes = [i32, vp, vp, vp, vp, vp, dbl, dbl, i32, vp]
+        self._check(self._configure(self.num_real, int(padded), self.num_normal, self.num_pairs))
+
+    def drude_step(self, num_atoms, num_cells, zmax, posq, corr, velm, force, pos_delta, random4, random_index,
+                   inv_order, stream=0):
+        c = self.dummy_corr if corr is None else corr
+        s = self.scalars
+        self._check(self._dpart1(self.num_real, velm.data_ptr(), force.data_ptr(), pos_delta.data_ptr(),
+                                 self.normal.data_ptr(), self.pairs.data_ptr(), self.dt.data_ptr(), *s[:6],
+                                 random4.data_ptr(), random_index, self.max_blocks, stream))
+        self._check(self._dpart2(self.num_real, posq.data_ptr(), c.data_ptr(), pos_delta.data_ptr(), velm.data_ptr(),
+                                 self.dt.data_ptr(), self.max_blocks, stream))
+        if s[6] > 0 and self.num_pairs > 0:
+            self._check(self._hardwall(self.num_pairs, posq.data_ptr(), c.data_ptr(), velm.data_ptr(),
+                                       self.pairs.data_ptr(), self.dt.data_ptr(), s[6], s[7], self.max_blocks, stream))
         self.mirror(num_atoms // num_cells, num_cells, zmax, posq, corr, inv_order, stream)

@@ -35,21 +35,35 @@
 #define selectConstVLangevinStepSize CONSTV_REF_NAME(selectConstVLangevinStepSize)
 #define updateImageParticlePositions CONSTV_REF_NAME(updateImageParticlePositions)
 #define reorderInverseAtomOrderIndexes CONSTV_REF_NAME(reorderInverseAtomOrderIndexes)
+#define integrateConstVDrudeLangevinPart1 CONSTV_REF_NAME(integrateConstVDrudeLangevinPart1)
+#define integrateConstVDrudeLangevinPart2 CONSTV_REF_NAME(integrateConstVDrudeLangevinPart2)
+#define applyHardWallConstraints CONSTV_REF_NAME(applyHardWallConstraints)
 
 #ifndef __CUDACC__
 /* ---- host build: the CUDA dialect the kernel source is written in ---------------------------- */
 #include <algorithm>
 #include <cmath>
+struct int2 { int x, y; };
+struct int3 { int x, y, z; };
+struct int4 { int x, y, z, w; };
 struct float2 { float x, y; };
 struct float3 { float x, y, z; };
 struct float4 { float x, y, z, w; };
 struct double2 { double x, y; };
 struct double3 { double x, y, z; };
 struct double4 { double x, y, z, w; };
+static inline int2 make_int2(int x, int y) { return int2{x, y}; }
+static inline int3 make_int3(int x, int y, int z) { return int3{x, y, z}; }
+static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float3 make_float3(float x, float y, float z) { return float3{x, y, z}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 static inline double3 make_double3(double x, double y, double z) { return double3{x, y, z}; }
 static inline double4 make_double4(double x, double y, double z, double w) { return double4{x, y, z, w}; }
+static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+#define __device__
 struct ConstVRefDim3 { unsigned int x, y, z; };
 /* one emulated CUDA thread per host thread at a time; grid and block shape are launch-wide */
 static thread_local ConstVRefDim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0};
@@ -59,6 +73,7 @@ static ConstVRefDim3 blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
 #define __syncthreads() ((void) 0)
 #define __CUDA_ARCH__ 1000 /* the kernel source selects its double-precision 1/dt branch with >= 130 */
 using std::exp;
+using std::fabs;
 using std::min;
 using std::sqrt;
 /* `extern __shared__ mixed params[];` in the (never launched) step-size kernel: give it storage */
