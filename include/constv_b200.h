@@ -225,6 +225,72 @@ CONSTV_API int constv_step_host_submit(constv_slab* slab, const void* host_force
                                        uint64_t* ticket_out, void* stream);
 CONSTV_API int constv_step_host_collect(constv_slab* slab, uint64_t ticket, double* host_ke_out);
 
+/* ---- chains: overlapping consecutive steps of one slab ---------------------------------------- */
+
+/* A step of the reference is a sequence of whole-slab launches on one stream (Kernels.cpp:146-166), so
+ * step k+1 cannot touch memory before the last block of step k has retired: every step pays its own
+ * ramp-up and drain (~2 us of a 12 us step at 1 M atoms).  The update of an atom depends on nothing but
+ * its own record, so a slab may be cut into `num_chains` contiguous ranges of real atoms (boundaries on
+ * 256-atom tiles), each with its own device step counter; constv_step_fused_chain advances ONE range and
+ * may be issued on a different stream per chain, so that the drain of one chain's step overlaps the ramp
+ * of another's.  Results are bit-identical to the single launch (the Philox key is the atom index and
+ * the step index, not the launch).  constv_step_fused on a chained slab launches every chain in turn on
+ * the given stream.  Identity slot order and the plain-load kernel only.  num_chains in 1..16 (clamped
+ * to the number of tiles); setting it synchronises the device. */
+CONSTV_API int constv_set_chains(constv_slab* slab, int32_t num_chains);
+CONSTV_API int constv_get_chains(const constv_slab* slab, int32_t* num_chains);
+CONSTV_API int constv_step_fused_chain(constv_slab* slab, int32_t chain, const void* random4,
+                                       uint32_t random_index, void* stream);
+
+/* ---- ConstVDrudeLangevinIntegrator ------------------------------------------- */
+/* "Drude.cu" = platforms/cuda/src/kernels/constVDrudeLangevin.cu.  The same slab object carries the
+ * Drude integrator: create / bind as above, then configure the pair list and use the constv_drude_*
+ * parameter and step calls instead of constv_set_parameters / constv_step_*. */
+
+/* Replaces the pair identification of CudaIntegrateConstVDrudeLangevinStepKernel::initialize,
+ * Kernels.cpp:213-230: pair_particles = num_pairs x (Drude particle, parent) as
+ * DrudeForce::getParticleParameters returns (p, p1), HOST memory; every other real atom is an
+ * "ordinary" particle.  The reference uses these indices directly as slots (it never translates them
+ * through the atom order; OpenMM only swaps identical molecules), and so does this library.
+ * Both particles must be distinct real atoms and belong to one pair only. */
+CONSTV_API int constv_drude_configure(constv_slab* slab, int32_t num_pairs, const int32_t* pair_particles);
+
+/* numNormal + 2*numPairs: the count the reference hands to prepareRandomNumbers (Kernels.cpp:307).
+ * Pool addressing is the reference's: ordinary particle `index` reads random4[random_index + index]
+ * (Drude.cu:18), pair i reads random4[random_index + numNormal + 2i] and the next entry (Drude.cu:30,46-47). */
+CONSTV_API int constv_drude_random_count(const constv_slab* slab, int32_t* count);
+
+/* Replaces the coefficient block of execute, Kernels.cpp:261-301: the (temperature, friction) thermostat
+ * of ordinary particles and of each pair's centre of mass, the (drude_temperature, drude_friction)
+ * thermostat of each pair's relative motion, max_drude_distance (hard wall, <= 0 disables it) and
+ * hardwallscaleDrude = sqrt(kB*drude_temperature); rounded to float in single precision. */
+CONSTV_API int constv_drude_set_parameters(constv_slab* slab, double temperature, double friction,
+                                           double drude_temperature, double drude_friction,
+                                           double max_drude_distance, double step_size);
+
+/* out[0..8] = vscale, fscale/2^32, noisescale, vscaleDrude, fscaleDrude/2^32, noisescaleDrude,
+ * maxDrudeDistance, hardwallscaleDrude, dt as the kernels see them. */
+CONSTV_API int constv_drude_get_parameters(const constv_slab* slab, double out[9]);
+
+/* Replaces the integrateConstVDrudeLangevinPart1 launch, Kernels.cpp:307-311 / Drude.cu:5-66.
+ * random4 == NULL: Philox; an ordinary particle draws its own block, a pair the Drude particle's block
+ * for the centre of mass and the parent's for the relative motion. */
+CONSTV_API int constv_drude_step_part1(constv_slab* slab, const void* random4, uint32_t random_index,
+                                       void* stream);
+
+/* Replaces integrateConstVDrudeLangevinPart2 + applyHardWallConstraints + updateImageParticlePositions
+ * (Kernels.cpp:321-344 / Drude.cu:72-211, Langevin.cu:138-164) in ONE kernel, plus the image zeroing;
+ * advances time and step count.  The caller applies constraints to pos_delta before it (Kernels.cpp:315). */
+CONSTV_API int constv_drude_step_part2(constv_slab* slab, void* stream);
+
+/* The whole of execute (Kernels.cpp:303-349) for a system without constraints in ONE kernel. */
+CONSTV_API int constv_drude_step_fused(constv_slab* slab, const void* random4, uint32_t random_index,
+                                       void* stream);
+
+/* applyHardWallConstraints alone (Kernels.cpp:336-340 / Drude.cu:108-211), thread <-> pair, for hosts
+ * that run their own part 2.  No-op when max_drude_distance <= 0. */
+CONSTV_API int constv_drude_hardwall(constv_slab* slab, void* stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 
 CONSTV_API const char* constv_last_error(void);

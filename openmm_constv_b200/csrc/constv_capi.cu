@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "constv_kernels.cuh"
+#include "constv_drude_kernels.cuh"
 
 using namespace constv;
 
@@ -42,6 +43,7 @@ int fail(int code, const char* fmt, ...) {
 constexpr double kBoltzDefault = 8.31446261815324e-3;  // OpenMM SimTKOpenMMRealType.h BOLTZ (>= 7.4)
 constexpr int kBlock = 256;
 constexpr int kBatchMax = 128;  // slabs per batched launch (descriptors travel as kernel parameters)
+constexpr int kMaxChains = 16;  // independent real-atom ranges of one slab (constv_set_chains)
 
 size_t realSize(int prec) { return prec == CONSTV_PRECISION_DOUBLE ? 8 : 4; }
 size_t mixedSize(int prec) { return prec == CONSTV_PRECISION_SINGLE ? 4 : 8; }
@@ -81,6 +83,19 @@ struct constv_slab {
     int tmaBlock = 256;  // pairs per chunk = threads per CTA of the TMA kernel
     int tmaStages = 4;
     int tmaCtasPerSM = 0;  // 0 = as many as shared memory allows
+    // ConstVDrudeLangevinIntegrator (constv_drude_*): per-slot roles, the pair list, the second thermostat
+    struct Drude {
+        int* role = nullptr;     // device int[numReal]
+        int2* pairs = nullptr;   // device int2[numPairs]
+        int numNormal = 0, numPairs = 0;
+        bool configured = false;
+        double temperature = 0, friction = 0;
+        double vscale = 0, fscaleFixed = 0, noisescale = 0, maxDistance = 0, hardwallScale = 0;
+    } drude;
+    int paramsKind = 0;  // which integrator's coefficients vscale/fscaleFixed/noisescale hold: 1 Langevin, 2 Drude
+    // chains (constv_set_chains): chain q advances real atoms [chainLo[q], chainLo[q+1]) with counters[q]
+    int chains = 1;
+    int chainLo[kMaxChains + 1] = {0};
     // pipelined host stepping (constv_step_host_submit / _collect): two slots
     struct HostPipe {
         bool ready = false;
@@ -146,6 +161,17 @@ SlabDev makeDev(const constv_slab* s) {
     d.zeroVelm = (s->cfg.flags & CONSTV_FLAG_ZERO_IMAGE_VELM) ? 1u : 0u;
     d.zeroForce = (s->cfg.flags & CONSTV_FLAG_ZERO_IMAGE_FORCE) ? 1u : 0u;
     d.tileBase = 0;
+    d.rangeLo = 0;
+    d.rangeHi = s->numReal;
+    return d;
+}
+
+// the descriptor of chain q: its range of real atoms and its own step counter / ticket
+SlabDev makeChainDev(const constv_slab* s, int q) {
+    SlabDev d = makeDev(s);
+    d.counters = s->counters + q;
+    d.rangeLo = s->chainLo[q];
+    d.rangeHi = s->chainLo[q + 1];
     return d;
 }
 
@@ -154,6 +180,12 @@ int checkReady(const constv_slab* s, bool needDelta) {
     if (s->cfg.precision == CONSTV_PRECISION_MIXED && !s->corr) return fail(CONSTV_ERR_STATE, "mixed precision needs posq_correction");
     if (needDelta && !s->posDelta) return fail(CONSTV_ERR_STATE, "the split path needs pos_delta");
     if (!s->paramsSet) return fail(CONSTV_ERR_STATE, "constv_set_parameters has not been called");
+    return CONSTV_OK;
+}
+
+// the plain Langevin entry points refuse a slab whose coefficients were set by constv_drude_set_parameters
+int checkLangevin(const constv_slab* s) {
+    if (s->paramsKind != 1) return fail(CONSTV_ERR_STATE, "the slab holds ConstVDrudeLangevinIntegrator coefficients: call constv_set_parameters");
     return CONSTV_OK;
 }
 
@@ -188,9 +220,9 @@ template <int PREC, bool STREAM>
 int launchFusedS(constv_slab* s, const SlabDev& d, const float4* random, unsigned randomIndex, cudaStream_t st) {
     const bool pdl = s->cfg.flags & CONSTV_FLAG_PDL;
     switch (s->ilp) {
-        case 1: return launch(constv_fused_step_kernel<PREC, kBlock, 1, STREAM>, gridFor(s, s->numReal, kBlock * 1, s->ctasPerSM), kBlock, pdl, st, d, random, randomIndex);
-        case 4: return launch(constv_fused_step_kernel<PREC, kBlock, 4, STREAM>, gridFor(s, s->numReal, kBlock * 4, s->ctasPerSM), kBlock, pdl, st, d, random, randomIndex);
-        default: return launch(constv_fused_step_kernel<PREC, kBlock, 2, STREAM>, gridFor(s, s->numReal, kBlock * 2, s->ctasPerSM), kBlock, pdl, st, d, random, randomIndex);
+        case 1: return launch(constv_fused_step_kernel<PREC, kBlock, 1, STREAM>, gridFor(s, d.rangeHi - d.rangeLo, kBlock * 1, s->ctasPerSM), kBlock, pdl, st, d, random, randomIndex);
+        case 4: return launch(constv_fused_step_kernel<PREC, kBlock, 4, STREAM>, gridFor(s, d.rangeHi - d.rangeLo, kBlock * 4, s->ctasPerSM), kBlock, pdl, st, d, random, randomIndex);
+        default: return launch(constv_fused_step_kernel<PREC, kBlock, 2, STREAM>, gridFor(s, d.rangeHi - d.rangeLo, kBlock * 2, s->ctasPerSM), kBlock, pdl, st, d, random, randomIndex);
     }
 }
 
@@ -366,8 +398,9 @@ int constv_create(const constv_config* config, constv_slab** out) {
     };
     if ((e = cudaMalloc(&s->invAtomOrder, sizeof(int) * (size_t) P)) != cudaSuccess) return cleanup(e, "cudaMalloc(invAtomOrder)");
     if ((e = cudaMalloc(&s->imageCharge, realSize(config->precision) * (size_t) (config->num_atoms - s->numReal))) != cudaSuccess) return cleanup(e, "cudaMalloc(imageCharge)");
-    if ((e = cudaMalloc(&s->counters, sizeof(DevCounters))) != cudaSuccess) return cleanup(e, "cudaMalloc(counters)");
-    if ((e = cudaMemset(s->counters, 0, sizeof(DevCounters))) != cudaSuccess) return cleanup(e, "cudaMemset(counters)");
+    if ((e = cudaMalloc(&s->counters, sizeof(DevCounters) * kMaxChains)) != cudaSuccess) return cleanup(e, "cudaMalloc(counters)");
+    if ((e = cudaMemset(s->counters, 0, sizeof(DevCounters) * kMaxChains)) != cudaSuccess) return cleanup(e, "cudaMemset(counters)");
+    s->chainLo[1] = s->numReal;
     const int maxBlocks = s->numSMs * 16;
     if ((e = cudaMalloc(&s->kePartials, sizeof(double) * (size_t) maxBlocks)) != cudaSuccess) return cleanup(e, "cudaMalloc(kePartials)");
     if ((e = cudaMalloc(&s->keOut, sizeof(double))) != cudaSuccess) return cleanup(e, "cudaMalloc(keOut)");
@@ -389,6 +422,8 @@ int constv_destroy(constv_slab* s) {
         cudaFree(s->posq); cudaFree(s->corr); cudaFree(s->velm); cudaFree(s->force); cudaFree(s->posDelta);
     }
     cudaFree(s->invAtomOrder);
+    cudaFree(s->drude.role);
+    cudaFree(s->drude.pairs);
     cudaFree(s->imageCharge);
     cudaFree(s->counters);
     cudaFree(s->kePartials);
@@ -470,7 +505,7 @@ int constv_get_arrays(constv_slab* s, void** posq, void** posq_correction, void*
 int constv_set_parameters(constv_slab* s, double temperature, double friction, double step_size) {
     if (!s) return fail(CONSTV_ERR_INVALID, "null slab");
     if (!(step_size > 0)) return fail(CONSTV_ERR_INVALID, "step size must be positive");
-    if (s->paramsSet && temperature == s->temperature && friction == s->friction && step_size == s->stepSize)
+    if (s->paramsSet && s->paramsKind == 1 && temperature == s->temperature && friction == s->friction && step_size == s->stepSize)
         return CONSTV_OK;  // Kernels.cpp:113: recompute only on change
     const double kT = s->cfg.boltz * temperature;
     const double vscale = std::exp(-step_size * friction);
@@ -494,6 +529,7 @@ int constv_set_parameters(constv_slab* s, double temperature, double friction, d
     s->friction = friction;
     s->stepSize = step_size;
     s->paramsSet = true;
+    s->paramsKind = 1;
     return CONSTV_OK;
 }
 
@@ -535,6 +571,7 @@ int constv_step_fused(constv_slab* s, const void* random4, uint32_t random_index
     GUARD(s);
     int rc = checkReady(s, false);
     if (rc) return rc;
+    if ((rc = checkLangevin(s))) return rc;
     if ((s->cfg.flags & CONSTV_FLAG_CACHE_IMAGE_CHARGE) && !s->imageChargeValid) {
         rc = constv_refresh_image_charges(s, stream);
         if (rc) return rc;
@@ -545,7 +582,14 @@ int constv_step_fused(constv_slab* s, const void* random4, uint32_t random_index
     const bool tma = s->variant == 2 && tmaEligible(s, random4);
     if (s->variant == 2 && !tma)
         return fail(CONSTV_ERR_STATE, "the TMA kernel needs identity order, Philox noise, CONSTV_FLAG_CACHE_IMAGE_CHARGE and even padded_num_atoms");
-    if (s->atomIndex) {
+    if (s->chains > 1) {  // every chain in turn on this stream: same result, one step counter per chain
+        if (s->atomIndex || tma) return fail(CONSTV_ERR_STATE, "chains need identity slot order and the plain-load kernel");
+        for (int q = 0; q < s->chains; q++) {
+            const SlabDev dq = makeChainDev(s, q);
+            DISPATCH_PREC(s->cfg.precision, launchFused<PR>(s, dq, rnd, random_index, st));
+            if (rc) return rc;
+        }
+    } else if (s->atomIndex) {
         DISPATCH_PREC(s->cfg.precision, launchFusedIndexed<PR>(s, d, rnd, random_index, st));
     } else if (tma) {
         DISPATCH_PREC(s->cfg.precision, launchFusedTma<PR>(s, d, st));
@@ -556,10 +600,51 @@ int constv_step_fused(constv_slab* s, const void* random4, uint32_t random_index
     return rc;
 }
 
+int constv_set_chains(constv_slab* s, int32_t num_chains) {
+    GUARD(s);
+    if (num_chains < 1 || num_chains > kMaxChains) return fail(CONSTV_ERR_INVALID, "num_chains must be 1..%d", kMaxChains);
+    uint64_t step = 0;
+    int rc = constv_get_step_count(s, &step);  // synchronises; refuses if the current chains are out of step
+    if (rc) return rc;
+    const long long tiles = ((long long) s->numReal + kBlock - 1) / kBlock;
+    if (num_chains > tiles) num_chains = (int) (tiles < 1 ? 1 : tiles);
+    s->chains = num_chains;
+    for (int q = 0; q <= num_chains; q++) {
+        const long long lo = tiles * q / num_chains * kBlock;  // chain boundaries on tile boundaries
+        s->chainLo[q] = (int) (lo < s->numReal ? lo : s->numReal);
+    }
+    return constv_set_step_count(s, step);
+}
+
+int constv_get_chains(const constv_slab* s, int32_t* num_chains) {
+    if (!s || !num_chains) return fail(CONSTV_ERR_INVALID, "null argument");
+    *num_chains = s->chains;
+    return CONSTV_OK;
+}
+
+int constv_step_fused_chain(constv_slab* s, int32_t chain, const void* random4, uint32_t random_index, void* stream) {
+    GUARD(s);
+    int rc = checkReady(s, false);
+    if (rc) return rc;
+    if ((rc = checkLangevin(s))) return rc;
+    if (chain < 0 || chain >= s->chains) return fail(CONSTV_ERR_INVALID, "chain %d out of range (the slab has %d)", chain, s->chains);
+    if (s->atomIndex || s->variant == 2) return fail(CONSTV_ERR_STATE, "chains need identity slot order and the plain-load kernel");
+    if ((s->cfg.flags & CONSTV_FLAG_CACHE_IMAGE_CHARGE) && !s->imageChargeValid) {
+        rc = constv_refresh_image_charges(s, stream);
+        if (rc) return rc;
+    }
+    const SlabDev d = makeChainDev(s, chain);
+    DISPATCH_PREC(s->cfg.precision, launchFused<PR>(s, d, static_cast<const float4*>(random4), random_index, (cudaStream_t) stream));
+    if (rc == CONSTV_OK && chain == 0) advanceTime(s);
+    return rc;
+}
+
 int constv_step_part1(constv_slab* s, const void* random4, uint32_t random_index, void* stream) {
     GUARD(s);
     int rc = checkReady(s, true);
     if (rc) return rc;
+    if (s->chains > 1) return fail(CONSTV_ERR_STATE, "chains are for the fused step only (constv_set_chains(slab, 1) first)");
+    if ((rc = checkLangevin(s))) return rc;
     const SlabDev d = makeDev(s);
     DISPATCH_PREC(s->cfg.precision, launchPart1<PR>(s, d, static_cast<const float4*>(random4), random_index, (cudaStream_t) stream));
     return rc;
@@ -569,6 +654,7 @@ int constv_step_part2_mirror(constv_slab* s, void* stream) {
     GUARD(s);
     int rc = checkReady(s, true);
     if (rc) return rc;
+    if ((rc = checkLangevin(s))) return rc;
     if ((s->cfg.flags & CONSTV_FLAG_CACHE_IMAGE_CHARGE) && !s->imageChargeValid) {
         rc = constv_refresh_image_charges(s, stream);
         if (rc) return rc;
@@ -590,7 +676,9 @@ int constv_step_fused_batched(constv_slab* const* slabs, int32_t n, void* stream
         if (s->cfg.precision != lead->cfg.precision || s->cfg.device != lead->cfg.device)
             return fail(CONSTV_ERR_INVALID, "batched slabs must share device and precision");
         if (s->atomIndex) return fail(CONSTV_ERR_INVALID, "batched launch needs identity slot order");
+        if (s->chains > 1) return fail(CONSTV_ERR_STATE, "chains are for the fused step only (constv_set_chains(slab, 1) first)");
         if ((rc = checkReady(s, false))) return rc;
+        if ((rc = checkLangevin(s))) return rc;
         if ((s->cfg.flags & CONSTV_FLAG_CACHE_IMAGE_CHARGE) && !s->imageChargeValid)
             if ((rc = constv_refresh_image_charges(s, stream))) return rc;
     }
@@ -647,18 +735,23 @@ int constv_generate_noise(constv_slab* s, uint64_t step, void* out4, void* strea
 int constv_get_step_count(constv_slab* s, uint64_t* count) {
     GUARD(s);
     if (!count) return fail(CONSTV_ERR_INVALID, "null output");
-    unsigned long long v = 0;
+    DevCounters host[kMaxChains];
     CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemcpy(&v, &s->counters->step, sizeof v, cudaMemcpyDeviceToHost));
-    *count = v;
+    CUDA_TRY(cudaMemcpy(host, s->counters, sizeof(DevCounters) * (size_t) s->chains, cudaMemcpyDeviceToHost));
+    for (int q = 1; q < s->chains; q++)
+        if (host[q].step != host[0].step)
+            return fail(CONSTV_ERR_STATE, "chains are out of step (chain 0 at %llu, chain %d at %llu): advance every chain equally",
+                        host[0].step, q, host[q].step);
+    *count = host[0].step;
     return CONSTV_OK;
 }
 
 int constv_set_step_count(constv_slab* s, uint64_t count) {
     GUARD(s);
-    const unsigned long long v = count;
+    DevCounters host[kMaxChains];
     CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemcpy(&s->counters->step, &v, sizeof v, cudaMemcpyHostToDevice));
+    for (int q = 0; q < kMaxChains; q++) host[q] = DevCounters{(unsigned long long) count, 0u, 0u};
+    CUDA_TRY(cudaMemcpy(s->counters, host, sizeof host, cudaMemcpyHostToDevice));
     return CONSTV_OK;
 }
 
@@ -815,3 +908,5 @@ int constv_set_kernel_variant(constv_slab* s, int32_t variant, int32_t block_siz
 }
 
 }  // extern "C"
+
+#include "constv_drude_capi.inc"

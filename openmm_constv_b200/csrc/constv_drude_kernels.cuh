@@ -1,0 +1,424 @@
+// Device code of the B200-native ConstVDrudeLangevinIntegrator step (sm_100a).
+//
+// What it replaces in the reference (scychon/openmm_constV), "Drude.cu" =
+// platforms/cuda/src/kernels/constVDrudeLangevin.cu, host sequence
+// platforms/cuda/src/CudaConstVKernels.cpp:252-349:
+//   integrateConstVDrudeLangevinPart1 (Drude.cu:5-66)    ordinary particles: the Langevin update;
+//                                                        (Drude particle, parent) pairs: centre of mass
+//                                                        thermalised at (T, friction), relative motion
+//                                                        at (T_drude, friction_drude)
+//   integrateConstVDrudeLangevinPart2 (Drude.cu:72-103)  x += delta, v = delta/dt over the real atoms
+//   applyHardWallConstraints (Drude.cu:108-211)          the Drude displacement bounces off a hard wall
+//   updateImageParticlePositions (Langevin.cu:138-164)   image rewrite (+ the explicit image zeroing)
+// The reference launches four kernels that each stream the state through HBM; here ONE kernel does the
+// whole constraint-free step (MODE_FUSED) and the constraint hand-off path is two (MODE_PART1, then
+// MODE_PART2 = part 2 + hard wall + image rewrite + zeroing).
+//
+// Work decomposition: thread <-> slot of a real atom, so every thread's own record is a coalesced
+// 8/16-byte vector access.  A per-slot role table (built on the host from the pair list) says whether the
+// slot is an ordinary particle, the Drude particle of pair k (it then OWNS the pair: gathers the parent's
+// record -- in practice the neighbouring 16 bytes -- computes both atoms and stores both) or a parent
+// (nothing to do: its owner handles it).  One thread per pair, not two, because both atoms' new state
+// depends on both atoms' old state: two threads would race on each other's records.
+//
+// The reference's Drude kernels use the particle indices of the DrudeForce directly as slots
+// (normalParticles / pairParticles are never translated through the atom order; OpenMM only swaps whole
+// identical molecules, so a slot keeps its role) -- only the image rewrite goes through invAtomOrder.
+// Same here: roles are per slot; INDEXED adds the atomIndex / invAtomOrder gathers of the image rewrite.
+//
+// Canonical arithmetic: the contraction nvcc applies to the reference's expressions, written out with
+// explicit fma / __f*_rn (file compiled with -fmad=false); restated by the CPU oracle (test infrastructure)
+// and checked bit for bit against the reference's kernels on the GPU (tests/test_gpu_drude.py).
+#pragma once
+
+#include "constv_kernels.cuh"
+
+namespace constv {
+
+enum { DRUDE_ROLE_NORMAL = -1, DRUDE_ROLE_PASSIVE = -2 };  // >= 0: owner of that pair
+enum { DRUDE_FUSED = 0, DRUDE_PART1 = 1, DRUDE_PART2 = 2 };
+
+struct DrudeDev {
+    const int* role;     // int[numReal]: DRUDE_ROLE_NORMAL | pair index (slot is particles.x) | DRUDE_ROLE_PASSIVE (slot is particles.y)
+    const int2* pairs;   // (Drude particle, parent) slots, CudaConstVKernels.cpp:222-228
+    int numNormal, numPairs;
+    double vscale, fscaleFixed, noisescale;        // the Drude (relative-motion) thermostat, rounded to `mixed`
+    double maxDistance, hardwallScale;             // maxDrudeDistance, sqrt(kB T_drude)
+    float vscaleF, fscaleFixedF, noisescaleF, maxDistanceF, hardwallScaleF;
+    int pad_;
+};
+
+template <typename M> struct DrudeScalars { M vscale, fs, noisescale, maxDistance, hardwallScale; };
+template <typename M> __device__ __forceinline__ DrudeScalars<M> drude_scalars_of(const DrudeDev& d);
+template <> __device__ __forceinline__ DrudeScalars<float> drude_scalars_of<float>(const DrudeDev& d) {
+    return {d.vscaleF, d.fscaleFixedF, d.noisescaleF, d.maxDistanceF, d.hardwallScaleF};
+}
+template <> __device__ __forceinline__ DrudeScalars<double> drude_scalars_of<double>(const DrudeDev& d) {
+    return {d.vscale, d.fscaleFixed, d.noisescale, d.maxDistance, d.hardwallScale};
+}
+
+__device__ __forceinline__ float  rcp_rn(float a)  { return __frcp_rn(a); }
+__device__ __forceinline__ double rcp_rn(double a) { return __drcp_rn(a); }
+__device__ __forceinline__ float  div_rn(float a, float b)   { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float  abs_of(float a)  { return fabsf(a); }
+__device__ __forceinline__ double abs_of(double a) { return fabs(a); }
+
+template <typename T> __device__ __forceinline__ T& comp(Vec4<T>& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+template <typename T> __device__ __forceinline__ const T& comp(const Vec4<T>& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+
+// Drude.cu:31-63.  f1/f2 = fixed-point forces of the Drude particle / the parent, r1/r2 = the pair's
+// two Gaussian float4s.  Writes the new velocities (w untouched) and posDelta = dt * v (w = 0).
+template <typename M>
+__device__ __forceinline__ void drude_pair_part1(Vec4<M>& v1, Vec4<M>& v2, Vec4<M>& d1, Vec4<M>& d2,
+                                                 const long long (&f1)[3], const long long (&f2)[3],
+                                                 const float4 r1, const float4 r2,
+                                                 const StepScalars<M>& s, const DrudeScalars<M>& ds) {
+    const M mass1 = rcp_rn(v1.w);
+    const M mass2 = rcp_rn(v2.w);
+    const M total = add_rn(mass1, mass2);
+    const M invTotalMass = rcp_rn(total);
+    const M invReducedMass = mul_rn(mul_rn(total, v1.w), v2.w);
+    const M mass1fract = mul_rn(invTotalMass, mass1);
+    const M mass2fract = mul_rn(invTotalMass, mass2);
+    const M fcm = mul_rn(s.fs, invTotalMass);
+    const M frel = mul_rn(ds.fs, invReducedMass);
+    const M ncm = mul_rn(s.noisescale, sqrt_rn(invTotalMass));
+    const M nrel = mul_rn(ds.noisescale, sqrt_rn(invReducedMass));
+    const float xi1[3] = {r1.x, r1.y, r1.z}, xi2[3] = {r2.x, r2.y, r2.z};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const M a = from_fixed(f1[k], M()), b = from_fixed(f2[k], M());
+        M cm = fma_rn(comp(v1, k), mass1fract, mul_rn(comp(v2, k), mass2fract));
+        M rel = add_rn(comp(v2, k), -comp(v1, k));
+        const M cmForce = add_rn(a, b);
+        const M relForce = fma_rn(mass1fract, b, -mul_rn(mass2fract, a));
+        cm = fma_rn((M) xi1[k], ncm, fma_rn(cm, s.vscale, mul_rn(cmForce, fcm)));
+        rel = fma_rn((M) xi2[k], nrel, fma_rn(rel, ds.vscale, mul_rn(relForce, frel)));
+        comp(v1, k) = fma_rn(-mass2fract, rel, cm);
+        comp(v2, k) = fma_rn(mass1fract, rel, cm);
+        comp(d1, k) = mul_rn(s.dt, comp(v1, k));
+        comp(d2, k) = mul_rn(s.dt, comp(v2, k));
+    }
+    d1.w = 0;
+    d2.w = 0;
+}
+
+// position of one particle as the `mixed` value the hard wall works on (Drude.cu:113-123) and back
+// (:150-155): posq + posqCorrection in mixed precision, posq alone otherwise
+template <int PREC>
+__device__ __forceinline__ void drude_pos_load(const Vec4<typename Prec<PREC>::Real>& p, const Vec4<typename Prec<PREC>::Real>& c,
+                                               typename Prec<PREC>::Mixed (&out)[3]) {
+    using M = typename Prec<PREC>::Mixed;
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        out[k] = Prec<PREC>::kSplitPos ? add_rn((M) comp(p, k), (M) comp(c, k)) : (M) comp(p, k);
+}
+template <int PREC>
+__device__ __forceinline__ void drude_pos_store(Vec4<typename Prec<PREC>::Real>& p, Vec4<typename Prec<PREC>::Real>& c,
+                                                const typename Prec<PREC>::Mixed (&in)[3]) {
+    using M = typename Prec<PREC>::Mixed;
+    using R = typename Prec<PREC>::Real;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        comp(p, k) = (R) in[k];
+        if (Prec<PREC>::kSplitPos) comp(c, k) = (R) add_rn(in[k], -(M) comp(p, k));
+    }
+    if (Prec<PREC>::kSplitPos) c.w = 0;
+}
+
+// Drude.cu:108-211 for one pair (1 = Drude particle, 2 = parent).  Returns true when the pair bounced.
+template <int PREC>
+__device__ __forceinline__ bool drude_hardwall(Vec4<typename Prec<PREC>::Mixed>& v1, Vec4<typename Prec<PREC>::Mixed>& v2,
+                                               Vec4<typename Prec<PREC>::Real>& p1, Vec4<typename Prec<PREC>::Real>& c1,
+                                               Vec4<typename Prec<PREC>::Real>& p2, Vec4<typename Prec<PREC>::Real>& c2,
+                                               const typename Prec<PREC>::Mixed stepSize,
+                                               const typename Prec<PREC>::Mixed maxDistance,
+                                               const typename Prec<PREC>::Mixed hardwallScale) {
+    using M = typename Prec<PREC>::Mixed;
+    M pos1[3], pos2[3], delta[3], b[3];
+    drude_pos_load<PREC>(p1, c1, pos1);
+    drude_pos_load<PREC>(p2, c2, pos2);
+#pragma unroll
+    for (int k = 0; k < 3; k++) delta[k] = add_rn(pos1[k], -pos2[k]);
+    const M r = sqrt_rn(fma_rn(delta[2], delta[2], fma_rn(delta[0], delta[0], mul_rn(delta[1], delta[1]))));
+    const M rInv = rcp_rn(r);
+    if (!(mul_rn(rInv, maxDistance) < 1)) return false;
+#pragma unroll
+    for (int k = 0; k < 3; k++) b[k] = mul_rn(delta[k], rInv);
+    const M mass1 = rcp_rn(v1.w);
+    const M mass2 = rcp_rn(v2.w);
+    const M deltaR = add_rn(r, -maxDistance);
+    M deltaT = stepSize;
+    M dotvr1 = fma_rn(b[2], v1.z, fma_rn(b[0], v1.x, mul_rn(b[1], v1.y)));
+    M vp1[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) vp1[k] = fma_rn(-b[k], dotvr1, comp(v1, k));
+    if (v2.w == 0) {
+        // the parent is massless: only the Drude particle moves (:141-165)
+        if (dotvr1 != 0) deltaT = div_rn(deltaR, abs_of(dotvr1));
+        if (deltaT > stepSize) deltaT = stepSize;
+        dotvr1 = div_rn(mul_rn(-dotvr1, hardwallScale), mul_rn(abs_of(dotvr1), sqrt_rn(mass1)));
+        const M dr = fma_rn(deltaT, dotvr1, -deltaR);
+#pragma unroll
+        for (int k = 0; k < 3; k++) pos1[k] = fma_rn(b[k], dr, pos1[k]);
+        drude_pos_store<PREC>(p1, c1, pos1);
+#pragma unroll
+        for (int k = 0; k < 3; k++) comp(v1, k) = fma_rn(b[k], dotvr1, vp1[k]);
+    } else {
+        // both particles move (:166-208)
+        const M invTotalMass = rcp_rn(add_rn(mass1, mass2));
+        M dotvr2 = fma_rn(b[2], v2.z, fma_rn(b[1], v2.y, mul_rn(b[0], v2.x)));
+        M vp2[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) vp2[k] = fma_rn(-b[k], dotvr2, comp(v2, k));
+        const M vbCMass = mul_rn(fma_rn(dotvr1, mass1, mul_rn(dotvr2, mass2)), invTotalMass);
+        dotvr1 = add_rn(dotvr1, -vbCMass);
+        dotvr2 = add_rn(dotvr2, -vbCMass);
+        if (dotvr1 != dotvr2) deltaT = div_rn(deltaR, abs_of(add_rn(dotvr1, -dotvr2)));
+        if (deltaT > stepSize) deltaT = stepSize;
+        const M vBond = div_rn(hardwallScale, sqrt_rn(mass1));
+        dotvr1 = div_rn(mul_rn(mul_rn(mul_rn(-dotvr1, vBond), mass2), invTotalMass), abs_of(dotvr1));
+        dotvr2 = div_rn(mul_rn(mul_rn(mul_rn(-dotvr2, vBond), mass1), invTotalMass), abs_of(dotvr2));
+        const M dr1 = fma_rn(deltaT, dotvr1, -mul_rn(mul_rn(deltaR, mass2), invTotalMass));
+        const M dr2 = fma_rn(mul_rn(deltaR, mass1), invTotalMass, mul_rn(deltaT, dotvr2));
+        dotvr1 = add_rn(dotvr1, vbCMass);
+        dotvr2 = add_rn(dotvr2, vbCMass);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            pos1[k] = fma_rn(b[k], dr1, pos1[k]);
+            pos2[k] = fma_rn(b[k], dr2, pos2[k]);
+        }
+        drude_pos_store<PREC>(p1, c1, pos1);
+        drude_pos_store<PREC>(p2, c2, pos2);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            comp(v1, k) = fma_rn(b[k], dotvr1, vp1[k]);
+            comp(v2, k) = fma_rn(b[k], dotvr2, vp2[k]);
+        }
+    }
+    return true;
+}
+
+// One real atom's registers.
+template <int PREC> struct DrudeAtom {
+    Vec4<typename Prec<PREC>::Mixed> v, delta;
+    Vec4<typename Prec<PREC>::Real> p, c;
+    long long f[3];
+    typename Prec<PREC>::Real q1;  // charge of the cell-1 image (identity order: fetched with the record)
+};
+
+template <int PREC, int MODE, bool INDEXED, bool STREAM>
+__device__ __forceinline__ void drude_load(const SlabDev& d, const int slot, DrudeAtom<PREC>& a) {
+    using Real = typename Prec<PREC>::Real;
+    using Mixed = typename Prec<PREC>::Mixed;
+    const size_t P = (size_t) d.padded;
+    a.v = load4x<STREAM>(static_cast<const Mixed*>(d.velm), (size_t) slot);
+    a.c = Vec4<Real>{0, 0, 0, 0};
+    a.delta = Vec4<Mixed>{0, 0, 0, 0};
+    a.q1 = 0;
+    if (MODE != DRUDE_PART1) {
+        a.p = load4x<STREAM>(static_cast<const Real*>(d.posq), (size_t) slot);
+        if (Prec<PREC>::kSplitPos) a.c = load4x<STREAM>(static_cast<const Real*>(d.corr), (size_t) slot);
+        if (!INDEXED)
+            a.q1 = d.imageCharge ? static_cast<const Real*>(d.imageCharge)[slot]
+                                 : static_cast<const Real*>(d.posq)[4 * ((size_t) d.numReal + slot) + 3];
+    }
+    if (MODE != DRUDE_PART2) {
+        a.f[0] = load_force(d.force + slot);
+        a.f[1] = load_force(d.force + P + slot);
+        a.f[2] = load_force(d.force + 2 * P + slot);
+    } else {
+        a.delta = load4x<STREAM>(static_cast<const Mixed*>(d.posDelta), (size_t) slot);
+    }
+}
+
+// What one real atom leaves in HBM after part 2 (+ hard wall): its record, its rewritten images
+// (charged atoms only, Langevin.cu:143) and, identity order only, its zeroed image slots (reordered
+// slots zero themselves).  `a` = original index of the atom held by `slot`.
+template <int PREC, bool INDEXED, bool STREAM>
+__device__ __forceinline__ void drude_emit(const SlabDev& d, const int slot, const int a, const bool moved,
+                                           const DrudeAtom<PREC>& r) {
+    using Real = typename Prec<PREC>::Real;
+    using Mixed = typename Prec<PREC>::Mixed;
+    constexpr bool kSplit = Prec<PREC>::kSplitPos;
+    if (!INDEXED) {
+        emit_atom<PREC, STREAM>(d, d.zshift, slot, moved, r.v, r.p, r.c, r.q1);
+        return;
+    }
+    const int R = d.numReal;
+    Real* __restrict__ posq = static_cast<Real*>(d.posq);
+    Real* __restrict__ corrA = static_cast<Real*>(d.corr);
+    if (moved) {
+        store4(static_cast<Mixed*>(d.velm), (size_t) slot, r.v);
+        store4(posq, (size_t) slot, r.p);
+        if (kSplit) store4(corrA, (size_t) slot, r.c);
+    }
+    if (r.p.w != -r.p.w) {
+        ImageCursor<PREC> cur(r.p, r.c);
+        for (int cell = 1; cell < d.numCells; cell++) {
+            const size_t t = (size_t) d.invAtomOrder[a + R * cell];
+            const Real qc = d.imageCharge ? static_cast<const Real*>(d.imageCharge)[(size_t) (cell - 1) * R + a]
+                                          : posq[4 * t + 3];
+            cur.advance(cell, d.zshift);
+            store4(posq, t, cur.posq(qc));
+            if (kSplit) store4(corrA, t, cur.corr());
+        }
+    }
+}
+
+// The Drude step.  MODE_FUSED: the whole constraint-free step; MODE_PART1: velocities + posDelta;
+// MODE_PART2: part 2 + hard wall + image rewrite + zeroing (after the caller's constraints).
+// Gaussians: random != nullptr reads the caller's pool with the reference's addressing (ordinary
+// particle `index`: random[randomIndex + index], Drude.cu:18; pair i: random[randomIndex +
+// NUM_NORMAL_PARTICLES + 2i] and the next one, :30,46-47); otherwise the Philox stream, keyed by the
+// original atom index: an ordinary particle uses its own block, a pair the Drude particle's block for
+// the centre of mass and the parent's block for the relative motion.
+template <int PREC, int BLOCK, int MODE, bool INDEXED, bool STREAM>
+__global__ void __launch_bounds__(BLOCK)
+constv_drude_step_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ DrudeDev dd,
+                         const float4* __restrict__ random, const unsigned int randomIndex) {
+    using Real = typename Prec<PREC>::Real;
+    using Mixed = typename Prec<PREC>::Mixed;
+    __shared__ StepBox box;
+    pdl_wait();
+    pdl_launch();
+    const int R = d.numReal;
+    const size_t P = (size_t) d.padded;
+    // reordered slots: image slots take part (they zero themselves), so the slot space is all atoms
+    const int numSlots = (INDEXED && MODE != DRUDE_PART1) ? d.numAtoms : R;
+    const unsigned int holders = (unsigned int) ((numSlots + BLOCK - 1) / BLOCK);
+    const StepScalars<Mixed> s = scalars_of<Mixed>(d);
+    const DrudeScalars<Mixed> ds = drude_scalars_of<Mixed>(dd);
+
+    for (long long base = (long long) blockIdx.x * BLOCK; base < numSlots; base += (long long) gridDim.x * BLOCK) {
+        const int slot = (int) base + (int) threadIdx.x;
+        const bool inRange = slot < numSlots;
+        // original index of the atom in this slot; real atoms keep slots [0, R) (roles are per slot)
+        const int a = (INDEXED && inRange && d.atomIndex) ? d.atomIndex[slot] : slot;
+        const bool isReal = inRange && slot < R;
+        const int role = isReal ? dd.role[slot] : DRUDE_ROLE_PASSIVE;
+        DrudeAtom<PREC> me, other;
+        int2 pair = make_int2(slot, slot);
+        if (role != DRUDE_ROLE_PASSIVE) drude_load<PREC, MODE, INDEXED, STREAM>(d, slot, me);
+        if (role >= 0) {
+            pair = dd.pairs[role];
+            drude_load<PREC, MODE, INDEXED, STREAM>(d, pair.y, other);
+        }
+        float4 xi1 = make_float4(0.f, 0.f, 0.f, 0.f), xi2 = xi1;
+        if (MODE != DRUDE_PART2 && random != nullptr) {
+            if (role == DRUDE_ROLE_NORMAL) xi1 = __ldcs(random + (size_t) randomIndex + slot);
+            if (role >= 0) {
+                const size_t at = (size_t) randomIndex + (size_t) dd.numNormal + 2 * (size_t) role;
+                xi1 = __ldcs(random + at);
+                xi2 = __ldcs(random + at + 1);
+            }
+        }
+
+        // step index (the Philox counter) and this tile's ticket
+        unsigned long long step = 0;
+        unsigned int ticket = 0;
+        if (MODE == DRUDE_FUSED) {
+            publish_step(box, d.counters);
+            __syncthreads();
+            step = box.step;
+            ticket = take_ticket(d.counters, holders);
+        } else if (MODE == DRUDE_PART1) {
+            step = __ldcg(&d.counters->step);
+        }
+
+        if (INDEXED && MODE != DRUDE_PART1 && inRange && a >= R) {  // an image slot zeroes itself
+            if (d.zeroVelm) store4(static_cast<Mixed*>(d.velm), (size_t) slot, Vec4<Mixed>{0, 0, 0, 0});
+            if (d.zeroForce) {
+                __stcs(d.force + slot, 0LL);
+                __stcs(d.force + P + slot, 0LL);
+                __stcs(d.force + 2 * P + slot, 0LL);
+            }
+        }
+
+        if (role == DRUDE_ROLE_NORMAL) {
+            const bool moved = me.v.w != 0;
+            if (moved) {
+                if (MODE != DRUDE_PART2) {
+                    if (random == nullptr && s.noisescale != 0)
+                        xi1 = gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) a, step);
+                    part1_update(me.v, me.delta, me.f[0], me.f[1], me.f[2], xi1.x, xi1.y, xi1.z, s);
+                }
+                if (MODE != DRUDE_PART1) part2_update<PREC>(me.p, me.c, me.v, me.delta, s.invDt);
+            }
+            if (MODE == DRUDE_PART1) {
+                if (moved) {
+                    store4(static_cast<Mixed*>(d.velm), (size_t) slot, me.v);
+                    store4(static_cast<Mixed*>(d.posDelta), (size_t) slot, me.delta);
+                }
+            } else {
+                drude_emit<PREC, INDEXED, STREAM>(d, slot, a, moved, me);
+            }
+        } else if (role >= 0) {
+            const int a2 = (INDEXED && d.atomIndex) ? d.atomIndex[pair.y] : pair.y;
+            if (MODE != DRUDE_PART2) {
+                if (random == nullptr) {
+                    xi1 = gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) a, step);
+                    xi2 = gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) a2, step);
+                }
+                drude_pair_part1(me.v, other.v, me.delta, other.delta, me.f, other.f, xi1, xi2, s, ds);
+            }
+            if (MODE == DRUDE_PART1) {  // Drude.cu:60-63: unconditional
+                store4(static_cast<Mixed*>(d.velm), (size_t) slot, me.v);
+                store4(static_cast<Mixed*>(d.velm), (size_t) pair.y, other.v);
+                store4(static_cast<Mixed*>(d.posDelta), (size_t) slot, me.delta);
+                store4(static_cast<Mixed*>(d.posDelta), (size_t) pair.y, other.delta);
+            } else {
+                if (me.v.w != 0) part2_update<PREC>(me.p, me.c, me.v, me.delta, s.invDt);
+                if (other.v.w != 0) part2_update<PREC>(other.p, other.c, other.v, other.delta, s.invDt);
+                if (ds.maxDistance > 0)  // CudaConstVKernels.cpp:336
+                    drude_hardwall<PREC>(me.v, other.v, me.p, me.c, other.p, other.c, s.dt, ds.maxDistance, ds.hardwallScale);
+                // a pair's records are always written back: part 1 stores the velocities unconditionally,
+                // and records that neither part 2 nor the wall touched are stored with the bits they had
+                drude_emit<PREC, INDEXED, STREAM>(d, slot, a, true, me);
+                drude_emit<PREC, INDEXED, STREAM>(d, pair.y, a2, true, other);
+            }
+        }
+
+        if (MODE == DRUDE_FUSED) {
+            close_step(d.counters, ticket, holders, step);
+            if (base + (long long) gridDim.x * BLOCK < numSlots) __syncthreads();  // box is rewritten by the next tile
+        }
+    }
+    // part 2 closes a split step: nobody in this launch reads the counter (part 1 did)
+    if (MODE == DRUDE_PART2 && blockIdx.x == 0 && threadIdx.x == 0) d.counters->step = __ldcg(&d.counters->step) + 1;
+}
+
+// applyHardWallConstraints alone (Drude.cu:108-211, launch CudaConstVKernels.cpp:336-340): thread <-> pair.
+template <int PREC, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+constv_drude_hardwall_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ DrudeDev dd) {
+    using Real = typename Prec<PREC>::Real;
+    using Mixed = typename Prec<PREC>::Mixed;
+    constexpr bool kSplit = Prec<PREC>::kSplitPos;
+    Real* __restrict__ posq = static_cast<Real*>(d.posq);
+    Real* __restrict__ corrA = static_cast<Real*>(d.corr);
+    Mixed* __restrict__ velm = static_cast<Mixed*>(d.velm);
+    const StepScalars<Mixed> s = scalars_of<Mixed>(d);
+    const DrudeScalars<Mixed> ds = drude_scalars_of<Mixed>(dd);
+    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < dd.numPairs; i += gridDim.x * BLOCK) {
+        const int2 pair = dd.pairs[i];
+        Vec4<Mixed> v1 = load4(velm, (size_t) pair.x), v2 = load4(velm, (size_t) pair.y);
+        Vec4<Real> p1 = load4(posq, (size_t) pair.x), p2 = load4(posq, (size_t) pair.y);
+        Vec4<Real> c1{0, 0, 0, 0}, c2{0, 0, 0, 0};
+        if (kSplit) { c1 = load4(corrA, (size_t) pair.x); c2 = load4(corrA, (size_t) pair.y); }
+        const bool parentMoves = v2.w != 0;
+        if (drude_hardwall<PREC>(v1, v2, p1, c1, p2, c2, s.dt, ds.maxDistance, ds.hardwallScale)) {
+            store4(posq, (size_t) pair.x, p1);
+            if (kSplit) store4(corrA, (size_t) pair.x, c1);
+            store4(velm, (size_t) pair.x, v1);
+            if (parentMoves) {
+                store4(posq, (size_t) pair.y, p2);
+                if (kSplit) store4(corrA, (size_t) pair.y, c2);
+                store4(velm, (size_t) pair.y, v2);
+            }
+        }
+    }
+}
+
+}  // namespace constv

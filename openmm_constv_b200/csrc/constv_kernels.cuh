@@ -61,6 +61,8 @@ struct SlabDev {
     unsigned long long seed, globalAtomOffset;
     unsigned int zeroVelm, zeroForce;
     int tileBase;                // batched launch: first tile of this slab in the global tile space
+    int rangeLo, rangeHi;        // real atoms [rangeLo, rangeHi) this launch advances (a chain, see
+                                 // constv_set_chains; the whole slab = [0, numReal)); `counters` is the chain's
     int pad_;
 };
 
@@ -470,11 +472,12 @@ constv_fused_step_kernel(const __grid_constant__ SlabDev d, const float4* __rest
     // scheduler then keeps the memory access front sequential and balances the tail, which measured
     // 10-15 % faster than a persistent grid for this 11-stream pattern); grid-stride otherwise.
     constexpr int kTile = BLOCK * ILP;
-    const unsigned int holders = (unsigned int) ((d.numReal + kTile - 1) / kTile);  // one ticket per tile
-    for (long long base = (long long) blockIdx.x * kTile; base < d.numReal; base += (long long) gridDim.x * kTile) {
+    const int lo = d.rangeLo, hi = d.rangeHi;
+    const unsigned int holders = (unsigned int) ((hi - lo + kTile - 1) / kTile);  // one ticket per tile
+    for (long long base = lo + (long long) blockIdx.x * kTile; base < hi; base += (long long) gridDim.x * kTile) {
         unsigned int ticket = 0;
         unsigned long long step = 0;
-        fused_tile<PREC, BLOCK, ILP, STREAM>(d, (int) base, d.numReal, [&]() {
+        fused_tile<PREC, BLOCK, ILP, STREAM>(d, (int) base, hi, [&]() {
             publish_step(box, d.counters);
             __syncthreads();
             step = box.step;
@@ -482,7 +485,7 @@ constv_fused_step_kernel(const __grid_constant__ SlabDev d, const float4* __rest
             return step;
         }, random, randomIndex);
         close_step(d.counters, ticket, holders, step);
-        if (base + (long long) gridDim.x * kTile < d.numReal) __syncthreads();  // box is rewritten by the next tile
+        if (base + (long long) gridDim.x * kTile < hi) __syncthreads();  // box is rewritten by the next tile
     }
 }
 

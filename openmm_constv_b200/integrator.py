@@ -12,6 +12,14 @@ Same names, argument meaning and error behaviour as the reference (scychon/openm
                                       not available here.  Forces are injected: the context's
                                       ``force_fn`` plays the role of context.calcForcesAndEnergy.
 
+  ConstVDrudeLangevinIntegrator       openmmapi/include/openmm/ConstVDrudeLangevinIntegrator.h,
+                                      openmmapi/src/ConstVDrudeLangevinIntegrator.cpp:44-129,
+                                      python/constvplugin.i:82-100
+  IntegrateConstVDrudeLangevinStepKernel  ConstVKernels.h:82-108 (interface),
+                                      platforms/cuda/src/CudaConstVKernels.cpp:179-357 (CUDA impl)
+  DrudeForce                          the part of OpenMM's DrudeForce the kernel reads
+                                      (getNumParticles / getParticleParameters, Kernels.cpp:219-224)
+
 All compute goes through the C ABI (``_capi``); torch is used for device memory and streams only.
 """
 from __future__ import annotations
@@ -45,6 +53,17 @@ class SlabSystem:
     def __init__(self):
         self._masses: list[float] = []
         self._box = ((1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0))
+        self._forces: list = []
+
+    def addForce(self, force) -> int:
+        self._forces.append(force)
+        return len(self._forces) - 1
+
+    def getNumForces(self) -> int:
+        return len(self._forces)
+
+    def getForce(self, index: int):
+        return self._forces[index]
 
     def addParticle(self, mass: float) -> int:
         self._masses.append(float(mass))
@@ -70,6 +89,27 @@ class SlabSystem:
 
     def getDefaultPeriodicBoxVectors(self):
         return self._box
+
+
+class DrudeForce:
+    """The slice of OpenMM::DrudeForce the Drude kernel reads (CudaConstVKernels.cpp:219-224):
+    per entry the Drude particle ``particle``, its parent ``particle1`` and the parameters the
+    integrator ignores."""
+
+    def __init__(self):
+        self._particles: list[tuple] = []
+
+    def addParticle(self, particle, particle1, particle2=-1, particle3=-1, particle4=-1, charge=0.0,
+                    polarizability=0.0, aniso12=0.0, aniso34=0.0) -> int:
+        self._particles.append((int(particle), int(particle1), int(particle2), int(particle3), int(particle4),
+                                float(charge), float(polarizability), float(aniso12), float(aniso34)))
+        return len(self._particles) - 1
+
+    def getNumParticles(self) -> int:
+        return len(self._particles)
+
+    def getParticleParameters(self, index: int):
+        return self._particles[index]
 
 
 class ConstVLangevinIntegrator:
@@ -256,6 +296,93 @@ class IntegrateConstVLangevinStepKernel:
             pass
 
 
+class ConstVDrudeLangevinIntegrator(ConstVLangevinIntegrator):
+    """Dual-thermostat Langevin dynamics for Drude oscillators with exact image charges.
+
+    ``ConstVDrudeLangevinIntegrator(temperature, frictionCoeff, drudeTemperature, drudeFrictionCoeff,
+    stepSize, numCells=2, zmax=-1)`` (ConstVDrudeLangevinIntegrator.cpp:44-55): ordinary particles and
+    each pair's centre of mass are thermalised at (temperature, frictionCoeff), each pair's relative
+    motion at (drudeTemperature, drudeFrictionCoeff); maxDrudeDistance (default 0 = off) is the hard
+    wall on the Drude displacement.  The System must hold exactly one DrudeForce.
+    """
+
+    def __init__(self, temperature, frictionCoeff, drudeTemperature, drudeFrictionCoeff, stepSize,
+                 numCells=2, zmax=-1):
+        super().__init__(temperature, frictionCoeff, stepSize, numCells, zmax)
+        self.setDrudeTemperature(drudeTemperature)
+        self.setDrudeFriction(drudeFrictionCoeff)
+        self.setMaxDrudeDistance(0)
+
+    def getDrudeTemperature(self): return self._drude_temperature
+    def setDrudeTemperature(self, temp): self._drude_temperature = float(temp)
+    def getDrudeFriction(self): return self._drude_friction
+    def setDrudeFriction(self, coeff): self._drude_friction = float(coeff)
+    def getMaxDrudeDistance(self): return self._max_drude_distance
+
+    def setMaxDrudeDistance(self, distance):
+        if distance < 0:  # ConstVDrudeLangevinIntegrator.cpp:61-65
+            raise OpenMMException("setMaxDrudeDistance: Distance cannot be negative")
+        self._max_drude_distance = float(distance)
+
+    def _initialize(self, context: "SlabContext") -> None:
+        if self._context is not None and self._context is not context:
+            raise OpenMMException("This Integrator is already bound to a context")
+        system = context.getSystem()
+        force = None  # ConstVDrudeLangevinIntegrator.cpp:70-80
+        for i in range(system.getNumForces()):
+            if isinstance(system.getForce(i), DrudeForce):
+                if force is not None:
+                    raise OpenMMException("The System contains multiple DrudeForces")
+                force = system.getForce(i)
+        if force is None:
+            raise OpenMMException("The System does not contain a DrudeForce")
+        self._context = context
+        self._kernel = IntegrateConstVDrudeLangevinStepKernel(IntegrateConstVDrudeLangevinStepKernel.Name(), context)
+        self._kernel.initialize(system, self, force)
+
+    def getKernelNames(self):
+        return [IntegrateConstVDrudeLangevinStepKernel.Name()]
+
+
+class IntegrateConstVDrudeLangevinStepKernel(IntegrateConstVLangevinStepKernel):
+    """B200 implementation of ConstVKernels.h:82-108, the analogue of
+    CudaIntegrateConstVDrudeLangevinStepKernel (CudaConstVKernels.cpp:179-357)."""
+
+    @staticmethod
+    def Name() -> str:
+        return "IntegrateConstVDrudeLangevinStep"
+
+    def initialize(self, system: SlabSystem, integrator: ConstVDrudeLangevinIntegrator, force: DrudeForce = None) -> None:
+        super().initialize(system, integrator)
+        pairs = np.zeros((max(force.getNumParticles(), 1), 2), np.int32)
+        for i in range(force.getNumParticles()):  # CudaConstVKernels.cpp:219-225
+            prm = force.getParticleParameters(i)
+            pairs[i] = prm[0], prm[1]
+        check(self._lib.constv_drude_configure(self._slab, force.getNumParticles(), pairs.ctypes.data_as(C.c_void_p)))
+        n = C.c_int32(0)
+        check(self._lib.constv_drude_random_count(self._slab, C.byref(n)))
+        self.random_count = n.value
+        self.num_pairs = force.getNumParticles()
+
+    def execute(self, context: "SlabContext", integrator: ConstVDrudeLangevinIntegrator) -> None:
+        lib, slab, st = self._lib, self._slab, context.stream_ptr()
+        check(lib.constv_drude_set_parameters(slab, integrator._temperature, integrator._friction,
+                                              integrator._drude_temperature, integrator._drude_friction,
+                                              integrator._max_drude_distance, integrator.getStepSize()))
+        if context.atoms_were_reordered:  # CudaConstVKernels.cpp:303-306
+            check(lib.constv_update_inverse_order(slab, st))
+            context.atoms_were_reordered = False
+        rnd, idx = context.prepare_random_numbers(self.random_count)  # :307
+        if context.apply_constraints is None:
+            check(lib.constv_drude_step_fused(slab, rnd, idx, st))
+        else:  # :308-344 with the constraint hand-off at :315
+            check(lib.constv_drude_step_part1(slab, rnd, idx, st))
+            context.apply_constraints(context, integrator.getConstraintTolerance())
+            check(lib.constv_drude_step_part2(slab, st))
+        context.time += integrator.getStepSize()
+        context.step_count += 1
+
+
 class SlabContext:
     """Device-resident state in OpenMM's CUDA layouts plus the Context calls the integrator makes
     (updateContextState, calcForcesAndEnergy, getState-like accessors).
@@ -319,15 +446,16 @@ class SlabContext:
     def stream_ptr(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
 
-    def prepare_random_numbers(self):
+    def prepare_random_numbers(self, count=None):
         """Mirrors integration.prepareRandomNumbers / getRandom (CudaConstVKernels.cpp:146,148)
         when a pool of injected Gaussians is attached; (None, 0) selects the Philox stream."""
         if self.random_pool is None:
             return None, 0
+        count = self.padded if count is None else int(count)
         idx = self.random_index
-        if idx + self.padded > self.random_pool.shape[0]:
+        if idx + count > self.random_pool.shape[0]:
             raise RuntimeError("injected random pool exhausted")
-        self.random_index += self.padded
+        self.random_index += count
         return self.random_pool.data_ptr(), idx
 
     # -- state I/O -------------------------------------------------------------------------------
