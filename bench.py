@@ -12,6 +12,12 @@ data-path collective (weak scaling: per-GPU shard fixed, so N=8 with --atoms 200
 slab of configs[3]); the only collective is the scalar kinetic-energy all-reduce, issued once after
 the timed region as a report, never per step.
 
+Chains (default 2): the slab is cut into contiguous ranges of real atoms, each with its own device step
+counter and its own stream (constv_set_chains / constv_step_fused_chain), so that the drain of one
+range's step k overlaps the ramp-up of another range's step k+1; results are bit-identical to one launch
+per step (tests/test_gpu_parity.py::test_chains_are_bit_identical_to_the_single_launch).  --chains 1 is
+the single launch per step.
+
 L2 policy: a 1M-atom slab is 58 MB, smaller than B200's 126 MB L2, so the timed loop rotates over
 ``replicas`` independent copies of the slab whose total footprint exceeds 2x L2: every step streams
 its slab from HBM.
@@ -64,6 +70,10 @@ def parse_args():
     ap.add_argument("--tma-block", type=int, default=0)
     ap.add_argument("--tma-stages", type=int, default=0)
     ap.add_argument("--tma-ctas", type=int, default=0)
+    ap.add_argument("--chains", type=int, default=2,
+                    help="cut the slab into this many independent real-atom ranges, each advanced on its own stream "
+                         "(constv_set_chains): the drain of one range's step overlaps the ramp of another's; for --ensemble, "
+                         "the slabs of a step are advanced by this many batched launches on as many streams")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cache-image-charge", action="store_true")
     ap.add_argument("--keep-in-l2", action="store_true", help="default cache policy instead of evict-first")
@@ -86,12 +96,12 @@ def peaks():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def traffic_from_profile(atoms):
+def traffic_from_profile(atoms, chains):
     """dram bytes per launch from the committed ncu capture, if it was taken on this workload."""
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     try:
         rec = json.load(open(path))
-        if int(rec.get("atoms", -1)) == int(atoms):
+        if int(rec.get("atoms", -1)) == int(atoms) and int(rec.get("chains", 1)) == int(chains):
             return rec["dram_bytes_per_launch"]
     except Exception:
         pass
@@ -432,7 +442,38 @@ def main():
 
     groups = [(C.c_void_p * M)(*handles[g * M:(g + 1) * M]) for g in range(replicas)]
 
+    chains = 1
+    if args.chains > 1 and not args.ensemble:
+        got = C.c_int32(0)
+        for h in handles:
+            _capi.check(lib.constv_set_chains(h, args.chains))
+        _capi.check(lib.constv_get_chains(handles[0], C.byref(got)))
+        chains = got.value
+    elif args.chains > 1:
+        chains = min(args.chains, M)
+    side_streams = [torch.cuda.Stream(device=dev) for _ in range(chains - 1)]
+    # ensemble: sub-group q of every replica's M slabs = one batched launch on stream q
+    bounds = [M * q // chains for q in range(chains + 1)]
+    subgroups = [[(C.c_void_p * (bounds[q + 1] - bounds[q]))(*handles[g * M + bounds[q]:g * M + bounds[q + 1]])
+                  for q in range(chains)] for g in range(replicas)]
+
     def launch_steps(first, count):
+        if chains > 1:  # fork: chain q's steps on stream q, in step order; join back into `stream`
+            fork = torch.cuda.Event()
+            fork.record(stream)
+            for q, cs in enumerate([stream] + side_streams):
+                if q:
+                    cs.wait_event(fork)
+                for k in range(first, first + count):
+                    if args.ensemble:
+                        _capi.check(lib.constv_step_fused_batched(subgroups[k % replicas][q], bounds[q + 1] - bounds[q], cs.cuda_stream))
+                    else:
+                        _capi.check(lib.constv_step_fused_chain(handles[k % replicas], q, None, 0, cs.cuda_stream))
+            for cs in side_streams:
+                join = torch.cuda.Event()
+                join.record(cs)
+                stream.wait_event(join)
+            return
         for k in range(first, first + count):
             if args.ensemble:
                 _capi.check(lib.constv_step_fused_batched(groups[k % replicas], M, sptr))
@@ -615,7 +656,7 @@ def main():
         peak, peak_src = peaks()
         launch_ms = ms_max / K
         alg_bytes *= M
-        achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+        achieved = alg_bytes / (launch_ms * 1e-3) / 1e9  # = (alg_bytes / chains) x (K x chains launches) / time
         line = {
             "metric": "atom-steps/s", "value": value, "unit": "atom-steps/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": launch_ms, "higher_is_better": True,
@@ -630,6 +671,7 @@ def main():
                 "pair_classes": shard.pair_classes(), "rng": "in-kernel Philox4x32-10",
                 "l2": f"rotating {replicas} replicas of the per-step working set ({replicas * M * rec_bytes / 1e6:.0f} MB) > 126 MB L2: every step streams from HBM",
                 "launch": ("CUDA graph of %d steps, PDL" % chunk) if graph is not None else "eager, PDL",
+                "chains": chains,
                 "image_charge": "re-read from posq" if args.no_cache_image_charge else "side array",
                 "kernel_variant": {"variant": args.variant, "tma_block": args.tma_block, "tma_stages": args.tma_stages,
                                    "tma_ctas": args.tma_ctas, "pairs_per_thread": args.pairs_per_thread, "ctas_per_sm": args.ctas_per_sm},
@@ -638,14 +680,18 @@ def main():
             "steps_per_s": K / (ms_max * 1e-3),
             "atom_steps_per_s_per_gpu": value / world,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None if args.ensemble else traffic_from_profile(shard.num_atoms), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "traffic": None if args.ensemble else traffic_from_profile(shard.num_atoms, chains), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes / chains, "launches_per_step": chains,
+                         "algorithmic_bytes_per_step": alg_bytes,
+                         "note": ("a step is %d launches, one per chain (contiguous range of real atoms) on its own stream; "
+                                  "achieved = algorithmic bytes per launch x launches in the timed region / its duration" % chains)
+                                 if chains > 1 else "one launch per step",
                          "frac_of_8TBs_nominal": achieved / 8000.0,
                          "kernel": "constv_fused_step_batched_kernel" if args.ensemble else "constv_fused_step_kernel"},
             "cpu_baseline": cpu,
             "reference_gpu": ref_gpu,
             "e2e": e2e,
-            "gpu_launches": int(K),
+            "gpu_launches": int(K * chains),
             "eager_launches_in_region": int(eager_launches),
             "clocks": clocks,
             "kinetic_energy_kj_mol": ke_total, "temperature_K": temperature,

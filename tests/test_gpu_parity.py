@@ -295,6 +295,90 @@ def test_cuda_graph_replay_advances_the_stream(gpu):
     ctx_b.close()
 
 
+# ---- chains: independent real-atom ranges with their own step counters --------------------------------
+
+@pytest.mark.parametrize("precision", slabmod.PRECISIONS)
+@pytest.mark.parametrize("chains", [2, 5, 16])
+def test_chains_are_bit_identical_to_the_single_launch(gpu, precision, chains):
+    """constv_set_chains cuts the slab into contiguous ranges (one step counter each); whether the ranges
+    are launched in turn on one stream or each on a stream of its own, every array equals the
+    unchained step's bit for bit (the Philox key is (seed; atom, step), not the launch)."""
+    import ctypes as C
+    import torch
+    from openmm_constv_b200 import _capi
+    lib = _capi.load()
+    s0 = slabmod.make_slab(70001, precision, seed=12)
+    nsteps = 5
+    ctx_a, it_a = make_context(gpu, s0, seed=9)
+    it_a.step(nsteps)
+    want = download(ctx_a, s0)
+    ctx_a.close()
+
+    # every chain in turn on the caller's stream
+    ctx_b, it_b = make_context(gpu, s0, seed=9)
+    _capi.check(lib.constv_set_chains(it_b._kernel.handle, chains))
+    got = C.c_int32(0)
+    _capi.check(lib.constv_get_chains(it_b._kernel.handle, C.byref(got)))
+    assert got.value == chains
+    launches = _capi.launch_count()
+    it_b.step(nsteps)
+    assert _capi.launch_count() - launches == nsteps * chains
+    assert it_b._kernel.get_step_count() == nsteps
+    assert_slab_bits_equal(download(ctx_b, s0), want)
+    ctx_b.close()
+
+    # one stream per chain, all steps of a chain back to back: chains run ahead of each other
+    ctx_c, it_c = make_context(gpu, s0, seed=9)
+    h = it_c._kernel.handle
+    _capi.check(lib.constv_set_chains(h, chains))
+    _capi.check(lib.constv_set_parameters(h, T, GAMMA, DT))
+    streams = [torch.cuda.Stream() for _ in range(chains)]
+    torch.cuda.synchronize()
+    for q in reversed(range(chains)):
+        for _ in range(nsteps):
+            _capi.check(lib.constv_step_fused_chain(h, q, None, 0, streams[q].cuda_stream))
+    torch.cuda.synchronize()
+    assert it_c._kernel.get_step_count() == nsteps
+    assert_slab_bits_equal(download(ctx_c, s0), want)
+    t = C.c_double(0.0)
+    _capi.check(lib.constv_get_time(h, C.byref(t)))
+    assert t.value == pytest.approx(nsteps * DT)
+    ctx_c.close()
+
+
+def test_chains_guard_rails(gpu):
+    import ctypes as C
+    from openmm_constv_b200 import _capi
+    lib = _capi.load()
+    s0 = slabmod.make_slab(1000, "single", seed=13)  # 4 tiles of 256 pairs
+    ctx, it = make_context(gpu, s0, seed=9, apply_constraints=None)
+    h = it._kernel.handle
+    assert lib.constv_set_chains(h, 0) == _capi.ERR_INVALID
+    assert lib.constv_set_chains(h, 17) == _capi.ERR_INVALID
+    _capi.check(lib.constv_set_chains(h, 16))  # clamped to the number of tiles
+    got = C.c_int32(0)
+    _capi.check(lib.constv_get_chains(h, C.byref(got)))
+    assert got.value == 4
+    _capi.check(lib.constv_set_parameters(h, T, GAMMA, DT))
+    assert lib.constv_step_fused_chain(h, 4, None, 0, None) == _capi.ERR_INVALID
+    _capi.check(lib.constv_step_fused_chain(h, 1, None, 0, None))
+    count = C.c_uint64(0)
+    assert lib.constv_get_step_count(h, C.byref(count)) == _capi.ERR_STATE  # chain 1 is ahead
+    assert b"out of step" in lib.constv_last_error()
+    assert lib.constv_set_chains(h, 1) == _capi.ERR_STATE
+    for q in (0, 2, 3):
+        _capi.check(lib.constv_step_fused_chain(h, q, None, 0, None))
+    _capi.check(lib.constv_get_step_count(h, C.byref(count)))
+    assert count.value == 1
+    assert lib.constv_step_part1(h, None, 0, None) == _capi.ERR_STATE  # the split path is unchained
+    _capi.check(lib.constv_set_chains(h, 1))
+    _capi.check(lib.constv_get_step_count(h, C.byref(count)))
+    assert count.value == 1  # the counter survives re-chaining
+    it.step(1)
+    assert it._kernel.get_step_count() == 2
+    ctx.close()
+
+
 # ---- kinetic energy ----------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("precision", slabmod.PRECISIONS)
