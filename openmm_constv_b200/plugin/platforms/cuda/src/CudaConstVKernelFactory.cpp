@@ -19,7 +19,9 @@ extern "C" OPENMM_EXPORT void registerPlatforms() {
 extern "C" OPENMM_EXPORT void registerKernelFactories() {
     try {
         Platform& cuda = Platform::getPlatformByName("CUDA");
-        cuda.registerKernelFactory(IntegrateConstVLangevinStepKernel::Name(), new CudaConstVKernelFactory());
+        CudaConstVKernelFactory* factory = new CudaConstVKernelFactory();  // one factory, both kernel names (reference :44-46)
+        cuda.registerKernelFactory(IntegrateConstVLangevinStepKernel::Name(), factory);
+        cuda.registerKernelFactory(IntegrateConstVDrudeLangevinStepKernel::Name(), factory);
     } catch (const std::exception&) {
     }
 }
@@ -39,5 +41,7 @@ KernelImpl* CudaConstVKernelFactory::createKernelImpl(std::string name, const Pl
     CudaContext& cu = *data.contexts[0];  // the integrator runs on the first device, as in the reference
     if (name == IntegrateConstVLangevinStepKernel::Name())
         return new CudaIntegrateConstVLangevinStepKernel(name, platform, cu);
+    if (name == IntegrateConstVDrudeLangevinStepKernel::Name())
+        return new CudaIntegrateConstVDrudeLangevinStepKernel(name, platform, cu);
     throw OpenMMException((std::string("Tried to create kernel with illegal kernel name '") + name + "'").c_str());
 }

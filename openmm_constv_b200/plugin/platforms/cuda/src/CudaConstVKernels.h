@@ -36,6 +36,31 @@ private:
     bool slotsPermuted;  // true once OpenMM has re-sorted the atoms at least once
 };
 
+// CUDA-platform implementation of IntegrateConstVDrudeLangevinStepKernel; replaces the reference's
+// class of the same name (CudaConstVKernels.h:84-118, CudaConstVKernels.cpp:179-357): its four
+// runtime-compiled kernels per step (part 1, part 2, hard wall, image rewrite) become one precompiled
+// kernel, or two around the constraint solver.
+class CudaIntegrateConstVDrudeLangevinStepKernel : public IntegrateConstVDrudeLangevinStepKernel {
+public:
+    CudaIntegrateConstVDrudeLangevinStepKernel(std::string name, const Platform& platform, CudaContext& cu)
+        : IntegrateConstVDrudeLangevinStepKernel(name, platform), cu(cu), slab(NULL), zmax(0), hasConstraints(false), slotsPermuted(false) {
+    }
+    ~CudaIntegrateConstVDrudeLangevinStepKernel();
+    void initialize(const System& system, const ConstVDrudeLangevinIntegrator& integrator, const DrudeForce& force);
+    void execute(ContextImpl& context, const ConstVDrudeLangevinIntegrator& integrator);
+    double computeKineticEnergy(ContextImpl& context, const ConstVDrudeLangevinIntegrator& integrator);
+    constv_slab* getSlab() { return slab; }
+    double getCellSize() const { return zmax; }
+
+private:
+    void bindArrays();
+    CudaContext& cu;
+    constv_slab* slab;
+    double zmax;
+    bool hasConstraints;
+    bool slotsPermuted;
+};
+
 }  // namespace OpenMM
 
 #endif /* CUDA_CONSTV_KERNELS_H_ */

@@ -68,6 +68,23 @@ private:
     std::vector<Well> wells;
 };
 
+// The slice of OpenMM's DrudeForce (Drude plugin) the Drude integrator reads: one entry per Drude
+// particle with its parent `particle1` (CudaConstVKernels.cpp:219-224).  In the shim the force itself is
+// the isotropic spring 0.5*k*|r - r1|^2 with k = ONE_4PI_EPS0*charge^2/polarizability; anisotropy and
+// Thole screening are not modelled.
+class OPENMM_EXPORT DrudeForce : public Force {
+public:
+    int addParticle(int particle, int particle1, int particle2, int particle3, int particle4, double charge,
+                    double polarizability, double aniso12, double aniso34);
+    int getNumParticles() const { return (int) particles.size(); }
+    void getParticleParameters(int index, int& particle, int& particle1, int& particle2, int& particle3, int& particle4,
+                               double& charge, double& polarizability, double& aniso12, double& aniso34) const;
+    double compute(const std::vector<Vec3>& positions, std::vector<Vec3>& forces) const;
+private:
+    struct Entry { int p, p1, p2, p3, p4; double charge, polarizability, aniso12, aniso34; };
+    std::vector<Entry> particles;
+};
+
 class OPENMM_EXPORT System {
 public:
     System();

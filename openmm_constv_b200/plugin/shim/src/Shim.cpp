@@ -58,6 +58,33 @@ double HarmonicWellForce::compute(const vector<Vec3>& pos, vector<Vec3>& f) cons
     return energy;
 }
 
+int DrudeForce::addParticle(int particle, int particle1, int particle2, int particle3, int particle4, double charge,
+                            double polarizability, double aniso12, double aniso34) {
+    particles.push_back({particle, particle1, particle2, particle3, particle4, charge, polarizability, aniso12, aniso34});
+    return (int) particles.size() - 1;
+}
+
+void DrudeForce::getParticleParameters(int index, int& particle, int& particle1, int& particle2, int& particle3, int& particle4,
+                                       double& charge, double& polarizability, double& aniso12, double& aniso34) const {
+    const Entry& e = particles.at(index);
+    particle = e.p; particle1 = e.p1; particle2 = e.p2; particle3 = e.p3; particle4 = e.p4;
+    charge = e.charge; polarizability = e.polarizability; aniso12 = e.aniso12; aniso34 = e.aniso34;
+}
+
+double DrudeForce::compute(const vector<Vec3>& pos, vector<Vec3>& f) const {
+    const double ONE_4PI_EPS0 = 138.935456;
+    double energy = 0;
+    for (const Entry& e : particles) {
+        if (!(e.polarizability > 0)) continue;
+        const double k = ONE_4PI_EPS0 * e.charge * e.charge / e.polarizability;
+        Vec3 d = pos[e.p] - pos[e.p1];
+        energy += 0.5 * k * d.dot(d);
+        f[e.p] = f[e.p] - d * k;
+        f[e.p1] = f[e.p1] + d * k;
+    }
+    return energy;
+}
+
 // ---- System ---------------------------------------------------------------------------------------
 
 System::System() {

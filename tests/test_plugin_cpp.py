@@ -36,13 +36,22 @@ def test_plugin_surface_without_gpu(plugin_built):
 
 
 def test_plugin_exports_the_reference_symbols(plugin_built):
-    """CudaConstVKernelFactory.cpp:38-61 and ConstVSerializationProxyRegistration.cpp:63-65."""
-    ctypes.CDLL(os.path.join(PLUGIN, "lib", "libOpenMMShim.so"), mode=ctypes.RTLD_GLOBAL)
-    api = ctypes.CDLL(os.path.join(PLUGIN, "lib", "libOpenMMConstV.so"), mode=ctypes.RTLD_GLOBAL)
-    assert hasattr(api, "registerConstVSerializationProxies")
-    plugin = ctypes.CDLL(os.path.join(PLUGIN, "lib", "plugins", "libConstVPluginCUDA.so"))
-    for name in ("registerPlatforms", "registerKernelFactories", "registerConstVCudaKernelFactories"):
-        assert hasattr(plugin, name), name
+    """CudaConstVKernelFactory.cpp:38-61 and ConstVSerializationProxyRegistration.cpp:63-65.  In a child
+    process: loading the shim RTLD_GLOBAL brings the system libcudart into this process's global symbol
+    scope, which a later `import torch` (with its own bundled CUDA runtime) does not survive."""
+    code = f"""
+import ctypes, os
+P = {PLUGIN!r}
+ctypes.CDLL(os.path.join(P, "lib", "libOpenMMShim.so"), mode=ctypes.RTLD_GLOBAL)
+api = ctypes.CDLL(os.path.join(P, "lib", "libOpenMMConstV.so"), mode=ctypes.RTLD_GLOBAL)
+assert hasattr(api, "registerConstVSerializationProxies")
+plugin = ctypes.CDLL(os.path.join(P, "lib", "plugins", "libConstVPluginCUDA.so"))
+for name in ("registerPlatforms", "registerKernelFactories", "registerConstVCudaKernelFactories"):
+    assert hasattr(plugin, name), name
+print("ok")
+"""
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stdout + res.stderr
 
 
 def test_constvplugin_python_module():
@@ -73,3 +82,38 @@ def test_constvplugin_python_module():
 def test_cuda_integrator_through_the_plugin(plugin_built, precision):
     out = run("TestCudaConstVLangevinIntegrator", precision, timeout=900)
     assert f"Done ({precision})" in out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["single", "mixed", "double"])
+def test_cuda_drude_integrator_through_the_plugin(plugin_built, precision):
+    """ConstVDrudeLangevinIntegrator -> IntegrateConstVDrudeLangevinStepKernel -> constv_drude_* (the reference
+    has no test for this integrator; properties of its algorithm, see the C++ file's header)."""
+    out = run("TestCudaConstVDrudeLangevinIntegrator", precision, timeout=900)
+    assert f"Done ({precision})" in out
+
+
+def test_constvplugin_python_module_drude():
+    """python/constvplugin.i:82-100: ConstVDrudeLangevinIntegrator(temperature, friction, drudeTemperature,
+    drudeFriction, stepSize, numCells=2, zmax=-1) and its accessors."""
+    sys.path.insert(0, os.path.join(PLUGIN, "python"))
+    try:
+        import constvplugin
+    finally:
+        sys.path.pop(0)
+    integ = constvplugin.ConstVDrudeLangevinIntegrator(300.0, 5.0, 1.0, 20.0, 0.001)
+    assert integ.getNumCells() == 2 and integ.getCellSize() == -1 and integ.getMaxDrudeDistance() == 0
+    for setter, getter, value in (("setDrudeTemperature", "getDrudeTemperature", 2.0), ("setDrudeFriction", "getDrudeFriction", 10.0),
+                                  ("setMaxDrudeDistance", "getMaxDrudeDistance", 0.02), ("setTemperature", "getTemperature", 310.0),
+                                  ("setFriction", "getFriction", 0.5), ("setNumCells", "getNumCells", 4)):
+        getattr(integ, setter)(value)
+        got = getattr(integ, getter)()
+        got = getattr(got, "_value", got)
+        assert got == value
+    with pytest.raises(constvplugin.OpenMMException, match="Distance cannot be negative"):
+        integ.setMaxDrudeDistance(-1)
+    with pytest.raises(constvplugin.OpenMMException, match="not bound to a context"):
+        integ.step(1)
+    assert integ.getKernelNames() == ["IntegrateConstVDrudeLangevinStep"]
+    text = open(os.path.join(PLUGIN, "python", "constvplugin.i")).read()
+    assert "class ConstVDrudeLangevinIntegrator : public Integrator" in text
