@@ -74,6 +74,11 @@ def parse_args():
                     help="cut the slab into this many independent real-atom ranges, each advanced on its own stream "
                          "(constv_set_chains): the drain of one range's step overlaps the ramp of another's; for --ensemble, "
                          "the slabs of a step are advanced by this many batched launches on as many streams")
+    ap.add_argument("--rigid-water", default="", choices=["", "fused", "split"],
+                    help="BASELINE configs[0-1] shape: the slab's water molecules are rigid (constraints=AllBonds on SPC/E, "
+                         "example/nacl_1m_spce/nacl_constv.py:56).  fused = constv_step_fused_settle, one kernel per step; "
+                         "split = the reference's structure, part 1 | constraint solver on posDelta | part 2 + image rewrite "
+                         "(three launches).  Implies --chains 1.")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cache-image-charge", action="store_true")
     ap.add_argument("--keep-in-l2", action="store_true", help="default cache policy instead of evict-first")
@@ -396,9 +401,17 @@ def main():
 
     # ---- workload: this rank's shard of the range-partitioned slab ------------------------------
     R = args.atoms // 2
-    shard = slabmod.make_slab(R, args.precision, seed=12345 + rank)
+    water = None
+    if args.rigid_water:
+        if args.ensemble:
+            raise SystemExit("--rigid-water and --ensemble are separate configurations")
+        args.chains = 1
+        shard, w_atoms, w_params, w_cons = slabmod.make_water_slab(R, args.precision, seed=12345 + rank)
+        water = (w_atoms, w_params, w_cons)
+    else:
+        shard = slabmod.make_slab(R, args.precision, seed=12345 + rank)
     shard.global_atom_offset = partition.shard_range(R * world, rank, world)[0]
-    alg_bytes = slabmod.algorithmic_bytes_per_step(shard)
+    alg_bytes = slabmod.algorithmic_bytes_per_step(shard, rigid_molecules=len(water[0]) if water else 0)
     rec_bytes = shard.posq.nbytes + shard.velm.nbytes + shard.force.nbytes + (shard.corr.nbytes if shard.corr is not None else 0)
     M = max(1, args.ensemble)  # slabs advanced per step on this GPU (1 = the plain slab configs)
     replicas = args.replicas or max(2, int(np.ceil(2.0 * L2_BYTES / (rec_bytes * M))) + 1)
@@ -414,6 +427,8 @@ def main():
         sysm = hostapi.SlabSystem()
         sysm.addParticles(shard.masses)
         sysm.setDefaultPeriodicBoxVectors((shard.box[0], 0, 0), (0, shard.box[1], 0), (0, 0, shard.num_cells * shard.zmax))
+        if water:
+            sysm.addConstraints(*water[2])
         it = hostapi.ConstVLangevinIntegrator(args.temperature, FRICTION, DT, shard.num_cells)
         it.setRandomNumberSeed(2024 + (r % M))
         ctx = hostapi.SlabContext(sysm, it, precision=args.precision, device=local_rank, flags=flags,
@@ -477,6 +492,13 @@ def main():
         for k in range(first, first + count):
             if args.ensemble:
                 _capi.check(lib.constv_step_fused_batched(groups[k % replicas], M, sptr))
+            elif args.rigid_water == "fused":
+                _capi.check(lib.constv_step_fused_settle(handles[k % replicas], None, 0, sptr))
+            elif args.rigid_water == "split":
+                h = handles[k % replicas]
+                _capi.check(lib.constv_step_part1(h, None, 0, sptr))
+                _capi.check(lib.constv_settle_positions(h, sptr))
+                _capi.check(lib.constv_step_part2_mirror(h, sptr))
             else:
                 _capi.check(lib.constv_step_fused(handles[k % replicas], None, 0, sptr))
 
@@ -535,7 +557,7 @@ def main():
     # a StateDataReporter asks for every step (kinetic energy); `full_state` also reads back posq of
     # all atoms (what a DCD frame needs) and is reported beside it.
     e2e = None
-    if not args.skip_e2e and not args.ensemble:
+    if not args.skip_e2e and not args.ensemble and not args.rigid_water:
         ctx0, it0 = ctxs[0]
         n_e2e = max(3, args.e2e_steps)
         host_force = [torch.from_numpy(np.ascontiguousarray(slabmod.new_forces(shard, j)[:, :R])).pin_memory() for j in range(2)]
@@ -618,7 +640,7 @@ def main():
 
     # ---- the reference's own CUDA kernels on this GPU (information beside the headline) ---------------
     ref_gpu = None
-    if rank == 0 and world == 1 and not args.skip_ref_gpu and not args.ensemble:
+    if rank == 0 and world == 1 and not args.skip_ref_gpu and not args.ensemble and not args.rigid_water:
         from oracle import ref as refmod
         if refmod.available("cuda"):
             for ctx, _ in ctxs:
@@ -639,7 +661,7 @@ def main():
 
     # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.skip_cpu and not args.ensemble:
+    if rank == 0 and world == 1 and not args.skip_cpu and not args.ensemble and not args.rigid_water:
         rate_fn, kind = cpu_leg()
         rate, done, threads, per_step, el = rate_fn(shard, args.cpu_seconds, replicas=replicas)
         what = ("steps of the reference's constVLangevin.cu compiled for the host (part 1, part 2, image rewrite; oracle/_ref)"
@@ -666,6 +688,8 @@ def main():
             "config": {
                 "workload": (f"ensemble of {M * world} independent synthetic slabs of {shard.num_atoms} atoms, {M} per GPU advanced by one batched launch per step (BASELINE configs[4])"
                              if args.ensemble else
+                             f"synthetic slab with RIGID water ({len(water[0])} SPC/E molecules, constraints solved {'inside the step kernel' if args.rigid_water == 'fused' else 'by a separate launch between part 1 and part 2'}), {shard.num_atoms} atoms per GPU, ConstV Langevin step incl. constraints (BASELINE configs[0-1] shape); range partition over {world} GPU(s)"
+                             if water else
                              f"synthetic slab, {shard.num_atoms} atoms per GPU ({R} real + {shard.num_atoms - R} image), fused ConstV Langevin step only (BASELINE configs[2]); range partition over {world} GPU(s)"),
                 "atoms_per_gpu": shard.num_atoms, "total_atoms": atoms_per_step_job, "precision": args.precision,
                 "pair_classes": shard.pair_classes(), "rng": "in-kernel Philox4x32-10",
@@ -687,11 +711,14 @@ def main():
                                   "achieved = algorithmic bytes per launch x launches in the timed region / its duration" % chains)
                                  if chains > 1 else "one launch per step",
                          "frac_of_8TBs_nominal": achieved / 8000.0,
-                         "kernel": "constv_fused_step_batched_kernel" if args.ensemble else "constv_fused_step_kernel"},
+                         "kernel": "constv_fused_step_batched_kernel" if args.ensemble else
+                                   ("constv_settle_step_kernel" if args.rigid_water == "fused" else
+                                    ("constv_part1_kernel + constv_settle_positions_kernel + constv_part2_mirror_kernel"
+                                     if args.rigid_water == "split" else "constv_fused_step_kernel"))},
             "cpu_baseline": cpu,
             "reference_gpu": ref_gpu,
             "e2e": e2e,
-            "gpu_launches": int(K * chains),
+            "gpu_launches": int(K * (3 if args.rigid_water == "split" else chains)),
             "eager_launches_in_region": int(eager_launches),
             "clocks": clocks,
             "kinetic_energy_kj_mol": ke_total, "temperature_K": temperature,

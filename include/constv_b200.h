@@ -291,6 +291,40 @@ CONSTV_API int constv_drude_step_fused(constv_slab* slab, const void* random4, u
  * that run their own part 2.  No-op when max_drude_distance <= 0. */
 CONSTV_API int constv_drude_hardwall(constv_slab* slab, void* stream);
 
+/* ---- rigid three-site molecules inside the step ------------------------------ */
+/* The reference hands posDelta to OpenMM's constraint solver between part 1 and part 2
+ * (integration.applyConstraints, Kernels.cpp:153).  For its example system -- SPC/E water with
+ * constraints=AllBonds, example/nacl_1m_spce/nacl_constv.py:56 -- every constraint belongs to a rigid 3-site
+ * molecule, which OpenMM's CUDA platform solves analytically (SETTLE, Miyamoto & Kollman 1992).  These
+ * entry points take that case into the step: part 1, SETTLE, part 2, the image rewrite and the zeroing in ONE
+ * kernel, posDelta never leaving registers.  The solver is OpenMM's, not the reference's: it is restated from
+ * the published algorithm (parity unpinned). */
+
+/* The rule by which OpenMM's CudaIntegrationUtilities picks the constraints SETTLE solves [recalled]: atoms
+ * with exactly two constraints each, closing a triangle; two of the three distances equal, the atom between
+ * them is the apex.  Pure host code.  cluster_atoms (3 per molecule: apex, b, c) and cluster_params (2 per
+ * molecule: d(apex-b) = d(apex-c), d(b-c)) may be NULL to count only; they need room for num_constraints/3
+ * molecules.  *num_other_constraints_out = constraints left for a general solver (0 = the fused step applies).
+ * Three unequal distances: CONSTV_ERR_SYSTEM "Two of the three distances constrained with SETTLE must be the same." */
+CONSTV_API int constv_settle_find_clusters(int32_t num_atoms, int32_t num_constraints, const int32_t* atom1,
+                                           const int32_t* atom2, const double* distance, int32_t* cluster_atoms,
+                                           float* cluster_params, int32_t* num_clusters_out,
+                                           int32_t* num_other_constraints_out);
+
+/* Upload the molecule list (HOST arrays, layout as above; atoms are slots of real atoms, used directly as
+ * OpenMM's solver uses them; OpenMM only swaps identical molecules, so a slot keeps its role). */
+CONSTV_API int constv_settle_configure(constv_slab* slab, int32_t num_clusters, const int32_t* cluster_atoms,
+                                       const float* cluster_params);
+
+/* The whole of execute (Kernels.cpp:139-172) INCLUDING the constraint hand-off at :153, for a system whose
+ * constraints are all in the configured molecules, in one kernel.  random4 / Philox as constv_step_part1. */
+CONSTV_API int constv_step_fused_settle(constv_slab* slab, const void* random4, uint32_t random_index,
+                                        void* stream);
+
+/* The solver alone on pos_delta, thread <-> molecule: what applyConstraints does for these molecules, for
+ * the split path constv_step_part1 | constv_settle_positions | constv_step_part2_mirror. */
+CONSTV_API int constv_settle_positions(constv_slab* slab, void* stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 
 CONSTV_API const char* constv_last_error(void);

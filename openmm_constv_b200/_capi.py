@@ -38,6 +38,7 @@ SYMBOLS = [
     "constv_drude_configure", "constv_drude_random_count", "constv_drude_set_parameters",
     "constv_drude_get_parameters", "constv_drude_step_part1", "constv_drude_step_part2",
     "constv_drude_step_fused", "constv_drude_hardwall",
+    "constv_settle_find_clusters", "constv_settle_configure", "constv_step_fused_settle", "constv_settle_positions",
 ]
 
 
@@ -110,6 +111,10 @@ def load() -> C.CDLL:
         "constv_drude_step_part2": [vp, vp],
         "constv_drude_step_fused": [vp, vp, u32, vp],
         "constv_drude_hardwall": [vp, vp],
+        "constv_settle_find_clusters": [i32, i32, vp, vp, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)],
+        "constv_settle_configure": [vp, i32, vp, vp],
+        "constv_step_fused_settle": [vp, vp, u32, vp],
+        "constv_settle_positions": [vp, vp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)

@@ -45,7 +45,8 @@ def _stale(target: str, sources: list[str]) -> bool:
 def build_capi(force: bool = False, verbose: bool = False) -> str:
     sources = [os.path.join(CSRC, "constv_capi.cu")]
     deps = sources + [os.path.join(CSRC, "constv_kernels.cuh"), os.path.join(CSRC, "constv_drude_kernels.cuh"),
-                      os.path.join(CSRC, "constv_drude_capi.inc"),
+                      os.path.join(CSRC, "constv_drude_capi.inc"), os.path.join(CSRC, "constv_settle_kernels.cuh"),
+                      os.path.join(CSRC, "constv_settle_capi.inc"),
                       os.path.join(ROOT, "include", "constv_b200.h"), os.path.abspath(__file__)]
     if force or _stale(LIB, deps):
         cmd = [nvcc(), *NVCC_FLAGS, "-shared", "-I", os.path.join(ROOT, "include"), "-I", CSRC,

@@ -15,6 +15,7 @@
 
 #include "constv_kernels.cuh"
 #include "constv_drude_kernels.cuh"
+#include "constv_settle_kernels.cuh"
 
 using namespace constv;
 
@@ -92,6 +93,15 @@ struct constv_slab {
         double temperature = 0, friction = 0;
         double vscale = 0, fscaleFixed = 0, noisescale = 0, maxDistance = 0, hardwallScale = 0;
     } drude;
+    // rigid three-site molecules solved inside the step (constv_settle_*)
+    struct Settle {
+        int2* items = nullptr;     // device int2[numItems]: (slot, -1 | molecule index), slot order
+        int4* atoms = nullptr;     // device int4[numClusters]: (apex, b, c, 0)
+        float2* params = nullptr;  // device float2[numClusters]
+        int numItems = 0, numClusters = 0;
+        SettleSegments segments{};  // count > 0: the work items form a few arithmetic runs
+        bool configured = false;
+    } settle;
     int paramsKind = 0;  // which integrator's coefficients vscale/fscaleFixed/noisescale hold: 1 Langevin, 2 Drude
     // chains (constv_set_chains): chain q advances real atoms [chainLo[q], chainLo[q+1]) with counters[q]
     int chains = 1;
@@ -424,6 +434,9 @@ int constv_destroy(constv_slab* s) {
     cudaFree(s->invAtomOrder);
     cudaFree(s->drude.role);
     cudaFree(s->drude.pairs);
+    cudaFree(s->settle.items);
+    cudaFree(s->settle.atoms);
+    cudaFree(s->settle.params);
     cudaFree(s->imageCharge);
     cudaFree(s->counters);
     cudaFree(s->kePartials);
@@ -910,3 +923,4 @@ int constv_set_kernel_variant(constv_slab* s, int32_t variant, int32_t block_siz
 }  // extern "C"
 
 #include "constv_drude_capi.inc"
+#include "constv_settle_capi.inc"

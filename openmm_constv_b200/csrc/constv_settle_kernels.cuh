@@ -1,0 +1,460 @@
+// Device code for rigid three-site molecules inside the ConstV Langevin step (sm_100a): SURVEY.md 8f.3.
+//
+// What it replaces in the reference (scychon/openmm_constV): the constraint hand-off of
+// platforms/cuda/src/CudaConstVKernels.cpp:146-166 -- part 1 | integration.applyConstraints(tol) | part 2 |
+// image rewrite -- for the systems the reference's example runs, SPC/E water with constraints=AllBonds
+// (example/nacl_1m_spce/nacl_constv.py:56).  Three distance constraints on a rigid 3-site molecule are what
+// OpenMM's CUDA platform solves analytically with SETTLE (Miyamoto & Kollman, J. Comput. Chem. 13, 952
+// (1992)); the solver lives in OpenMM, not in the reference tree, so it is restated here from the published
+// algorithm in the formulation OpenMM's kernel uses [recalled]: displacements (posDelta) relative to the
+// apex atom's old position, float parameters (d(apex-b) = d(apex-c), d(b-c)).
+//
+// The reference streams posDelta and velm through HBM three times around the solver (part 1 writes them,
+// the solver reads and rewrites posDelta, part 2 reads them back).  Here the thread that owns a molecule's
+// apex does part 1 for its three atoms, solves the constraints in registers, does part 2, rewrites the three
+// images and zeroes them: ONE kernel, each record crossing HBM once, posDelta never leaving registers.
+// constv_settle_positions_kernel is the solver alone (thread <-> molecule), for the split path.
+//
+// Arithmetic: every operation of the solver is rounded separately (struct RN: operators on __f*_rn /
+// __d*_rn intrinsics, which the compiler never contracts), divisions and square roots IEEE-correct; the CPU
+// oracle spells the same sequence, so results agree bit for bit.
+#pragma once
+
+#include "constv_drude_kernels.cuh"
+
+namespace constv {
+
+enum { SETTLE_ROLE_NORMAL = -1, SETTLE_ROLE_PASSIVE = -2 };  // item kinds; >= 0: that molecule
+
+// When the work items form a few runs -- ordinary atoms in consecutive slots, or molecules laid out
+// (apex, apex+1, apex+2) one after the other with the same parameters: ions, then water, then wall atoms --
+// a thread finds its slots arithmetically instead of through two dependent loads (item list, molecule list).
+constexpr int kSettleMaxSegments = 8;
+struct SettleSegments {
+    int count;                              // 0 = not segmented: use the item list
+    int itemStart[kSettleMaxSegments + 1];  // first work item of each run; [count] = numItems
+    int slotStart[kSettleMaxSegments];      // slot of that item
+    int atomsPerItem[kSettleMaxSegments];   // 1 (ordinary atoms) or 3 (molecules)
+    float2 params[kSettleMaxSegments];      // molecule runs: (d(apex-b), d(b-c))
+    int tileStart[kSettleMaxSegments + 1];  // tiled kernel: first CTA of each run (tiles of kSettleTile items)
+};
+constexpr int kSettleTile = 128;            // work items per CTA of the tiled kernel
+
+struct SettleDev {
+    const int2* items;    // work items of the fused step in slot order: (slot, SETTLE_ROLE_NORMAL) = an ordinary
+                          // real atom, (apex slot, molecule index) = a molecule; b and c atoms are not listed
+    const int4* atoms;    // (apex, b, c, 0) slots
+    const float2* params; // (d(apex-b) = d(apex-c), d(b-c))
+    int numItems, numClusters;
+};
+
+// A value whose +, -, *, / are individually rounded IEEE operations, whatever the compiler flags.
+template <typename M> struct RN {
+    M v;
+    __device__ __forceinline__ RN() : v(0) {}
+    __device__ __forceinline__ RN(M x) : v(x) {}
+};
+template <typename M> __device__ __forceinline__ RN<M> operator+(RN<M> a, RN<M> b) { return RN<M>(add_rn(a.v, b.v)); }
+template <typename M> __device__ __forceinline__ RN<M> operator-(RN<M> a, RN<M> b) { return RN<M>(add_rn(a.v, -b.v)); }
+template <typename M> __device__ __forceinline__ RN<M> operator*(RN<M> a, RN<M> b) { return RN<M>(mul_rn(a.v, b.v)); }
+template <typename M> __device__ __forceinline__ RN<M> operator/(RN<M> a, RN<M> b) { return RN<M>(div_rn(a.v, b.v)); }
+template <typename M> __device__ __forceinline__ RN<M> operator-(RN<M> a) { return RN<M>(-a.v); }
+template <typename M> __device__ __forceinline__ RN<M> sqrt_of(RN<M> a) { return RN<M>(sqrt_rn(a.v)); }
+
+// SETTLE for one molecule.  pos* = old positions as `mixed`; d* = displacements to the unconstrained new
+// positions, overwritten with the constrained ones (w untouched); m* = masses.
+template <typename M>
+__device__ __forceinline__ void settle_molecule(const M (&pos0)[3], const M (&pos1)[3], const M (&pos2)[3],
+                                                Vec4<M>& d0, Vec4<M>& d1, Vec4<M>& d2,
+                                                const M mass0, const M mass1, const M mass2,
+                                                const float distAB, const float distBC) {
+    using R = RN<M>;
+    const R m0(mass0), m1(mass1), m2(mass2), one((M) 1), two((M) 2), four((M) 4), half((M) 0.5);
+    // old bond vectors, from the apex
+    const R xb0 = R(pos1[0]) - R(pos0[0]), yb0 = R(pos1[1]) - R(pos0[1]), zb0 = R(pos1[2]) - R(pos0[2]);
+    const R xc0 = R(pos2[0]) - R(pos0[0]), yc0 = R(pos2[1]) - R(pos0[1]), zc0 = R(pos2[2]) - R(pos0[2]);
+
+    const R invTotalMass = one / (m0 + m1 + m2);
+    const R xcom = (R(d0.x) * m0 + (xb0 + R(d1.x)) * m1 + (xc0 + R(d2.x)) * m2) * invTotalMass;
+    const R ycom = (R(d0.y) * m0 + (yb0 + R(d1.y)) * m1 + (yc0 + R(d2.y)) * m2) * invTotalMass;
+    const R zcom = (R(d0.z) * m0 + (zb0 + R(d1.z)) * m1 + (zc0 + R(d2.z)) * m2) * invTotalMass;
+
+    // unconstrained new positions relative to the new centre of mass
+    const R xa1 = R(d0.x) - xcom, ya1 = R(d0.y) - ycom, za1 = R(d0.z) - zcom;
+    const R xb1 = xb0 + R(d1.x) - xcom, yb1 = yb0 + R(d1.y) - ycom, zb1 = zb0 + R(d1.z) - zcom;
+    const R xc1 = xc0 + R(d2.x) - xcom, yc1 = yc0 + R(d2.y) - ycom, zc1 = zc0 + R(d2.z) - zcom;
+
+    // orthonormal frame: Z = normal of the old molecular plane, X = a1 x Z, Y = Z x X
+    const R xaksZd = yb0 * zc0 - zb0 * yc0;
+    const R yaksZd = zb0 * xc0 - xb0 * zc0;
+    const R zaksZd = xb0 * yc0 - yb0 * xc0;
+    const R xaksXd = ya1 * zaksZd - za1 * yaksZd;
+    const R yaksXd = za1 * xaksZd - xa1 * zaksZd;
+    const R zaksXd = xa1 * yaksZd - ya1 * xaksZd;
+    const R xaksYd = yaksZd * zaksXd - zaksZd * yaksXd;
+    const R yaksYd = zaksZd * xaksXd - xaksZd * zaksXd;
+    const R zaksYd = xaksZd * yaksXd - yaksZd * xaksXd;
+
+    const R axlng = sqrt_of(xaksXd * xaksXd + yaksXd * yaksXd + zaksXd * zaksXd);
+    const R aylng = sqrt_of(xaksYd * xaksYd + yaksYd * yaksYd + zaksYd * zaksYd);
+    const R azlng = sqrt_of(xaksZd * xaksZd + yaksZd * yaksZd + zaksZd * zaksZd);
+    const R trns11 = xaksXd / axlng, trns21 = yaksXd / axlng, trns31 = zaksXd / axlng;
+    const R trns12 = xaksYd / aylng, trns22 = yaksYd / aylng, trns32 = zaksYd / aylng;
+    const R trns13 = xaksZd / azlng, trns23 = yaksZd / azlng, trns33 = zaksZd / azlng;
+
+    const R xb0d = trns11 * xb0 + trns21 * yb0 + trns31 * zb0;
+    const R yb0d = trns12 * xb0 + trns22 * yb0 + trns32 * zb0;
+    const R xc0d = trns11 * xc0 + trns21 * yc0 + trns31 * zc0;
+    const R yc0d = trns12 * xc0 + trns22 * yc0 + trns32 * zc0;
+    const R za1d = trns13 * xa1 + trns23 * ya1 + trns33 * za1;
+    const R xb1d = trns11 * xb1 + trns21 * yb1 + trns31 * zb1;
+    const R yb1d = trns12 * xb1 + trns22 * yb1 + trns32 * zb1;
+    const R zb1d = trns13 * xb1 + trns23 * yb1 + trns33 * zb1;
+    const R xc1d = trns11 * xc1 + trns21 * yc1 + trns31 * zc1;
+    const R yc1d = trns12 * xc1 + trns22 * yc1 + trns32 * zc1;
+    const R zc1d = trns13 * xc1 + trns23 * yc1 + trns33 * zc1;
+
+    // step 2: the canonical triangle (apex at +ra on Y, b and c at -rb, x = -+rc), tilted by phi and psi.
+    // The squared parameters are float arithmetic, as in the formulation restated (float2 parameters).
+    const float rcf = __fmul_rn(0.5f, distBC);
+    const R rc((M) rcf);
+    R rb = sqrt_of(R((M) __fadd_rn(__fmul_rn(distAB, distAB), -__fmul_rn(rcf, rcf))));
+    const R ra = rb * (m1 + m2) * invTotalMass;
+    rb = rb - ra;
+    const R sinphi = za1d / ra;
+    const R cosphi = sqrt_of(one - sinphi * sinphi);
+    const R sinpsi = (zb1d - zc1d) / (two * rc * cosphi);
+    const R cospsi = sqrt_of(one - sinpsi * sinpsi);
+
+    const R ya2d = ra * cosphi;
+    R xb2d = -(rc * cospsi);
+    const R yb2d = -(rb * cosphi) - rc * sinpsi * sinphi;
+    const R yc2d = -(rb * cosphi) + rc * sinpsi * sinphi;
+    const R xb2d2 = xb2d * xb2d;
+    const R hh2 = four * xb2d2 + (yb2d - yc2d) * (yb2d - yc2d) + (zb1d - zc1d) * (zb1d - zc1d);
+    const R deltx = two * xb2d + sqrt_of(four * xb2d2 - hh2 + R((M) __fmul_rn(distBC, distBC)));
+    xb2d = xb2d - deltx * half;
+
+    // step 3: the in-plane rotation theta that conserves the angular momentum about Z
+    const R alpha = xb2d * (xb0d - xc0d) + yb0d * yb2d + yc0d * yc2d;
+    const R beta = xb2d * (yc0d - yb0d) + xb0d * yb2d + xc0d * yc2d;
+    const R gamma = xb0d * yb1d - xb1d * yb0d + xc0d * yc1d - xc1d * yc0d;
+    const R al2be2 = alpha * alpha + beta * beta;
+    const R sintheta = (alpha * gamma - beta * sqrt_of(al2be2 - gamma * gamma)) / al2be2;
+
+    // step 4
+    const R costheta = sqrt_of(one - sintheta * sintheta);
+    const R xa3d = -(ya2d * sintheta);
+    const R ya3d = ya2d * costheta;
+    const R za3d = za1d;
+    const R xb3d = xb2d * costheta - yb2d * sintheta;
+    const R yb3d = xb2d * sintheta + yb2d * costheta;
+    const R zb3d = zb1d;
+    const R xc3d = -(xb2d * costheta) - yc2d * sintheta;
+    const R yc3d = -(xb2d * sintheta) + yc2d * costheta;
+    const R zc3d = zc1d;
+
+    // step 5: back to the laboratory frame
+    const R xa3 = trns11 * xa3d + trns12 * ya3d + trns13 * za3d;
+    const R ya3 = trns21 * xa3d + trns22 * ya3d + trns23 * za3d;
+    const R za3 = trns31 * xa3d + trns32 * ya3d + trns33 * za3d;
+    const R xb3 = trns11 * xb3d + trns12 * yb3d + trns13 * zb3d;
+    const R yb3 = trns21 * xb3d + trns22 * yb3d + trns23 * zb3d;
+    const R zb3 = trns31 * xb3d + trns32 * yb3d + trns33 * zb3d;
+    const R xc3 = trns11 * xc3d + trns12 * yc3d + trns13 * zc3d;
+    const R yc3 = trns21 * xc3d + trns22 * yc3d + trns23 * zc3d;
+    const R zc3 = trns31 * xc3d + trns32 * yc3d + trns33 * zc3d;
+
+    d0.x = (xcom + xa3).v;
+    d0.y = (ycom + ya3).v;
+    d0.z = (zcom + za3).v;
+    d1.x = (xcom + xb3 - xb0).v;
+    d1.y = (ycom + yb3 - yb0).v;
+    d1.z = (zcom + zb3 - zb0).v;
+    d2.x = (xcom + xc3 - xc0).v;
+    d2.y = (ycom + yc3 - yc0).v;
+    d2.z = (zcom + zc3 - zc0).v;
+}
+
+// The solver alone on posDelta (the constraint step of the split path): thread <-> molecule.
+template <int PREC, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+constv_settle_positions_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ SettleDev sd) {
+    using Real = typename Prec<PREC>::Real;
+    using Mixed = typename Prec<PREC>::Mixed;
+    constexpr bool kSplit = Prec<PREC>::kSplitPos;
+    const Real* __restrict__ posq = static_cast<const Real*>(d.posq);
+    const Real* __restrict__ corrA = static_cast<const Real*>(d.corr);
+    const Mixed* __restrict__ velm = static_cast<const Mixed*>(d.velm);
+    Mixed* __restrict__ posDelta = static_cast<Mixed*>(d.posDelta);
+    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < sd.numClusters; i += gridDim.x * BLOCK) {
+        const int4 at = sd.atoms[i];
+        const float2 prm = sd.params[i];
+        const int slot[3] = {at.x, at.y, at.z};
+        Mixed pos[3][3], mass[3];
+        Vec4<Mixed> delta[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const Vec4<Real> p = load4(posq, (size_t) slot[k]);
+            Vec4<Real> c{0, 0, 0, 0};
+            if (kSplit) c = load4(corrA, (size_t) slot[k]);
+            drude_pos_load<PREC>(p, c, pos[k]);
+            delta[k] = load4(posDelta, (size_t) slot[k]);
+            mass[k] = rcp_rn(velm[4 * (size_t) slot[k] + 3]);
+        }
+        settle_molecule<Mixed>(pos[0], pos[1], pos[2], delta[0], delta[1], delta[2], mass[0], mass[1], mass[2], prm.x, prm.y);
+#pragma unroll
+        for (int k = 0; k < 3; k++) store4(posDelta, (size_t) slot[k], delta[k]);
+    }
+}
+
+// The whole step of a system whose constraints are all rigid 3-site molecules, in one kernel.
+// Thread <-> work item, in slot order: an ordinary real atom (the plain Langevin step) or a molecule (part 1
+// for its three atoms, SETTLE, part 2, the image rewrite and the zeroing).  Items, not slots, so that the
+// lanes of a warp inside the water region ALL solve a molecule (a thread-per-slot version with two idle
+// lanes in three was issue-bound at 3x the unconstrained step's time).  A lane's three records are
+// neighbours in memory (stride 48 B across the warp): the three gathers of a warp cover the same lines.
+// Reordered slots (INDEXED): threads past the item list are the image slots, which zero themselves.
+// Gaussians: the caller's pool with the reference's addressing (random[randomIndex + slot],
+// constVLangevin.cu:14) or the Philox stream keyed by the original atom index.
+template <int PREC, int BLOCK, bool INDEXED, bool STREAM, bool SEGMENTED>
+__global__ void __launch_bounds__(BLOCK)
+constv_settle_step_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ SettleDev sd,
+                          const __grid_constant__ SettleSegments seg,
+                          const float4* __restrict__ random, const unsigned int randomIndex) {
+    using Real = typename Prec<PREC>::Real;
+    using Mixed = typename Prec<PREC>::Mixed;
+    __shared__ StepBox box;
+    pdl_wait();
+    pdl_launch();
+    const int R = d.numReal;
+    const size_t P = (size_t) d.padded;
+    const int numWork = sd.numItems + (INDEXED ? d.numAtoms - R : 0);
+    const unsigned int holders = (unsigned int) ((numWork + BLOCK - 1) / BLOCK);
+    const StepScalars<Mixed> s = scalars_of<Mixed>(d);
+
+    for (long long base = (long long) blockIdx.x * BLOCK; base < numWork; base += (long long) gridDim.x * BLOCK) {
+        const int t = (int) base + (int) threadIdx.x;
+        int2 item = make_int2(0, SETTLE_ROLE_PASSIVE);
+        float2 prm = make_float2(0.f, 0.f);
+        int slots[3] = {0, 0, 0};
+        if (SEGMENTED) {
+            if (t < sd.numItems) {
+                int k = 0;
+#pragma unroll
+                for (int q = 1; q < kSettleMaxSegments; q++)
+                    if (q < seg.count && t >= seg.itemStart[q]) k = q;
+                const int per = seg.atomsPerItem[k];
+                item.x = seg.slotStart[k] + (t - seg.itemStart[k]) * per;
+                item.y = per == 3 ? 0 : SETTLE_ROLE_NORMAL;
+                prm = seg.params[k];
+            }
+            slots[0] = item.x;
+            slots[1] = item.x + 1;
+            slots[2] = item.x + 2;
+        } else {
+            if (t < sd.numItems) item = sd.items[t];
+            slots[0] = slots[1] = slots[2] = item.x;
+            if (item.y >= 0) {
+                const int4 at = sd.atoms[item.y];
+                slots[1] = at.y;
+                slots[2] = at.z;
+                prm = sd.params[item.y];
+            }
+        }
+        const int role = item.y;
+        DrudeAtom<PREC> atom[3];
+        float4 xi[3];
+        xi[0] = xi[1] = xi[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int count = role >= 0 ? 3 : (role == SETTLE_ROLE_NORMAL ? 1 : 0);
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            if (k < count) {
+                drude_load<PREC, DRUDE_FUSED, INDEXED, STREAM>(d, slots[k], atom[k]);
+                if (random != nullptr) xi[k] = __ldcs(random + (size_t) randomIndex + slots[k]);
+            }
+
+        publish_step(box, d.counters);
+        __syncthreads();
+        const unsigned long long step = box.step;
+        const unsigned int ticket = take_ticket(d.counters, holders);
+
+        if (INDEXED && t >= sd.numItems && t < numWork) {  // an image slot zeroes itself
+            const int slot = R + (t - sd.numItems);
+            if (d.zeroVelm) store4(static_cast<Mixed*>(d.velm), (size_t) slot, Vec4<Mixed>{0, 0, 0, 0});
+            if (d.zeroForce) {
+                __stcs(d.force + slot, 0LL);
+                __stcs(d.force + P + slot, 0LL);
+                __stcs(d.force + 2 * P + slot, 0LL);
+            }
+        }
+
+        int orig[3] = {slots[0], slots[1], slots[2]};
+        bool moved[3] = {false, false, false};
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            if (k < count) {
+                if (INDEXED && d.atomIndex) orig[k] = d.atomIndex[slots[k]];
+                moved[k] = atom[k].v.w != 0;
+                if (moved[k]) {
+                    if (random == nullptr)
+                        xi[k] = (s.noisescale != 0) ? gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) orig[k], step)
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                    part1_update(atom[k].v, atom[k].delta, atom[k].f[0], atom[k].f[1], atom[k].f[2], xi[k].x, xi[k].y, xi[k].z, s);
+                }
+            }
+        if (role >= 0) {
+            Mixed pos[3][3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) drude_pos_load<PREC>(atom[k].p, atom[k].c, pos[k]);
+            settle_molecule<Mixed>(pos[0], pos[1], pos[2], atom[0].delta, atom[1].delta, atom[2].delta,
+                                   rcp_rn(atom[0].v.w), rcp_rn(atom[1].v.w), rcp_rn(atom[2].v.w), prm.x, prm.y);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            if (k < count) {
+                if (moved[k]) part2_update<PREC>(atom[k].p, atom[k].c, atom[k].v, atom[k].delta, s.invDt);
+                drude_emit<PREC, INDEXED, STREAM>(d, slots[k], orig[k], moved[k], atom[k]);
+            }
+
+        close_step(d.counters, ticket, holders, step);
+        if (base + (long long) gridDim.x * BLOCK < numWork) __syncthreads();  // box is rewritten by the next tile
+    }
+}
+
+
+// ---- the same step, staged through shared memory (identity slot order, segmented item list) -----------
+// A molecule's three records are neighbours in memory, so a thread that gathers "its" three records makes
+// every warp-wide access a stride-48-byte pattern: half-filled sectors on the way in and, worse, on the
+// way out (measured: 20 us per step at 1 M atoms with the arithmetic REMOVED, against 12.5 us for the
+// unconstrained step).  Here a CTA owns a tile of BLOCK work items of one run = BLOCK*per consecutive
+// slots and moves them like the unconstrained kernel does -- thread j loads slots base + j + i*BLOCK, every
+// access a full 16-byte (8-byte for force planes) coalesced vector -- into a structure-of-arrays stage in
+// shared memory; after a barrier thread j computes item j from stage entries per*j + k (stride 3: free of
+// bank conflicts), writes the new velocity and position back, and after a second barrier every thread
+// emits "its" slots again: own record, rewritten images, zeroed images, all coalesced.
+template <int PREC, int BLOCK> struct SettleStage {
+    using Real = typename Prec<PREC>::Real;
+    using Mixed = typename Prec<PREC>::Mixed;
+    static constexpr int kSlots = 3 * BLOCK;
+    Vec4<Mixed> v[kSlots];
+    Vec4<Real> p[kSlots];
+    Vec4<Real> c[Prec<PREC>::kSplitPos ? kSlots : 1];
+    long long f[3][kSlots];
+    Real q1[kSlots];
+};
+
+template <int PREC, int BLOCK, bool STREAM>
+__global__ void __launch_bounds__(BLOCK)
+constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ SettleSegments seg,
+                                const float4* __restrict__ random, const unsigned int randomIndex) {
+    using Real = typename Prec<PREC>::Real;
+    using Mixed = typename Prec<PREC>::Mixed;
+    constexpr bool kSplit = Prec<PREC>::kSplitPos;
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    SettleStage<PREC, BLOCK>& st = *reinterpret_cast<SettleStage<PREC, BLOCK>*>(smemRaw);
+    __shared__ StepBox box;
+    pdl_wait();
+    pdl_launch();
+    const int R = d.numReal;
+    const size_t P = (size_t) d.padded;
+    const unsigned int holders = (unsigned int) seg.tileStart[seg.count];
+    const StepScalars<Mixed> s = scalars_of<Mixed>(d);
+    const Real* __restrict__ posq = static_cast<const Real*>(d.posq);
+    const Real* __restrict__ corrA = static_cast<const Real*>(d.corr);
+    const Mixed* __restrict__ velm = static_cast<const Mixed*>(d.velm);
+    const long long* __restrict__ force = d.force;
+    const Real* qbase = d.imageCharge ? static_cast<const Real*>(d.imageCharge) : posq + 4 * (size_t) R + 3;
+    const size_t qstride = d.imageCharge ? 1 : 4;
+    const int j = (int) threadIdx.x;
+
+    for (int tile = (int) blockIdx.x; tile < (int) holders; tile += (int) gridDim.x) {
+        int q = 0;
+#pragma unroll
+        for (int k = 1; k < kSettleMaxSegments; k++)
+            if (k < seg.count && tile >= seg.tileStart[k]) q = k;
+        const int per = seg.atomsPerItem[q];
+        const int firstItem = (tile - seg.tileStart[q]) * BLOCK;
+        const int items = min(BLOCK, seg.itemStart[q + 1] - seg.itemStart[q] - firstItem);
+        const int base = seg.slotStart[q] + firstItem * per;
+        const int slotsInTile = items * per;
+        const float2 prm = seg.params[q];
+
+        // stage in: coalesced
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const int idx = j + i * BLOCK;
+            if (idx < slotsInTile) {
+                const size_t slot = (size_t) (base + idx);
+                st.v[idx] = load4x<STREAM>(velm, slot);
+                st.p[idx] = load4x<STREAM>(posq, slot);
+                if (kSplit) st.c[idx] = load4x<STREAM>(corrA, slot);
+                st.f[0][idx] = load_force(force + slot);
+                st.f[1][idx] = load_force(force + P + slot);
+                st.f[2][idx] = load_force(force + 2 * P + slot);
+                st.q1[idx] = qbase[qstride * slot];
+            }
+        }
+        publish_step(box, d.counters);
+        __syncthreads();
+        const unsigned long long step = box.step;
+        const unsigned int ticket = take_ticket(d.counters, holders);
+
+        // compute item j from the stage
+        if (j < items) {
+            Vec4<Mixed> v[3], delta[3];
+            Vec4<Real> p[3], c[3];
+            bool moved[3] = {false, false, false};
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                if (k < per) {
+                    const int idx = per * j + k;
+                    v[k] = st.v[idx];
+                    p[k] = st.p[idx];
+                    c[k] = kSplit ? st.c[idx] : Vec4<Real>{0, 0, 0, 0};
+                    delta[k] = Vec4<Mixed>{0, 0, 0, 0};
+                    moved[k] = v[k].w != 0;
+                    if (moved[k]) {
+                        float4 xi;
+                        if (random != nullptr) xi = __ldcs(random + (size_t) randomIndex + base + idx);
+                        else xi = (s.noisescale != 0) ? gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) (base + idx), step)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                        part1_update(v[k], delta[k], st.f[0][idx], st.f[1][idx], st.f[2][idx], xi.x, xi.y, xi.z, s);
+                    }
+                }
+            if (per == 3) {
+                Mixed pos[3][3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) drude_pos_load<PREC>(p[k], c[k], pos[k]);
+                settle_molecule<Mixed>(pos[0], pos[1], pos[2], delta[0], delta[1], delta[2], rcp_rn(v[0].w), rcp_rn(v[1].w),
+                                       rcp_rn(v[2].w), prm.x, prm.y);
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                if (k < per && moved[k]) {
+                    const int idx = per * j + k;
+                    part2_update<PREC>(p[k], c[k], v[k], delta[k], s.invDt);
+                    st.v[idx] = v[k];
+                    st.p[idx] = p[k];
+                    if (kSplit) st.c[idx] = c[k];
+                }
+        }
+        __syncthreads();
+
+        // stage out: own record, rewritten images, zeroed images -- coalesced
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const int idx = j + i * BLOCK;
+            if (idx < slotsInTile) {
+                const Vec4<Mixed> v = st.v[idx];
+                const Vec4<Real> p = st.p[idx];
+                const Vec4<Real> c = kSplit ? st.c[idx] : Vec4<Real>{0, 0, 0, 0};
+                emit_atom<PREC, STREAM>(d, s.zshift, base + idx, v.w != 0, v, p, c, st.q1[idx]);
+            }
+        }
+        close_step(d.counters, ticket, holders, step);
+        if (tile + (int) gridDim.x < (int) holders) __syncthreads();  // stage and box are rewritten by the next tile
+    }
+}
+
+}  // namespace constv

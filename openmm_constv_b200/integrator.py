@@ -54,6 +54,20 @@ class SlabSystem:
         self._masses: list[float] = []
         self._box = ((1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0))
         self._forces: list = []
+        self._constraints: list[tuple] = []
+
+    def addConstraint(self, particle1: int, particle2: int, distance: float) -> int:
+        self._constraints.append((int(particle1), int(particle2), float(distance)))
+        return len(self._constraints) - 1
+
+    def addConstraints(self, particle1, particle2, distance) -> None:
+        self._constraints.extend((int(a), int(b), float(d)) for a, b, d in zip(particle1, particle2, distance))
+
+    def getNumConstraints(self) -> int:
+        return len(self._constraints)
+
+    def getConstraintParameters(self, index: int):
+        return self._constraints[index]
 
     def addForce(self, force) -> int:
         self._forces.append(force)
@@ -226,6 +240,37 @@ class IntegrateConstVLangevinStepKernel:
         self.zmax = zmax
         self.seed = cfg.seed
         self.rebind()
+        self._configure_rigid_molecules(system)
+
+    def _configure_rigid_molecules(self, system: SlabSystem) -> None:
+        """The constraint hand-off (CudaConstVKernels.cpp:153): when EVERY constraint of the System belongs
+        to a rigid 3-site molecule (the reference's example: SPC/E water, constraints=AllBonds) the solver
+        runs inside the step kernel; otherwise the split path hands posDelta to the caller's solver."""
+        self.num_rigid_molecules = 0
+        self.fused_constraints = False
+        nc = system.getNumConstraints() if hasattr(system, "getNumConstraints") else 0
+        if nc == 0:
+            return
+        cons = [system.getConstraintParameters(i) for i in range(nc)]
+        p1 = np.ascontiguousarray([c[0] for c in cons], np.int32)
+        p2 = np.ascontiguousarray([c[1] for c in cons], np.int32)
+        dist = np.ascontiguousarray([c[2] for c in cons], np.float64)
+        atoms = np.zeros((max(nc // 3, 1), 3), np.int32)
+        params = np.zeros((max(nc // 3, 1), 2), np.float32)
+        found, other = C.c_int32(0), C.c_int32(0)
+        vp = C.c_void_p
+        try:
+            check(self._lib.constv_settle_find_clusters(system.getNumParticles(), nc, p1.ctypes.data_as(vp),
+                                                        p2.ctypes.data_as(vp), dist.ctypes.data_as(vp),
+                                                        atoms.ctypes.data_as(vp), params.ctypes.data_as(vp),
+                                                        C.byref(found), C.byref(other)))
+        except ConstVError as err:
+            _raise_openmm(err)
+        self.num_rigid_molecules = found.value
+        if other.value == 0 and found.value > 0:
+            check(self._lib.constv_settle_configure(self._slab, found.value, atoms.ctypes.data_as(vp),
+                                                    params.ctypes.data_as(vp)))
+            self.fused_constraints = True
 
     def rebind(self) -> None:
         ctx = self._ctx
@@ -245,7 +290,13 @@ class IntegrateConstVLangevinStepKernel:
             check(lib.constv_update_inverse_order(slab, st))
             context.atoms_were_reordered = False
         rnd, idx = context.prepare_random_numbers()
-        if context.apply_constraints is None:
+        if context.apply_constraints is None and getattr(self, "fused_constraints", False):
+            # part 1, the constraints (rigid 3-site molecules), part 2 and the image rewrite in one kernel
+            check(lib.constv_step_fused_settle(slab, rnd, idx, st))
+        elif context.apply_constraints is None:
+            if context.getSystem().getNumConstraints() > 0:
+                raise OpenMMException("the System has constraints the step kernel cannot solve itself: "
+                                      "give the context an apply_constraints callback")
             check(lib.constv_step_fused(slab, rnd, idx, st))
         else:  # CudaConstVKernels.cpp:146-166 with the constraint hand-off at :153
             check(lib.constv_step_part1(slab, rnd, idx, st))
@@ -276,6 +327,10 @@ class IntegrateConstVLangevinStepKernel:
 
     def set_step_count(self, count: int) -> None:
         check(self._lib.constv_set_step_count(self._slab, count))
+
+    def settle_positions(self) -> None:
+        """The solver alone on pos_delta (for an apply_constraints callback of the split path)."""
+        check(self._lib.constv_settle_positions(self._slab, self._ctx.stream_ptr()))
 
     def set_launch_shape(self, pairs_per_thread: int = 0, ctas_per_sm: int = 0) -> None:
         check(self._lib.constv_set_launch_shape(self._slab, pairs_per_thread, ctas_per_sm))

@@ -84,6 +84,33 @@ void CudaIntegrateConstVLangevinStepKernel::initialize(const System& system, con
     hasConstraints = system.getNumConstraints() > 0;
     slotsPermuted = false;
     bindArrays();
+
+    // The constraint hand-off (reference :153).  When every constraint belongs to a rigid 3-site molecule --
+    // the reference's example: SPC/E water with constraints=AllBonds -- the library solves them inside the
+    // step kernel (SETTLE, as OpenMM's own solver would) and nothing is handed over.
+    fusedConstraints = false;
+    numRigidMolecules = 0;
+    if (hasConstraints) {
+        const int numConstraints = system.getNumConstraints();
+        std::vector<int32_t> atom1(numConstraints), atom2(numConstraints);
+        std::vector<double> distance(numConstraints);
+        for (int i = 0; i < numConstraints; i++) {
+            int p1, p2;
+            system.getConstraintParameters(i, p1, p2, distance[i]);
+            atom1[i] = p1;
+            atom2[i] = p2;
+        }
+        std::vector<int32_t> clusterAtoms(numConstraints + 3);
+        std::vector<float> clusterParams(numConstraints + 2);
+        int32_t found = 0, other = 0;
+        check(constv_settle_find_clusters(system.getNumParticles(), numConstraints, atom1.data(), atom2.data(), distance.data(),
+                                          clusterAtoms.data(), clusterParams.data(), &found, &other));
+        numRigidMolecules = found;
+        if (found > 0 && other == 0 && std::getenv("CONSTV_NO_FUSED_CONSTRAINTS") == NULL) {
+            check(constv_settle_configure(slab, found, clusterAtoms.data(), clusterParams.data()));
+            fusedConstraints = true;
+        }
+    }
 }
 
 void CudaIntegrateConstVLangevinStepKernel::bindArrays() {
@@ -109,6 +136,9 @@ void CudaIntegrateConstVLangevinStepKernel::execute(ContextImpl& context, const 
     if (!hasConstraints) {
         // nothing to hand to the constraint solver: the whole step is one kernel
         check(constv_step_fused(slab, NULL, 0, stream));
+    } else if (fusedConstraints) {
+        // rigid 3-site molecules only: part 1, SETTLE, part 2 and the image rewrite in one kernel
+        check(constv_step_fused_settle(slab, NULL, 0, stream));
     } else {
         check(constv_step_part1(slab, NULL, 0, stream));
         integration.applyConstraints(integrator.getConstraintTolerance());

@@ -17,7 +17,8 @@ namespace OpenMM {
 class CudaIntegrateConstVLangevinStepKernel : public IntegrateConstVLangevinStepKernel {
 public:
     CudaIntegrateConstVLangevinStepKernel(std::string name, const Platform& platform, CudaContext& cu)
-        : IntegrateConstVLangevinStepKernel(name, platform), cu(cu), slab(NULL), zmax(0), hasConstraints(false), slotsPermuted(false) {
+        : IntegrateConstVLangevinStepKernel(name, platform), cu(cu), slab(NULL), zmax(0), hasConstraints(false),
+          fusedConstraints(false), numRigidMolecules(0), slotsPermuted(false) {
     }
     ~CudaIntegrateConstVLangevinStepKernel();
     void initialize(const System& system, const ConstVLangevinIntegrator& integrator);
@@ -26,6 +27,10 @@ public:
     /** The C-ABI handle (tests and tools). */
     constv_slab* getSlab() { return slab; }
     double getCellSize() const { return zmax; }
+    /** True when every constraint of the System is part of a rigid 3-site molecule: the constraints are then
+     *  solved inside the step kernel instead of being handed to integration.applyConstraints. */
+    bool getConstraintsAreFused() const { return fusedConstraints; }
+    int getNumRigidMolecules() const { return numRigidMolecules; }
 
 private:
     void bindArrays();
@@ -33,6 +38,8 @@ private:
     constv_slab* slab;
     double zmax;
     bool hasConstraints;
+    bool fusedConstraints;
+    int numRigidMolecules;
     bool slotsPermuted;  // true once OpenMM has re-sorted the atoms at least once
 };
 

@@ -279,6 +279,83 @@ static void testConstraintHandOff() {
 
 // getState(Energy) goes through computeKineticEnergy (CudaConstVKernels.cpp:175-177): the
 // half-step-shifted kinetic energy of the massive atoms.
+// Rigid 3-site water (the reference's example: constraints=AllBonds on SPC/E): every constraint is part of a
+// triangle, so the kernel solves them inside the step (SETTLE) and nothing is handed to applyConstraints --
+// the shim has no solver at all, yet the molecules stay rigid.
+static void testRigidWater() {
+    const int numMolecules = 150;
+    const double dOH = 0.1, dHH = 0.16330;
+    System system;
+    vector<double> masses;
+    for (int k = 0; k < numMolecules; k++) {
+        masses.push_back(15.9994);
+        masses.push_back(1.008);
+        masses.push_back(1.008);
+    }
+    addSlabParticles(system, masses);
+    const int numReal = 3 * numMolecules;
+    HarmonicWellForce* wells = new HarmonicWellForce();
+    vector<Vec3> positions(2 * numReal);
+    vector<double> charges(2 * numReal);
+    const double c = std::sqrt(dOH * dOH - 0.25 * dHH * dHH), h = 0.5 * dHH;
+    for (int k = 0; k < numMolecules; k++) {
+        const Vec3 o(0.35 * (k % 10), 0.35 * ((k / 10) % 10), 0.4 + 1.2 * ((k * 7) % 15) / 15.0);
+        // three different orientations of the same rigid triangle
+        const Vec3 u = k % 3 == 0 ? Vec3(1, 0, 0) : (k % 3 == 1 ? Vec3(0, 1, 0) : Vec3(0, 0, 1));
+        const Vec3 w = k % 3 == 0 ? Vec3(0, 1, 0) : (k % 3 == 1 ? Vec3(0, 0, 1) : Vec3(1, 0, 0));
+        positions[3 * k] = o;
+        positions[3 * k + 1] = o + u * c + w * h;
+        positions[3 * k + 2] = o + u * c - w * h;
+        charges[3 * k] = -0.8476;
+        charges[3 * k + 1] = charges[3 * k + 2] = 0.4238;
+        wells->addParticle(3 * k, o, 300.0);
+        system.addConstraint(3 * k, 3 * k + 1, dOH);
+        system.addConstraint(3 * k, 3 * k + 2, dOH);
+        system.addConstraint(3 * k + 1, 3 * k + 2, dHH);
+    }
+    for (int i = 0; i < numReal; i++) {
+        positions[i + numReal] = Vec3(positions[i][0], positions[i][1], -positions[i][2]);
+        charges[i + numReal] = -charges[i];
+    }
+    system.addForce(wells);
+    const double temp = 300.0;
+    ConstVLangevinIntegrator integrator(temp, 5.0, 0.002);
+    integrator.setRandomNumberSeed(11);
+    Platform& platform = Platform::getPlatformByName("CUDA");
+    Context context(system, integrator, platform, properties);
+    context.setPositions(positions);
+    context.setCharges(charges);
+    Kernel kernel = platform.createKernel(IntegrateConstVLangevinStepKernel::Name(), context.getImpl());
+    CudaContext& cu = cudaContextOf(context);
+
+    integrator.step(1000);
+    double ke = 0;
+    const int samples = 400;
+    for (int n = 0; n < samples; n++) {
+        integrator.step(5);
+        const State state = context.getState(State::Positions | State::Velocities);
+        const vector<Vec3>& p = state.getPositions();
+        const vector<Vec3>& v = state.getVelocities();
+        const double tol = precision == "single" ? 2e-5 : 2e-7;
+        for (int k = 0; k < numMolecules; k++) {
+            const Vec3 a = p[3 * k + 1] - p[3 * k], b = p[3 * k + 2] - p[3 * k], bc = p[3 * k + 2] - p[3 * k + 1];
+            CHECK_CLOSE(dOH, std::sqrt(a.dot(a)), tol);
+            CHECK_CLOSE(dOH, std::sqrt(b.dot(b)), tol);
+            CHECK_CLOSE(dHH, std::sqrt(bc.dot(bc)), tol);
+        }
+        for (int i = 0; i < numReal; i++) ke += 0.5 * masses[i] * v[i].dot(v[i]);
+    }
+    ke /= samples;
+    // a rigid triangle has 6 degrees of freedom; v = delta/dt lies on the constraint surface
+    const double expected = 0.5 * 6 * numMolecules * BOLTZ * temp;
+    CHECK_CLOSE(expected, ke, 0.05);
+    CHECK_EQ(0, cu.getIntegrationUtilities().constraintCalls);  // nothing was handed over
+    // every (charged) atom's image followed it
+    const vector<Vec3> p = context.getState(State::Positions).getPositions();
+    for (int i = 0; i < numReal; i++)
+        CHECK_CLOSE(mirroredZ(p[i][2], 2.0), p[i + numReal][2], precision == "single" ? 1e-6 : 1e-12);
+}
+
 static void testKineticEnergy() {
     System system;
     vector<Vec3> positions;
@@ -352,6 +429,7 @@ int main(int argc, char* argv[]) {
         testRandomSeed();
         testReorderedAtoms();
         testConstraintHandOff();
+        testRigidWater();
         testKineticEnergy();
         testValidation();
     } catch (const std::exception& e) {

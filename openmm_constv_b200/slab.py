@@ -227,6 +227,59 @@ def make_drude_slab(num_real: int, precision: str = "single", num_cells: int = 2
     return s, normal, np.ascontiguousarray(pairs)
 
 
+D_OH = 0.1                                                   # nm, SPC/E (spce.xml)
+ANGLE_HOH = np.deg2rad(109.47)
+D_HH = float(2.0 * D_OH * np.sin(0.5 * ANGLE_HOH))           # 0.16330 nm
+
+
+def make_water_slab(num_real: int, precision: str = "single", num_cells: int = 2, seed: int = 12345, **kw):
+    """``make_slab`` whose water atoms form RIGID SPC/E molecules (O-H 0.1 nm, H-O-H 109.47 degrees) in
+    random orientations: the system of the reference's example, ``constraints=AllBonds`` on 3-site water
+    (example/nacl_1m_spce/nacl_constv.py:56), whose constraint hand-off is SETTLE.
+
+    Returns ``(slab, cluster_atoms, cluster_params, constraints)``: ``cluster_atoms`` (n, 3) int32 =
+    (O, H1, H2) original indices, ``cluster_params`` (n, 2) float32 = (d_OH, d_HH), and ``constraints`` =
+    (p1, p2, distance) arrays as System.getConstraintParameters would list them (O-H1, O-H2, H1-H2).
+    """
+    s = make_slab(num_real, precision, num_cells=num_cells, seed=seed, **kw)
+    rng = np.random.Generator(np.random.Philox(seed + 77))
+    R = s.num_real
+    n_ion, n_water = s.meta["n_ion"], s.meta["n_water"]
+    n_mol = n_water // 3
+    real = REAL[precision]
+    oxy = n_ion + 3 * np.arange(n_mol)
+    p64 = s.posq[:, :3].astype(np.float64)
+    if s.corr is not None:
+        p64 += s.corr[:, :3]
+    u = rng.standard_normal((n_mol, 3))
+    u /= np.linalg.norm(u, axis=1)[:, None]
+    t = rng.standard_normal((n_mol, 3))
+    w = t - np.einsum("nk,nk->n", t, u)[:, None] * u
+    w /= np.linalg.norm(w, axis=1)[:, None]
+    c, sn = np.cos(0.5 * ANGLE_HOH), np.sin(0.5 * ANGLE_HOH)
+    p64[oxy + 1] = p64[oxy] + D_OH * (c * u + sn * w)
+    p64[oxy + 2] = p64[oxy] + D_OH * (c * u - sn * w)
+    charge = s.posq[:R, 3].astype(np.float64)
+    for i in range(1, num_cells):
+        img = slice(i * R, (i + 1) * R)
+        zi = p64[:R, 2].copy()
+        for j in range(1, i + 1):
+            zi = -zi + 2.0 * j * s.zmax if j > 1 else -zi
+        p64[img, 0], p64[img, 1] = p64[:R, 0], p64[:R, 1]
+        p64[img, 2] = np.where(charge != 0, zi, zi + 0.001)
+    s.posq[:, :3] = p64.astype(real)
+    if s.corr is not None:
+        s.corr[:, :3] = (p64 - s.posq[:, :3].astype(np.float64)).astype(real)
+    atoms = np.stack([oxy, oxy + 1, oxy + 2], axis=1).astype(np.int32)
+    params = np.tile(np.asarray([D_OH, D_HH], np.float32), (n_mol, 1))
+    p1 = np.concatenate([oxy, oxy, oxy + 1]).astype(np.int32)
+    p2 = np.concatenate([oxy + 1, oxy + 2, oxy + 2]).astype(np.int32)
+    dist = np.concatenate([np.full(n_mol, float(np.float32(D_OH))), np.full(n_mol, float(np.float32(D_OH))),
+                           np.full(n_mol, float(np.float32(D_HH)))])
+    s.meta.update(n_molecules=int(n_mol))
+    return s, np.ascontiguousarray(atoms), np.ascontiguousarray(params), (p1, p2, dist)
+
+
 def slice_slab(slab: Slab, lo: int, hi: int) -> Slab:
     """The shard holding real atoms [lo, hi) and their images (multi-GPU range partition:
     every image lives with its real partner)."""
@@ -258,8 +311,11 @@ def new_forces(slab: Slab, step_index: int, force_sigma: float = 1000.0) -> np.n
     return force
 
 
-def algorithmic_bytes_per_step(slab: Slab, zero_images: bool = True) -> int:
+def algorithmic_bytes_per_step(slab: Slab, zero_images: bool = True, rigid_molecules: int = 0) -> int:
     """Bytes the fused step must move for this slab (DESIGN.md "bytes per pair").
+
+    ``rigid_molecules`` > 0 (the step that solves the constraints of rigid 3-site molecules itself) adds
+    the work-item list, 8 B per ordinary atom or molecule, and the molecule list, 16 + 8 B per molecule.
 
     single precision, numCells = 2, per real/image pair:
       always read   velm 16 + posq 16
@@ -281,4 +337,6 @@ def algorithmic_bytes_per_step(slab: Slab, zero_images: bool = True) -> int:
     total += charged * n_img * (r + pos_b)
     if zero_images:
         total += slab.num_real * n_img * (vel_b + 24)
+    if rigid_molecules:  # work-item list: 8 B per ordinary atom or molecule; molecule list: 16 + 8 B per molecule
+        total += 8 * (slab.num_real - 2 * rigid_molecules) + 24 * rigid_molecules
     return int(total)

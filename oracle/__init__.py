@@ -42,7 +42,8 @@ def build(force: bool = False) -> str:
     if force or any(
         not os.path.exists(t) or any(
             os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(t)
-            for f in ("constv_oracle.c", "constv_oracle_impl.h", "constv_oracle_drude_impl.h", "Makefile"))
+            for f in ("constv_oracle.c", "constv_oracle_impl.h", "constv_oracle_drude_impl.h",
+                      "constv_oracle_settle_impl.h", "Makefile"))
         for t in (_LIB_PATH, _LIB_PATH_NOFMA)
     ):
         subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True, capture_output=True)
@@ -253,6 +254,33 @@ def drude_step(precision, num_atoms, num_cells, zshift_per_cell, posq, posq_corr
        C.c_int(len(normal)), _p(normal, np.int32), C.c_int(len(pairs)), _p(pairs, np.int32), _p(s),
        _mixed_scalar(precision, step_size), _p(random4, np.float32), C.c_uint(random_index),
        _p(inv_order, np.int32), C.c_int(zero_velm), C.c_int(zero_force))
+
+
+# ---- rigid 3-site molecules: the constraint hand-off (SETTLE, constv_oracle_settle_impl.h) --------------
+
+def settle_positions(precision, posq, posq_corr, pos_delta, velm, cluster_atoms, cluster_params):
+    """SETTLE on posDelta for every (apex, b, c) molecule; params = (d(apex-b), d(b-c)) float32."""
+    r, m = REAL[precision], MIXED[precision]
+    atoms = np.ascontiguousarray(cluster_atoms, np.int32).reshape(-1, 3)
+    prm = np.ascontiguousarray(cluster_params, np.float32).reshape(-1, 2)
+    fn = getattr(lib(), "oracle_settle_positions_" + _SUFFIX[precision])
+    fn(C.c_int(len(atoms)), _p(posq, r), _p(posq_corr, r) if posq_corr is not None else None, _p(pos_delta, m),
+       _p(velm, m), _p(atoms), _p(prm))
+
+
+def settle_step(precision, num_atoms, num_cells, zshift_per_cell, posq, posq_corr, velm, force, pos_delta, prm,
+                step_size, random4, random_index, inv_order, cluster_atoms, cluster_params, zero_velm=True,
+                zero_force=True):
+    """part 1 -> SETTLE -> part 2 -> image rewrite -> image zeroing."""
+    r, m = REAL[precision], MIXED[precision]
+    atoms = np.ascontiguousarray(cluster_atoms, np.int32).reshape(-1, 3)
+    cp = np.ascontiguousarray(cluster_params, np.float32).reshape(-1, 2)
+    prm = np.ascontiguousarray(prm, m)
+    fn = getattr(lib(), "oracle_settle_step_" + _SUFFIX[precision])
+    fn(C.c_int(num_atoms), C.c_int(velm.shape[0]), C.c_int(num_cells), C.c_double(zshift_per_cell), _p(posq, r),
+       _p(posq_corr, r) if posq_corr is not None else None, _p(velm, m), _p(force, np.int64), _p(pos_delta, m),
+       _p(prm), _mixed_scalar(precision, step_size), _p(random4, np.float32), C.c_uint(random_index),
+       _p(inv_order, np.int32), C.c_int(zero_velm), C.c_int(zero_force), C.c_int(len(atoms)), _p(atoms), _p(cp))
 
 
 def philox4x32_10(counter, key):

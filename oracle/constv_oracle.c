@@ -14,6 +14,9 @@
  *   platforms/cuda/src/CudaConstVKernels.cpp:76-96        system validation, zmax derivation
  *   platforms/cuda/src/CudaConstVKernels.cpp:139-172      per-step launch sequence
  *   platforms/reference/src/ReferenceConstVKernels.cpp:70-98  shifted kinetic energy formula
+ *   platforms/cuda/src/kernels/constVDrudeLangevin.cu         the Drude integrator (constv_oracle_drude_impl.h)
+ *   platforms/cuda/src/CudaConstVKernels.cpp:153              the constraint hand-off for rigid 3-site molecules
+ *                                                             (SETTLE, constv_oracle_settle_impl.h; lives in OpenMM)
  *
  * PARITY STATUS.  The reference ships no CPU implementation of this path, no golden vectors and
  * no test that touches an image particle, and neither it nor OpenMM can
@@ -47,6 +50,7 @@
 #define MIXED_IS_DOUBLE 0
 #include "constv_oracle_impl.h"
 #include "constv_oracle_drude_impl.h"
+#include "constv_oracle_settle_impl.h"
 #undef REAL
 #undef MIXED
 #undef SUFFIX
@@ -60,6 +64,7 @@
 #define MIXED_IS_DOUBLE 1
 #include "constv_oracle_impl.h"
 #include "constv_oracle_drude_impl.h"
+#include "constv_oracle_settle_impl.h"
 #undef REAL
 #undef MIXED
 #undef SUFFIX
@@ -73,6 +78,7 @@
 #define MIXED_IS_DOUBLE 1
 #include "constv_oracle_impl.h"
 #include "constv_oracle_drude_impl.h"
+#include "constv_oracle_settle_impl.h"
 #undef REAL
 #undef MIXED
 #undef SUFFIX

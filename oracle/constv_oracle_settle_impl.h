@@ -1,0 +1,194 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- included by constv_oracle.c once per precision mode (REAL, MIXED,
+ * SUFFIX, MIXED_POS, MIXED_IS_DOUBLE as for constv_oracle_impl.h).
+ *
+ * The constraint hand-off of the reference, /root/reference/platforms/cuda/src/CudaConstVKernels.cpp:153
+ * (`integration.applyConstraints(tol)` between part 1 and part 2), for the systems the reference's
+ * example runs: SPC/E water with constraints=AllBonds (example/nacl_1m_spce/nacl_constv.py:56) is
+ * three distance constraints per rigid 3-site molecule, which OpenMM's CUDA platform solves
+ * analytically with SETTLE (Miyamoto & Kollman, J. Comput. Chem. 13, 952 (1992)).
+ *
+ * PARITY UNPINNED.  The solver lives in OpenMM (un-vendored, unpinned, absent here: SURVEY.md 8c), not
+ * in the reference tree.  What is restated below is the published algorithm in the formulation OpenMM's
+ * CUDA kernel `applySettleToPositions` uses [recalled]: positions relative to the apex atom's old
+ * position, the new positions given as displacements (posDelta), masses from velm.w, parameters
+ * (d(apex-b) = d(apex-c), d(b-c)) as floats.  It is validated against an INDEPENDENT solution of the same
+ * constraint problem (iterative SHAKE in float64, oracle/settle_numpy.py) and by its invariants
+ * (distances restored, centre of mass and the molecule's angular momentum direction unchanged) in
+ * tests/test_oracle_settle.py -- not against OpenMM.
+ *
+ * Arithmetic: every operation rounded separately (no fused multiply-add anywhere in the solver), square
+ * roots and divisions IEEE-correct; the CUDA kernel (compiled -fmad=false) spells the same sequence.
+ */
+#define CAT_(a, b) a##_##b
+#define CAT(a, b) CAT_(a, b)
+#define FN(name) CAT(name, SUFFIX)
+
+#if MIXED_IS_DOUBLE
+#define M_SQRT(a) sqrt(a)
+#else
+#define M_SQRT(a) sqrtf(a)
+#endif
+
+/*
+ * One molecule.  pos0/pos1/pos2 = old (constrained) positions as `mixed`; d0/d1/d2 = displacements to the
+ * unconstrained new positions, overwritten with the constrained displacements; m = masses; distAB =
+ * apex-b = apex-c distance, distBC = b-c distance.
+ */
+static inline void FN(settle_molecule)(const MIXED pos0[3], const MIXED pos1[3], const MIXED pos2[3], MIXED d0[3],
+                                       MIXED d1[3], MIXED d2[3], MIXED m0, MIXED m1, MIXED m2, float distAB,
+                                       float distBC) {
+    /* old bond vectors, from the apex */
+    const MIXED xb0 = pos1[0] - pos0[0], yb0 = pos1[1] - pos0[1], zb0 = pos1[2] - pos0[2];
+    const MIXED xc0 = pos2[0] - pos0[0], yc0 = pos2[1] - pos0[1], zc0 = pos2[2] - pos0[2];
+
+    const MIXED invTotalMass = (MIXED) 1 / (m0 + m1 + m2);
+    const MIXED xcom = (d0[0] * m0 + (xb0 + d1[0]) * m1 + (xc0 + d2[0]) * m2) * invTotalMass;
+    const MIXED ycom = (d0[1] * m0 + (yb0 + d1[1]) * m1 + (yc0 + d2[1]) * m2) * invTotalMass;
+    const MIXED zcom = (d0[2] * m0 + (zb0 + d1[2]) * m1 + (zc0 + d2[2]) * m2) * invTotalMass;
+
+    /* unconstrained new positions relative to the new centre of mass */
+    const MIXED xa1 = d0[0] - xcom, ya1 = d0[1] - ycom, za1 = d0[2] - zcom;
+    const MIXED xb1 = xb0 + d1[0] - xcom, yb1 = yb0 + d1[1] - ycom, zb1 = zb0 + d1[2] - zcom;
+    const MIXED xc1 = xc0 + d2[0] - xcom, yc1 = yc0 + d2[1] - ycom, zc1 = zc0 + d2[2] - zcom;
+
+    /* orthonormal frame: Z = normal of the old molecular plane, X = a1 x Z, Y = Z x X */
+    const MIXED xaksZd = yb0 * zc0 - zb0 * yc0;
+    const MIXED yaksZd = zb0 * xc0 - xb0 * zc0;
+    const MIXED zaksZd = xb0 * yc0 - yb0 * xc0;
+    const MIXED xaksXd = ya1 * zaksZd - za1 * yaksZd;
+    const MIXED yaksXd = za1 * xaksZd - xa1 * zaksZd;
+    const MIXED zaksXd = xa1 * yaksZd - ya1 * xaksZd;
+    const MIXED xaksYd = yaksZd * zaksXd - zaksZd * yaksXd;
+    const MIXED yaksYd = zaksZd * xaksXd - xaksZd * zaksXd;
+    const MIXED zaksYd = xaksZd * yaksXd - yaksZd * xaksXd;
+
+    const MIXED axlng = M_SQRT(xaksXd * xaksXd + yaksXd * yaksXd + zaksXd * zaksXd);
+    const MIXED aylng = M_SQRT(xaksYd * xaksYd + yaksYd * yaksYd + zaksYd * zaksYd);
+    const MIXED azlng = M_SQRT(xaksZd * xaksZd + yaksZd * yaksZd + zaksZd * zaksZd);
+    const MIXED trns11 = xaksXd / axlng, trns21 = yaksXd / axlng, trns31 = zaksXd / axlng;
+    const MIXED trns12 = xaksYd / aylng, trns22 = yaksYd / aylng, trns32 = zaksYd / aylng;
+    const MIXED trns13 = xaksZd / azlng, trns23 = yaksZd / azlng, trns33 = zaksZd / azlng;
+
+    const MIXED xb0d = trns11 * xb0 + trns21 * yb0 + trns31 * zb0;
+    const MIXED yb0d = trns12 * xb0 + trns22 * yb0 + trns32 * zb0;
+    const MIXED xc0d = trns11 * xc0 + trns21 * yc0 + trns31 * zc0;
+    const MIXED yc0d = trns12 * xc0 + trns22 * yc0 + trns32 * zc0;
+    const MIXED za1d = trns13 * xa1 + trns23 * ya1 + trns33 * za1;
+    const MIXED xb1d = trns11 * xb1 + trns21 * yb1 + trns31 * zb1;
+    const MIXED yb1d = trns12 * xb1 + trns22 * yb1 + trns32 * zb1;
+    const MIXED zb1d = trns13 * xb1 + trns23 * yb1 + trns33 * zb1;
+    const MIXED xc1d = trns11 * xc1 + trns21 * yc1 + trns31 * zc1;
+    const MIXED yc1d = trns12 * xc1 + trns22 * yc1 + trns32 * zc1;
+    const MIXED zc1d = trns13 * xc1 + trns23 * yc1 + trns33 * zc1;
+
+    /* step 2: the canonical triangle (apex at +ra on Y, b and c at -rb, x = -+rc), tilted by phi and psi */
+    const float rc = 0.5f * distBC;
+    MIXED rb = M_SQRT((MIXED) (distAB * distAB - rc * rc));
+    const MIXED ra = rb * (m1 + m2) * invTotalMass;
+    rb = rb - ra;
+    const MIXED sinphi = za1d / ra;
+    const MIXED cosphi = M_SQRT((MIXED) 1 - sinphi * sinphi);
+    const MIXED sinpsi = (zb1d - zc1d) / ((MIXED) 2 * rc * cosphi);
+    const MIXED cospsi = M_SQRT((MIXED) 1 - sinpsi * sinpsi);
+
+    const MIXED ya2d = ra * cosphi;
+    MIXED xb2d = -(rc * cospsi);
+    const MIXED yb2d = -(rb * cosphi) - rc * sinpsi * sinphi;
+    const MIXED yc2d = -(rb * cosphi) + rc * sinpsi * sinphi;
+    const MIXED xb2d2 = xb2d * xb2d;
+    const MIXED hh2 = (MIXED) 4 * xb2d2 + (yb2d - yc2d) * (yb2d - yc2d) + (zb1d - zc1d) * (zb1d - zc1d);
+    const MIXED deltx = (MIXED) 2 * xb2d + M_SQRT((MIXED) 4 * xb2d2 - hh2 + (MIXED) (distBC * distBC));
+    xb2d = xb2d - deltx * (MIXED) 0.5;
+
+    /* step 3: the in-plane rotation theta that conserves the angular momentum about Z */
+    const MIXED alpha = xb2d * (xb0d - xc0d) + yb0d * yb2d + yc0d * yc2d;
+    const MIXED beta = xb2d * (yc0d - yb0d) + xb0d * yb2d + xc0d * yc2d;
+    const MIXED gamma = xb0d * yb1d - xb1d * yb0d + xc0d * yc1d - xc1d * yc0d;
+    const MIXED al2be2 = alpha * alpha + beta * beta;
+    const MIXED sintheta = (alpha * gamma - beta * M_SQRT(al2be2 - gamma * gamma)) / al2be2;
+
+    /* step 4 */
+    const MIXED costheta = M_SQRT((MIXED) 1 - sintheta * sintheta);
+    const MIXED xa3d = -(ya2d * sintheta);
+    const MIXED ya3d = ya2d * costheta;
+    const MIXED za3d = za1d;
+    const MIXED xb3d = xb2d * costheta - yb2d * sintheta;
+    const MIXED yb3d = xb2d * sintheta + yb2d * costheta;
+    const MIXED zb3d = zb1d;
+    const MIXED xc3d = -(xb2d * costheta) - yc2d * sintheta;
+    const MIXED yc3d = -(xb2d * sintheta) + yc2d * costheta;
+    const MIXED zc3d = zc1d;
+
+    /* step 5: back to the laboratory frame */
+    const MIXED xa3 = trns11 * xa3d + trns12 * ya3d + trns13 * za3d;
+    const MIXED ya3 = trns21 * xa3d + trns22 * ya3d + trns23 * za3d;
+    const MIXED za3 = trns31 * xa3d + trns32 * ya3d + trns33 * za3d;
+    const MIXED xb3 = trns11 * xb3d + trns12 * yb3d + trns13 * zb3d;
+    const MIXED yb3 = trns21 * xb3d + trns22 * yb3d + trns23 * zb3d;
+    const MIXED zb3 = trns31 * xb3d + trns32 * yb3d + trns33 * zb3d;
+    const MIXED xc3 = trns11 * xc3d + trns12 * yc3d + trns13 * zc3d;
+    const MIXED yc3 = trns21 * xc3d + trns22 * yc3d + trns23 * zc3d;
+    const MIXED zc3 = trns31 * xc3d + trns32 * yc3d + trns33 * zc3d;
+
+    d0[0] = xcom + xa3;
+    d0[1] = ycom + ya3;
+    d0[2] = zcom + za3;
+    d1[0] = xcom + xb3 - xb0;
+    d1[1] = ycom + yb3 - yb0;
+    d1[2] = zcom + zb3 - zb0;
+    d2[0] = xcom + xc3 - xc0;
+    d2[1] = ycom + yc3 - yc0;
+    d2[2] = zcom + zc3 - zc0;
+}
+
+static inline void FN(settle_load_pos)(const REAL* posq, const REAL* corr, size_t a, MIXED out[3]) {
+#if MIXED_POS
+    for (int k = 0; k < 3; k++) out[k] = (MIXED) posq[4 * a + k] + (MIXED) corr[4 * a + k];
+#else
+    (void) corr;
+    for (int k = 0; k < 3; k++) out[k] = (MIXED) posq[4 * a + k];
+#endif
+}
+
+/*
+ * The constraint step on posDelta for every molecule: clusterAtoms = (apex, b, c) slots, clusterParams =
+ * (d(apex-b), d(b-c)) floats.  posq/posqCorrection hold the positions of the previous step.
+ */
+void FN(oracle_settle_positions)(int numClusters, const REAL* posq, const REAL* posqCorrection, MIXED* posDelta,
+                                 const MIXED* velm, const int* clusterAtoms, const float* clusterParams) {
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < numClusters; i++) {
+        const size_t a0 = (size_t) clusterAtoms[3 * i], a1 = (size_t) clusterAtoms[3 * i + 1], a2 = (size_t) clusterAtoms[3 * i + 2];
+        MIXED p0[3], p1[3], p2[3];
+        FN(settle_load_pos)(posq, posqCorrection, a0, p0);
+        FN(settle_load_pos)(posq, posqCorrection, a1, p1);
+        FN(settle_load_pos)(posq, posqCorrection, a2, p2);
+        const MIXED m0 = (MIXED) 1 / velm[4 * a0 + 3], m1 = (MIXED) 1 / velm[4 * a1 + 3], m2 = (MIXED) 1 / velm[4 * a2 + 3];
+        FN(settle_molecule)(p0, p1, p2, posDelta + 4 * a0, posDelta + 4 * a1, posDelta + 4 * a2, m0, m1, m2,
+                            clusterParams[2 * i], clusterParams[2 * i + 1]);
+    }
+}
+
+/*
+ * One whole step of a system whose constraints are all rigid 3-site molecules, in the reference's launch
+ * order (CudaConstVKernels.cpp:146-166): part 1 -> constraints (SETTLE on posDelta) -> part 2 -> image
+ * rewrite; then the explicit image zeroing of the B200 path.
+ */
+void FN(oracle_settle_step)(int numAtoms, int paddedNumAtoms, int numCells, double zshiftPerCell, REAL* posq,
+                            REAL* posqCorrection, MIXED* velm, long long* force, MIXED* posDelta, const MIXED* params,
+                            MIXED stepSize, const float* random4, unsigned int randomIndex, const int* invAtomOrder,
+                            int zeroVelm, int zeroForce, int numClusters, const int* clusterAtoms,
+                            const float* clusterParams) {
+    const int numRealAtoms = numAtoms / numCells;
+    FN(oracle_part1)(numAtoms, paddedNumAtoms, velm, force, posDelta, params, stepSize, random4, randomIndex);
+    FN(oracle_settle_positions)(numClusters, posq, posqCorrection, posDelta, velm, clusterAtoms, clusterParams);
+    FN(oracle_part2)(numAtoms, posq, posqCorrection, posDelta, velm, stepSize);
+    FN(oracle_mirror)(numRealAtoms, numCells, zshiftPerCell, posq, posqCorrection, invAtomOrder);
+    FN(oracle_zero_images)(numAtoms, numRealAtoms, paddedNumAtoms, velm, force, invAtomOrder, zeroVelm, zeroForce);
+}
+
+#undef M_SQRT
+#undef FN
+#undef CAT
+#undef CAT_

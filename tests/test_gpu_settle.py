@@ -1,0 +1,227 @@
+"""Parity of the rigid-molecule step (constv_step_fused_settle / constv_settle_positions) against the CPU
+oracle (oracle/constv_oracle_settle_impl.h), through the C ABI.  The solver is OpenMM's, not the reference's
+(CudaConstVKernels.cpp:153 hands posDelta to integration.applyConstraints): PARITY UNPINNED against OpenMM;
+the oracle is pinned on converged SHAKE and on the algorithm's invariants (tests/test_oracle_settle.py).
+Here: the CUDA kernels reproduce the oracle BIT FOR BIT -- fused step, split path, reordered slots, Philox
+noise, three precision models -- and molecules stay rigid over a trajectory."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from openmm_constv_b200 import slab as slabmod
+from tests import helpers as H
+from tests.test_gpu_parity import assert_slab_bits_equal, download, gpu  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+T, GAMMA, DT = 300.0, 1.0, 0.002
+
+
+def make_water_context(gpu, s, constraints, seed=77, flags=None, pool=None, **kw):
+    from openmm_constv_b200 import _capi
+    import torch
+    sysm = gpu.SlabSystem()
+    sysm.addParticles(s.masses)
+    sysm.setDefaultPeriodicBoxVectors((s.box[0], 0, 0), (0, s.box[1], 0), (0, 0, s.num_cells * s.zmax))
+    sysm.addConstraints(*constraints)
+    it = gpu.ConstVLangevinIntegrator(T, GAMMA, DT, s.num_cells)
+    it.setRandomNumberSeed(seed)
+    ctx = gpu.SlabContext(sysm, it, precision=s.precision, flags=_capi.FLAGS_DEFAULT if flags is None else flags,
+                          random_pool=None if pool is None else torch.as_tensor(pool).cuda(),
+                          global_atom_offset=s.global_atom_offset, padded=s.padded, **kw)
+    ctx.load_slab(s)
+    return ctx, it
+
+
+def oracle_settle_step(oracle, s, atoms, params, xi, random_index=0, inv=None):
+    prm, dt = H.oracle_params_for(oracle, s.precision, T, GAMMA, DT)
+    delta = np.zeros((s.padded, 4), H.MIXED[s.precision])
+    oracle.settle_step(s.precision, s.num_atoms, s.num_cells, s.zmax, s.posq, s.corr, s.velm, s.force.reshape(-1), delta, prm,
+                       dt, xi, random_index, H.identity_order(s.padded) if inv is None else inv, atoms, params)
+    return delta
+
+
+def bond_errors(s, atoms, params):
+    p = s.posq[:, :3].astype(np.float64)
+    if s.corr is not None:
+        p = p + s.corr[:, :3]
+    out = []
+    for (i, j, d) in ((0, 1, params[:, 0]), (0, 2, params[:, 0]), (1, 2, params[:, 1])):
+        out.append(np.max(np.abs(np.linalg.norm(p[atoms[:, i]] - p[atoms[:, j]], axis=1) / d - 1)))
+    return max(out)
+
+
+@pytest.mark.parametrize("precision", slabmod.PRECISIONS)
+@pytest.mark.parametrize("num_cells", [2, 4])
+@pytest.mark.parametrize("num_real", [37, 6007])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_fused_settle_step_bit_exact(gpu, oracle, precision, num_cells, num_real, variant):
+    """variant 0 = the kernel staged through shared memory (tiles of 128 work items, coalesced both ways),
+    variant 1 = the gather kernel (a thread reads its three records itself)."""
+    import torch
+    s0, atoms, params, cons = slabmod.make_water_slab(num_real, precision, num_cells=num_cells, seed=31)
+    nsteps = 4
+    pool = np.random.default_rng(2).standard_normal((nsteps * s0.padded, 4)).astype(np.float32)
+    ctx, it = make_water_context(gpu, s0, cons, pool=pool)
+    it._kernel.set_kernel_variant(variant)
+    assert it._kernel.fused_constraints and it._kernel.num_rigid_molecules == len(atoms)
+    ref = s0.copy()
+    launches = __import__("openmm_constv_b200")._capi.launch_count()
+    for k in range(nsteps):
+        f = slabmod.new_forces(s0, k)
+        ctx.force.copy_(torch.from_numpy(f))
+        ref.force[:] = f
+        it.step(1)
+        oracle_settle_step(oracle, ref, atoms, params, pool, random_index=k * s0.padded)
+        assert_slab_bits_equal(download(ctx, s0), ref)
+    assert __import__("openmm_constv_b200")._capi.launch_count() - launches == nsteps  # ONE kernel per step
+    assert it._kernel.get_step_count() == nsteps
+    assert bond_errors(ref, atoms, params) < (5e-6 if precision == "single" else 2e-7)
+    ctx.close()
+
+
+@pytest.mark.parametrize("precision", slabmod.PRECISIONS)
+def test_split_path_with_the_library_solver_equals_fused(gpu, oracle, precision):
+    """part 1 | constv_settle_positions on pos_delta | part 2 + image rewrite: three launches, same bits."""
+    s0, atoms, params, cons = slabmod.make_water_slab(3001, precision, num_cells=2, seed=32)
+    pool = np.random.default_rng(3).standard_normal((s0.padded, 4)).astype(np.float32)
+    seen = {}
+
+    def constraints(ctx, tol):
+        seen["before"] = ctx.pos_delta.cpu().numpy()
+        ctx.getIntegrator()._kernel.settle_positions()
+        seen["after"] = ctx.pos_delta.cpu().numpy()
+
+    ctx, it = make_water_context(gpu, s0, cons, pool=pool, apply_constraints=constraints)
+    it.step(1)
+    ref = s0.copy()
+    delta = oracle_settle_step(oracle, ref, atoms, params, pool)
+    assert_slab_bits_equal(download(ctx, s0), ref)
+    massive = s0.velm[:, 3] != 0
+    H.assert_bits_equal(seen["after"][massive], delta[massive], "constrained posDelta")
+    assert not np.array_equal(seen["before"][atoms.reshape(-1)], seen["after"][atoms.reshape(-1)])
+    ctx.close()
+
+
+@pytest.mark.parametrize("precision", slabmod.PRECISIONS)
+def test_fused_settle_scattered_molecules(gpu, oracle, precision):
+    """Molecules whose atoms are NOT laid out (apex, apex+1, apex+2) -- here neighbouring molecules trade the
+    slots of their second hydrogen -- take the item-list path of the kernel (two dependent gathers) instead of
+    the arithmetic runs; same bits."""
+    import torch
+    s0, atoms, params, _ = slabmod.make_water_slab(4001, precision, num_cells=2, seed=36)
+    R, n = s0.num_real, len(atoms) // 2 * 2
+    a_h2, b_h2 = atoms[0:n:2, 2].copy(), atoms[1:n:2, 2].copy()
+    for cell in range(s0.num_cells):  # trade the records (and those of their images)
+        x, y = a_h2 + cell * R, b_h2 + cell * R
+        for arr in (s0.posq, s0.velm) + ((s0.corr,) if s0.corr is not None else ()):
+            arr[x], arr[y] = arr[y].copy(), arr[x].copy()
+        s0.force[:, x], s0.force[:, y] = s0.force[:, y].copy(), s0.force[:, x].copy()
+    atoms = atoms.copy()
+    atoms[0:n:2, 2], atoms[1:n:2, 2] = b_h2, a_h2
+    p1 = np.concatenate([atoms[:, 0], atoms[:, 0], atoms[:, 1]])
+    p2 = np.concatenate([atoms[:, 1], atoms[:, 2], atoms[:, 2]])
+    dist = np.concatenate([params[:, 0], params[:, 0], params[:, 1]]).astype(np.float64)
+    # (apex, b, c) as the detection rule orders them (b < c): SETTLE is not bitwise symmetric in b <-> c
+    from oracle import settle_numpy
+    atoms, params, other = settle_numpy.find_settle_clusters(s0.num_atoms, p1, p2, dist)
+    assert other == 0 and np.any(atoms[:, 2] != atoms[:, 0] + 2)
+    pool = np.random.default_rng(9).standard_normal((3 * s0.padded, 4)).astype(np.float32)
+    ctx, it = make_water_context(gpu, s0, (p1, p2, dist), pool=pool)
+    assert it._kernel.fused_constraints and it._kernel.num_rigid_molecules == len(atoms)
+    ref = s0.copy()
+    for k in range(3):
+        it.step(1)
+        oracle_settle_step(oracle, ref, atoms, params, pool, random_index=k * s0.padded)
+        assert_slab_bits_equal(download(ctx, s0), ref)
+    assert bond_errors(ref, atoms, params) < (5e-6 if precision == "single" else 2e-7)
+    ctx.close()
+
+
+def molecule_preserving_permutation(s, rng):
+    R, N = s.num_real, s.num_atoms
+    n_ion, n_mol = s.meta["n_ion"], s.meta["n_molecules"]
+    perm = np.arange(N, dtype=np.int32)
+    order = rng.permutation(n_mol)
+    for k in range(3):
+        perm[n_ion + k: n_ion + 3 * n_mol: 3] = n_ion + 3 * order + k
+    perm[R:N] = R + rng.permutation(N - R)
+    return perm
+
+
+@pytest.mark.parametrize("precision", slabmod.PRECISIONS)
+def test_fused_settle_reordered_slots(gpu, oracle, precision):
+    """OpenMM swaps whole identical molecules: slots keep their roles, images move freely."""
+    s0, atoms, params, cons = slabmod.make_water_slab(2501, precision, num_cells=2, seed=33)
+    perm = molecule_preserving_permutation(s0, np.random.default_rng(6))
+    sp, atom_index = H.permute_slab(s0, perm)
+    inv = np.empty_like(atom_index)
+    inv[atom_index] = np.arange(len(atom_index), dtype=np.int32)
+    pool = np.random.default_rng(4).standard_normal((2 * s0.padded, 4)).astype(np.float32)
+    ctx, it = make_water_context(gpu, sp, cons, pool=pool)
+    ctx.set_atom_order(perm)
+    ref = sp.copy()
+    for k in range(2):
+        it.step(1)
+        oracle_settle_step(oracle, ref, atoms, params, pool, random_index=k * s0.padded, inv=inv)
+        assert_slab_bits_equal(download(ctx, sp), ref)
+    ctx.close()
+
+
+@pytest.mark.parametrize("precision", ["single", "mixed"])
+def test_fused_settle_philox_and_rigid_trajectory(gpu, oracle, precision):
+    import torch
+    from openmm_constv_b200._capi import check
+    s0, atoms, params, cons = slabmod.make_water_slab(20011, precision, seed=34)
+    ctx, it = make_water_context(gpu, s0, cons, seed=4321)
+    lib, slab = it._kernel._lib, it._kernel.handle
+    g = torch.zeros((s0.padded, 4), dtype=torch.float32, device="cuda")
+    check(lib.constv_generate_noise(slab, 0, g.data_ptr(), ctx.stream_ptr()))
+    it.step(1)
+    ref = s0.copy()
+    oracle_settle_step(oracle, ref, atoms, params, g.cpu().numpy())
+    assert_slab_bits_equal(download(ctx, s0), ref)
+    # 300 more steps under the same (unphysically large, constant) forces: the molecules stay rigid
+    it.step(300)
+    got = download(ctx, s0)
+    assert np.all(np.isfinite(got.posq)) and np.all(np.isfinite(got.velm))
+    assert bond_errors(got, atoms, params) < (1e-4 if precision == "single" else 2e-7)  # rounding random-walks in float
+    # same seed, same trajectory
+    ctx2, it2 = make_water_context(gpu, s0, cons, seed=4321)
+    it2.step(301)
+    assert_slab_bits_equal(download(ctx2, s0), got)
+    ctx.close()
+    ctx2.close()
+
+
+def test_settle_guard_rails(gpu):
+    from openmm_constv_b200 import _capi
+    s0, atoms, params, cons = slabmod.make_water_slab(301, "single", seed=35)
+    ctx, it = make_water_context(gpu, s0, cons)
+    lib, slab = it._kernel._lib, it._kernel.handle
+    vp = C.c_void_p
+    bad = np.array([[atoms[0, 0], atoms[0, 1], atoms[0, 2]], [atoms[0, 2], atoms[1, 1], atoms[1, 2]]], np.int32)
+    prm = np.ascontiguousarray(params[:2])
+    assert lib.constv_settle_configure(slab, 2, bad.ctypes.data_as(vp), prm.ctypes.data_as(vp)) == _capi.ERR_INVALID
+    assert b"one molecule only" in lib.constv_last_error()
+    bad = np.array([[s0.num_real, 0, 1]], np.int32)  # an image particle
+    assert lib.constv_settle_configure(slab, 1, bad.ctypes.data_as(vp), prm.ctypes.data_as(vp)) == _capi.ERR_INVALID
+    flat = np.array([[0.1, 0.25]], np.float32)  # d(b-c) >= 2 d(apex-b): no triangle
+    assert lib.constv_settle_configure(slab, 1, atoms[:1].ctypes.data_as(vp), flat.ctypes.data_as(vp)) == _capi.ERR_INVALID
+    it.step(1)  # the failed calls left the slab usable
+    ctx.close()
+    # constraints the step kernel cannot solve (a lone bond) need the caller's solver
+    p1, p2, dist = cons
+    sysm = gpu.SlabSystem()
+    sysm.addParticles(s0.masses)
+    sysm.setDefaultPeriodicBoxVectors((s0.box[0], 0, 0), (0, s0.box[1], 0), (0, 0, s0.num_cells * s0.zmax))
+    sysm.addConstraints(p1, p2, dist)
+    sysm.addConstraint(0, 1, 0.3)
+    it = gpu.ConstVLangevinIntegrator(T, GAMMA, DT)
+    ctx = gpu.SlabContext(sysm, it, padded=s0.padded)
+    ctx.load_slab(s0)
+    assert not it._kernel.fused_constraints and it._kernel.num_rigid_molecules == len(atoms)
+    with pytest.raises(gpu.OpenMMException, match="apply_constraints"):
+        it.step(1)
+    ctx.close()
