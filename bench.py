@@ -48,6 +48,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 T_KELVIN, FRICTION, DT = 300.0, 1.0, 0.001  # example/nacl_1m_spce/nacl_constv.py:12-16
+DRUDE_FRICTION_CM, DRUDE_T, DRUDE_FRICTION, DRUDE_WALL = 5.0, 1.0, 20.0, 0.02  # usual Drude-oscillator settings
 L2_BYTES = 126 * 1024 * 1024
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback
 
@@ -79,6 +80,9 @@ def parse_args():
                          "example/nacl_1m_spce/nacl_constv.py:56).  fused = constv_step_fused_settle, one kernel per step; "
                          "split = the reference's structure, part 1 | constraint solver on posDelta | part 2 + image rewrite "
                          "(three launches).  Implies --chains 1.")
+    ap.add_argument("--drude", action="store_true",
+                    help="ConstVDrudeLangevinIntegrator on a slab of polarizable 4-site water (SURVEY.md 8f.4): one fused kernel "
+                         "per step, timed beside the reference's own four Drude kernels on the same GPU.  Implies --chains 1.")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cache-image-charge", action="store_true")
     ap.add_argument("--keep-in-l2", action="store_true", help="default cache policy instead of evict-first")
@@ -402,7 +406,14 @@ def main():
     # ---- workload: this rank's shard of the range-partitioned slab ------------------------------
     R = args.atoms // 2
     water = None
-    if args.rigid_water:
+    drude = None
+    if args.drude:
+        if args.ensemble or args.rigid_water:
+            raise SystemExit("--drude, --rigid-water and --ensemble are separate configurations")
+        args.chains = 1
+        shard, d_normal, d_pairs = slabmod.make_drude_slab(R, args.precision, seed=12345 + rank)
+        drude = (d_normal, d_pairs)
+    elif args.rigid_water:
         if args.ensemble:
             raise SystemExit("--rigid-water and --ensemble are separate configurations")
         args.chains = 1
@@ -411,7 +422,8 @@ def main():
     else:
         shard = slabmod.make_slab(R, args.precision, seed=12345 + rank)
     shard.global_atom_offset = partition.shard_range(R * world, rank, world)[0]
-    alg_bytes = slabmod.algorithmic_bytes_per_step(shard, rigid_molecules=len(water[0]) if water else 0)
+    alg_bytes = slabmod.algorithmic_bytes_per_step(shard, rigid_molecules=len(water[0]) if water else 0,
+                                                   drude=drude is not None, drude_pairs=len(drude[1]) if drude else 0)
     rec_bytes = shard.posq.nbytes + shard.velm.nbytes + shard.force.nbytes + (shard.corr.nbytes if shard.corr is not None else 0)
     M = max(1, args.ensemble)  # slabs advanced per step on this GPU (1 = the plain slab configs)
     replicas = args.replicas or max(2, int(np.ceil(2.0 * L2_BYTES / (rec_bytes * M))) + 1)
@@ -429,7 +441,15 @@ def main():
         sysm.setDefaultPeriodicBoxVectors((shard.box[0], 0, 0), (0, shard.box[1], 0), (0, 0, shard.num_cells * shard.zmax))
         if water:
             sysm.addConstraints(*water[2])
-        it = hostapi.ConstVLangevinIntegrator(args.temperature, FRICTION, DT, shard.num_cells)
+        if drude:
+            dforce = hostapi.DrudeForce()
+            for a, b in drude[1]:
+                dforce.addParticle(int(a), int(b))
+            sysm.addForce(dforce)
+            it = hostapi.ConstVDrudeLangevinIntegrator(args.temperature, DRUDE_FRICTION_CM, DRUDE_T, DRUDE_FRICTION, DT, shard.num_cells)
+            it.setMaxDrudeDistance(DRUDE_WALL)
+        else:
+            it = hostapi.ConstVLangevinIntegrator(args.temperature, FRICTION, DT, shard.num_cells)
         it.setRandomNumberSeed(2024 + (r % M))
         ctx = hostapi.SlabContext(sysm, it, precision=args.precision, device=local_rank, flags=flags,
                                   global_atom_offset=shard.global_atom_offset, padded=shard.padded)
@@ -437,7 +457,11 @@ def main():
         if args.pairs_per_thread or args.ctas_per_sm:
             it._kernel.set_launch_shape(args.pairs_per_thread, args.ctas_per_sm)
         it._kernel.set_kernel_variant(args.variant, args.tma_block, args.tma_stages, args.tma_ctas)
-        _capi.check(lib.constv_set_parameters(it._kernel.handle, args.temperature, FRICTION, DT))
+        if drude:
+            _capi.check(lib.constv_drude_set_parameters(it._kernel.handle, args.temperature, DRUDE_FRICTION_CM, DRUDE_T,
+                                                        DRUDE_FRICTION, DRUDE_WALL, DT))
+        else:
+            _capi.check(lib.constv_set_parameters(it._kernel.handle, args.temperature, FRICTION, DT))
         ctxs.append((ctx, it))
     handles = [it._kernel.handle for _, it in ctxs]
 
@@ -492,6 +516,8 @@ def main():
         for k in range(first, first + count):
             if args.ensemble:
                 _capi.check(lib.constv_step_fused_batched(groups[k % replicas], M, sptr))
+            elif drude:
+                _capi.check(lib.constv_drude_step_fused(handles[k % replicas], None, 0, sptr))
             elif args.rigid_water == "fused":
                 _capi.check(lib.constv_step_fused_settle(handles[k % replicas], None, 0, sptr))
             elif args.rigid_water == "split":
@@ -557,7 +583,7 @@ def main():
     # a StateDataReporter asks for every step (kinetic energy); `full_state` also reads back posq of
     # all atoms (what a DCD frame needs) and is reported beside it.
     e2e = None
-    if not args.skip_e2e and not args.ensemble and not args.rigid_water:
+    if not args.skip_e2e and not args.ensemble and not args.rigid_water and not drude:
         ctx0, it0 = ctxs[0]
         n_e2e = max(3, args.e2e_steps)
         host_force = [torch.from_numpy(np.ascontiguousarray(slabmod.new_forces(shard, j)[:, :R])).pin_memory() for j in range(2)]
@@ -659,9 +685,53 @@ def main():
                                "(6 blocks/SM, recalled) and an uncapped grid",
                        "speedup_of_fused_step": best / launch_ms_for_ref}
 
+    if rank == 0 and world == 1 and not args.skip_ref_gpu and drude:
+        from oracle import ref as refmod
+        import oracle
+        if refmod.available("cuda") and hasattr(refmod.cuda(), "constv_ref_drude_cuda_part1_single"):
+            for ctx, _ in ctxs:
+                ctx.load_slab(shard)
+            m = np.float32 if args.precision == "single" else np.float64
+            scal = oracle.drude_params(args.temperature, DRUDE_FRICTION_CM, DRUDE_T, DRUDE_FRICTION, DRUDE_WALL, DT)
+            rr = refmod.CudaDrudeReference(args.precision, scal, m(DT), dev, drude[0], drude[1], R, shard.padded, max_blocks=0)
+            pool = torch.randn((R + 8, 4), dtype=torch.float32, device=dev)
+            inv = torch.arange(shard.padded, dtype=torch.int32, device=dev)
+            n_ref = max(60, min(K, 6000))
+
+            def ref_launch(first, count):
+                for k in range(first, first + count):
+                    c = ctxs[k % replicas][0]
+                    rr.drude_step(shard.num_atoms, shard.num_cells, shard.zmax, c.posq, c.corr, c.velm, c.force, c.pos_delta,
+                                  pool, 0, inv, stream=sptr)
+
+            with torch.cuda.stream(stream):
+                ref_launch(0, replicas)
+                stream.synchronize()
+                rchunk = replicas * max(1, min(20, n_ref // replicas))
+                rgraph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(rgraph, stream=stream):
+                    ref_launch(0, rchunk)
+                for _ in range(3):
+                    rgraph.replay()
+                stream.synchronize()
+                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = max(1, n_ref // rchunk)
+                r0.record(stream)
+                for _ in range(reps):
+                    rgraph.replay()
+                r1.record(stream)
+                stream.synchronize()
+            ms_ref = r0.elapsed_time(r1) / (reps * rchunk)
+            ref_gpu = {"value": shard.num_atoms / (ms_ref * 1e-3), "unit": "atom-steps/s", "ms_per_step": ms_ref, "steps": reps * rchunk,
+                       "launches_per_step": 4,
+                       "what": "the reference's constVDrudeLangevin.cu + constVLangevin.cu compiled by nvcc for sm_100a (oracle/_ref): "
+                               "Drude part 1 (pre-filled Gaussian pool; refill not charged), part 2, hard wall, image rewrite; 128-thread "
+                               "blocks, uncapped grid; same rotating replicas, same CUDA-graph launch",
+                       "speedup_of_fused_step": ms_ref / launch_ms_for_ref}
+
     # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.skip_cpu and not args.ensemble and not args.rigid_water:
+    if rank == 0 and world == 1 and not args.skip_cpu and not args.ensemble and not args.rigid_water and not drude:
         rate_fn, kind = cpu_leg()
         rate, done, threads, per_step, el = rate_fn(shard, args.cpu_seconds, replicas=replicas)
         what = ("steps of the reference's constVLangevin.cu compiled for the host (part 1, part 2, image rewrite; oracle/_ref)"
@@ -690,6 +760,8 @@ def main():
                              if args.ensemble else
                              f"synthetic slab with RIGID water ({len(water[0])} SPC/E molecules, constraints solved {'inside the step kernel' if args.rigid_water == 'fused' else 'by a separate launch between part 1 and part 2'}), {shard.num_atoms} atoms per GPU, ConstV Langevin step incl. constraints (BASELINE configs[0-1] shape); range partition over {world} GPU(s)"
                              if water else
+                             f"synthetic slab of polarizable water ({len(drude[1])} Drude pairs, {len(drude[0])} ordinary particles), {shard.num_atoms} atoms per GPU, fused ConstVDrudeLangevinIntegrator step incl. hard wall (SURVEY 8f.4); range partition over {world} GPU(s)"
+                             if drude else
                              f"synthetic slab, {shard.num_atoms} atoms per GPU ({R} real + {shard.num_atoms - R} image), fused ConstV Langevin step only (BASELINE configs[2]); range partition over {world} GPU(s)"),
                 "atoms_per_gpu": shard.num_atoms, "total_atoms": atoms_per_step_job, "precision": args.precision,
                 "pair_classes": shard.pair_classes(), "rng": "in-kernel Philox4x32-10",
@@ -712,7 +784,8 @@ def main():
                                  if chains > 1 else "one launch per step",
                          "frac_of_8TBs_nominal": achieved / 8000.0,
                          "kernel": "constv_fused_step_batched_kernel" if args.ensemble else
-                                   ("constv_settle_step_kernel" if args.rigid_water == "fused" else
+                                   "constv_drude_step_kernel" if drude else
+                                   ("constv_settle_step_tiled_kernel" if args.rigid_water == "fused" else
                                     ("constv_part1_kernel + constv_settle_positions_kernel + constv_part2_mirror_kernel"
                                      if args.rigid_water == "split" else "constv_fused_step_kernel"))},
             "cpu_baseline": cpu,

@@ -35,11 +35,13 @@
 
 namespace constv {
 
-enum { DRUDE_ROLE_NORMAL = -1, DRUDE_ROLE_PASSIVE = -2 };  // >= 0: owner of that pair
+// role of a real slot: >= 0 owner of that pair (the Drude particle); -1 ordinary particle;
+// <= -2 owned (the parent): role = DRUDE_ROLE_PASSIVE - (slot of its owner)
+enum { DRUDE_ROLE_NORMAL = -1, DRUDE_ROLE_PASSIVE = -2 };
 enum { DRUDE_FUSED = 0, DRUDE_PART1 = 1, DRUDE_PART2 = 2 };
 
 struct DrudeDev {
-    const int* role;     // int[numReal]: DRUDE_ROLE_NORMAL | pair index (slot is particles.x) | DRUDE_ROLE_PASSIVE (slot is particles.y)
+    const int* role;     // int[numReal]: DRUDE_ROLE_NORMAL | pair index (slot is particles.x) | <= DRUDE_ROLE_PASSIVE (slot is particles.y)
     const int2* pairs;   // (Drude particle, parent) slots, CudaConstVKernels.cpp:222-228
     int numNormal, numPairs;
     double vscale, fscaleFixed, noisescale;        // the Drude (relative-motion) thermostat, rounded to `mixed`
@@ -300,7 +302,7 @@ constv_drude_step_kernel(const __grid_constant__ SlabDev d, const __grid_constan
         const int role = isReal ? dd.role[slot] : DRUDE_ROLE_PASSIVE;
         DrudeAtom<PREC> me, other;
         int2 pair = make_int2(slot, slot);
-        if (role != DRUDE_ROLE_PASSIVE) drude_load<PREC, MODE, INDEXED, STREAM>(d, slot, me);
+        if (role > DRUDE_ROLE_PASSIVE) drude_load<PREC, MODE, INDEXED, STREAM>(d, slot, me);
         if (role >= 0) {
             pair = dd.pairs[role];
             drude_load<PREC, MODE, INDEXED, STREAM>(d, pair.y, other);
@@ -387,6 +389,176 @@ constv_drude_step_kernel(const __grid_constant__ SlabDev d, const __grid_constan
     }
     // part 2 closes a split step: nobody in this launch reads the counter (part 1 did)
     if (MODE == DRUDE_PART2 && blockIdx.x == 0 && threadIdx.x == 0) d.counters->step = __ldcg(&d.counters->step) + 1;
+}
+
+
+// ---- the fused Drude step staged through shared memory (identity slot order) -----------------------------
+// The kernel above runs thread <-> slot: in a warp the pair owners (~500 instructions: two Philox blocks, the
+// centre-of-mass / relative-motion transform with its IEEE reciprocals and square roots, the hard wall), the
+// ordinary particles (~200) and the owned parents (nothing) sit side by side, so every warp pays for both
+// branches -- 12.5 M warp instructions per step at 1 M atoms, issue-bound at 22 us -- and an owner's gather of
+// its parent fills a quarter of each sector.  Here a CTA
+//   1. stages its 256-slot tile in shared memory, every thread loading ITS OWN slot (all roles: full
+//      coalesced vectors);
+//   2. compacts the work: a block-wide ballot scan lists the tile's pair owners first, then its ordinary
+//      particles, so that thread t takes work item t and whole warps run one branch;
+//   3. computes item t from the stage (a parent inside the tile is read from and written back to the stage;
+//      a parent outside it -- pairs straddling a tile boundary, or far apart -- is handled by the owner in
+//      global memory, and that parent's own thread, which finds its owner's slot in its role, stays silent);
+//   4. after a barrier every thread emits its own slot (record, rewritten images, zeroed images), coalesced.
+template <int PREC, int BLOCK> struct DrudeStage {
+    using Real = typename Prec<PREC>::Real;
+    using Mixed = typename Prec<PREC>::Mixed;
+    Vec4<Mixed> v[BLOCK];
+    Vec4<Real> p[BLOCK];
+    Vec4<Real> c[Prec<PREC>::kSplitPos ? BLOCK : 1];
+    long long f[3][BLOCK];
+    int role[BLOCK];
+    int list[BLOCK];             // work items: tile-local slot of each owner, then of each ordinary particle
+    int warpOwners[BLOCK / 32], warpNormals[BLOCK / 32];
+};
+
+template <int PREC, int BLOCK, bool STREAM>
+__global__ void __launch_bounds__(BLOCK)
+constv_drude_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ DrudeDev dd,
+                               const float4* __restrict__ random, const unsigned int randomIndex) {
+    using Real = typename Prec<PREC>::Real;
+    using Mixed = typename Prec<PREC>::Mixed;
+    constexpr bool kSplit = Prec<PREC>::kSplitPos;
+    constexpr int kWarps = BLOCK / 32;
+    __shared__ DrudeStage<PREC, BLOCK> st;
+    __shared__ StepBox box;
+    pdl_wait();
+    pdl_launch();
+    const int R = d.numReal;
+    const size_t P = (size_t) d.padded;
+    const unsigned int holders = (unsigned int) ((R + BLOCK - 1) / BLOCK);
+    const StepScalars<Mixed> s = scalars_of<Mixed>(d);
+    const DrudeScalars<Mixed> ds = drude_scalars_of<Mixed>(dd);
+    const int tid = (int) threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (long long base = (long long) blockIdx.x * BLOCK; base < R; base += (long long) gridDim.x * BLOCK) {
+        const int slot = (int) base + tid;
+        const bool inRange = slot < R;
+        const int role = inRange ? dd.role[slot] : DRUDE_ROLE_PASSIVE;
+        typename Prec<PREC>::Real q1 = 0;
+        // 1. stage in
+        if (inRange) {
+            DrudeAtom<PREC> me;
+            drude_load<PREC, DRUDE_FUSED, false, STREAM>(d, slot, me);
+            st.v[tid] = me.v;
+            st.p[tid] = me.p;
+            if (kSplit) st.c[tid] = me.c;
+            st.f[0][tid] = me.f[0];
+            st.f[1][tid] = me.f[1];
+            st.f[2][tid] = me.f[2];
+            q1 = me.q1;
+        }
+        st.role[tid] = role;
+        // 2. compaction: owners first, then ordinary particles
+        const bool isOwner = role >= 0, isNormal = inRange && role == DRUDE_ROLE_NORMAL;
+        const unsigned int ownerMask = __ballot_sync(0xffffffffu, isOwner), normalMask = __ballot_sync(0xffffffffu, isNormal);
+        if (lane == 0) {
+            st.warpOwners[warp] = __popc(ownerMask);
+            st.warpNormals[warp] = __popc(normalMask);
+        }
+        publish_step(box, d.counters);
+        __syncthreads();
+        const unsigned long long step = box.step;
+        const unsigned int ticket = take_ticket(d.counters, holders);
+        int ownersBefore = 0, normalsBefore = 0, numOwners = 0, numNormals = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; w++) {
+            const int o = st.warpOwners[w], n = st.warpNormals[w];
+            if (w < warp) { ownersBefore += o; normalsBefore += n; }
+            numOwners += o;
+            numNormals += n;
+        }
+        const unsigned int below = (1u << lane) - 1u;
+        if (isOwner) st.list[ownersBefore + __popc(ownerMask & below)] = tid;
+        if (isNormal) st.list[numOwners + normalsBefore + __popc(normalMask & below)] = tid;
+        __syncthreads();
+
+        // 3. compute work item `tid`
+        if (tid < numOwners) {
+            const int a = st.list[tid];                       // tile-local slot of the Drude particle
+            const int pairIndex = st.role[a];
+            const int2 pair = dd.pairs[pairIndex];
+            const int b = pair.y - (int) base;                // tile-local slot of the parent, if inside
+            const bool partnerInTile = b >= 0 && b < BLOCK;
+            Vec4<Mixed> v1 = st.v[a], v2, delta1{0, 0, 0, 0}, delta2{0, 0, 0, 0};
+            Vec4<Real> p1 = st.p[a], p2, c1 = kSplit ? st.c[a] : Vec4<Real>{0, 0, 0, 0}, c2{0, 0, 0, 0};
+            long long f1[3] = {st.f[0][a], st.f[1][a], st.f[2][a]}, f2[3];
+            Real q2 = 0;
+            if (partnerInTile) {
+                v2 = st.v[b];
+                p2 = st.p[b];
+                if (kSplit) c2 = st.c[b];
+                f2[0] = st.f[0][b]; f2[1] = st.f[1][b]; f2[2] = st.f[2][b];
+            } else {
+                DrudeAtom<PREC> far;
+                drude_load<PREC, DRUDE_FUSED, false, STREAM>(d, pair.y, far);
+                v2 = far.v; p2 = far.p; c2 = far.c; q2 = far.q1;
+                f2[0] = far.f[0]; f2[1] = far.f[1]; f2[2] = far.f[2];
+            }
+            float4 xi1, xi2;
+            if (random != nullptr) {
+                const size_t at = (size_t) randomIndex + (size_t) dd.numNormal + 2 * (size_t) pairIndex;
+                xi1 = __ldcs(random + at);
+                xi2 = __ldcs(random + at + 1);
+            } else {
+                xi1 = gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) pair.x, step);
+                xi2 = gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) pair.y, step);
+            }
+            drude_pair_part1(v1, v2, delta1, delta2, f1, f2, xi1, xi2, s, ds);
+            if (v1.w != 0) part2_update<PREC>(p1, c1, v1, delta1, s.invDt);
+            if (v2.w != 0) part2_update<PREC>(p2, c2, v2, delta2, s.invDt);
+            if (ds.maxDistance > 0)
+                drude_hardwall<PREC>(v1, v2, p1, c1, p2, c2, s.dt, ds.maxDistance, ds.hardwallScale);
+            st.v[a] = v1;
+            st.p[a] = p1;
+            if (kSplit) st.c[a] = c1;
+            if (partnerInTile) {
+                st.v[b] = v2;
+                st.p[b] = p2;
+                if (kSplit) st.c[b] = c2;
+            } else {
+                emit_atom<PREC, STREAM>(d, d.zshift, pair.y, true, v2, p2, c2, q2);
+            }
+        } else if (tid < numOwners + numNormals) {
+            const int a = st.list[tid];
+            Vec4<Mixed> v = st.v[a];
+            if (v.w != 0) {
+                Vec4<Real> p = st.p[a], c = kSplit ? st.c[a] : Vec4<Real>{0, 0, 0, 0};
+                Vec4<Mixed> delta;
+                float4 xi = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (random != nullptr) xi = __ldcs(random + (size_t) randomIndex + (size_t) base + a);
+                else if (s.noisescale != 0) xi = gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) (base + a), step);
+                part1_update(v, delta, st.f[0][a], st.f[1][a], st.f[2][a], xi.x, xi.y, xi.z, s);
+                part2_update<PREC>(p, c, v, delta, s.invDt);
+                st.v[a] = v;
+                st.p[a] = p;
+                if (kSplit) st.c[a] = c;
+            }
+        }
+        __syncthreads();
+
+        // 4. every thread emits its own slot; a parent whose owner sits in another tile was emitted by that owner
+        bool mine = inRange;
+        if (role <= DRUDE_ROLE_PASSIVE && inRange) {
+            const int owner = DRUDE_ROLE_PASSIVE - role;
+            mine = owner >= (int) base && owner < (int) base + BLOCK;
+        }
+        if (mine) {
+            const Vec4<Mixed> v = st.v[tid];
+            const Vec4<Real> p = st.p[tid];
+            const Vec4<Real> c = kSplit ? st.c[tid] : Vec4<Real>{0, 0, 0, 0};
+            // a pair's records are always written back (constVDrudeLangevin.cu:60-63 stores unconditionally)
+            emit_atom<PREC, STREAM>(d, d.zshift, slot, role != DRUDE_ROLE_NORMAL || v.w != 0, v, p, c, q1);
+        }
+        close_step(d.counters, ticket, holders, step);
+        if (base + (long long) gridDim.x * BLOCK < R) __syncthreads();  // stage and box are rewritten by the next tile
+    }
 }
 
 // applyHardWallConstraints alone (Drude.cu:108-211, launch CudaConstVKernels.cpp:336-340): thread <-> pair.

@@ -15,9 +15,10 @@
 // images and zeroes them: ONE kernel, each record crossing HBM once, posDelta never leaving registers.
 // constv_settle_positions_kernel is the solver alone (thread <-> molecule), for the split path.
 //
-// Arithmetic: every operation of the solver is rounded separately (struct RN: operators on __f*_rn /
-// __d*_rn intrinsics, which the compiler never contracts), divisions and square roots IEEE-correct; the CPU
-// oracle spells the same sequence, so results agree bit for bit.
+// Arithmetic: a canonical sequence of individually rounded operations and explicit fused multiply-adds
+// (struct RN: operators on __f*_rn / __d*_rn intrinsics, which the compiler never contracts or reorders),
+// divisions, reciprocals and square roots IEEE-correct; the CPU oracle spells the same sequence, so results
+// agree bit for bit.
 #pragma once
 
 #include "constv_drude_kernels.cuh"
@@ -61,8 +62,17 @@ template <typename M> __device__ __forceinline__ RN<M> operator/(RN<M> a, RN<M> 
 template <typename M> __device__ __forceinline__ RN<M> operator-(RN<M> a) { return RN<M>(-a.v); }
 template <typename M> __device__ __forceinline__ RN<M> sqrt_of(RN<M> a) { return RN<M>(sqrt_rn(a.v)); }
 
+template <typename M> __device__ __forceinline__ RN<M> fma_of(RN<M> a, RN<M> b, RN<M> c) { return RN<M>(fma_rn(a.v, b.v, c.v)); }
+template <typename M> __device__ __forceinline__ RN<M> rcp_of(RN<M> a) { return RN<M>(rcp_rn(a.v)); }
+// a1*b1 + a2*b2 + a3*b3 as fma(a3, b3, fma(a2, b2, a1*b1))
+template <typename M> __device__ __forceinline__ RN<M> dot3(RN<M> a1, RN<M> b1, RN<M> a2, RN<M> b2, RN<M> a3, RN<M> b3) {
+    return fma_of(a3, b3, fma_of(a2, b2, a1 * b1));
+}
+
 // SETTLE for one molecule.  pos* = old positions as `mixed`; d* = displacements to the unconstrained new
-// positions, overwritten with the constrained ones (w untouched); m* = masses.
+// positions, overwritten with the constrained ones (w untouched); m* = masses.  The canonical sequence:
+// fused multiply-adds exactly where written, everything else rounded separately, one correctly rounded
+// reciprocal per frame axis.
 template <typename M>
 __device__ __forceinline__ void settle_molecule(const M (&pos0)[3], const M (&pos1)[3], const M (&pos2)[3],
                                                 Vec4<M>& d0, Vec4<M>& d1, Vec4<M>& d2,
@@ -74,10 +84,10 @@ __device__ __forceinline__ void settle_molecule(const M (&pos0)[3], const M (&po
     const R xb0 = R(pos1[0]) - R(pos0[0]), yb0 = R(pos1[1]) - R(pos0[1]), zb0 = R(pos1[2]) - R(pos0[2]);
     const R xc0 = R(pos2[0]) - R(pos0[0]), yc0 = R(pos2[1]) - R(pos0[1]), zc0 = R(pos2[2]) - R(pos0[2]);
 
-    const R invTotalMass = one / (m0 + m1 + m2);
-    const R xcom = (R(d0.x) * m0 + (xb0 + R(d1.x)) * m1 + (xc0 + R(d2.x)) * m2) * invTotalMass;
-    const R ycom = (R(d0.y) * m0 + (yb0 + R(d1.y)) * m1 + (yc0 + R(d2.y)) * m2) * invTotalMass;
-    const R zcom = (R(d0.z) * m0 + (zb0 + R(d1.z)) * m1 + (zc0 + R(d2.z)) * m2) * invTotalMass;
+    const R invTotalMass = rcp_of(m0 + m1 + m2);
+    const R xcom = fma_of(xc0 + R(d2.x), m2, fma_of(xb0 + R(d1.x), m1, R(d0.x) * m0)) * invTotalMass;
+    const R ycom = fma_of(yc0 + R(d2.y), m2, fma_of(yb0 + R(d1.y), m1, R(d0.y) * m0)) * invTotalMass;
+    const R zcom = fma_of(zc0 + R(d2.z), m2, fma_of(zb0 + R(d1.z), m1, R(d0.z) * m0)) * invTotalMass;
 
     // unconstrained new positions relative to the new centre of mass
     const R xa1 = R(d0.x) - xcom, ya1 = R(d0.y) - ycom, za1 = R(d0.z) - zcom;
@@ -85,34 +95,34 @@ __device__ __forceinline__ void settle_molecule(const M (&pos0)[3], const M (&po
     const R xc1 = xc0 + R(d2.x) - xcom, yc1 = yc0 + R(d2.y) - ycom, zc1 = zc0 + R(d2.z) - zcom;
 
     // orthonormal frame: Z = normal of the old molecular plane, X = a1 x Z, Y = Z x X
-    const R xaksZd = yb0 * zc0 - zb0 * yc0;
-    const R yaksZd = zb0 * xc0 - xb0 * zc0;
-    const R zaksZd = xb0 * yc0 - yb0 * xc0;
-    const R xaksXd = ya1 * zaksZd - za1 * yaksZd;
-    const R yaksXd = za1 * xaksZd - xa1 * zaksZd;
-    const R zaksXd = xa1 * yaksZd - ya1 * xaksZd;
-    const R xaksYd = yaksZd * zaksXd - zaksZd * yaksXd;
-    const R yaksYd = zaksZd * xaksXd - xaksZd * zaksXd;
-    const R zaksYd = xaksZd * yaksXd - yaksZd * xaksXd;
+    const R xaksZd = fma_of(yb0, zc0, -(zb0 * yc0));
+    const R yaksZd = fma_of(zb0, xc0, -(xb0 * zc0));
+    const R zaksZd = fma_of(xb0, yc0, -(yb0 * xc0));
+    const R xaksXd = fma_of(ya1, zaksZd, -(za1 * yaksZd));
+    const R yaksXd = fma_of(za1, xaksZd, -(xa1 * zaksZd));
+    const R zaksXd = fma_of(xa1, yaksZd, -(ya1 * xaksZd));
+    const R xaksYd = fma_of(yaksZd, zaksXd, -(zaksZd * yaksXd));
+    const R yaksYd = fma_of(zaksZd, xaksXd, -(xaksZd * zaksXd));
+    const R zaksYd = fma_of(xaksZd, yaksXd, -(yaksZd * xaksXd));
 
-    const R axlng = sqrt_of(xaksXd * xaksXd + yaksXd * yaksXd + zaksXd * zaksXd);
-    const R aylng = sqrt_of(xaksYd * xaksYd + yaksYd * yaksYd + zaksYd * zaksYd);
-    const R azlng = sqrt_of(xaksZd * xaksZd + yaksZd * yaksZd + zaksZd * zaksZd);
-    const R trns11 = xaksXd / axlng, trns21 = yaksXd / axlng, trns31 = zaksXd / axlng;
-    const R trns12 = xaksYd / aylng, trns22 = yaksYd / aylng, trns32 = zaksYd / aylng;
-    const R trns13 = xaksZd / azlng, trns23 = yaksZd / azlng, trns33 = zaksZd / azlng;
+    const R invX = rcp_of(sqrt_of(fma_of(zaksXd, zaksXd, fma_of(yaksXd, yaksXd, xaksXd * xaksXd))));
+    const R invY = rcp_of(sqrt_of(fma_of(zaksYd, zaksYd, fma_of(yaksYd, yaksYd, xaksYd * xaksYd))));
+    const R invZ = rcp_of(sqrt_of(fma_of(zaksZd, zaksZd, fma_of(yaksZd, yaksZd, xaksZd * xaksZd))));
+    const R trns11 = xaksXd * invX, trns21 = yaksXd * invX, trns31 = zaksXd * invX;
+    const R trns12 = xaksYd * invY, trns22 = yaksYd * invY, trns32 = zaksYd * invY;
+    const R trns13 = xaksZd * invZ, trns23 = yaksZd * invZ, trns33 = zaksZd * invZ;
 
-    const R xb0d = trns11 * xb0 + trns21 * yb0 + trns31 * zb0;
-    const R yb0d = trns12 * xb0 + trns22 * yb0 + trns32 * zb0;
-    const R xc0d = trns11 * xc0 + trns21 * yc0 + trns31 * zc0;
-    const R yc0d = trns12 * xc0 + trns22 * yc0 + trns32 * zc0;
-    const R za1d = trns13 * xa1 + trns23 * ya1 + trns33 * za1;
-    const R xb1d = trns11 * xb1 + trns21 * yb1 + trns31 * zb1;
-    const R yb1d = trns12 * xb1 + trns22 * yb1 + trns32 * zb1;
-    const R zb1d = trns13 * xb1 + trns23 * yb1 + trns33 * zb1;
-    const R xc1d = trns11 * xc1 + trns21 * yc1 + trns31 * zc1;
-    const R yc1d = trns12 * xc1 + trns22 * yc1 + trns32 * zc1;
-    const R zc1d = trns13 * xc1 + trns23 * yc1 + trns33 * zc1;
+    const R xb0d = dot3(trns11, xb0, trns21, yb0, trns31, zb0);
+    const R yb0d = dot3(trns12, xb0, trns22, yb0, trns32, zb0);
+    const R xc0d = dot3(trns11, xc0, trns21, yc0, trns31, zc0);
+    const R yc0d = dot3(trns12, xc0, trns22, yc0, trns32, zc0);
+    const R za1d = dot3(trns13, xa1, trns23, ya1, trns33, za1);
+    const R xb1d = dot3(trns11, xb1, trns21, yb1, trns31, zb1);
+    const R yb1d = dot3(trns12, xb1, trns22, yb1, trns32, zb1);
+    const R zb1d = dot3(trns13, xb1, trns23, yb1, trns33, zb1);
+    const R xc1d = dot3(trns11, xc1, trns21, yc1, trns31, zc1);
+    const R yc1d = dot3(trns12, xc1, trns22, yc1, trns32, zc1);
+    const R zc1d = dot3(trns13, xc1, trns23, yc1, trns33, zc1);
 
     // step 2: the canonical triangle (apex at +ra on Y, b and c at -rb, x = -+rc), tilted by phi and psi.
     // The squared parameters are float arithmetic, as in the formulation restated (float2 parameters).
@@ -122,58 +132,49 @@ __device__ __forceinline__ void settle_molecule(const M (&pos0)[3], const M (&po
     const R ra = rb * (m1 + m2) * invTotalMass;
     rb = rb - ra;
     const R sinphi = za1d / ra;
-    const R cosphi = sqrt_of(one - sinphi * sinphi);
+    const R cosphi = sqrt_of(fma_of(-sinphi, sinphi, one));
     const R sinpsi = (zb1d - zc1d) / (two * rc * cosphi);
-    const R cospsi = sqrt_of(one - sinpsi * sinpsi);
+    const R cospsi = sqrt_of(fma_of(-sinpsi, sinpsi, one));
 
     const R ya2d = ra * cosphi;
     R xb2d = -(rc * cospsi);
-    const R yb2d = -(rb * cosphi) - rc * sinpsi * sinphi;
-    const R yc2d = -(rb * cosphi) + rc * sinpsi * sinphi;
+    const R tilt = rc * sinpsi * sinphi;
+    const R yb2d = -(rb * cosphi) - tilt;
+    const R yc2d = -(rb * cosphi) + tilt;
     const R xb2d2 = xb2d * xb2d;
-    const R hh2 = four * xb2d2 + (yb2d - yc2d) * (yb2d - yc2d) + (zb1d - zc1d) * (zb1d - zc1d);
-    const R deltx = two * xb2d + sqrt_of(four * xb2d2 - hh2 + R((M) __fmul_rn(distBC, distBC)));
-    xb2d = xb2d - deltx * half;
+    const R hh2 = fma_of(zb1d - zc1d, zb1d - zc1d, fma_of(yb2d - yc2d, yb2d - yc2d, four * xb2d2));
+    const R deltx = fma_of(two, xb2d, sqrt_of(fma_of(four, xb2d2, -hh2) + R((M) __fmul_rn(distBC, distBC))));
+    xb2d = fma_of(-deltx, half, xb2d);
 
     // step 3: the in-plane rotation theta that conserves the angular momentum about Z
-    const R alpha = xb2d * (xb0d - xc0d) + yb0d * yb2d + yc0d * yc2d;
-    const R beta = xb2d * (yc0d - yb0d) + xb0d * yb2d + xc0d * yc2d;
-    const R gamma = xb0d * yb1d - xb1d * yb0d + xc0d * yc1d - xc1d * yc0d;
-    const R al2be2 = alpha * alpha + beta * beta;
-    const R sintheta = (alpha * gamma - beta * sqrt_of(al2be2 - gamma * gamma)) / al2be2;
+    const R alpha = fma_of(yc0d, yc2d, fma_of(yb0d, yb2d, xb2d * (xb0d - xc0d)));
+    const R beta = fma_of(xc0d, yc2d, fma_of(xb0d, yb2d, xb2d * (yc0d - yb0d)));
+    const R gamma = fma_of(xc0d, yc1d, -(xc1d * yc0d)) + fma_of(xb0d, yb1d, -(xb1d * yb0d));
+    const R al2be2 = fma_of(beta, beta, alpha * alpha);
+    const R sintheta = fma_of(alpha, gamma, -(beta * sqrt_of(fma_of(-gamma, gamma, al2be2)))) / al2be2;
 
     // step 4
-    const R costheta = sqrt_of(one - sintheta * sintheta);
+    const R costheta = sqrt_of(fma_of(-sintheta, sintheta, one));
     const R xa3d = -(ya2d * sintheta);
     const R ya3d = ya2d * costheta;
     const R za3d = za1d;
-    const R xb3d = xb2d * costheta - yb2d * sintheta;
-    const R yb3d = xb2d * sintheta + yb2d * costheta;
+    const R xb3d = fma_of(xb2d, costheta, -(yb2d * sintheta));
+    const R yb3d = fma_of(xb2d, sintheta, yb2d * costheta);
     const R zb3d = zb1d;
-    const R xc3d = -(xb2d * costheta) - yc2d * sintheta;
-    const R yc3d = -(xb2d * sintheta) + yc2d * costheta;
+    const R xc3d = -fma_of(xb2d, costheta, yc2d * sintheta);
+    const R yc3d = fma_of(-xb2d, sintheta, yc2d * costheta);
     const R zc3d = zc1d;
 
-    // step 5: back to the laboratory frame
-    const R xa3 = trns11 * xa3d + trns12 * ya3d + trns13 * za3d;
-    const R ya3 = trns21 * xa3d + trns22 * ya3d + trns23 * za3d;
-    const R za3 = trns31 * xa3d + trns32 * ya3d + trns33 * za3d;
-    const R xb3 = trns11 * xb3d + trns12 * yb3d + trns13 * zb3d;
-    const R yb3 = trns21 * xb3d + trns22 * yb3d + trns23 * zb3d;
-    const R zb3 = trns31 * xb3d + trns32 * yb3d + trns33 * zb3d;
-    const R xc3 = trns11 * xc3d + trns12 * yc3d + trns13 * zc3d;
-    const R yc3 = trns21 * xc3d + trns22 * yc3d + trns23 * zc3d;
-    const R zc3 = trns31 * xc3d + trns32 * yc3d + trns33 * zc3d;
-
-    d0.x = (xcom + xa3).v;
-    d0.y = (ycom + ya3).v;
-    d0.z = (zcom + za3).v;
-    d1.x = (xcom + xb3 - xb0).v;
-    d1.y = (ycom + yb3 - yb0).v;
-    d1.z = (zcom + zb3 - zb0).v;
-    d2.x = (xcom + xc3 - xc0).v;
-    d2.y = (ycom + yc3 - yc0).v;
-    d2.z = (zcom + zc3 - zc0).v;
+    // step 5: back to the laboratory frame, and to displacements
+    d0.x = (xcom + dot3(trns11, xa3d, trns12, ya3d, trns13, za3d)).v;
+    d0.y = (ycom + dot3(trns21, xa3d, trns22, ya3d, trns23, za3d)).v;
+    d0.z = (zcom + dot3(trns31, xa3d, trns32, ya3d, trns33, za3d)).v;
+    d1.x = (xcom + dot3(trns11, xb3d, trns12, yb3d, trns13, zb3d) - xb0).v;
+    d1.y = (ycom + dot3(trns21, xb3d, trns22, yb3d, trns23, zb3d) - yb0).v;
+    d1.z = (zcom + dot3(trns31, xb3d, trns32, yb3d, trns33, zb3d) - zb0).v;
+    d2.x = (xcom + dot3(trns11, xc3d, trns12, yc3d, trns13, zc3d) - xc0).v;
+    d2.y = (ycom + dot3(trns21, xc3d, trns22, yc3d, trns23, zc3d) - yc0).v;
+    d2.z = (zcom + dot3(trns31, xc3d, trns32, yc3d, trns33, zc3d) - zc0).v;
 }
 
 // The solver alone on posDelta (the constraint step of the split path): thread <-> molecule.

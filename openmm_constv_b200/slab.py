@@ -311,7 +311,8 @@ def new_forces(slab: Slab, step_index: int, force_sigma: float = 1000.0) -> np.n
     return force
 
 
-def algorithmic_bytes_per_step(slab: Slab, zero_images: bool = True, rigid_molecules: int = 0) -> int:
+def algorithmic_bytes_per_step(slab: Slab, zero_images: bool = True, rigid_molecules: int = 0,
+                               drude_pairs: int = 0, drude: bool = False) -> int:
     """Bytes the fused step must move for this slab (DESIGN.md "bytes per pair").
 
     ``rigid_molecules`` > 0 (the step that solves the constraints of rigid 3-site molecules itself) adds
@@ -337,6 +338,8 @@ def algorithmic_bytes_per_step(slab: Slab, zero_images: bool = True, rigid_molec
     total += charged * n_img * (r + pos_b)
     if zero_images:
         total += slab.num_real * n_img * (vel_b + 24)
+    if drude:  # role table: 4 B per real atom; pair list: 8 B per pair
+        total += 4 * slab.num_real + 8 * drude_pairs
     if rigid_molecules:  # work-item list: 8 B per ordinary atom or molecule; molecule list: 16 + 8 B per molecule
         total += 8 * (slab.num_real - 2 * rigid_molecules) + 24 * rigid_molecules
     return int(total)

@@ -17,8 +17,9 @@
  * (distances restored, centre of mass and the molecule's angular momentum direction unchanged) in
  * tests/test_oracle_settle.py -- not against OpenMM.
  *
- * Arithmetic: every operation rounded separately (no fused multiply-add anywhere in the solver), square
- * roots and divisions IEEE-correct; the CUDA kernel (compiled -fmad=false) spells the same sequence.
+ * Arithmetic: the canonical sequence below -- fused multiply-adds exactly where S_FMA says, everything else
+ * rounded separately, square roots / divisions / reciprocals IEEE-correct, one reciprocal per frame axis; the
+ * CUDA kernel spells the same sequence with explicit intrinsics.
  */
 #define CAT_(a, b) a##_##b
 #define CAT(a, b) CAT_(a, b)
@@ -26,8 +27,10 @@
 
 #if MIXED_IS_DOUBLE
 #define M_SQRT(a) sqrt(a)
+#define S_FMA(a, b, c) fma((a), (b), (c))
 #else
 #define M_SQRT(a) sqrtf(a)
+#define S_FMA(a, b, c) fmaf((a), (b), (c))
 #endif
 
 /*
@@ -43,9 +46,9 @@ static inline void FN(settle_molecule)(const MIXED pos0[3], const MIXED pos1[3],
     const MIXED xc0 = pos2[0] - pos0[0], yc0 = pos2[1] - pos0[1], zc0 = pos2[2] - pos0[2];
 
     const MIXED invTotalMass = (MIXED) 1 / (m0 + m1 + m2);
-    const MIXED xcom = (d0[0] * m0 + (xb0 + d1[0]) * m1 + (xc0 + d2[0]) * m2) * invTotalMass;
-    const MIXED ycom = (d0[1] * m0 + (yb0 + d1[1]) * m1 + (yc0 + d2[1]) * m2) * invTotalMass;
-    const MIXED zcom = (d0[2] * m0 + (zb0 + d1[2]) * m1 + (zc0 + d2[2]) * m2) * invTotalMass;
+    const MIXED xcom = S_FMA(xc0 + d2[0], m2, S_FMA(xb0 + d1[0], m1, d0[0] * m0)) * invTotalMass;
+    const MIXED ycom = S_FMA(yc0 + d2[1], m2, S_FMA(yb0 + d1[1], m1, d0[1] * m0)) * invTotalMass;
+    const MIXED zcom = S_FMA(zc0 + d2[2], m2, S_FMA(zb0 + d1[2], m1, d0[2] * m0)) * invTotalMass;
 
     /* unconstrained new positions relative to the new centre of mass */
     const MIXED xa1 = d0[0] - xcom, ya1 = d0[1] - ycom, za1 = d0[2] - zcom;
@@ -53,93 +56,88 @@ static inline void FN(settle_molecule)(const MIXED pos0[3], const MIXED pos1[3],
     const MIXED xc1 = xc0 + d2[0] - xcom, yc1 = yc0 + d2[1] - ycom, zc1 = zc0 + d2[2] - zcom;
 
     /* orthonormal frame: Z = normal of the old molecular plane, X = a1 x Z, Y = Z x X */
-    const MIXED xaksZd = yb0 * zc0 - zb0 * yc0;
-    const MIXED yaksZd = zb0 * xc0 - xb0 * zc0;
-    const MIXED zaksZd = xb0 * yc0 - yb0 * xc0;
-    const MIXED xaksXd = ya1 * zaksZd - za1 * yaksZd;
-    const MIXED yaksXd = za1 * xaksZd - xa1 * zaksZd;
-    const MIXED zaksXd = xa1 * yaksZd - ya1 * xaksZd;
-    const MIXED xaksYd = yaksZd * zaksXd - zaksZd * yaksXd;
-    const MIXED yaksYd = zaksZd * xaksXd - xaksZd * zaksXd;
-    const MIXED zaksYd = xaksZd * yaksXd - yaksZd * xaksXd;
+    const MIXED xaksZd = S_FMA(yb0, zc0, -(zb0 * yc0));
+    const MIXED yaksZd = S_FMA(zb0, xc0, -(xb0 * zc0));
+    const MIXED zaksZd = S_FMA(xb0, yc0, -(yb0 * xc0));
+    const MIXED xaksXd = S_FMA(ya1, zaksZd, -(za1 * yaksZd));
+    const MIXED yaksXd = S_FMA(za1, xaksZd, -(xa1 * zaksZd));
+    const MIXED zaksXd = S_FMA(xa1, yaksZd, -(ya1 * xaksZd));
+    const MIXED xaksYd = S_FMA(yaksZd, zaksXd, -(zaksZd * yaksXd));
+    const MIXED yaksYd = S_FMA(zaksZd, xaksXd, -(xaksZd * zaksXd));
+    const MIXED zaksYd = S_FMA(xaksZd, yaksXd, -(yaksZd * xaksXd));
 
-    const MIXED axlng = M_SQRT(xaksXd * xaksXd + yaksXd * yaksXd + zaksXd * zaksXd);
-    const MIXED aylng = M_SQRT(xaksYd * xaksYd + yaksYd * yaksYd + zaksYd * zaksYd);
-    const MIXED azlng = M_SQRT(xaksZd * xaksZd + yaksZd * yaksZd + zaksZd * zaksZd);
-    const MIXED trns11 = xaksXd / axlng, trns21 = yaksXd / axlng, trns31 = zaksXd / axlng;
-    const MIXED trns12 = xaksYd / aylng, trns22 = yaksYd / aylng, trns32 = zaksYd / aylng;
-    const MIXED trns13 = xaksZd / azlng, trns23 = yaksZd / azlng, trns33 = zaksZd / azlng;
+    /* one correctly rounded square root and one correctly rounded reciprocal per axis */
+    const MIXED invX = (MIXED) 1 / M_SQRT(S_FMA(zaksXd, zaksXd, S_FMA(yaksXd, yaksXd, xaksXd * xaksXd)));
+    const MIXED invY = (MIXED) 1 / M_SQRT(S_FMA(zaksYd, zaksYd, S_FMA(yaksYd, yaksYd, xaksYd * xaksYd)));
+    const MIXED invZ = (MIXED) 1 / M_SQRT(S_FMA(zaksZd, zaksZd, S_FMA(yaksZd, yaksZd, xaksZd * xaksZd)));
+    const MIXED trns11 = xaksXd * invX, trns21 = yaksXd * invX, trns31 = zaksXd * invX;
+    const MIXED trns12 = xaksYd * invY, trns22 = yaksYd * invY, trns32 = zaksYd * invY;
+    const MIXED trns13 = xaksZd * invZ, trns23 = yaksZd * invZ, trns33 = zaksZd * invZ;
 
-    const MIXED xb0d = trns11 * xb0 + trns21 * yb0 + trns31 * zb0;
-    const MIXED yb0d = trns12 * xb0 + trns22 * yb0 + trns32 * zb0;
-    const MIXED xc0d = trns11 * xc0 + trns21 * yc0 + trns31 * zc0;
-    const MIXED yc0d = trns12 * xc0 + trns22 * yc0 + trns32 * zc0;
-    const MIXED za1d = trns13 * xa1 + trns23 * ya1 + trns33 * za1;
-    const MIXED xb1d = trns11 * xb1 + trns21 * yb1 + trns31 * zb1;
-    const MIXED yb1d = trns12 * xb1 + trns22 * yb1 + trns32 * zb1;
-    const MIXED zb1d = trns13 * xb1 + trns23 * yb1 + trns33 * zb1;
-    const MIXED xc1d = trns11 * xc1 + trns21 * yc1 + trns31 * zc1;
-    const MIXED yc1d = trns12 * xc1 + trns22 * yc1 + trns32 * zc1;
-    const MIXED zc1d = trns13 * xc1 + trns23 * yc1 + trns33 * zc1;
+#define S_DOT3(a1, b1, a2, b2, a3, b3) S_FMA(a3, b3, S_FMA(a2, b2, (a1) * (b1)))
+    const MIXED xb0d = S_DOT3(trns11, xb0, trns21, yb0, trns31, zb0);
+    const MIXED yb0d = S_DOT3(trns12, xb0, trns22, yb0, trns32, zb0);
+    const MIXED xc0d = S_DOT3(trns11, xc0, trns21, yc0, trns31, zc0);
+    const MIXED yc0d = S_DOT3(trns12, xc0, trns22, yc0, trns32, zc0);
+    const MIXED za1d = S_DOT3(trns13, xa1, trns23, ya1, trns33, za1);
+    const MIXED xb1d = S_DOT3(trns11, xb1, trns21, yb1, trns31, zb1);
+    const MIXED yb1d = S_DOT3(trns12, xb1, trns22, yb1, trns32, zb1);
+    const MIXED zb1d = S_DOT3(trns13, xb1, trns23, yb1, trns33, zb1);
+    const MIXED xc1d = S_DOT3(trns11, xc1, trns21, yc1, trns31, zc1);
+    const MIXED yc1d = S_DOT3(trns12, xc1, trns22, yc1, trns32, zc1);
+    const MIXED zc1d = S_DOT3(trns13, xc1, trns23, yc1, trns33, zc1);
 
-    /* step 2: the canonical triangle (apex at +ra on Y, b and c at -rb, x = -+rc), tilted by phi and psi */
+    /* step 2: the canonical triangle (apex at +ra on Y, b and c at -rb, x = -+rc), tilted by phi and psi.
+     * The squared parameters are float arithmetic (float2 parameters in the formulation restated). */
     const float rc = 0.5f * distBC;
     MIXED rb = M_SQRT((MIXED) (distAB * distAB - rc * rc));
     const MIXED ra = rb * (m1 + m2) * invTotalMass;
     rb = rb - ra;
     const MIXED sinphi = za1d / ra;
-    const MIXED cosphi = M_SQRT((MIXED) 1 - sinphi * sinphi);
+    const MIXED cosphi = M_SQRT(S_FMA(-sinphi, sinphi, (MIXED) 1));
     const MIXED sinpsi = (zb1d - zc1d) / ((MIXED) 2 * rc * cosphi);
-    const MIXED cospsi = M_SQRT((MIXED) 1 - sinpsi * sinpsi);
+    const MIXED cospsi = M_SQRT(S_FMA(-sinpsi, sinpsi, (MIXED) 1));
 
     const MIXED ya2d = ra * cosphi;
     MIXED xb2d = -(rc * cospsi);
-    const MIXED yb2d = -(rb * cosphi) - rc * sinpsi * sinphi;
-    const MIXED yc2d = -(rb * cosphi) + rc * sinpsi * sinphi;
+    const MIXED tilt = rc * sinpsi * sinphi;
+    const MIXED yb2d = -(rb * cosphi) - tilt;
+    const MIXED yc2d = -(rb * cosphi) + tilt;
     const MIXED xb2d2 = xb2d * xb2d;
-    const MIXED hh2 = (MIXED) 4 * xb2d2 + (yb2d - yc2d) * (yb2d - yc2d) + (zb1d - zc1d) * (zb1d - zc1d);
-    const MIXED deltx = (MIXED) 2 * xb2d + M_SQRT((MIXED) 4 * xb2d2 - hh2 + (MIXED) (distBC * distBC));
-    xb2d = xb2d - deltx * (MIXED) 0.5;
+    const MIXED hh2 = S_FMA(zb1d - zc1d, zb1d - zc1d, S_FMA(yb2d - yc2d, yb2d - yc2d, (MIXED) 4 * xb2d2));
+    const MIXED deltx = S_FMA((MIXED) 2, xb2d, M_SQRT(S_FMA((MIXED) 4, xb2d2, -hh2) + (MIXED) (distBC * distBC)));
+    xb2d = S_FMA(-deltx, (MIXED) 0.5, xb2d);
 
     /* step 3: the in-plane rotation theta that conserves the angular momentum about Z */
-    const MIXED alpha = xb2d * (xb0d - xc0d) + yb0d * yb2d + yc0d * yc2d;
-    const MIXED beta = xb2d * (yc0d - yb0d) + xb0d * yb2d + xc0d * yc2d;
-    const MIXED gamma = xb0d * yb1d - xb1d * yb0d + xc0d * yc1d - xc1d * yc0d;
-    const MIXED al2be2 = alpha * alpha + beta * beta;
-    const MIXED sintheta = (alpha * gamma - beta * M_SQRT(al2be2 - gamma * gamma)) / al2be2;
+    const MIXED alpha = S_FMA(yc0d, yc2d, S_FMA(yb0d, yb2d, xb2d * (xb0d - xc0d)));
+    const MIXED beta = S_FMA(xc0d, yc2d, S_FMA(xb0d, yb2d, xb2d * (yc0d - yb0d)));
+    const MIXED gamma = S_FMA(xc0d, yc1d, -(xc1d * yc0d)) + S_FMA(xb0d, yb1d, -(xb1d * yb0d));
+    const MIXED al2be2 = S_FMA(beta, beta, alpha * alpha);
+    const MIXED sintheta = S_FMA(alpha, gamma, -(beta * M_SQRT(S_FMA(-gamma, gamma, al2be2)))) / al2be2;
 
     /* step 4 */
-    const MIXED costheta = M_SQRT((MIXED) 1 - sintheta * sintheta);
+    const MIXED costheta = M_SQRT(S_FMA(-sintheta, sintheta, (MIXED) 1));
     const MIXED xa3d = -(ya2d * sintheta);
     const MIXED ya3d = ya2d * costheta;
     const MIXED za3d = za1d;
-    const MIXED xb3d = xb2d * costheta - yb2d * sintheta;
-    const MIXED yb3d = xb2d * sintheta + yb2d * costheta;
+    const MIXED xb3d = S_FMA(xb2d, costheta, -(yb2d * sintheta));
+    const MIXED yb3d = S_FMA(xb2d, sintheta, yb2d * costheta);
     const MIXED zb3d = zb1d;
-    const MIXED xc3d = -(xb2d * costheta) - yc2d * sintheta;
-    const MIXED yc3d = -(xb2d * sintheta) + yc2d * costheta;
+    const MIXED xc3d = -S_FMA(xb2d, costheta, yc2d * sintheta);
+    const MIXED yc3d = S_FMA(-xb2d, sintheta, yc2d * costheta);
     const MIXED zc3d = zc1d;
 
-    /* step 5: back to the laboratory frame */
-    const MIXED xa3 = trns11 * xa3d + trns12 * ya3d + trns13 * za3d;
-    const MIXED ya3 = trns21 * xa3d + trns22 * ya3d + trns23 * za3d;
-    const MIXED za3 = trns31 * xa3d + trns32 * ya3d + trns33 * za3d;
-    const MIXED xb3 = trns11 * xb3d + trns12 * yb3d + trns13 * zb3d;
-    const MIXED yb3 = trns21 * xb3d + trns22 * yb3d + trns23 * zb3d;
-    const MIXED zb3 = trns31 * xb3d + trns32 * yb3d + trns33 * zb3d;
-    const MIXED xc3 = trns11 * xc3d + trns12 * yc3d + trns13 * zc3d;
-    const MIXED yc3 = trns21 * xc3d + trns22 * yc3d + trns23 * zc3d;
-    const MIXED zc3 = trns31 * xc3d + trns32 * yc3d + trns33 * zc3d;
-
-    d0[0] = xcom + xa3;
-    d0[1] = ycom + ya3;
-    d0[2] = zcom + za3;
-    d1[0] = xcom + xb3 - xb0;
-    d1[1] = ycom + yb3 - yb0;
-    d1[2] = zcom + zb3 - zb0;
-    d2[0] = xcom + xc3 - xc0;
-    d2[1] = ycom + yc3 - yc0;
-    d2[2] = zcom + zc3 - zc0;
+    /* step 5: back to the laboratory frame, and to displacements */
+    d0[0] = xcom + S_DOT3(trns11, xa3d, trns12, ya3d, trns13, za3d);
+    d0[1] = ycom + S_DOT3(trns21, xa3d, trns22, ya3d, trns23, za3d);
+    d0[2] = zcom + S_DOT3(trns31, xa3d, trns32, ya3d, trns33, za3d);
+    d1[0] = xcom + S_DOT3(trns11, xb3d, trns12, yb3d, trns13, zb3d) - xb0;
+    d1[1] = ycom + S_DOT3(trns21, xb3d, trns22, yb3d, trns23, zb3d) - yb0;
+    d1[2] = zcom + S_DOT3(trns31, xb3d, trns32, yb3d, trns33, zb3d) - zb0;
+    d2[0] = xcom + S_DOT3(trns11, xc3d, trns12, yc3d, trns13, zc3d) - xc0;
+    d2[1] = ycom + S_DOT3(trns21, xc3d, trns22, yc3d, trns23, zc3d) - yc0;
+    d2[2] = zcom + S_DOT3(trns31, xc3d, trns32, yc3d, trns33, zc3d) - zc0;
+#undef S_DOT3
 }
 
 static inline void FN(settle_load_pos)(const REAL* posq, const REAL* corr, size_t a, MIXED out[3]) {
@@ -189,6 +187,7 @@ void FN(oracle_settle_step)(int numAtoms, int paddedNumAtoms, int numCells, doub
 }
 
 #undef M_SQRT
+#undef S_FMA
 #undef FN
 #undef CAT
 #undef CAT_

@@ -62,12 +62,15 @@ def mixed_scalars(oracle, precision, max_dist):
 @pytest.mark.parametrize("num_cells", [2, 4])
 @pytest.mark.parametrize("max_dist", [0.0, 0.02])
 @pytest.mark.parametrize("num_real", [41, 6007])
-def test_drude_fused_step_bit_exact(gpu, oracle, precision, num_cells, max_dist, num_real):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_drude_fused_step_bit_exact(gpu, oracle, precision, num_cells, max_dist, num_real, variant):
+    """variant 0 = the kernel staged through shared memory, variant 1 = the gather kernel."""
     import torch
     s0, normal, pairs = slabmod.make_drude_slab(num_real, precision, num_cells=num_cells, seed=11)
     nsteps, R = 4, s0.num_real
     pool = np.random.default_rng(5).standard_normal((nsteps * R + 7, 4)).astype(np.float32)
     ctx, it = make_drude_context(gpu, s0, pairs, max_dist, pool=pool)
+    it._kernel.set_kernel_variant(variant)
     assert it._kernel.random_count == len(normal) + 2 * len(pairs) == R
     ref = s0.copy()
     scalars = mixed_scalars(oracle, precision, max_dist)
@@ -82,6 +85,27 @@ def test_drude_fused_step_bit_exact(gpu, oracle, precision, num_cells, max_dist,
     if max_dist > 0 and len(pairs):
         d = ref.posq[pairs[:, 0], :3].astype(np.float64) - ref.posq[pairs[:, 1], :3]
         assert np.max(np.linalg.norm(d, axis=1)) < max_dist * (1 + 1e-3)
+    ctx.close()
+
+
+@pytest.mark.parametrize("precision", slabmod.PRECISIONS)
+@pytest.mark.parametrize("shift", [1, 37, 300])
+def test_drude_pairs_across_tiles(gpu, oracle, precision, shift):
+    """Pairs whose parent sits in another 256-slot tile than the Drude particle (here: every Drude particle
+    paired with the parent `shift` molecules further on; wall off, the geometry is meaningless): the owner
+    handles such a parent in global memory and the parent's own thread stays silent."""
+    s0, normal, pairs = slabmod.make_drude_slab(5003, precision, seed=19)
+    pairs = np.stack([pairs[:, 0], np.roll(pairs[:, 1], -shift)], axis=1).astype(np.int32)
+    pool = np.random.default_rng(10).standard_normal((2 * s0.num_real, 4)).astype(np.float32)
+    ctx, it = make_drude_context(gpu, s0, pairs, 0.0, pool=pool)
+    ref = s0.copy()
+    scalars = mixed_scalars(oracle, precision, 0.0)
+    far = np.sum(pairs[:, 0] // 256 != pairs[:, 1] // 256)
+    assert far > (0 if shift == 1 else len(pairs) // 2)
+    for k in range(2):
+        it.step(1)
+        oracle_drude_step(oracle, ref, normal, pairs, scalars, pool, random_index=k * s0.num_real)
+        assert_slab_bits_equal(download(ctx, s0), ref)
     ctx.close()
 
 
