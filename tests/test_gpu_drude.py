@@ -339,3 +339,46 @@ def test_drude_error_paths(gpu):
     assert lib.constv_drude_configure(slab, 1, bad.ctypes.data_as(C.c_void_p)) == _capi.ERR_INVALID
     it2.step(1)  # the failed configure calls left the slab usable
     ctx.close()
+
+
+import glob  # noqa: E402
+import os  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "ref_host_drude_*.npz"))))
+def test_drude_committed_reference_host_vectors(gpu, path):
+    """Fixtures recorded from the reference's Drude kernel source compiled for the HOST, where every
+    operation is rounded separately; the GPU contracts multiply-adds as nvcc does for the reference's own
+    kernels, so agreement is to rounding: 1e-6 of the thermal velocity / of the coordinate range per step
+    (north_star's fp32 tolerance), 1e-11 where velocities and positions are carried in double."""
+    import torch
+    g = np.load(path)
+    precision, num_cells, num_atoms, steps = str(g["precision"]), int(g["num_cells"]), int(g["num_atoms"]), int(g["steps"])
+    s = slabmod.make_drude_slab(num_atoms // num_cells, precision, num_cells=num_cells, seed=1)[0]
+    s.posq, s.velm, s.force, s.masses = g["posq0"].copy(), g["velm0"].copy(), g["force"].copy(), g["masses"].copy()
+    if precision == "mixed":
+        s.corr = g["corr0"].copy()
+    s.zmax = float(g["zmax"])
+    R = num_atoms // num_cells
+    pool = np.zeros((steps * R + 8, 4), np.float32)
+    off = int(g["random_index"])
+    for k in range(steps):  # the context advances its pool index by R per step, starting at 0
+        pool[k * R: k * R + R] = g["noise"][k][off: off + R]
+    sc = g["scalars"]
+    ctx, it = make_drude_context(gpu, s, g["pairs"], float(sc[6]), flags=0, pool=pool)
+    ctx.velm.copy_(torch.as_tensor(s.velm))
+    it.step(steps)
+    n = num_atoms
+    got_v, got_p = ctx.velm.cpu().numpy().astype(np.float64), ctx.posq.cpu().numpy().astype(np.float64)
+    want_v, want_p = g["velm1"].astype(np.float64), g["posq1"].astype(np.float64)
+    if precision == "mixed":
+        got_p[:, :3] += ctx.corr.cpu().numpy()[:, :3]
+        want_p[:, :3] += g["corr1"][:, :3]
+    massive = g["velm0"][:R, 3] != 0
+    v_thermal = np.sqrt(np.mean(g["velm0"][:R, :3][massive].astype(np.float64) ** 2))
+    tol = 1e-6 if precision == "single" else 1e-11
+    assert np.max(np.abs(got_v[:n, :3] - want_v[:n, :3])) < steps * tol * v_thermal * 20
+    assert np.max(np.abs(got_p[:n, :3] - want_p[:n, :3])) < steps * tol * np.max(np.abs(want_p[:n, :3]))
+    ctx.close()

@@ -91,3 +91,32 @@ def test_drude_parameters(oracle):
     assert p[1] == (1 - p[0]) / 5.0 / 4294967296.0
     assert p[2] == np.sqrt(2 * kB * 300.0 * 5.0) * np.sqrt(0.5 * (1 - p[0] * p[0]) / 5.0)
     assert p[6] == 0.02 and p[7] == np.sqrt(kB * 1.0)
+
+
+import glob  # noqa: E402
+import os  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "ref_host_drude_*.npz"))))
+def test_drude_oracle_matches_committed_reference_vectors(oracle, path):
+    """Fixtures recorded from the reference's Drude kernel source compiled for the host
+    (tests/golden/make_drude_reference_vectors.py): the same check where /root/reference is absent."""
+    g = np.load(path)
+    precision, num_cells, num_atoms, steps = str(g["precision"]), int(g["num_cells"]), int(g["num_atoms"]), int(g["steps"])
+    m = H.MIXED[precision]
+    posq, velm, force = g["posq0"].copy(), g["velm0"].copy(), g["force"].copy()
+    corr = g["corr0"].copy() if precision == "mixed" else None
+    inv = H.identity_order(posq.shape[0])
+    delta = np.zeros((posq.shape[0], 4), m)
+    with oracle.uncontracted():
+        for k in range(steps):
+            oracle.drude_step(precision, num_atoms, num_cells, float(g["zmax"]), posq, corr, velm, force.reshape(-1), delta,
+                              g["normal"], g["pairs"], g["scalars"].astype(m), m(g["dt"]), g["noise"][k], int(g["random_index"]),
+                              inv, False, False)
+    H.assert_bits_equal(posq, g["posq1"], "posq")
+    H.assert_bits_equal(velm, g["velm1"], "velm")
+    if corr is not None:
+        H.assert_bits_equal(corr, g["corr1"], "posqCorrection")
+    assert not np.array_equal(g["velm0"], g["velm1"])
