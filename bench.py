@@ -83,6 +83,10 @@ def parse_args():
     ap.add_argument("--drude", action="store_true",
                     help="ConstVDrudeLangevinIntegrator on a slab of polarizable 4-site water (SURVEY.md 8f.4): one fused kernel "
                          "per step, timed beside the reference's own four Drude kernels on the same GPU.  Implies --chains 1.")
+    ap.add_argument("--reordered", action="store_true",
+                    help="the state behind OpenMM after cu.reorderAtoms(): whole molecules (and their images) have traded "
+                         "slots inside spatial windows; the step addresses images through atomIndex / invAtomOrder "
+                         "(constVLangevin.cu:142-158).  Implies --chains 1.")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cache-image-charge", action="store_true")
     ap.add_argument("--keep-in-l2", action="store_true", help="default cache policy instead of evict-first")
@@ -422,6 +426,15 @@ def main():
     else:
         shard = slabmod.make_slab(R, args.precision, seed=12345 + rank)
     shard.global_atom_offset = partition.shard_range(R * world, rank, world)[0]
+    reorder_perm = None
+    if args.reordered:
+        if args.ensemble:
+            raise SystemExit("--reordered and --ensemble are separate configurations")
+        args.chains = 1
+        per = 4 if drude else 3
+        n_mol = shard.meta["n_pairs"] if drude else shard.meta["n_water"] // 3
+        reorder_perm = slabmod.molecule_permutation(shard, shard.meta["n_ion"], per, n_mol, seed=7 + rank)
+        shard, _ = slabmod.permute_slab(shard, reorder_perm)
     alg_bytes = slabmod.algorithmic_bytes_per_step(shard, rigid_molecules=len(water[0]) if water else 0,
                                                    drude=drude is not None, drude_pairs=len(drude[1]) if drude else 0)
     rec_bytes = shard.posq.nbytes + shard.velm.nbytes + shard.force.nbytes + (shard.corr.nbytes if shard.corr is not None else 0)
@@ -454,6 +467,9 @@ def main():
         ctx = hostapi.SlabContext(sysm, it, precision=args.precision, device=local_rank, flags=flags,
                                   global_atom_offset=shard.global_atom_offset, padded=shard.padded)
         ctx.load_slab(shard)
+        if reorder_perm is not None:
+            ctx.set_atom_order(reorder_perm)
+            _capi.check(lib.constv_update_inverse_order(it._kernel.handle, ctx.stream_ptr()))
         if args.pairs_per_thread or args.ctas_per_sm:
             it._kernel.set_launch_shape(args.pairs_per_thread, args.ctas_per_sm)
         it._kernel.set_kernel_variant(args.variant, args.tma_block, args.tma_stages, args.tma_ctas)
@@ -767,7 +783,7 @@ def main():
                 "pair_classes": shard.pair_classes(), "rng": "in-kernel Philox4x32-10",
                 "l2": f"rotating {replicas} replicas of the per-step working set ({replicas * M * rec_bytes / 1e6:.0f} MB) > 126 MB L2: every step streams from HBM",
                 "launch": ("CUDA graph of %d steps, PDL" % chunk) if graph is not None else "eager, PDL",
-                "chains": chains,
+                "chains": chains, "reordered_slots": bool(args.reordered),
                 "image_charge": "re-read from posq" if args.no_cache_image_charge else "side array",
                 "kernel_variant": {"variant": args.variant, "tma_block": args.tma_block, "tma_stages": args.tma_stages,
                                    "tma_ctas": args.tma_ctas, "pairs_per_thread": args.pairs_per_thread, "ctas_per_sm": args.ctas_per_sm},

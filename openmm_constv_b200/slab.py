@@ -280,6 +280,42 @@ def make_water_slab(num_real: int, precision: str = "single", num_cells: int = 2
     return s, np.ascontiguousarray(atoms), np.ascontiguousarray(params), (p1, p2, dist)
 
 
+def permute_slab(slab: Slab, perm) -> tuple:
+    """A copy of ``slab`` whose slot ``k`` holds original atom ``perm[k]`` (what OpenMM's ``reorderAtoms``
+    leaves behind), plus the padded ``atom_index`` array (padding slots stay in place)."""
+    t = slab.copy()
+    n = slab.num_atoms
+    perm = np.asarray(perm)
+    t.posq[:n] = slab.posq[perm]
+    if slab.corr is not None:
+        t.corr[:n] = slab.corr[perm]
+    t.velm[:n] = slab.velm[perm]
+    t.force[:, :n] = slab.force[:, perm]
+    atom_index = np.arange(slab.padded, dtype=np.int32)
+    atom_index[:n] = perm
+    return t, atom_index
+
+
+def molecule_permutation(slab: Slab, first: int, atoms_per_molecule: int, num_molecules: int, window: int = 1024,
+                         seed: int = 1) -> np.ndarray:
+    """A slot permutation of the kind OpenMM produces: whole identical molecules trade places, real ones among
+    the real slots and their images among the image slots of the same cell, and -- because the re-sort is
+    spatial -- only with molecules nearby: molecules are shuffled inside windows of ``window`` molecules.
+    ``first`` = slot of the first molecule; other atoms (ions, walls) stay where they are."""
+    rng = np.random.default_rng(seed)
+    R, N = slab.num_real, slab.num_atoms
+    perm = np.arange(N, dtype=np.int32)
+    for cell in range(slab.num_cells):
+        order = np.arange(num_molecules)
+        for lo in range(0, num_molecules, window):
+            hi = min(num_molecules, lo + window)
+            order[lo:hi] = lo + rng.permutation(hi - lo)
+        for k in range(atoms_per_molecule):
+            dst = cell * R + first + k + atoms_per_molecule * np.arange(num_molecules)
+            perm[dst] = cell * R + first + k + atoms_per_molecule * order
+    return perm
+
+
 def slice_slab(slab: Slab, lo: int, hi: int) -> Slab:
     """The shard holding real atoms [lo, hi) and their images (multi-GPU range partition:
     every image lives with its real partner)."""

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Generates tests/golden/ref_host_drude_*.npz from the REFERENCE'S OWN Drude kernel source.
+"""Generates tests/golden/drude_ref_host_*.npz from the REFERENCE'S OWN Drude kernel source.
 
 Run in the build container (needs /root/reference):  python tests/golden/make_drude_reference_vectors.py
 It builds oracle/_ref/libconstv_ref_host.so (the reference's vectorOps.cu + constVDrudeLangevin.cu +
@@ -65,7 +65,7 @@ def main():
         rec.update(posq1=s.posq, velm1=s.velm)
         if s.corr is not None:
             rec["corr1"] = s.corr
-        name = f"ref_host_drude_{precision}_c{num_cells}.npz"
+        name = f"drude_ref_host_{precision}_c{num_cells}.npz"
         np.savez_compressed(os.path.join(out_dir, name), **rec)
         print("wrote", os.path.join(out_dir, name))
 

@@ -53,17 +53,8 @@ def numpy_step(s, prm, dt, xi, inv=None, zshift=None, zero=True, random_index=0)
 def permute_slab(s, perm):
     """Return a copy of ``s`` whose slot ``k`` holds original atom ``perm[k]`` (OpenMM's
     atomIndex array); padding slots stay in place."""
-    t = s.copy()
-    n = s.num_atoms
-    assert sorted(perm.tolist()) == list(range(n))
-    t.posq[:n] = s.posq[perm]
-    if s.corr is not None:
-        t.corr[:n] = s.corr[perm]
-    t.velm[:n] = s.velm[perm]
-    t.force[:, :n] = s.force[:, perm]
-    atom_index = identity_order(s.padded)
-    atom_index[:n] = perm
-    return t, atom_index
+    assert sorted(np.asarray(perm).tolist()) == list(range(s.num_atoms))
+    return slabmod.permute_slab(s, perm)
 
 
 def bits(a):

@@ -347,7 +347,7 @@ import os  # noqa: E402
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "ref_host_drude_*.npz"))))
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "drude_ref_host_*.npz"))))
 def test_drude_committed_reference_host_vectors(gpu, path):
     """Fixtures recorded from the reference's Drude kernel source compiled for the HOST, where every
     operation is rounded separately; the GPU contracts multiply-adds as nvcc does for the reference's own

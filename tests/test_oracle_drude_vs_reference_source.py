@@ -99,7 +99,7 @@ import os  # noqa: E402
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "ref_host_drude_*.npz"))))
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "drude_ref_host_*.npz"))))
 def test_drude_oracle_matches_committed_reference_vectors(oracle, path):
     """Fixtures recorded from the reference's Drude kernel source compiled for the host
     (tests/golden/make_drude_reference_vectors.py): the same check where /root/reference is absent."""
