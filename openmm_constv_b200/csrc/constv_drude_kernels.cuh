@@ -256,7 +256,7 @@ __device__ __forceinline__ void drude_emit(const SlabDev& d, const int slot, con
         store4(posq, (size_t) slot, r.p);
         if (kSplit) store4(corrA, (size_t) slot, r.c);
     }
-    if (r.p.w != -r.p.w) {
+    if (r.p.w != -r.p.w && a < R) {  // a < R: a neutral wall atom and its image may have traded slots; nothing else can
         ImageCursor<PREC> cur(r.p, r.c);
         for (int cell = 1; cell < d.numCells; cell++) {
             const size_t t = (size_t) d.invAtomOrder[a + R * cell];
@@ -414,11 +414,15 @@ template <int PREC, int BLOCK> struct DrudeStage {
     Vec4<Real> c[Prec<PREC>::kSplitPos ? BLOCK : 1];
     long long f[3][BLOCK];
     int role[BLOCK];
+    int orig[BLOCK];             // original index of the atom in the slot (= the slot in identity order)
     int list[BLOCK];             // work items: tile-local slot of each owner, then of each ordinary particle
     int warpOwners[BLOCK / 32], warpNormals[BLOCK / 32];
 };
 
-template <int PREC, int BLOCK, bool STREAM>
+// INDEXED = reordered slots: same tiles and arithmetic (the real atoms keep slots [0, R) and a slot keeps its
+// role); the Philox key is atomIndex[slot], images are written wherever invAtomOrder says, and the image slots
+// are zeroed by extra tiles in slot order.
+template <int PREC, int BLOCK, bool INDEXED, bool STREAM>
 __global__ void __launch_bounds__(BLOCK)
 constv_drude_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ DrudeDev dd,
                                const float4* __restrict__ random, const unsigned int randomIndex) {
@@ -432,12 +436,33 @@ constv_drude_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_c
     pdl_launch();
     const int R = d.numReal;
     const size_t P = (size_t) d.padded;
-    const unsigned int holders = (unsigned int) ((R + BLOCK - 1) / BLOCK);
+    const int realTiles = (R + BLOCK - 1) / BLOCK;
+    const int zeroTiles = INDEXED ? (d.numAtoms - R + BLOCK - 1) / BLOCK : 0;
+    const unsigned int holders = (unsigned int) (realTiles + zeroTiles);
     const StepScalars<Mixed> s = scalars_of<Mixed>(d);
     const DrudeScalars<Mixed> ds = drude_scalars_of<Mixed>(dd);
     const int tid = (int) threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (long long base = (long long) blockIdx.x * BLOCK; base < R; base += (long long) gridDim.x * BLOCK) {
+    for (int tile = (int) blockIdx.x; tile < (int) holders; tile += (int) gridDim.x) {
+        if (INDEXED && tile >= realTiles) {  // a tile of image slots: zero them, coalesced
+            publish_step(box, d.counters);
+            __syncthreads();
+            const unsigned long long zstep = box.step;
+            const unsigned int zticket = take_ticket(d.counters, holders);
+            const int zslot = R + (tile - realTiles) * BLOCK + tid;
+            if (zslot < d.numAtoms) {
+                if (d.zeroVelm) store4x<STREAM>(static_cast<Mixed*>(d.velm), (size_t) zslot, Vec4<Mixed>{0, 0, 0, 0});
+                if (d.zeroForce) {
+                    __stcs(d.force + zslot, 0LL);
+                    __stcs(d.force + P + zslot, 0LL);
+                    __stcs(d.force + 2 * P + zslot, 0LL);
+                }
+            }
+            close_step(d.counters, zticket, holders, zstep);
+            if (tile + (int) gridDim.x < (int) holders) __syncthreads();
+            continue;
+        }
+        const long long base = (long long) tile * BLOCK;
         const int slot = (int) base + tid;
         const bool inRange = slot < R;
         const int role = inRange ? dd.role[slot] : DRUDE_ROLE_PASSIVE;
@@ -445,7 +470,8 @@ constv_drude_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_c
         // 1. stage in
         if (inRange) {
             DrudeAtom<PREC> me;
-            drude_load<PREC, DRUDE_FUSED, false, STREAM>(d, slot, me);
+            drude_load<PREC, DRUDE_FUSED, INDEXED, STREAM>(d, slot, me);
+            st.orig[tid] = (INDEXED && d.atomIndex) ? d.atomIndex[slot] : slot;
             st.v[tid] = me.v;
             st.p[tid] = me.p;
             if (kSplit) st.c[tid] = me.c;
@@ -490,16 +516,19 @@ constv_drude_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_c
             Vec4<Real> p1 = st.p[a], p2, c1 = kSplit ? st.c[a] : Vec4<Real>{0, 0, 0, 0}, c2{0, 0, 0, 0};
             long long f1[3] = {st.f[0][a], st.f[1][a], st.f[2][a]}, f2[3];
             Real q2 = 0;
+            int orig2;
             if (partnerInTile) {
                 v2 = st.v[b];
                 p2 = st.p[b];
                 if (kSplit) c2 = st.c[b];
                 f2[0] = st.f[0][b]; f2[1] = st.f[1][b]; f2[2] = st.f[2][b];
+                orig2 = st.orig[b];
             } else {
                 DrudeAtom<PREC> far;
-                drude_load<PREC, DRUDE_FUSED, false, STREAM>(d, pair.y, far);
+                drude_load<PREC, DRUDE_FUSED, INDEXED, STREAM>(d, pair.y, far);
                 v2 = far.v; p2 = far.p; c2 = far.c; q2 = far.q1;
                 f2[0] = far.f[0]; f2[1] = far.f[1]; f2[2] = far.f[2];
+                orig2 = (INDEXED && d.atomIndex) ? d.atomIndex[pair.y] : pair.y;
             }
             float4 xi1, xi2;
             if (random != nullptr) {
@@ -507,8 +536,8 @@ constv_drude_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_c
                 xi1 = __ldcs(random + at);
                 xi2 = __ldcs(random + at + 1);
             } else {
-                xi1 = gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) pair.x, step);
-                xi2 = gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) pair.y, step);
+                xi1 = gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) st.orig[a], step);
+                xi2 = gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) orig2, step);
             }
             drude_pair_part1(v1, v2, delta1, delta2, f1, f2, xi1, xi2, s, ds);
             if (v1.w != 0) part2_update<PREC>(p1, c1, v1, delta1, s.invDt);
@@ -522,6 +551,10 @@ constv_drude_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_c
                 st.v[b] = v2;
                 st.p[b] = p2;
                 if (kSplit) st.c[b] = c2;
+            } else if (INDEXED) {
+                DrudeAtom<PREC> rec;
+                rec.v = v2; rec.p = p2; rec.c = c2;
+                drude_emit<PREC, true, STREAM>(d, pair.y, orig2, true, rec);
             } else {
                 emit_atom<PREC, STREAM>(d, d.zshift, pair.y, true, v2, p2, c2, q2);
             }
@@ -533,7 +566,7 @@ constv_drude_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_c
                 Vec4<Mixed> delta;
                 float4 xi = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (random != nullptr) xi = __ldcs(random + (size_t) randomIndex + (size_t) base + a);
-                else if (s.noisescale != 0) xi = gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) (base + a), step);
+                else if (s.noisescale != 0) xi = gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) st.orig[a], step);
                 part1_update(v, delta, st.f[0][a], st.f[1][a], st.f[2][a], xi.x, xi.y, xi.z, s);
                 part2_update<PREC>(p, c, v, delta, s.invDt);
                 st.v[a] = v;
@@ -554,10 +587,17 @@ constv_drude_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_c
             const Vec4<Real> p = st.p[tid];
             const Vec4<Real> c = kSplit ? st.c[tid] : Vec4<Real>{0, 0, 0, 0};
             // a pair's records are always written back (constVDrudeLangevin.cu:60-63 stores unconditionally)
-            emit_atom<PREC, STREAM>(d, d.zshift, slot, role != DRUDE_ROLE_NORMAL || v.w != 0, v, p, c, q1);
+            const bool moved = role != DRUDE_ROLE_NORMAL || v.w != 0;
+            if (INDEXED) {
+                DrudeAtom<PREC> rec;
+                rec.v = v; rec.p = p; rec.c = c;
+                drude_emit<PREC, true, STREAM>(d, slot, st.orig[tid], moved, rec);
+            } else {
+                emit_atom<PREC, STREAM>(d, d.zshift, slot, moved, v, p, c, q1);
+            }
         }
         close_step(d.counters, ticket, holders, step);
-        if (base + (long long) gridDim.x * BLOCK < R) __syncthreads();  // stage and box are rewritten by the next tile
+        if (tile + (int) gridDim.x < (int) holders) __syncthreads();  // stage and box are rewritten by the next tile
     }
 }
 

@@ -334,7 +334,7 @@ constv_settle_step_kernel(const __grid_constant__ SlabDev d, const __grid_consta
 // shared memory; after a barrier thread j computes item j from stage entries per*j + k (stride 3: free of
 // bank conflicts), writes the new velocity and position back, and after a second barrier every thread
 // emits "its" slots again: own record, rewritten images, zeroed images, all coalesced.
-template <int PREC, int BLOCK> struct SettleStage {
+template <int PREC, int BLOCK, bool INDEXED> struct SettleStage {
     using Real = typename Prec<PREC>::Real;
     using Mixed = typename Prec<PREC>::Mixed;
     static constexpr int kSlots = 3 * BLOCK;
@@ -342,10 +342,16 @@ template <int PREC, int BLOCK> struct SettleStage {
     Vec4<Real> p[kSlots];
     Vec4<Real> c[Prec<PREC>::kSplitPos ? kSlots : 1];
     long long f[3][kSlots];
-    Real q1[kSlots];
+    Real q1[INDEXED ? 1 : kSlots];   // identity order: charge of the cell-1 image, fetched with the record
+    int orig[INDEXED ? kSlots : 1];  // reordered slots: original index of the atom in the slot
 };
 
-template <int PREC, int BLOCK, bool STREAM>
+// INDEXED = reordered slots (behind OpenMM after cu.reorderAtoms()).  OpenMM swaps whole identical molecules,
+// so the real atoms keep slots [0, R) and a slot keeps its role: the tiles, the stage and the arithmetic are the
+// same; what changes is that the Philox key is the ORIGINAL index atomIndex[slot], that an atom's images sit
+// wherever invAtomOrder says (a scattered 16-byte store each, as in the reference, constVLangevin.cu:155-158),
+// and that the image slots are zeroed by extra tiles in slot order (coalesced) instead of by their partners.
+template <int PREC, int BLOCK, bool INDEXED, bool STREAM>
 __global__ void __launch_bounds__(BLOCK)
 constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ SettleSegments seg,
                                 const float4* __restrict__ random, const unsigned int randomIndex) {
@@ -353,13 +359,15 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
     using Mixed = typename Prec<PREC>::Mixed;
     constexpr bool kSplit = Prec<PREC>::kSplitPos;
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    SettleStage<PREC, BLOCK>& st = *reinterpret_cast<SettleStage<PREC, BLOCK>*>(smemRaw);
+    SettleStage<PREC, BLOCK, INDEXED>& st = *reinterpret_cast<SettleStage<PREC, BLOCK, INDEXED>*>(smemRaw);
     __shared__ StepBox box;
     pdl_wait();
     pdl_launch();
     const int R = d.numReal;
     const size_t P = (size_t) d.padded;
-    const unsigned int holders = (unsigned int) seg.tileStart[seg.count];
+    const int realTiles = seg.tileStart[seg.count];
+    const int zeroTiles = INDEXED ? (d.numAtoms - R + 3 * BLOCK - 1) / (3 * BLOCK) : 0;
+    const unsigned int holders = (unsigned int) (realTiles + zeroTiles);
     const StepScalars<Mixed> s = scalars_of<Mixed>(d);
     const Real* __restrict__ posq = static_cast<const Real*>(d.posq);
     const Real* __restrict__ corrA = static_cast<const Real*>(d.corr);
@@ -370,6 +378,27 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
     const int j = (int) threadIdx.x;
 
     for (int tile = (int) blockIdx.x; tile < (int) holders; tile += (int) gridDim.x) {
+        if (INDEXED && tile >= realTiles) {  // a tile of image slots: zero them, coalesced
+            publish_step(box, d.counters);
+            __syncthreads();
+            const unsigned long long step = box.step;
+            const unsigned int ticket = take_ticket(d.counters, holders);
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const int slot = R + (tile - realTiles) * 3 * BLOCK + j + i * BLOCK;
+                if (slot < d.numAtoms) {
+                    if (d.zeroVelm) store4x<STREAM>(static_cast<Mixed*>(d.velm), (size_t) slot, Vec4<Mixed>{0, 0, 0, 0});
+                    if (d.zeroForce) {
+                        __stcs(d.force + slot, 0LL);
+                        __stcs(d.force + P + slot, 0LL);
+                        __stcs(d.force + 2 * P + slot, 0LL);
+                    }
+                }
+            }
+            close_step(d.counters, ticket, holders, step);
+            if (tile + (int) gridDim.x < (int) holders) __syncthreads();
+            continue;
+        }
         int q = 0;
 #pragma unroll
         for (int k = 1; k < kSettleMaxSegments; k++)
@@ -393,7 +422,8 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
                 st.f[0][idx] = load_force(force + slot);
                 st.f[1][idx] = load_force(force + P + slot);
                 st.f[2][idx] = load_force(force + 2 * P + slot);
-                st.q1[idx] = qbase[qstride * slot];
+                if (INDEXED) st.orig[idx] = d.atomIndex[slot];
+                else st.q1[idx] = qbase[qstride * slot];
             }
         }
         publish_step(box, d.counters);
@@ -417,8 +447,9 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
                     moved[k] = v[k].w != 0;
                     if (moved[k]) {
                         float4 xi;
+                        const int a = INDEXED ? st.orig[idx] : base + idx;
                         if (random != nullptr) xi = __ldcs(random + (size_t) randomIndex + base + idx);
-                        else xi = (s.noisescale != 0) ? gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) (base + idx), step)
+                        else xi = (s.noisescale != 0) ? gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) a, step)
                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
                         part1_update(v[k], delta[k], st.f[0][idx], st.f[1][idx], st.f[2][idx], xi.x, xi.y, xi.z, s);
                     }
@@ -442,7 +473,7 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
         }
         __syncthreads();
 
-        // stage out: own record, rewritten images, zeroed images -- coalesced
+        // stage out: own record (coalesced), rewritten images, and (identity order) zeroed images
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             const int idx = j + i * BLOCK;
@@ -450,7 +481,13 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
                 const Vec4<Mixed> v = st.v[idx];
                 const Vec4<Real> p = st.p[idx];
                 const Vec4<Real> c = kSplit ? st.c[idx] : Vec4<Real>{0, 0, 0, 0};
-                emit_atom<PREC, STREAM>(d, s.zshift, base + idx, v.w != 0, v, p, c, st.q1[idx]);
+                if (INDEXED) {
+                    DrudeAtom<PREC> rec;
+                    rec.v = v; rec.p = p; rec.c = c;
+                    drude_emit<PREC, true, STREAM>(d, base + idx, st.orig[idx], v.w != 0, rec);
+                } else {
+                    emit_atom<PREC, STREAM>(d, s.zshift, base + idx, v.w != 0, v, p, c, st.q1[idx]);
+                }
             }
         }
         close_step(d.counters, ticket, holders, step);

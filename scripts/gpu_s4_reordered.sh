@@ -1,0 +1,17 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+: > gpurun_out/sweep_reordered.jsonl
+run() { timeout 300 python bench.py --steps 12000 --warmup 600 --skip-cpu --skip-e2e --skip-ref-gpu "$@" 2>gpurun_out/err_reord.log | tail -1 \
+    | python -c "import sys,json,os; d=json.loads(sys.stdin.read()); print(json.dumps({'args':'$*','us':round(d['ms_per_step']*1e3,3),'GBs':round(d['roofline']['achieved'],1),'frac':round(d['roofline']['frac'],4)}))" \
+    | tee -a gpurun_out/sweep_reordered.jsonl || tail -5 gpurun_out/err_reord.log; }
+run --chains 1
+run --reordered
+run --rigid-water fused
+run --rigid-water fused --reordered
+run --rigid-water split --reordered
+run --drude
+run --drude --reordered
+run --reordered --atoms 4000000 --steps 3000
+run --rigid-water fused --reordered --atoms 4000000 --steps 3000

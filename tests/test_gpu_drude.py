@@ -147,8 +147,9 @@ def role_preserving_permutation(s, rng):
 
 
 @pytest.mark.parametrize("precision", slabmod.PRECISIONS)
-@pytest.mark.parametrize("split", [False, True])
-def test_drude_reordered_slots(gpu, oracle, precision, split):
+@pytest.mark.parametrize("split,variant", [(False, 0), (False, 1), (True, 0)])
+def test_drude_reordered_slots(gpu, oracle, precision, split, variant):
+    """variant 0 = the staged kernel with its extra tiles zeroing the image slots, variant 1 = thread per slot."""
     s0, normal, pairs = slabmod.make_drude_slab(2501, precision, num_cells=2, seed=13)
     perm = role_preserving_permutation(s0, np.random.default_rng(4))
     sp, atom_index = H.permute_slab(s0, perm)
@@ -158,6 +159,7 @@ def test_drude_reordered_slots(gpu, oracle, precision, split):
     ctx, it = make_drude_context(gpu, sp, pairs, 0.02, pool=pool,
                                  apply_constraints=(lambda c, t: None) if split else None)
     ctx.set_atom_order(perm)
+    it._kernel.set_kernel_variant(variant)
     ref = sp.copy()
     scalars = mixed_scalars(oracle, precision, 0.02)
     for k in range(2):

@@ -151,9 +151,11 @@ def molecule_preserving_permutation(s, rng):
 
 
 @pytest.mark.parametrize("precision", slabmod.PRECISIONS)
-def test_fused_settle_reordered_slots(gpu, oracle, precision):
-    """OpenMM swaps whole identical molecules: slots keep their roles, images move freely."""
-    s0, atoms, params, cons = slabmod.make_water_slab(2501, precision, num_cells=2, seed=33)
+@pytest.mark.parametrize("variant,num_cells", [(0, 2), (1, 2), (0, 4)])
+def test_fused_settle_reordered_slots(gpu, oracle, precision, variant, num_cells):
+    """OpenMM swaps whole identical molecules: slots keep their roles, images move freely.  variant 0 = the
+    staged kernel (extra tiles zero the image slots), variant 1 = the gather kernel."""
+    s0, atoms, params, cons = slabmod.make_water_slab(2501, precision, num_cells=num_cells, seed=33)
     perm = molecule_preserving_permutation(s0, np.random.default_rng(6))
     sp, atom_index = H.permute_slab(s0, perm)
     inv = np.empty_like(atom_index)
@@ -161,6 +163,7 @@ def test_fused_settle_reordered_slots(gpu, oracle, precision):
     pool = np.random.default_rng(4).standard_normal((2 * s0.padded, 4)).astype(np.float32)
     ctx, it = make_water_context(gpu, sp, cons, pool=pool)
     ctx.set_atom_order(perm)
+    it._kernel.set_kernel_variant(variant)
     ref = sp.copy()
     for k in range(2):
         it.step(1)
