@@ -437,7 +437,8 @@ constv_drude_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_c
     const int R = d.numReal;
     const size_t P = (size_t) d.padded;
     const int realTiles = (R + BLOCK - 1) / BLOCK;
-    const int zeroTiles = INDEXED ? (d.numAtoms - R + BLOCK - 1) / BLOCK : 0;
+    constexpr int kZeroSpan = 8;  // a zeroing tile covers 8 * BLOCK image slots
+    const int zeroTiles = INDEXED ? (d.numAtoms - R + kZeroSpan * BLOCK - 1) / (kZeroSpan * BLOCK) : 0;
     const unsigned int holders = (unsigned int) (realTiles + zeroTiles);
     const StepScalars<Mixed> s = scalars_of<Mixed>(d);
     const DrudeScalars<Mixed> ds = drude_scalars_of<Mixed>(dd);
@@ -449,13 +450,16 @@ constv_drude_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_c
             __syncthreads();
             const unsigned long long zstep = box.step;
             const unsigned int zticket = take_ticket(d.counters, holders);
-            const int zslot = R + (tile - realTiles) * BLOCK + tid;
-            if (zslot < d.numAtoms) {
-                if (d.zeroVelm) store4x<STREAM>(static_cast<Mixed*>(d.velm), (size_t) zslot, Vec4<Mixed>{0, 0, 0, 0});
-                if (d.zeroForce) {
-                    __stcs(d.force + zslot, 0LL);
-                    __stcs(d.force + P + zslot, 0LL);
-                    __stcs(d.force + 2 * P + zslot, 0LL);
+#pragma unroll
+            for (int i = 0; i < kZeroSpan; i++) {
+                const int zslot = R + ((tile - realTiles) * kZeroSpan + i) * BLOCK + tid;
+                if (zslot < d.numAtoms) {
+                    if (d.zeroVelm) store4x<STREAM>(static_cast<Mixed*>(d.velm), (size_t) zslot, Vec4<Mixed>{0, 0, 0, 0});
+                    if (d.zeroForce) {
+                        __stcs(d.force + zslot, 0LL);
+                        __stcs(d.force + P + zslot, 0LL);
+                        __stcs(d.force + 2 * P + zslot, 0LL);
+                    }
                 }
             }
             close_step(d.counters, zticket, holders, zstep);

@@ -366,7 +366,8 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
     const int R = d.numReal;
     const size_t P = (size_t) d.padded;
     const int realTiles = seg.tileStart[seg.count];
-    const int zeroTiles = INDEXED ? (d.numAtoms - R + 3 * BLOCK - 1) / (3 * BLOCK) : 0;
+    constexpr int kZeroSpan = 12;  // a zeroing tile covers 12 * BLOCK image slots
+    const int zeroTiles = INDEXED ? (d.numAtoms - R + kZeroSpan * BLOCK - 1) / (kZeroSpan * BLOCK) : 0;
     const unsigned int holders = (unsigned int) (realTiles + zeroTiles);
     const StepScalars<Mixed> s = scalars_of<Mixed>(d);
     const Real* __restrict__ posq = static_cast<const Real*>(d.posq);
@@ -384,8 +385,8 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
             const unsigned long long step = box.step;
             const unsigned int ticket = take_ticket(d.counters, holders);
 #pragma unroll
-            for (int i = 0; i < 3; i++) {
-                const int slot = R + (tile - realTiles) * 3 * BLOCK + j + i * BLOCK;
+            for (int i = 0; i < kZeroSpan; i++) {
+                const int slot = R + ((tile - realTiles) * kZeroSpan + i) * BLOCK + j;
                 if (slot < d.numAtoms) {
                     if (d.zeroVelm) store4x<STREAM>(static_cast<Mixed*>(d.velm), (size_t) slot, Vec4<Mixed>{0, 0, 0, 0});
                     if (d.zeroForce) {

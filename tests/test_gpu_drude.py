@@ -91,7 +91,7 @@ def test_drude_fused_step_bit_exact(gpu, oracle, precision, num_cells, max_dist,
 @pytest.mark.parametrize("precision", slabmod.PRECISIONS)
 @pytest.mark.parametrize("shift", [1, 37, 300])
 def test_drude_pairs_across_tiles(gpu, oracle, precision, shift):
-    """Pairs whose parent sits in another 256-slot tile than the Drude particle (here: every Drude particle
+    """Pairs whose parent sits in another 128-slot tile than the Drude particle (here: every Drude particle
     paired with the parent `shift` molecules further on; wall off, the geometry is meaningless): the owner
     handles such a parent in global memory and the parent's own thread stays silent."""
     s0, normal, pairs = slabmod.make_drude_slab(5003, precision, seed=19)
@@ -100,7 +100,7 @@ def test_drude_pairs_across_tiles(gpu, oracle, precision, shift):
     ctx, it = make_drude_context(gpu, s0, pairs, 0.0, pool=pool)
     ref = s0.copy()
     scalars = mixed_scalars(oracle, precision, 0.0)
-    far = np.sum(pairs[:, 0] // 256 != pairs[:, 1] // 256)
+    far = np.sum(pairs[:, 0] // 128 != pairs[:, 1] // 128)
     assert far > (0 if shift == 1 else len(pairs) // 2)
     for k in range(2):
         it.step(1)
