@@ -25,6 +25,38 @@ def all_ranges(num_real: int, world: int, granule: int = 32) -> list[tuple[int, 
     return [shard_range(num_real, r, world, granule) for r in range(world)]
 
 
+def molecule_ranges(num_real: int, world: int, groups, granule: int = 32) -> list[tuple[int, int]]:
+    """Ranges for a slab whose step couples atoms (rigid molecules, Drude pairs): the balanced boundaries of
+    ``all_ranges`` moved down to the nearest point that cuts no group.  ``groups`` = (n, k) array of the slots
+    that must stay together (cluster atoms, or (Drude particle, parent) pairs).  A group is never split, so the
+    partitioned step is still free of inter-GPU traffic and reproduces the single-GPU trajectory bit for bit."""
+    import numpy as np
+    g = np.asarray(groups).reshape(len(groups), -1)
+    first, last = (g.min(axis=1), g.max(axis=1)) if len(g) else (np.zeros(0, int), np.zeros(0, int))
+    # cut[b] = number of groups that a boundary placed before slot b would split
+    cut = np.zeros(num_real + 2, np.int64)
+    np.add.at(cut, first + 1, 1)
+    np.add.at(cut, last + 1, -1)
+    cut = np.cumsum(cut)
+    bounds = [0]
+    for r in range(1, world):
+        b = shard_range(num_real, r, world, granule)[0]
+        while b > bounds[-1] and cut[b] != 0:
+            b -= 1
+        bounds.append(max(b, bounds[-1]))
+    bounds.append(num_real)
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+def slice_groups(groups, lo: int, hi: int):
+    """The groups (cluster atoms / Drude pairs) of the shard [lo, hi) in the shard's own slot numbering, and the
+    mask that selects them from the full list."""
+    import numpy as np
+    g = np.asarray(groups).reshape(len(groups), -1)
+    mask = (g.min(axis=1) >= lo) & (g.max(axis=1) < hi) if len(g) else np.zeros(0, bool)
+    return (g[mask] - lo).astype(np.int32), mask
+
+
 def allreduce_scalar_sum(value_tensor):
     """Sum a 1-element tensor over the process group in place (NCCL on GPUs over NVLink/NVSwitch,
     gloo in the CPU tests); a no-op without an initialised group."""
