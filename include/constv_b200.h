@@ -242,6 +242,13 @@ CONSTV_API int constv_get_chains(const constv_slab* slab, int32_t* num_chains);
 CONSTV_API int constv_step_fused_chain(constv_slab* slab, int32_t chain, const void* random4,
                                        uint32_t random_index, void* stream);
 
+/* num_steps fused steps (Philox noise) of one slab in one call: what `integrator.step(n)` is for a host whose
+ * forces do not change between the steps (replayed or constant forces, benchmarks).  On a chained slab the
+ * library forks onto one internal stream per chain, issues each chain's num_steps launches in order and joins
+ * back into `stream`, so the overlap of constv_set_chains is had without managing streams; the call can be
+ * captured in a CUDA graph.  Asynchronous. */
+CONSTV_API int constv_step_fused_multi(constv_slab* slab, int32_t num_steps, void* stream);
+
 /* ---- ConstVDrudeLangevinIntegrator ------------------------------------------- */
 /* "Drude.cu" = platforms/cuda/src/kernels/constVDrudeLangevin.cu.  The same slab object carries the
  * Drude integrator: create / bind as above, then configure the pair list and use the constv_drude_*

@@ -34,7 +34,7 @@ SYMBOLS = [
     "constv_upload_state", "constv_download_state", "constv_step_host", "constv_step_host_submit",
     "constv_step_host_collect", "constv_last_error",
     "constv_version", "constv_launch_count", "constv_set_launch_shape", "constv_set_kernel_variant",
-    "constv_set_chains", "constv_get_chains", "constv_step_fused_chain",
+    "constv_set_chains", "constv_get_chains", "constv_step_fused_chain", "constv_step_fused_multi",
     "constv_drude_configure", "constv_drude_random_count", "constv_drude_set_parameters",
     "constv_drude_get_parameters", "constv_drude_step_part1", "constv_drude_step_part2",
     "constv_drude_step_fused", "constv_drude_hardwall",
@@ -103,6 +103,7 @@ def load() -> C.CDLL:
         "constv_set_chains": [vp, i32],
         "constv_get_chains": [vp, C.POINTER(i32)],
         "constv_step_fused_chain": [vp, i32, vp, u32, vp],
+        "constv_step_fused_multi": [vp, i32, vp],
         "constv_drude_configure": [vp, i32, vp],
         "constv_drude_random_count": [vp, C.POINTER(i32)],
         "constv_drude_set_parameters": [vp, dbl, dbl, dbl, dbl, dbl, dbl],

@@ -106,6 +106,9 @@ struct constv_slab {
     // chains (constv_set_chains): chain q advances real atoms [chainLo[q], chainLo[q+1]) with counters[q]
     int chains = 1;
     int chainLo[kMaxChains + 1] = {0};
+    // constv_step_fused_multi: one side stream per chain beyond the first, fork/join events
+    cudaStream_t chainStream[kMaxChains] = {nullptr};
+    cudaEvent_t chainFork = nullptr, chainJoin[kMaxChains] = {nullptr};
     // pipelined host stepping (constv_step_host_submit / _collect): two slots
     struct HostPipe {
         bool ready = false;
@@ -432,6 +435,11 @@ int constv_destroy(constv_slab* s) {
     if (s->owned) {
         cudaFree(s->posq); cudaFree(s->corr); cudaFree(s->velm); cudaFree(s->force); cudaFree(s->posDelta);
     }
+    for (int q = 0; q < kMaxChains; q++) {
+        if (s->chainStream[q]) cudaStreamDestroy(s->chainStream[q]);
+        if (s->chainJoin[q]) cudaEventDestroy(s->chainJoin[q]);
+    }
+    if (s->chainFork) cudaEventDestroy(s->chainFork);
     cudaFree(s->invAtomOrder);
     cudaFree(s->drude.role);
     cudaFree(s->drude.pairs);
@@ -651,6 +659,43 @@ int constv_step_fused_chain(constv_slab* s, int32_t chain, const void* random4, 
     DISPATCH_PREC(s->cfg.precision, launchFused<PR>(s, d, static_cast<const float4*>(random4), random_index, (cudaStream_t) stream));
     if (rc == CONSTV_OK && chain == 0) advanceTime(s);
     return rc;
+}
+
+int constv_step_fused_multi(constv_slab* s, int32_t num_steps, void* stream) {
+    GUARD(s);
+    if (num_steps < 0) return fail(CONSTV_ERR_INVALID, "num_steps must be >= 0");
+    int rc = checkReady(s, false);
+    if (rc) return rc;
+    if ((rc = checkLangevin(s))) return rc;
+    if (s->chains == 1 || num_steps < 2) {
+        for (int k = 0; k < num_steps; k++)
+            if ((rc = constv_step_fused(s, nullptr, 0, stream))) return rc;
+        return CONSTV_OK;
+    }
+    if (s->atomIndex || s->variant == 2) return fail(CONSTV_ERR_STATE, "chains need identity slot order and the plain-load kernel");
+    if ((s->cfg.flags & CONSTV_FLAG_CACHE_IMAGE_CHARGE) && !s->imageChargeValid)
+        if ((rc = constv_refresh_image_charges(s, stream))) return rc;
+    cudaStream_t main = (cudaStream_t) stream;
+    if (!s->chainFork) CUDA_TRY(cudaEventCreateWithFlags(&s->chainFork, cudaEventDisableTiming));
+    for (int q = 1; q < s->chains; q++) {
+        if (!s->chainStream[q]) CUDA_TRY(cudaStreamCreateWithFlags(&s->chainStream[q], cudaStreamNonBlocking));
+        if (!s->chainJoin[q]) CUDA_TRY(cudaEventCreateWithFlags(&s->chainJoin[q], cudaEventDisableTiming));
+    }
+    // fork: chain q's steps, in order, on its own stream (chain 0 stays on the caller's); join back
+    CUDA_TRY(cudaEventRecord(s->chainFork, main));
+    for (int q = 0; q < s->chains; q++) {
+        cudaStream_t st = q == 0 ? main : s->chainStream[q];
+        if (q > 0) CUDA_TRY(cudaStreamWaitEvent(st, s->chainFork, 0));
+        const SlabDev dq = makeChainDev(s, q);
+        for (int k = 0; k < num_steps; k++) {
+            DISPATCH_PREC(s->cfg.precision, launchFused<PR>(s, dq, nullptr, 0u, st));
+            if (rc) return rc;
+        }
+        if (q > 0) CUDA_TRY(cudaEventRecord(s->chainJoin[q], st));
+    }
+    for (int q = 1; q < s->chains; q++) CUDA_TRY(cudaStreamWaitEvent(main, s->chainJoin[q], 0));
+    for (int k = 0; k < num_steps; k++) advanceTime(s);
+    return CONSTV_OK;
 }
 
 int constv_step_part1(constv_slab* s, const void* random4, uint32_t random_index, void* stream) {

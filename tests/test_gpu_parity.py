@@ -346,6 +346,41 @@ def test_chains_are_bit_identical_to_the_single_launch(gpu, precision, chains):
     ctx_c.close()
 
 
+@pytest.mark.parametrize("chains", [1, 3])
+def test_step_fused_multi(gpu, chains):
+    """constv_step_fused_multi(n) == n x constv_step_fused, eagerly and replayed from a CUDA graph; with chains
+    the library forks onto its own streams and joins back into the caller's."""
+    import ctypes as C
+    import torch
+    from openmm_constv_b200 import _capi
+    lib = _capi.load()
+    s0 = slabmod.make_slab(40001, "single", seed=14)
+    ctx_a, it_a = make_context(gpu, s0, seed=21)
+    it_a.step(12)
+    want = download(ctx_a, s0)
+    ctx_a.close()
+    ctx_b, it_b = make_context(gpu, s0, seed=21)
+    h = it_b._kernel.handle
+    _capi.check(lib.constv_set_chains(h, chains))
+    _capi.check(lib.constv_set_parameters(h, T, GAMMA, DT))
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        _capi.check(lib.constv_step_fused_multi(h, 4, stream.cuda_stream))   # eager (creates the side streams)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            _capi.check(lib.constv_step_fused_multi(h, 4, stream.cuda_stream))
+        g.replay()
+        g.replay()
+    torch.cuda.synchronize()
+    assert it_b._kernel.get_step_count() == 12
+    assert_slab_bits_equal(download(ctx_b, s0), want)
+    t = C.c_double(0.0)
+    _capi.check(lib.constv_get_time(h, C.byref(t)))
+    assert t.value == pytest.approx(8 * DT)  # host-side time advances when a call is issued, not when a graph replays
+    assert lib.constv_step_fused_multi(h, -1, None) == _capi.ERR_INVALID
+    ctx_b.close()
+
+
 def test_chains_guard_rails(gpu):
     import ctypes as C
     from openmm_constv_b200 import _capi
