@@ -352,7 +352,7 @@ template <int PREC, int BLOCK, bool INDEXED> struct SettleStage {
 // wherever invAtomOrder says (a scattered 16-byte store each, as in the reference, constVLangevin.cu:155-158),
 // and that the image slots are zeroed by extra tiles in slot order (coalesced) instead of by their partners.
 template <int PREC, int BLOCK, bool INDEXED, bool STREAM>
-__global__ void __launch_bounds__(BLOCK, (PREC == PREC_SINGLE && !INDEXED) ? 8 : 0)  // 64 registers, no spills: 8 CTAs per SM
+__global__ void __launch_bounds__(BLOCK, INDEXED ? 0 : (PREC == PREC_SINGLE ? 8 : 4))  // 64 registers, no spills: 8 CTAs per SM
 constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ SettleSegments seg,
                                 const float4* __restrict__ random, const unsigned int randomIndex) {
     using Real = typename Prec<PREC>::Real;
