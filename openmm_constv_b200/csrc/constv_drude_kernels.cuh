@@ -423,7 +423,7 @@ template <int PREC, int BLOCK> struct DrudeStage {
 // role); the Philox key is atomIndex[slot], images are written wherever invAtomOrder says, and the image slots
 // are zeroed by extra tiles in slot order.
 template <int PREC, int BLOCK, bool INDEXED, bool STREAM>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, PREC == PREC_SINGLE ? 0 : 5)
 constv_drude_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ DrudeDev dd,
                                const float4* __restrict__ random, const unsigned int randomIndex) {
     using Real = typename Prec<PREC>::Real;
