@@ -435,7 +435,8 @@ def main():
         n_mol = shard.meta["n_pairs"] if drude else shard.meta["n_water"] // 3
         reorder_perm = slabmod.molecule_permutation(shard, shard.meta["n_ion"], per, n_mol, seed=7 + rank)
         shard, _ = slabmod.permute_slab(shard, reorder_perm)
-    alg_bytes = slabmod.algorithmic_bytes_per_step(shard, rigid_molecules=len(water[0]) if water else 0,
+    # the staged rigid-water kernel finds its slots arithmetically; only the gather kernel (--variant 1) reads lists
+    alg_bytes = slabmod.algorithmic_bytes_per_step(shard, rigid_molecules=len(water[0]) if (water and args.variant == 1) else 0,
                                                    drude=drude is not None, drude_pairs=len(drude[1]) if drude else 0)
     rec_bytes = shard.posq.nbytes + shard.velm.nbytes + shard.force.nbytes + (shard.corr.nbytes if shard.corr is not None else 0)
     M = max(1, args.ensemble)  # slabs advanced per step on this GPU (1 = the plain slab configs)
