@@ -79,10 +79,10 @@ def parse_args():
                     help="BASELINE configs[0-1] shape: the slab's water molecules are rigid (constraints=AllBonds on SPC/E, "
                          "example/nacl_1m_spce/nacl_constv.py:56).  fused = constv_step_fused_settle, one kernel per step; "
                          "split = the reference's structure, part 1 | constraint solver on posDelta | part 2 + image rewrite "
-                         "(three launches).  Implies --chains 1.")
+                         "(three launches; implies --chains 1).")
     ap.add_argument("--drude", action="store_true",
                     help="ConstVDrudeLangevinIntegrator on a slab of polarizable 4-site water (SURVEY.md 8f.4): one fused kernel "
-                         "per step, timed beside the reference's own four Drude kernels on the same GPU.  Implies --chains 1.")
+                         "per step (per chain), timed beside the reference's own four Drude kernels on the same GPU.")
     ap.add_argument("--reordered", action="store_true",
                     help="the state behind OpenMM after cu.reorderAtoms(): whole molecules (and their images) have traded "
                          "slots inside spatial windows; the step addresses images through atomIndex / invAtomOrder "
@@ -414,13 +414,15 @@ def main():
     if args.drude:
         if args.ensemble or args.rigid_water:
             raise SystemExit("--drude, --rigid-water and --ensemble are separate configurations")
-        args.chains = 1
+        if args.variant == 1:
+            args.chains = 1
         shard, d_normal, d_pairs = slabmod.make_drude_slab(R, args.precision, seed=12345 + rank)
         drude = (d_normal, d_pairs)
     elif args.rigid_water:
         if args.ensemble:
             raise SystemExit("--rigid-water and --ensemble are separate configurations")
-        args.chains = 1
+        if args.rigid_water == "split" or args.variant == 1:
+            args.chains = 1
         shard, w_atoms, w_params, w_cons = slabmod.make_water_slab(R, args.precision, seed=12345 + rank)
         water = (w_atoms, w_params, w_cons)
     else:
@@ -523,6 +525,10 @@ def main():
                 for k in range(first, first + count):
                     if args.ensemble:
                         _capi.check(lib.constv_step_fused_batched(subgroups[k % replicas][q], bounds[q + 1] - bounds[q], cs.cuda_stream))
+                    elif drude:
+                        _capi.check(lib.constv_drude_step_fused_chain(handles[k % replicas], q, None, 0, cs.cuda_stream))
+                    elif args.rigid_water == "fused":
+                        _capi.check(lib.constv_step_fused_settle_chain(handles[k % replicas], q, None, 0, cs.cuda_stream))
                     else:
                         _capi.check(lib.constv_step_fused_chain(handles[k % replicas], q, None, 0, cs.cuda_stream))
             for cs in side_streams:

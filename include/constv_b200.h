@@ -236,7 +236,8 @@ CONSTV_API int constv_step_host_collect(constv_slab* slab, uint64_t ticket, doub
  * of another's.  Results are bit-identical to the single launch (the Philox key is the atom index and
  * the step index, not the launch).  constv_step_fused on a chained slab launches every chain in turn on
  * the given stream.  Identity slot order and the plain-load kernel only.  num_chains in 1..16 (clamped
- * to the number of tiles); setting it synchronises the device. */
+ * to the number of tiles); setting it synchronises the device.  The rigid-molecule and Drude steps have chain
+ * entry points of their own (constv_step_fused_settle_chain, constv_drude_step_fused_chain). */
 CONSTV_API int constv_set_chains(constv_slab* slab, int32_t num_chains);
 CONSTV_API int constv_get_chains(const constv_slab* slab, int32_t* num_chains);
 CONSTV_API int constv_step_fused_chain(constv_slab* slab, int32_t chain, const void* random4,
@@ -294,6 +295,11 @@ CONSTV_API int constv_drude_step_part2(constv_slab* slab, void* stream);
 CONSTV_API int constv_drude_step_fused(constv_slab* slab, const void* random4, uint32_t random_index,
                                        void* stream);
 
+/* One chain of that step (constv_set_chains; identity slot order, the staged kernel), as
+ * constv_step_fused_settle_chain. */
+CONSTV_API int constv_drude_step_fused_chain(constv_slab* slab, int32_t chain, const void* random4,
+                                             uint32_t random_index, void* stream);
+
 /* applyHardWallConstraints alone (Kernels.cpp:336-340 / Drude.cu:108-211), thread <-> pair, for hosts
  * that run their own part 2.  No-op when max_drude_distance <= 0. */
 CONSTV_API int constv_drude_hardwall(constv_slab* slab, void* stream);
@@ -327,6 +333,12 @@ CONSTV_API int constv_settle_configure(constv_slab* slab, int32_t num_clusters, 
  * constraints are all in the configured molecules, in one kernel.  random4 / Philox as constv_step_part1. */
 CONSTV_API int constv_step_fused_settle(constv_slab* slab, const void* random4, uint32_t random_index,
                                         void* stream);
+
+/* One chain of that step (constv_set_chains; identity slot order, the staged kernel): the chain's share of the
+ * step's tiles with its own step counter, to be issued on a stream of its own.  constv_step_fused_settle on a
+ * chained slab issues every chain in turn on the given stream. */
+CONSTV_API int constv_step_fused_settle_chain(constv_slab* slab, int32_t chain, const void* random4,
+                                              uint32_t random_index, void* stream);
 
 /* The solver alone on pos_delta, thread <-> molecule: what applyConstraints does for these molecules, for
  * the split path constv_step_part1 | constv_settle_positions | constv_step_part2_mirror. */

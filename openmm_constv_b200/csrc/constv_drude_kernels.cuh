@@ -439,12 +439,15 @@ constv_drude_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_c
     const int realTiles = (R + BLOCK - 1) / BLOCK;
     constexpr int kZeroSpan = 8;  // a zeroing tile covers 8 * BLOCK image slots
     const int zeroTiles = INDEXED ? (d.numAtoms - R + kZeroSpan * BLOCK - 1) / (kZeroSpan * BLOCK) : 0;
-    const unsigned int holders = (unsigned int) (realTiles + zeroTiles);
+    // a chain (constv_set_chains) advances tiles [rangeLo, rangeHi) of the tile space with its own counters;
+    // the whole step = [0, realTiles + zeroTiles)
+    const int tileLo = d.rangeLo, tileHi = d.rangeHi;
+    const unsigned int holders = (unsigned int) (tileHi - tileLo);
     const StepScalars<Mixed> s = scalars_of<Mixed>(d);
     const DrudeScalars<Mixed> ds = drude_scalars_of<Mixed>(dd);
     const int tid = (int) threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (int tile = (int) blockIdx.x; tile < (int) holders; tile += (int) gridDim.x) {
+    for (int tile = tileLo + (int) blockIdx.x; tile < tileHi; tile += (int) gridDim.x) {
         if (INDEXED && tile >= realTiles) {  // a tile of image slots: zero them, coalesced
             publish_step(box, d.counters);
             __syncthreads();
@@ -463,7 +466,7 @@ constv_drude_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_c
                 }
             }
             close_step(d.counters, zticket, holders, zstep);
-            if (tile + (int) gridDim.x < (int) holders) __syncthreads();
+            if (tile + (int) gridDim.x < tileHi) __syncthreads();
             continue;
         }
         const long long base = (long long) tile * BLOCK;
@@ -601,7 +604,7 @@ constv_drude_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_c
             }
         }
         close_step(d.counters, ticket, holders, step);
-        if (tile + (int) gridDim.x < (int) holders) __syncthreads();  // stage and box are rewritten by the next tile
+        if (tile + (int) gridDim.x < tileHi) __syncthreads();  // stage and box are rewritten by the next tile
     }
 }
 

@@ -368,7 +368,10 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
     const int realTiles = seg.tileStart[seg.count];
     constexpr int kZeroSpan = 12;  // a zeroing tile covers 12 * BLOCK image slots
     const int zeroTiles = INDEXED ? (d.numAtoms - R + kZeroSpan * BLOCK - 1) / (kZeroSpan * BLOCK) : 0;
-    const unsigned int holders = (unsigned int) (realTiles + zeroTiles);
+    // a chain (constv_set_chains) advances tiles [rangeLo, rangeHi) of the tile space with its own counters;
+    // the whole step = [0, realTiles + zeroTiles)
+    const int tileLo = d.rangeLo, tileHi = d.rangeHi;
+    const unsigned int holders = (unsigned int) (tileHi - tileLo);
     const StepScalars<Mixed> s = scalars_of<Mixed>(d);
     const Real* __restrict__ posq = static_cast<const Real*>(d.posq);
     const Real* __restrict__ corrA = static_cast<const Real*>(d.corr);
@@ -378,7 +381,7 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
     const size_t qstride = d.imageCharge ? 1 : 4;
     const int j = (int) threadIdx.x;
 
-    for (int tile = (int) blockIdx.x; tile < (int) holders; tile += (int) gridDim.x) {
+    for (int tile = tileLo + (int) blockIdx.x; tile < tileHi; tile += (int) gridDim.x) {
         if (INDEXED && tile >= realTiles) {  // a tile of image slots: zero them, coalesced
             publish_step(box, d.counters);
             __syncthreads();
@@ -397,7 +400,7 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
                 }
             }
             close_step(d.counters, ticket, holders, step);
-            if (tile + (int) gridDim.x < (int) holders) __syncthreads();
+            if (tile + (int) gridDim.x < tileHi) __syncthreads();
             continue;
         }
         int q = 0;
@@ -492,7 +495,7 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
             }
         }
         close_step(d.counters, ticket, holders, step);
-        if (tile + (int) gridDim.x < (int) holders) __syncthreads();  // stage and box are rewritten by the next tile
+        if (tile + (int) gridDim.x < tileHi) __syncthreads();  // stage and box are rewritten by the next tile
     }
 }
 

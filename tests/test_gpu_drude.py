@@ -286,6 +286,41 @@ def test_drude_philox_stream(gpu, oracle, precision):
         c.close()
 
 
+@pytest.mark.parametrize("precision", ["single", "mixed"])
+@pytest.mark.parametrize("chains", [2, 7])
+def test_drude_chains(gpu, precision, chains):
+    """The fused Drude step as chains: the single launch's bits, in turn on one stream or one stream per chain."""
+    import torch
+    from openmm_constv_b200 import _capi
+    lib = _capi.load()
+    s0, normal, pairs = slabmod.make_drude_slab(20011, precision, seed=21)
+    nsteps = 4
+    ctx_a, it_a = make_drude_context(gpu, s0, pairs, 0.02, seed=6)
+    it_a.step(nsteps)
+    want = download(ctx_a, s0)
+    ctx_a.close()
+    ctx_b, it_b = make_drude_context(gpu, s0, pairs, 0.02, seed=6)
+    _capi.check(lib.constv_set_chains(it_b._kernel.handle, chains))
+    it_b.step(nsteps)
+    assert it_b._kernel.get_step_count() == nsteps
+    assert_slab_bits_equal(download(ctx_b, s0), want)
+    ctx_b.close()
+    ctx_c, it_c = make_drude_context(gpu, s0, pairs, 0.02, seed=6)
+    h = it_c._kernel.handle
+    _capi.check(lib.constv_set_chains(h, chains))
+    _capi.check(lib.constv_drude_set_parameters(h, T, FRICTION, TD, FRICTION_D, 0.02, DT))
+    streams = [torch.cuda.Stream() for _ in range(chains)]
+    torch.cuda.synchronize()
+    for q in reversed(range(chains)):
+        for _ in range(nsteps):
+            _capi.check(lib.constv_drude_step_fused_chain(h, q, None, 0, streams[q].cuda_stream))
+    torch.cuda.synchronize()
+    assert it_c._kernel.get_step_count() == nsteps
+    assert_slab_bits_equal(download(ctx_c, s0), want)
+    assert lib.constv_drude_step_fused_chain(h, -1, None, 0, None) == _capi.ERR_INVALID
+    ctx_c.close()
+
+
 def test_drude_relative_motion_thermalises_at_the_drude_temperature(gpu):
     """Free pairs (no forces), Philox noise: after many relaxation times the pair's relative velocity
     carries kB*T_drude per degree of freedom and its centre of mass kB*T (the dual thermostat of

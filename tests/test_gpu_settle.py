@@ -198,6 +198,44 @@ def test_fused_settle_philox_and_rigid_trajectory(gpu, oracle, precision):
     ctx2.close()
 
 
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("chains", [2, 5])
+def test_fused_settle_chains(gpu, precision, chains):
+    """The rigid-water step as chains (shares of the staged kernel's tiles, one step counter each): in turn on
+    one stream, or each on a stream of its own and running ahead of the others -- the single launch's bits."""
+    import torch
+    from openmm_constv_b200 import _capi
+    lib = _capi.load()
+    s0, atoms, params, cons = slabmod.make_water_slab(20011, precision, seed=37)
+    nsteps = 4
+    ctx_a, it_a = make_water_context(gpu, s0, cons, seed=5)
+    it_a.step(nsteps)
+    want = download(ctx_a, s0)
+    ctx_a.close()
+    ctx_b, it_b = make_water_context(gpu, s0, cons, seed=5)
+    _capi.check(lib.constv_set_chains(it_b._kernel.handle, chains))
+    it_b.step(nsteps)
+    assert it_b._kernel.get_step_count() == nsteps
+    assert_slab_bits_equal(download(ctx_b, s0), want)
+    ctx_b.close()
+    ctx_c, it_c = make_water_context(gpu, s0, cons, seed=5)
+    h = it_c._kernel.handle
+    _capi.check(lib.constv_set_chains(h, chains))
+    _capi.check(lib.constv_set_parameters(h, T, GAMMA, DT))
+    streams = [torch.cuda.Stream() for _ in range(chains)]
+    torch.cuda.synchronize()
+    for q in reversed(range(chains)):
+        for _ in range(nsteps):
+            _capi.check(lib.constv_step_fused_settle_chain(h, q, None, 0, streams[q].cuda_stream))
+    torch.cuda.synchronize()
+    assert it_c._kernel.get_step_count() == nsteps
+    assert_slab_bits_equal(download(ctx_c, s0), want)
+    assert lib.constv_step_fused_settle_chain(h, chains, None, 0, None) == _capi.ERR_INVALID
+    it_c._kernel.set_kernel_variant(1)  # the gather kernel has no chains
+    assert lib.constv_step_fused_settle_chain(h, 0, None, 0, None) == _capi.ERR_STATE
+    ctx_c.close()
+
+
 def test_settle_guard_rails(gpu):
     from openmm_constv_b200 import _capi
     s0, atoms, params, cons = slabmod.make_water_slab(301, "single", seed=35)
