@@ -680,11 +680,7 @@ constv_fused_step_indexed_kernel(const __grid_constant__ SlabDev d, const float4
     constexpr bool kSplit = Prec<PREC>::kSplitPos;
     __shared__ StepBox box;
     pdl_wait();
-    publish_step(box, d.counters);
-    __syncthreads();
     pdl_launch();
-    const unsigned long long step = box.step;
-    const unsigned int ticket = take_ticket(d.counters, gridDim.x);  // one ticket per CTA
     const int R = d.numReal;
     const size_t P = (size_t) d.padded;
     Real* __restrict__ posq = static_cast<Real*>(d.posq);
@@ -692,25 +688,55 @@ constv_fused_step_indexed_kernel(const __grid_constant__ SlabDev d, const float4
     Mixed* __restrict__ velm = static_cast<Mixed*>(d.velm);
     long long* __restrict__ force = d.force;
     const StepScalars<Mixed> s = scalars_of<Mixed>(d);
-    for (int slot = blockIdx.x * BLOCK + threadIdx.x; slot < d.numAtoms; slot += gridDim.x * BLOCK) {
-        const int a = d.atomIndex[slot];
-        if (a >= R) {
-            if (d.zeroVelm) store4(velm, (size_t) slot, Vec4<Mixed>{0, 0, 0, 0});
-            if (d.zeroForce) {
-                __stcs(force + slot, 0LL);
-                __stcs(force + P + slot, 0LL);
-                __stcs(force + 2 * P + slot, 0LL);
-            }
-            continue;
+
+    // One slot per thread (one-shot grid).  Everything a slot may need is requested before the barrier that
+    // publishes the step counter: its atom index and -- for the low slots, where OpenMM's re-sorting (whole
+    // identical molecules trade places) leaves the real atoms -- its record.  Any slot may still hold any atom.
+    const int slot = blockIdx.x * BLOCK + threadIdx.x;
+    const bool inRange = slot < d.numAtoms;
+    const bool early = inRange && slot < R;
+    int a = R;
+    Vec4<Mixed> v{0, 0, 0, 0};
+    Vec4<Real> p{0, 0, 0, 0}, c{0, 0, 0, 0};
+    long long fx = 0, fy = 0, fz = 0;
+    if (inRange) a = d.atomIndex[slot];
+    if (early) {
+        v = load4x<true>(velm, (size_t) slot);
+        p = load4x<true>(posq, (size_t) slot);
+        if (kSplit) c = load4x<true>(corrA, (size_t) slot);
+        fx = load_force(force + slot);
+        fy = load_force(force + P + slot);
+        fz = load_force(force + 2 * P + slot);
+    }
+    publish_step(box, d.counters);
+    __syncthreads();
+    const unsigned long long step = box.step;
+    const unsigned int ticket = take_ticket(d.counters, gridDim.x);  // one ticket per CTA
+
+    if (inRange && a >= R) {  // an image: zero it
+        if (d.zeroVelm) store4x<true>(velm, (size_t) slot, Vec4<Mixed>{0, 0, 0, 0});
+        if (d.zeroForce) {
+            __stcs(force + slot, 0LL);
+            __stcs(force + P + slot, 0LL);
+            __stcs(force + 2 * P + slot, 0LL);
         }
-        Vec4<Mixed> v = load4(velm, (size_t) slot);
-        Vec4<Real> p = load4(posq, (size_t) slot);
-        Vec4<Real> c{};
-        if (kSplit) c = load4(corrA, (size_t) slot);
+    } else if (inRange) {
+        if (!early) {  // a real atom in a high slot
+            v = load4x<true>(velm, (size_t) slot);
+            p = load4x<true>(posq, (size_t) slot);
+            if (kSplit) c = load4x<true>(corrA, (size_t) slot);
+            fx = load_force(force + slot);
+            fy = load_force(force + P + slot);
+            fz = load_force(force + 2 * P + slot);
+        }
+        const bool charged = p.w != -p.w;
+        size_t t1 = 0;
+        Real q1 = 0;
+        if (charged) {  // the cell-1 image's slot and charge: requested before the arithmetic
+            t1 = (size_t) d.invAtomOrder[a + R];
+            q1 = d.imageCharge ? static_cast<const Real*>(d.imageCharge)[a] : posq[4 * t1 + 3];
+        }
         if (v.w != 0) {
-            const long long fx = load_force(force + slot);
-            const long long fy = load_force(force + P + slot);
-            const long long fz = load_force(force + 2 * P + slot);
             float4 xi;
             if (random) xi = __ldcs(random + (size_t) randomIndex + slot);
             else xi = (s.noisescale != 0) ? gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) a, step)
@@ -718,13 +744,16 @@ constv_fused_step_indexed_kernel(const __grid_constant__ SlabDev d, const float4
             Vec4<Mixed> delta;
             part1_update(v, delta, fx, fy, fz, xi.x, xi.y, xi.z, s);
             part2_update<PREC>(p, c, v, delta, s.invDt);
-            store4(velm, (size_t) slot, v);
-            store4(posq, (size_t) slot, p);
-            if (kSplit) store4(corrA, (size_t) slot, c);
+            store4x<true>(velm, (size_t) slot, v);
+            store4x<true>(posq, (size_t) slot, p);
+            if (kSplit) store4x<true>(corrA, (size_t) slot, c);
         }
-        if (p.w != -p.w) {
+        if (charged) {
             ImageCursor<PREC> cur(p, c);
-            for (int cell = 1; cell < d.numCells; cell++) {
+            cur.advance(1, s.zshift);
+            store4(posq, t1, cur.posq(q1));
+            if (kSplit) store4(corrA, t1, cur.corr());
+            for (int cell = 2; cell < d.numCells; cell++) {
                 const size_t t = (size_t) d.invAtomOrder[a + R * cell];
                 const Real qc = d.imageCharge ? static_cast<const Real*>(d.imageCharge)[(size_t) (cell - 1) * R + a]
                                               : posq[4 * t + 3];
