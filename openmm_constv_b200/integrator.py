@@ -407,6 +407,11 @@ class IntegrateConstVDrudeLangevinStepKernel(IntegrateConstVLangevinStepKernel):
     def Name() -> str:
         return "IntegrateConstVDrudeLangevinStep"
 
+    def _configure_rigid_molecules(self, system: SlabSystem) -> None:
+        # the Drude step always hands constraints over (CudaConstVKernels.cpp:315)
+        self.num_rigid_molecules = 0
+        self.fused_constraints = False
+
     def initialize(self, system: SlabSystem, integrator: ConstVDrudeLangevinIntegrator, force: DrudeForce = None) -> None:
         super().initialize(system, integrator)
         pairs = np.zeros((max(force.getNumParticles(), 1), 2), np.int32)
@@ -429,6 +434,9 @@ class IntegrateConstVDrudeLangevinStepKernel(IntegrateConstVLangevinStepKernel):
             context.atoms_were_reordered = False
         rnd, idx = context.prepare_random_numbers(self.random_count)  # :307
         if context.apply_constraints is None:
+            if context.getSystem().getNumConstraints() > 0:
+                raise OpenMMException("the System has constraints: the Drude step hands them to the caller's solver, "
+                                      "give the context an apply_constraints callback")
             check(lib.constv_drude_step_fused(slab, rnd, idx, st))
         else:  # :308-344 with the constraint hand-off at :315
             check(lib.constv_drude_step_part1(slab, rnd, idx, st))

@@ -376,6 +376,21 @@ def test_drude_error_paths(gpu):
     assert lib.constv_drude_configure(slab, 1, bad.ctypes.data_as(C.c_void_p)) == _capi.ERR_INVALID
     it2.step(1)  # the failed configure calls left the slab usable
     ctx.close()
+    # a Drude System with constraints and no solver to hand them to
+    sysm = gpu.SlabSystem()
+    sysm.addParticles(s0.masses)
+    sysm.setDefaultPeriodicBoxVectors((s0.box[0], 0, 0), (0, s0.box[1], 0), (0, 0, s0.num_cells * s0.zmax))
+    force = gpu.DrudeForce()
+    for p, p1 in pairs:
+        force.addParticle(int(p), int(p1))
+    sysm.addForce(force)
+    sysm.addConstraint(int(normal[0]), int(normal[1]), 0.1)
+    it3 = gpu.ConstVDrudeLangevinIntegrator(T, FRICTION, TD, FRICTION_D, DT)
+    ctx3 = gpu.SlabContext(sysm, it3, padded=s0.padded)
+    ctx3.load_slab(s0)
+    with pytest.raises(gpu.OpenMMException, match="apply_constraints"):
+        it3.step(1)
+    ctx3.close()
 
 
 import glob  # noqa: E402
