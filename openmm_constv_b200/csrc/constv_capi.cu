@@ -300,8 +300,8 @@ bool tmaEligible(const constv_slab* s, const void* random4) {
 
 template <int PREC>
 int launchFusedIndexed(constv_slab* s, const SlabDev& d, const float4* random, unsigned randomIndex, cudaStream_t st) {
-    // one slot per thread: always a one-shot grid
-    return launch(constv_fused_step_indexed_kernel<PREC, kBlock>, gridFor(s, s->cfg.num_atoms, kBlock, 0), kBlock,
+    // thread i owns slot i and its numCells-1 image-cell slots: a one-shot grid over the real-atom count
+    return launch(constv_fused_step_indexed_kernel<PREC, kBlock>, gridFor(s, s->numReal, kBlock, 0), kBlock,
                   (bool) (s->cfg.flags & CONSTV_FLAG_PDL), st, d, random, randomIndex);
 }
 

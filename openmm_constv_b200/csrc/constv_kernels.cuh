@@ -669,10 +669,10 @@ constv_fused_step_batched_kernel(const __grid_constant__ BatchParams<CAP> b) {
 
 // ---- the fused step for reordered slots --------------------------------------------------------
 // Behind OpenMM the slots are periodically re-sorted (cu.reorderAtoms(), Kernels.cpp:172); slot s
-// holds original atom atomIndex[s].  Thread <-> slot: a real atom updates itself (coalesced) and
-// scatters its images through invAtomOrder; an image slot zeroes itself (coalesced).
+// holds original atom atomIndex[s].  Thread i owns slot i and slots i + R*cell: a real atom is updated
+// (coalesced) and scatters its images through invAtomOrder; an image slot is zeroed (coalesced).
 template <int PREC, int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, PREC == PREC_SINGLE ? 0 : 4)  // mixed/double: 64 registers, 4 CTAs per SM
 constv_fused_step_indexed_kernel(const __grid_constant__ SlabDev d, const float4* __restrict__ random,
                                  const unsigned int randomIndex) {
     using Real = typename Prec<PREC>::Real;
@@ -689,46 +689,41 @@ constv_fused_step_indexed_kernel(const __grid_constant__ SlabDev d, const float4
     long long* __restrict__ force = d.force;
     const StepScalars<Mixed> s = scalars_of<Mixed>(d);
 
-    // One slot per thread (one-shot grid).  Everything a slot may need is requested before the barrier that
-    // publishes the step counter: its atom index and -- for the low slots, where OpenMM's re-sorting (whole
-    // identical molecules trade places) leaves the real atoms -- its record.  Any slot may still hold any atom.
-    const int slot = blockIdx.x * BLOCK + threadIdx.x;
-    const bool inRange = slot < d.numAtoms;
-    const bool early = inRange && slot < R;
-    int a = R;
+    // Thread i < R owns slot i and slots i + R*cell (one-shot grid over R).  OpenMM's re-sorting (whole identical
+    // molecules trade places) leaves the real atoms in the low slots and the images in the high ones, so a thread
+    // normally updates one real atom and zeroes numCells-1 image slots -- no CTA is left with nothing but
+    // zeroing to do -- but any slot may hold any atom and is treated by what atomIndex says it holds.
+    // Everything the low slot needs is requested before the barrier that publishes the step counter.
+    const int i = blockIdx.x * BLOCK + threadIdx.x;
+    const bool inRange = i < R;
+    int a0 = R, a1 = R;
     Vec4<Mixed> v{0, 0, 0, 0};
     Vec4<Real> p{0, 0, 0, 0}, c{0, 0, 0, 0};
     long long fx = 0, fy = 0, fz = 0;
-    if (inRange) a = d.atomIndex[slot];
-    if (early) {
-        v = load4x<true>(velm, (size_t) slot);
-        p = load4x<true>(posq, (size_t) slot);
-        if (kSplit) c = load4x<true>(corrA, (size_t) slot);
-        fx = load_force(force + slot);
-        fy = load_force(force + P + slot);
-        fz = load_force(force + 2 * P + slot);
+    if (inRange) {
+        a0 = d.atomIndex[i];
+        a1 = d.atomIndex[i + R];
+        v = load4x<true>(velm, (size_t) i);
+        p = load4x<true>(posq, (size_t) i);
+        if (kSplit) c = load4x<true>(corrA, (size_t) i);
+        fx = load_force(force + i);
+        fy = load_force(force + P + i);
+        fz = load_force(force + 2 * P + i);
     }
     publish_step(box, d.counters);
     __syncthreads();
     const unsigned long long step = box.step;
     const unsigned int ticket = take_ticket(d.counters, gridDim.x);  // one ticket per CTA
 
-    if (inRange && a >= R) {  // an image: zero it
+    auto zeroSlot = [&](int slot) {
         if (d.zeroVelm) store4x<true>(velm, (size_t) slot, Vec4<Mixed>{0, 0, 0, 0});
         if (d.zeroForce) {
             __stcs(force + slot, 0LL);
             __stcs(force + P + slot, 0LL);
             __stcs(force + 2 * P + slot, 0LL);
         }
-    } else if (inRange) {
-        if (!early) {  // a real atom in a high slot
-            v = load4x<true>(velm, (size_t) slot);
-            p = load4x<true>(posq, (size_t) slot);
-            if (kSplit) c = load4x<true>(corrA, (size_t) slot);
-            fx = load_force(force + slot);
-            fy = load_force(force + P + slot);
-            fz = load_force(force + 2 * P + slot);
-        }
+    };
+    auto updateReal = [&](int slot, int a, Vec4<Mixed> v, Vec4<Real> p, Vec4<Real> c, long long fx, long long fy, long long fz) {
         const bool charged = p.w != -p.w;
         size_t t1 = 0;
         Real q1 = 0;
@@ -760,6 +755,24 @@ constv_fused_step_indexed_kernel(const __grid_constant__ SlabDev d, const float4
                 cur.advance(cell, s.zshift);
                 store4(posq, t, cur.posq(qc));
                 if (kSplit) store4(corrA, t, cur.corr());
+            }
+        }
+    };
+
+    if (inRange) {
+        if (a0 >= R) zeroSlot(i);
+        else updateReal(i, a0, v, p, c, fx, fy, fz);
+#pragma unroll 1
+        for (int cell = 1; cell < d.numCells; cell++) {
+            const int slot = i + R * cell;
+            const int a = cell == 1 ? a1 : d.atomIndex[slot];
+            if (a >= R) {
+                zeroSlot(slot);
+            } else {  // a real atom in a high slot
+                Vec4<Real> c2{0, 0, 0, 0};
+                if (kSplit) c2 = load4x<true>(corrA, (size_t) slot);
+                updateReal(slot, a, load4x<true>(velm, (size_t) slot), load4x<true>(posq, (size_t) slot), c2,
+                           load_force(force + slot), load_force(force + P + slot), load_force(force + 2 * P + slot));
             }
         }
     }
