@@ -68,8 +68,7 @@ def main():
         integrator.step(n)
         done += n
         pos = context.getPositions()
-        vel = context.getVelocities()
-        ke = 0.5 * float(np.sum(slab.masses[:R, None] * vel[:R] ** 2))
+        ke = context.getKineticEnergy()   # half-step-shifted velocities, projected onto the constraints
         temp = 2 * ke / (n_dof * slabmod.BOLTZ)
         oh = np.linalg.norm(pos[molecules[:, 1]] - pos[molecules[:, 0]], axis=1)
         charged = slab.posq[:R, 3] != 0

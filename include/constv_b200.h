@@ -168,7 +168,9 @@ CONSTV_API int constv_step_fused_batched(constv_slab* const* slabs, int32_t n, v
 
 /* Replaces computeKineticEnergy, Kernels.cpp:175-177 (OpenMM's
  * integration.computeKineticEnergy(0.5*dt)): KE = 0.5*sum m|v + time_shift*F/m|^2 over massive
- * atoms, accumulated in double.  Synchronises `stream` and writes *ke_out on the host. */
+ * atoms, accumulated in double.  On a slab with configured rigid molecules (constv_settle_configure) the
+ * shifted velocities of the molecule atoms are first projected onto the constraints, as OpenMM's
+ * computeKineticEnergy does for a constrained System.  Synchronises `stream` and writes *ke_out on the host. */
 CONSTV_API int constv_kinetic_energy(constv_slab* slab, double time_shift, double* ke_out,
                                      void* stream);
 

@@ -767,6 +767,20 @@ int constv_kinetic_energy_device(constv_slab* s, double time_shift, double* ke_d
     const SlabDev d = makeDev(s);
     const double scale = time_shift / 4294967296.0;
     int rc;
+    if (s->settle.configured && s->settle.numClusters > 0 && s->paramsKind != 2) {
+        // rigid molecules: the shifted velocities are projected onto the constraints first, as OpenMM's
+        // computeKineticEnergy does for a constrained System
+        SettleDev sd{};
+        sd.items = s->settle.items;
+        sd.atoms = s->settle.atoms;
+        sd.params = s->settle.params;
+        sd.numItems = s->settle.numItems;
+        sd.numClusters = s->settle.numClusters;
+        const int grid = gridFor(s, sd.numItems, kBlock, 4);
+        DISPATCH_PREC(s->cfg.precision, launch(constv_kinetic_energy_rigid_kernel<PR, kBlock>, grid, kBlock, false, (cudaStream_t) stream,
+                                               d, sd, scale, s->kePartials, ke_device));
+        return rc;
+    }
     DISPATCH_PREC(s->cfg.precision, launchKE<PR>(s, d, scale, ke_device, (cudaStream_t) stream));
     return rc;
 }

@@ -499,4 +499,117 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
     }
 }
 
+
+// ---- kinetic energy of a system with rigid molecules ------------------------------------------------------
+// OpenMM's integration.computeKineticEnergy (CudaConstVKernels.cpp:175-177) projects the half-step-shifted
+// velocities onto the constraints before summing; for rigid 3-site molecules that is a 3x3 linear system in the
+// three Lagrange multipliers, solved here by Cramer's rule in double (an on-demand report).  Thread <-> work
+// item; reduction as constv_kinetic_energy_kernel (warp shuffle -> shared -> one partial per CTA -> the last
+// CTA adds the partials in index order).
+__device__ __forceinline__ void settle_velocity_molecule(const double (&x)[3][3], double (&v)[3][3], const double (&w)[3]) {
+    using D = RN<double>;
+    D r[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        r[0][k] = D(x[0][k]) - D(x[1][k]);
+        r[1][k] = D(x[0][k]) - D(x[2][k]);
+        r[2][k] = D(x[1][k]) - D(x[2][k]);
+    }
+    D g[3][3];
+#pragma unroll
+    for (int p = 0; p < 3; p++)
+#pragma unroll
+        for (int q = 0; q < 3; q++) g[p][q] = r[p][0] * r[q][0] + r[p][1] * r[q][1] + r[p][2] * r[q][2];
+    const D w0(w[0]), w1(w[1]), w2(w[2]);
+    const D a00 = (w0 + w1) * g[0][0], a01 = w0 * g[1][0], a02 = (-w1) * g[2][0];
+    const D a10 = w0 * g[0][1], a11 = (w0 + w2) * g[1][1], a12 = w2 * g[2][1];
+    const D a20 = (-w1) * g[0][2], a21 = w2 * g[1][2], a22 = (w1 + w2) * g[2][2];
+    const D b0 = -((D(v[0][0]) - D(v[1][0])) * r[0][0] + (D(v[0][1]) - D(v[1][1])) * r[0][1] + (D(v[0][2]) - D(v[1][2])) * r[0][2]);
+    const D b1 = -((D(v[0][0]) - D(v[2][0])) * r[1][0] + (D(v[0][1]) - D(v[2][1])) * r[1][1] + (D(v[0][2]) - D(v[2][2])) * r[1][2]);
+    const D b2 = -((D(v[1][0]) - D(v[2][0])) * r[2][0] + (D(v[1][1]) - D(v[2][1])) * r[2][1] + (D(v[1][2]) - D(v[2][2])) * r[2][2]);
+    const D c00 = a11 * a22 - a12 * a21, c01 = a12 * a20 - a10 * a22, c02 = a10 * a21 - a11 * a20;
+    const D det = a00 * c00 + a01 * c01 + a02 * c02;
+    const D l0 = (b0 * c00 + a01 * (a12 * b2 - b1 * a22) + a02 * (b1 * a21 - a11 * b2)) / det;
+    const D l1 = (a00 * (b1 * a22 - a12 * b2) + b0 * c01 + a02 * (a10 * b2 - b1 * a20)) / det;
+    const D l2 = (a00 * (a11 * b2 - b1 * a21) + a01 * (b1 * a20 - a10 * b2) + b0 * c02) / det;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        v[0][k] = (D(v[0][k]) + w0 * (l0 * r[0][k] + l1 * r[1][k])).v;
+        v[1][k] = (D(v[1][k]) + w1 * (l2 * r[2][k] - l0 * r[0][k])).v;
+        v[2][k] = (D(v[2][k]) - w2 * (l1 * r[1][k] + l2 * r[2][k])).v;
+    }
+}
+
+template <int PREC, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+constv_kinetic_energy_rigid_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ SettleDev sd, const double scaleD,
+                                   double* __restrict__ partials, double* __restrict__ out) {
+    using Real = typename Prec<PREC>::Real;
+    using Mixed = typename Prec<PREC>::Mixed;
+    constexpr bool kSplit = Prec<PREC>::kSplitPos;
+    const size_t P = (size_t) d.padded;
+    const Real* __restrict__ posq = static_cast<const Real*>(d.posq);
+    const Real* __restrict__ corrA = static_cast<const Real*>(d.corr);
+    const Mixed* __restrict__ velm = static_cast<const Mixed*>(d.velm);
+    const long long* __restrict__ force = d.force;
+    const Mixed scale = (Mixed) scaleD;
+    double e = 0.0;
+    for (int t = blockIdx.x * BLOCK + threadIdx.x; t < sd.numItems; t += gridDim.x * BLOCK) {
+        const int2 item = sd.items[t];
+        if (item.y < 0) {
+            const Vec4<Mixed> v = load4(velm, (size_t) item.x);
+            if (v.w != 0) {
+                const double vx = (double) fma_rn(mul_rn(scale, from_fixed(force[item.x], Mixed())), v.w, v.x);
+                const double vy = (double) fma_rn(mul_rn(scale, from_fixed(force[P + item.x], Mixed())), v.w, v.y);
+                const double vz = (double) fma_rn(mul_rn(scale, from_fixed(force[2 * P + item.x], Mixed())), v.w, v.z);
+                e += (vx * vx + vy * vy + vz * vz) / (double) v.w;
+            }
+        } else {
+            const int4 at = sd.atoms[item.y];
+            const int slots[3] = {at.x, at.y, at.z};
+            double x[3][3], v[3][3], w[3];
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                const size_t s = (size_t) slots[a];
+                const Vec4<Mixed> vm = load4(velm, s);
+                const Vec4<Real> p = load4(posq, s);
+                Vec4<Real> c{0, 0, 0, 0};
+                if (kSplit) c = load4(corrA, s);
+                Mixed pos[3];
+                drude_pos_load<PREC>(p, c, pos);
+                w[a] = (double) vm.w;
+                x[a][0] = (double) pos[0]; x[a][1] = (double) pos[1]; x[a][2] = (double) pos[2];
+                v[a][0] = (double) fma_rn(mul_rn(scale, from_fixed(force[s], Mixed())), vm.w, vm.x);
+                v[a][1] = (double) fma_rn(mul_rn(scale, from_fixed(force[P + s], Mixed())), vm.w, vm.y);
+                v[a][2] = (double) fma_rn(mul_rn(scale, from_fixed(force[2 * P + s], Mixed())), vm.w, vm.z);
+            }
+            settle_velocity_molecule(x, v, w);
+#pragma unroll
+            for (int a = 0; a < 3; a++) e += (v[a][0] * v[a][0] + v[a][1] * v[a][1] + v[a][2] * v[a][2]) / w[a];
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
+    __shared__ double warpSum[BLOCK / 32];
+    __shared__ bool isLast;
+    if ((threadIdx.x & 31) == 0) warpSum[threadIdx.x >> 5] = e;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double b = 0.0;
+        for (int w = 0; w < BLOCK / 32; w++) b += warpSum[w];
+        partials[blockIdx.x] = b;
+        __threadfence();
+        isLast = atomicInc(&d.counters->keTicket, gridDim.x - 1) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (isLast && threadIdx.x < 32) {
+        __threadfence();
+        double t = 0.0;
+        for (int k = threadIdx.x; k < (int) gridDim.x; k += 32) t += __ldcg(partials + k);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        if (threadIdx.x == 0) *out = 0.5 * t;
+    }
+}
+
 }  // namespace constv

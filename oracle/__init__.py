@@ -74,6 +74,8 @@ def _load(path):
     so.oracle_kinetic_energy_f32.restype = C.c_double
     so.oracle_kinetic_energy_mixed.restype = C.c_double
     so.oracle_kinetic_energy_f64.restype = C.c_double
+    for sfx in ("f32", "mixed", "f64"):
+        getattr(so, "oracle_kinetic_energy_rigid_" + sfx).restype = C.c_double
     so.oracle_num_threads.restype = C.c_int
     return so
 
@@ -281,6 +283,21 @@ def settle_step(precision, num_atoms, num_cells, zshift_per_cell, posq, posq_cor
        _p(posq_corr, r) if posq_corr is not None else None, _p(velm, m), _p(force, np.int64), _p(pos_delta, m),
        _p(prm), _mixed_scalar(precision, step_size), _p(random4, np.float32), C.c_uint(random_index),
        _p(inv_order, np.int32), C.c_int(zero_velm), C.c_int(zero_force), C.c_int(len(atoms)), _p(atoms), _p(cp))
+
+
+def kinetic_energy_rigid(precision, posq, posq_corr, velm, force, time_shift, cluster_atoms, num_atoms=None,
+                         return_velocities=False):
+    """KE with the shifted velocities projected onto the rigid molecules' constraints (what OpenMM's
+    computeKineticEnergy reports for a constrained System)."""
+    r, m = REAL[precision], MIXED[precision]
+    n = velm.shape[0] if num_atoms is None else num_atoms
+    atoms = np.ascontiguousarray(cluster_atoms, np.int32).reshape(-1, 3)
+    out = np.zeros((n, 3), np.float64) if return_velocities else None
+    fn = getattr(lib(), "oracle_kinetic_energy_rigid_" + _SUFFIX[precision])
+    ke = fn(C.c_int(n), C.c_int(velm.shape[0]), _p(posq, r), _p(posq_corr, r) if posq_corr is not None else None,
+            _p(velm, m), _p(force, np.int64), C.c_double(time_shift), C.c_int(len(atoms)), _p(atoms),
+            _p(out) if out is not None else None)
+    return (ke, out) if return_velocities else ke
 
 
 def philox4x32_10(counter, key):

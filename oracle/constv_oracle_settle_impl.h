@@ -186,6 +186,95 @@ void FN(oracle_settle_step)(int numAtoms, int paddedNumAtoms, int numCells, doub
     FN(oracle_zero_images)(numAtoms, numRealAtoms, paddedNumAtoms, velm, force, invAtomOrder, zeroVelm, zeroForce);
 }
 
+
+/*
+ * Velocity constraints of one rigid molecule, in double whatever the precision model (an on-demand report, not
+ * the step): v_i' = v_i + w_i * sum_p s_ip lambda_p r_p over the pairs p0 = (0,1), p1 = (0,2), p2 = (1,2), with
+ * (v_c' - v_d') . r_q = 0 for every pair q = (c,d).  A 3x3 linear system in the lambdas, solved by Cramer's
+ * rule.  This is what OpenMM's applyVelocityConstraints does for these molecules inside
+ * integration.computeKineticEnergy (reached from CudaConstVKernels.cpp:175-177); PARITY UNPINNED like the
+ * position solver, pinned on its defining properties (tests/test_oracle_settle.py).  Every operation rounded
+ * separately; the CUDA kernel spells the same sequence.
+ */
+static inline void FN(settle_velocity_molecule)(const double x[3][3], double v[3][3], const double w[3]) {
+    double r[3][3];
+    for (int k = 0; k < 3; k++) {
+        r[0][k] = x[0][k] - x[1][k];
+        r[1][k] = x[0][k] - x[2][k];
+        r[2][k] = x[1][k] - x[2][k];
+    }
+    double g[3][3];
+    for (int p = 0; p < 3; p++)
+        for (int q = 0; q < 3; q++) g[p][q] = r[p][0] * r[q][0] + r[p][1] * r[q][1] + r[p][2] * r[q][2];
+    const double a00 = (w[0] + w[1]) * g[0][0], a01 = w[0] * g[1][0], a02 = -w[1] * g[2][0];
+    const double a10 = w[0] * g[0][1], a11 = (w[0] + w[2]) * g[1][1], a12 = w[2] * g[2][1];
+    const double a20 = -w[1] * g[0][2], a21 = w[2] * g[1][2], a22 = (w[1] + w[2]) * g[2][2];
+    double b[3];
+    b[0] = -((v[0][0] - v[1][0]) * r[0][0] + (v[0][1] - v[1][1]) * r[0][1] + (v[0][2] - v[1][2]) * r[0][2]);
+    b[1] = -((v[0][0] - v[2][0]) * r[1][0] + (v[0][1] - v[2][1]) * r[1][1] + (v[0][2] - v[2][2]) * r[1][2]);
+    b[2] = -((v[1][0] - v[2][0]) * r[2][0] + (v[1][1] - v[2][1]) * r[2][1] + (v[1][2] - v[2][2]) * r[2][2]);
+    const double c00 = a11 * a22 - a12 * a21, c01 = a12 * a20 - a10 * a22, c02 = a10 * a21 - a11 * a20;
+    const double det = a00 * c00 + a01 * c01 + a02 * c02;
+    const double l0 = (b[0] * c00 + a01 * (a12 * b[2] - b[1] * a22) + a02 * (b[1] * a21 - a11 * b[2])) / det;
+    const double l1 = (a00 * (b[1] * a22 - a12 * b[2]) + b[0] * c01 + a02 * (a10 * b[2] - b[1] * a20)) / det;
+    const double l2 = (a00 * (a11 * b[2] - b[1] * a21) + a01 * (b[1] * a20 - a10 * b[2]) + b[0] * c02) / det;
+    for (int k = 0; k < 3; k++) {
+        v[0][k] = v[0][k] + w[0] * (l0 * r[0][k] + l1 * r[1][k]);
+        v[1][k] = v[1][k] + w[1] * (l2 * r[2][k] - l0 * r[0][k]);
+        v[2][k] = v[2][k] - w[2] * (l1 * r[1][k] + l2 * r[2][k]);
+    }
+}
+
+/*
+ * Kinetic energy of a system with rigid molecules: the shifted velocities v + timeShift*F/m of
+ * oracle_kinetic_energy, projected onto the constraints for the molecule atoms, KE = 0.5 sum m |v'|^2.
+ */
+double FN(oracle_kinetic_energy_rigid)(int numAtoms, int paddedNumAtoms, const REAL* posq, const REAL* posqCorrection,
+                                       const MIXED* velm, const long long* force, double timeShift, int numClusters,
+                                       const int* clusterAtoms, double* projectedVelocities) {
+    const MIXED scale = (MIXED) (timeShift / 4294967296.0);
+    const size_t P = (size_t) paddedNumAtoms;
+    unsigned char* inMolecule = (unsigned char*) calloc((size_t) numAtoms + 1, 1);
+    double energy = 0.0;
+    for (int i = 0; i < numClusters; i++) {
+        double x[3][3], v[3][3], w[3];
+        for (int a = 0; a < 3; a++) {
+            const size_t at = (size_t) clusterAtoms[3 * i + a];
+            inMolecule[at] = 1;
+            MIXED pos[3];
+            FN(settle_load_pos)(posq, posqCorrection, at, pos);
+            w[a] = (double) velm[4 * at + 3];
+            for (int k = 0; k < 3; k++) {
+                x[a][k] = (double) pos[k];
+                const MIXED f = (MIXED) force[at + P * k];
+                v[a][k] = (double) S_FMA(scale * f, velm[4 * at + 3], velm[4 * at + k]);
+            }
+        }
+        FN(settle_velocity_molecule)(x, v, w);
+        for (int a = 0; a < 3; a++) {
+            energy += (v[a][0] * v[a][0] + v[a][1] * v[a][1] + v[a][2] * v[a][2]) / w[a];
+            if (projectedVelocities)
+                for (int k = 0; k < 3; k++) projectedVelocities[3 * (size_t) clusterAtoms[3 * i + a] + k] = v[a][k];
+        }
+    }
+    for (int index = 0; index < numAtoms; index++) {
+        const MIXED* vel = velm + 4 * (size_t) index;
+        const MIXED w = vel[3];
+        if (w != 0 && !inMolecule[index]) {
+            double e = 0.0;
+            for (int k = 0; k < 3; k++) {
+                const MIXED f = (MIXED) force[(size_t) index + P * k];
+                const MIXED v = S_FMA(scale * f, w, vel[k]);
+                e += (double) v * (double) v;
+                if (projectedVelocities) projectedVelocities[3 * (size_t) index + k] = (double) v;
+            }
+            energy += e / (double) w;
+        }
+    }
+    free(inMolecule);
+    return 0.5 * energy;
+}
+
 #undef M_SQRT
 #undef S_FMA
 #undef FN

@@ -236,6 +236,38 @@ def test_fused_settle_chains(gpu, precision, chains):
     ctx_c.close()
 
 
+@pytest.mark.parametrize("precision", slabmod.PRECISIONS)
+@pytest.mark.parametrize("num_real", [37, 100003])
+def test_kinetic_energy_of_rigid_water(gpu, oracle, precision, num_real):
+    """computeKineticEnergy on a System whose constraints are solved in the step: the half-step-shifted
+    velocities are projected onto the rigid molecules' constraints first (as OpenMM's computeKineticEnergy does
+    for a constrained System).  Against the oracle to 1e-12 (the per-molecule arithmetic is the same sequence of
+    double operations; only the order of the final sum differs), before and after a step, identity and
+    reordered slots."""
+    s0, atoms, params, cons = slabmod.make_water_slab(num_real, precision, seed=38)
+    ctx, it = make_water_context(gpu, s0, cons, seed=8)
+    want = oracle.kinetic_energy_rigid(precision, s0.posq, s0.corr, s0.velm, s0.force.reshape(-1), 0.5 * DT, atoms, s0.num_atoms)
+    free = oracle.kinetic_energy(precision, s0.velm, s0.force.reshape(-1), 0.5 * DT, s0.num_atoms)
+    got = it.computeKineticEnergy()
+    assert got == pytest.approx(want, rel=1e-12)
+    if len(atoms) > 10:
+        assert got < 0.9 * free  # Maxwell-Boltzmann velocities per atom: a third of the molecules' 9 dof is projected out
+    assert ctx.getKineticEnergy() == got  # deterministic reduction order
+    it.step(3)
+    after = download(ctx, s0)
+    want = oracle.kinetic_energy_rigid(precision, after.posq, after.corr, after.velm, after.force.reshape(-1), 0.5 * DT, atoms,
+                                       s0.num_atoms)
+    assert it.computeKineticEnergy() == pytest.approx(want, rel=1e-12)
+    ctx.close()
+    perm = molecule_preserving_permutation(s0, np.random.default_rng(7))
+    sp, _ = H.permute_slab(s0, perm)
+    ctx, it = make_water_context(gpu, sp, cons, seed=8)
+    ctx.set_atom_order(perm)
+    want = oracle.kinetic_energy_rigid(precision, sp.posq, sp.corr, sp.velm, sp.force.reshape(-1), 0.5 * DT, atoms, sp.num_atoms)
+    assert it.computeKineticEnergy() == pytest.approx(want, rel=1e-12)
+    ctx.close()
+
+
 def test_settle_guard_rails(gpu):
     from openmm_constv_b200 import _capi
     s0, atoms, params, cons = slabmod.make_water_slab(301, "single", seed=35)

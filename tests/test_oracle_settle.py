@@ -182,3 +182,56 @@ def test_capi_cluster_detection_matches_the_numpy_rule():
     assert rc == _capi.ERR_SYSTEM and b"must be the same" in lib.constv_last_error()
     rc, *_ = find(3, [0], [3], [0.1])
     assert rc == _capi.ERR_INVALID
+
+
+@pytest.mark.parametrize("precision", slabmod.PRECISIONS)
+def test_velocity_constraints_and_rigid_kinetic_energy(oracle, precision):
+    """oracle.kinetic_energy_rigid: the half-step-shifted velocities of the molecule atoms are projected onto
+    the constraints (what OpenMM's computeKineticEnergy does for a constrained System; PARITY UNPINNED).  The
+    projection is pinned by what defines it: relative velocities perpendicular to the bonds, each molecule's
+    linear and angular momentum unchanged (constraint forces are internal and central), idempotence, and the
+    kinetic energy never growing."""
+    s, atoms, params, _ = slabmod.make_water_slab(3000, precision, seed=26)
+    shift = 0.0005
+    ke, v = oracle.kinetic_energy_rigid(precision, s.posq, s.corr, s.velm, s.force.reshape(-1), shift, atoms, s.num_atoms, True)
+    ke_free = oracle.kinetic_energy(precision, s.velm, s.force.reshape(-1), shift, s.num_atoms)
+    assert 0.5 * ke_free < ke < ke_free
+    p = positions64(s)
+    m = 1.0 / s.velm[atoms, 3].astype(np.float64)
+    mixed = H.MIXED[precision]
+    f = s.force[:, : s.num_atoms].T.astype(mixed)
+    w = s.velm[: s.num_atoms, 3:4]
+    v_free = (s.velm[: s.num_atoms, :3] + (mixed(shift / 4294967296.0) * f) * w).astype(np.float64)
+    for i, j in ((0, 1), (0, 2), (1, 2)):
+        d = p[atoms[:, i]] - p[atoms[:, j]]
+        dv = v[atoms[:, i]] - v[atoms[:, j]]
+        cosine = np.abs(np.einsum("nk,nk->n", d, dv)) / (np.linalg.norm(d, axis=1) * np.linalg.norm(dv, axis=1))
+        assert np.max(cosine) < 1e-12
+    lin_before = np.einsum("na,nak->nk", m, v_free[atoms])
+    lin_after = np.einsum("na,nak->nk", m, v[atoms])
+    assert np.max(np.abs(lin_before - lin_after)) < 2e-5 * np.max(np.abs(lin_before))  # v_free is recomputed in numpy: float rounding
+    ang_before = np.einsum("na,nak->nk", m, np.cross(p[atoms], v_free[atoms]))
+    ang_after = np.einsum("na,nak->nk", m, np.cross(p[atoms], v[atoms]))
+    assert np.max(np.abs(ang_before - ang_after)) < 2e-5 * np.max(np.abs(ang_before))
+    untouched = np.ones(s.num_atoms, bool)
+    untouched[atoms.reshape(-1)] = False
+    massive = s.velm[: s.num_atoms, 3] != 0
+    assert np.allclose(v[untouched & massive], v_free[untouched & massive], rtol=1e-6, atol=0)
+    # idempotence: velocities already on the constraint surface are left alone
+    t = s.copy()
+    t.velm[: s.num_atoms, :3] = v.astype(mixed)
+    t.force[:] = 0
+    ke2, v2 = oracle.kinetic_energy_rigid(precision, t.posq, t.corr, t.velm, t.force.reshape(-1), 0.0, atoms, t.num_atoms, True)
+    scale = np.max(np.abs(v))
+    assert np.max(np.abs(v2 - t.velm[: s.num_atoms, :3].astype(np.float64))) < (1e-6 if precision == "single" else 1e-12) * scale
+    # after a constrained step (v = delta/dt of a rigid displacement) nothing is left to project at the mid-step
+    # geometry; at the end-of-step geometry the projection removes only the chord/arc difference
+    prm, dt = H.oracle_params_for(oracle, precision, T, GAMMA, DT)
+    a = s.copy()
+    xi = np.random.default_rng(6).standard_normal((s.padded, 4)).astype(np.float32)
+    oracle.settle_step(precision, a.num_atoms, 2, a.zmax, a.posq, a.corr, a.velm, a.force.reshape(-1),
+                       np.zeros((s.padded, 4), mixed), prm, dt, xi, 0, H.identity_order(s.padded), atoms, params)
+    a.force[:] = 0
+    ke_a = oracle.kinetic_energy_rigid(precision, a.posq, a.corr, a.velm, a.force.reshape(-1), 0.0, atoms, a.num_atoms)
+    ke_a_free = oracle.kinetic_energy(precision, a.velm, a.force.reshape(-1), 0.0, a.num_atoms)
+    assert 0.97 * ke_a_free < ke_a <= ke_a_free * (1 + 1e-12)
