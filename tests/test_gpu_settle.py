@@ -268,6 +268,47 @@ def test_kinetic_energy_of_rigid_water(gpu, oracle, precision, num_real):
     ctx.close()
 
 
+@pytest.mark.parametrize("precision", ["single", "mixed"])
+def test_example_sized_rigid_water_trajectory(gpu, oracle, precision):
+    """BASELINE configs[0-1] shape: the example's slab (7494 real + 7494 image particles, rigid SPC/E water,
+    T = 300 K, friction 1/ps, dt = 1 fs; example/nacl_1m_spce/nacl_constv.py:12-16,56) with the applied field
+    efield*q*z as the force, 200 steps with the in-kernel Philox noise, against the oracle driven with the
+    Gaussians the library publishes for each step: every array bit for bit all along the trajectory."""
+    import torch
+    from openmm_constv_b200._capi import check
+    s0, atoms, params, cons = slabmod.make_water_slab(7494, precision, seed=2024)
+    R = s0.num_real
+    efield = 1.0 * 96.48533212 / s0.zmax
+    fz = np.rint(-efield * s0.posq[:R, 3].astype(np.float64) * 4294967296.0).astype(np.int64)
+    s0.force[:] = 0
+    s0.force[2, :R] = fz
+    ctx, it = make_water_context(gpu, s0, cons, seed=99)
+    it.setStepSize(0.001)
+    lib, slab = it._kernel._lib, it._kernel.handle
+    g = torch.zeros((s0.padded, 4), dtype=torch.float32, device="cuda")
+    ref = s0.copy()
+    prm, dt = H.oracle_params_for(oracle, precision, T, GAMMA, 0.001)
+    inv = H.identity_order(s0.padded)
+    delta = np.zeros((s0.padded, 4), H.MIXED[precision])
+    for k in range(200):
+        check(lib.constv_generate_noise(slab, k, g.data_ptr(), ctx.stream_ptr()))
+        xi = g.cpu().numpy()
+        ctx.force.zero_()
+        ctx.force[2, :R] = torch.as_tensor(fz, device="cuda")  # the step zeroes image forces only; keep the field on
+        it.step(1)
+        ref.force[:] = 0
+        ref.force[2, :R] = fz
+        oracle.settle_step(precision, ref.num_atoms, 2, ref.zmax, ref.posq, ref.corr, ref.velm, ref.force.reshape(-1), delta,
+                           prm, dt, xi, 0, inv, atoms, params)
+        if k % 50 == 49:
+            assert_slab_bits_equal(download(ctx, s0), ref)
+    assert bond_errors(ref, atoms, params) < (2e-5 if precision == "single" else 2e-7)
+    ke = it.computeKineticEnergy()
+    assert ke == pytest.approx(oracle.kinetic_energy_rigid(precision, ref.posq, ref.corr, ref.velm, ref.force.reshape(-1),
+                                                           0.0005, atoms, ref.num_atoms), rel=1e-12)
+    ctx.close()
+
+
 def test_settle_guard_rails(gpu):
     from openmm_constv_b200 import _capi
     s0, atoms, params, cons = slabmod.make_water_slab(301, "single", seed=35)
