@@ -355,6 +355,12 @@ int launchBatched(constv_slab* lead, const SlabDev* table, int n, int totalTiles
 
 void advanceTime(constv_slab* s) { s->time += s->stepSize; }
 
+// A chain entry point that finds the image-charge snapshot stale takes it for the whole slab, and must not let
+// any chain -- the others run on other streams and rewrite posq[image] -- start before the snapshot is complete:
+// the device is drained before and after (a rare path: first step after binding or uploading posq; it cannot
+// happen inside a stream capture, where the error says to step once first).
+int refreshImageChargesForChains(constv_slab* s, void* stream);
+
 }  // namespace
 
 // =================================================================================================
@@ -651,10 +657,7 @@ int constv_step_fused_chain(constv_slab* s, int32_t chain, const void* random4, 
     if ((rc = checkLangevin(s))) return rc;
     if (chain < 0 || chain >= s->chains) return fail(CONSTV_ERR_INVALID, "chain %d out of range (the slab has %d)", chain, s->chains);
     if (s->atomIndex || s->variant == 2) return fail(CONSTV_ERR_STATE, "chains need identity slot order and the plain-load kernel");
-    if ((s->cfg.flags & CONSTV_FLAG_CACHE_IMAGE_CHARGE) && !s->imageChargeValid) {
-        rc = constv_refresh_image_charges(s, stream);
-        if (rc) return rc;
-    }
+    if ((rc = refreshImageChargesForChains(s, stream))) return rc;
     const SlabDev d = makeChainDev(s, chain);
     DISPATCH_PREC(s->cfg.precision, launchFused<PR>(s, d, static_cast<const float4*>(random4), random_index, (cudaStream_t) stream));
     if (rc == CONSTV_OK && chain == 0) advanceTime(s);
@@ -697,6 +700,26 @@ int constv_step_fused_multi(constv_slab* s, int32_t num_steps, void* stream) {
     for (int k = 0; k < num_steps; k++) advanceTime(s);
     return CONSTV_OK;
 }
+
+}  // extern "C"
+
+namespace {
+int refreshImageChargesForChains(constv_slab* s, void* stream) {
+    if (!(s->cfg.flags & CONSTV_FLAG_CACHE_IMAGE_CHARGE) || s->imageChargeValid) return CONSTV_OK;
+    if (s->chains > 1) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess)
+            return fail(CONSTV_ERR_CUDA, "the image-charge snapshot is stale and cannot be taken here (%s): step the slab once "
+                                         "outside stream capture first", cudaGetErrorString(e));
+    }
+    int rc = constv_refresh_image_charges(s, stream);
+    if (rc) return rc;
+    if (s->chains > 1) CUDA_TRY(cudaDeviceSynchronize());
+    return CONSTV_OK;
+}
+}  // namespace
+
+extern "C" {
 
 int constv_step_part1(constv_slab* s, const void* random4, uint32_t random_index, void* stream) {
     GUARD(s);

@@ -346,6 +346,34 @@ def test_chains_are_bit_identical_to_the_single_launch(gpu, precision, chains):
     ctx_c.close()
 
 
+def test_chains_with_the_image_charge_side_array(gpu):
+    """CONSTV_FLAG_CACHE_IMAGE_CHARGE: the snapshot of the images' charges is taken lazily by the first step.
+    When that first step is a chain on a stream of its own, no other chain may rewrite posq[image] before the
+    snapshot is complete (a race would freeze garbage charges into the side array)."""
+    import torch
+    from openmm_constv_b200 import _capi
+    lib = _capi.load()
+    s0 = slabmod.make_slab(200003, "single", seed=15)
+    flags = _capi.FLAGS_DEFAULT | _capi.FLAG_CACHE_IMAGE_CHARGE
+    ctx_a, it_a = make_context(gpu, s0, seed=31, flags=flags)
+    it_a.step(3)
+    want = download(ctx_a, s0)
+    ctx_a.close()
+    for trial in range(3):
+        ctx, it = make_context(gpu, s0, seed=31, flags=flags)
+        h = it._kernel.handle
+        _capi.check(lib.constv_set_chains(h, 8))
+        _capi.check(lib.constv_set_parameters(h, T, GAMMA, DT))
+        streams = [torch.cuda.Stream() for _ in range(8)]
+        torch.cuda.synchronize()
+        for k in range(3):
+            for q in reversed(range(8)):
+                _capi.check(lib.constv_step_fused_chain(h, q, None, 0, streams[q].cuda_stream))
+        torch.cuda.synchronize()
+        assert_slab_bits_equal(download(ctx, s0), want)
+        ctx.close()
+
+
 @pytest.mark.parametrize("chains", [1, 3])
 def test_step_fused_multi(gpu, chains):
     """constv_step_fused_multi(n) == n x constv_step_fused, eagerly and replayed from a CUDA graph; with chains
