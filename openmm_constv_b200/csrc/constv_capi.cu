@@ -307,18 +307,18 @@ int launchFusedIndexed(constv_slab* s, const SlabDev& d, const float4* random, u
 
 template <int PREC>
 int launchPart1(constv_slab* s, const SlabDev& d, const float4* random, unsigned randomIndex, cudaStream_t st) {
-    return launch(constv_part1_kernel<PREC, kBlock>, gridFor(s, s->cfg.num_atoms, kBlock, 8), kBlock,
+    return launch(constv_part1_kernel<PREC, kBlock>, gridFor(s, s->cfg.num_atoms, kBlock, s->ctasPerSM), kBlock,
                   (bool) (s->cfg.flags & CONSTV_FLAG_PDL), st, d, random, randomIndex);
 }
 
 template <int PREC>
 int launchPart2(constv_slab* s, const SlabDev& d, cudaStream_t st) {
     if (!s->atomIndex)
-        return launch(constv_part2_mirror_kernel<PREC, kBlock>, gridFor(s, s->numReal, kBlock, 8), kBlock,
+        return launch(constv_part2_mirror_kernel<PREC, kBlock>, gridFor(s, s->numReal, kBlock, s->ctasPerSM), kBlock,
                       (bool) (s->cfg.flags & CONSTV_FLAG_PDL), st, d);
-    int rc = launch(constv_part2_indexed_kernel<PREC, kBlock>, gridFor(s, s->cfg.num_atoms, kBlock, 8), kBlock, false, st, d);
+    int rc = launch(constv_part2_indexed_kernel<PREC, kBlock>, gridFor(s, s->cfg.num_atoms, kBlock, s->ctasPerSM), kBlock, false, st, d);
     if (rc) return rc;
-    return launch(constv_mirror_indexed_kernel<PREC, kBlock>, gridFor(s, s->numReal, kBlock, 8), kBlock, false, st, d);
+    return launch(constv_mirror_indexed_kernel<PREC, kBlock>, gridFor(s, s->numReal, kBlock, s->ctasPerSM), kBlock, false, st, d);
 }
 
 template <int PREC>
