@@ -37,7 +37,7 @@ extern "C" {
 
 #define CONSTV_API __attribute__((visibility("default")))
 
-#define CONSTV_VERSION 100 /* 0.1.0 */
+#define CONSTV_VERSION 110 /* 0.1.1: + chains, Drude integrator, rigid molecules */
 
 typedef struct constv_slab constv_slab; /* one Context's worth of integrator state (opaque) */
 

@@ -4,4 +4,4 @@ platforms/cuda ConstVLangevin kernels).  See DESIGN.md.
 The compute path is the C-ABI library built from ``csrc/`` (``include/constv_b200.h``); it has no
 CPU fallback: every entry point raises if ``libconstv_b200.so`` is missing.
 """
-__version__ = "0.1.0"
+__version__ = "0.1.1"
