@@ -1,21 +1,25 @@
-#ifndef OPENMM_CONSTVLANGEVIN_INTEGRATOR_PROXY_H_
-#define OPENMM_CONSTVLANGEVIN_INTEGRATOR_PROXY_H_
+#pragma once
 
-// XML proxy for ConstVLangevinIntegrator.  Node type "ConstVLangevinIntegrator" as in the reference
-// (serialization/src/ConstVLangevinIntegratorProxy.cpp:41-63).  Writes version 2, which adds the
-// numCells and cellSize properties the reference's version 1 silently dropped; reads both.
+// XML (de)serialization of ConstVLangevinIntegrator.  The node type is "ConstVLangevinIntegrator" and the
+// version-1 property names are the reference's (serialization/src/ConstVLangevinIntegratorProxy.cpp:41-63), so
+// files written by the reference load here.  Version 2, which this proxy writes, adds the two properties the
+// reference's version 1 silently dropped: numCells and cellSize.
 
-#include "openmm/serialization/XmlSerializer.h"
+#include "openmm/serialization/SerializationNode.h"
+#include "openmm/serialization/SerializationProxy.h"
 
 namespace OpenMM {
 
-class ConstVLangevinIntegratorProxy : public SerializationProxy {
+class ConstVLangevinIntegratorProxy final : public SerializationProxy {
 public:
+    /** Version written; files of every version from kOldestReadable on are read. */
+    static constexpr int kWritten = 2;
+    static constexpr int kOldestReadable = 1;
+
     ConstVLangevinIntegratorProxy();
-    void serialize(const void* object, SerializationNode& node) const;
-    void* deserialize(const SerializationNode& node) const;
+    /** Returns a new ConstVLangevinIntegrator owned by the caller; throws "Unsupported version number". */
+    void* deserialize(const SerializationNode& node) const override;
+    void serialize(const void* object, SerializationNode& node) const override;
 };
 
 }  // namespace OpenMM
-
-#endif /* OPENMM_CONSTVLANGEVIN_INTEGRATOR_PROXY_H_ */

@@ -11,7 +11,7 @@ ConstVLangevinIntegratorProxy::ConstVLangevinIntegratorProxy() : SerializationPr
 
 void ConstVLangevinIntegratorProxy::serialize(const void* object, SerializationNode& node) const {
     const ConstVLangevinIntegrator& integrator = *reinterpret_cast<const ConstVLangevinIntegrator*>(object);
-    node.setIntProperty("version", 2);
+    node.setIntProperty("version", kWritten);
     // version 1 properties (same names as the reference)
     node.setDoubleProperty("stepSize", integrator.getStepSize());
     node.setDoubleProperty("constraintTolerance", integrator.getConstraintTolerance());
@@ -25,7 +25,7 @@ void ConstVLangevinIntegratorProxy::serialize(const void* object, SerializationN
 
 void* ConstVLangevinIntegratorProxy::deserialize(const SerializationNode& node) const {
     const int version = node.getIntProperty("version");
-    if (version < 1 || version > 2)
+    if (version < kOldestReadable || version > kWritten)
         throw OpenMMException("Unsupported version number");
     // a version 1 file carries neither numCells nor cellSize: the reference's defaults apply
     ConstVLangevinIntegrator* integrator = new ConstVLangevinIntegrator(
