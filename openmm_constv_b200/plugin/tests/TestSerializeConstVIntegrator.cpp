@@ -9,6 +9,7 @@
 #include <sstream>
 
 #include "TestAssert.h"
+#include "openmm/ConstVDrudeLangevinIntegrator.h"
 #include "openmm/ConstVLangevinIntegrator.h"
 #include "openmm/serialization/XmlSerializer.h"
 
@@ -68,6 +69,34 @@ static void testWrittenDocument() {
         CHECK(text.find(key) != std::string::npos);
 }
 
+// The reference has no proxy for the Drude integrator; this one carries every constructor argument and setter.
+static void testDrudeRoundTrip() {
+    ConstVDrudeLangevinIntegrator original(299.5, 4.5, 1.25, 19.0, 0.00075, 4, 3.5);
+    original.setMaxDrudeDistance(0.021);
+    original.setConstraintTolerance(3.5e-6);
+    original.setRandomNumberSeed(-12);
+    std::stringstream buffer;
+    XmlSerializer::serialize<ConstVDrudeLangevinIntegrator>(&original, "Integrator", buffer);
+    CHECK(buffer.str().find("type=\"ConstVDrudeLangevinIntegrator\"") != std::string::npos);
+    ConstVDrudeLangevinIntegrator* copy = XmlSerializer::deserialize<ConstVDrudeLangevinIntegrator>(buffer);
+    CHECK_EQ(original.getTemperature(), copy->getTemperature());
+    CHECK_EQ(original.getFriction(), copy->getFriction());
+    CHECK_EQ(original.getDrudeTemperature(), copy->getDrudeTemperature());
+    CHECK_EQ(original.getDrudeFriction(), copy->getDrudeFriction());
+    CHECK_EQ(original.getMaxDrudeDistance(), copy->getMaxDrudeDistance());
+    CHECK_EQ(original.getStepSize(), copy->getStepSize());
+    CHECK_EQ(original.getConstraintTolerance(), copy->getConstraintTolerance());
+    CHECK_EQ(original.getRandomNumberSeed(), copy->getRandomNumberSeed());
+    CHECK_EQ(4, copy->getNumCells());
+    CHECK_EQ(3.5, copy->getCellSize());
+    delete copy;
+    std::stringstream v2(
+        "<Integrator type=\"ConstVDrudeLangevinIntegrator\" version=\"2\" stepSize=\".001\" constraintTolerance=\"1e-05\" "
+        "temperature=\"300\" friction=\"5\" drudeTemperature=\"1\" drudeFriction=\"20\" maxDrudeDistance=\"0\" randomSeed=\"0\" "
+        "numCells=\"2\" cellSize=\"-1\"/>\n");
+    CHECK_THROWS(XmlSerializer::deserialize<ConstVDrudeLangevinIntegrator>(v2), "Unsupported version number");
+}
+
 int main() {
     try {
         // no explicit registration first: loading the library must have registered the proxy
@@ -77,6 +106,7 @@ int main() {
         testReadsVersion1();
         testRejectsUnknownVersion();
         testWrittenDocument();
+        testDrudeRoundTrip();
     } catch (const std::exception& e) {
         std::cout << "exception: " << e.what() << std::endl;
         return 1;
