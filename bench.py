@@ -419,8 +419,8 @@ def main():
         shard, d_normal, d_pairs = slabmod.make_drude_slab(R, args.precision, seed=12345 + rank)
         drude = (d_normal, d_pairs)
     elif args.rigid_water:
-        if args.ensemble:
-            raise SystemExit("--rigid-water and --ensemble are separate configurations")
+        if args.ensemble and args.rigid_water != "fused":
+            raise SystemExit("--ensemble takes --rigid-water fused only")
         if args.rigid_water == "split" or args.variant == 1:
             args.chains = 1
         shard, w_atoms, w_params, w_cons = slabmod.make_water_slab(R, args.precision, seed=12345 + rank)
@@ -523,7 +523,10 @@ def main():
                 if q:
                     cs.wait_event(fork)
                 for k in range(first, first + count):
-                    if args.ensemble:
+                    if args.ensemble and water:  # rigid-water ensemble: one launch per slab, slabs spread over the streams
+                        for h in handles[(k % replicas) * M + bounds[q]:(k % replicas) * M + bounds[q + 1]]:
+                            _capi.check(lib.constv_step_fused_settle(h, None, 0, cs.cuda_stream))
+                    elif args.ensemble:
                         _capi.check(lib.constv_step_fused_batched(subgroups[k % replicas][q], bounds[q + 1] - bounds[q], cs.cuda_stream))
                     elif drude:
                         _capi.check(lib.constv_drude_step_fused_chain(handles[k % replicas], q, None, 0, cs.cuda_stream))
@@ -537,7 +540,10 @@ def main():
                 stream.wait_event(join)
             return
         for k in range(first, first + count):
-            if args.ensemble:
+            if args.ensemble and water:
+                for h in handles[(k % replicas) * M:(k % replicas + 1) * M]:
+                    _capi.check(lib.constv_step_fused_settle(h, None, 0, sptr))
+            elif args.ensemble:
                 _capi.check(lib.constv_step_fused_batched(groups[k % replicas], M, sptr))
             elif drude:
                 _capi.check(lib.constv_drude_step_fused(handles[k % replicas], None, 0, sptr))
@@ -779,7 +785,9 @@ def main():
             "dtype": "f32" if args.precision == "single" else ("f32+f64" if args.precision == "mixed" else "f64"),
             "data": "synthetic",
             "config": {
-                "workload": (f"ensemble of {M * world} independent synthetic slabs of {shard.num_atoms} atoms, {M} per GPU advanced by one batched launch per step (BASELINE configs[4])"
+                "workload": (f"ensemble of {M * world} independent synthetic RIGID-WATER slabs of {shard.num_atoms} atoms, {M} per GPU, one constraint-solving step launch per slab spread over {chains} stream(s) (BASELINE configs[4] with the example's constraints)"
+                             if (args.ensemble and water) else
+                             f"ensemble of {M * world} independent synthetic slabs of {shard.num_atoms} atoms, {M} per GPU advanced by one batched launch per step (BASELINE configs[4])"
                              if args.ensemble else
                              f"synthetic slab with RIGID water ({len(water[0])} SPC/E molecules, constraints solved {'inside the step kernel' if args.rigid_water == 'fused' else 'by a separate launch between part 1 and part 2'}), {shard.num_atoms} atoms per GPU, ConstV Langevin step incl. constraints (BASELINE configs[0-1] shape); range partition over {world} GPU(s)"
                              if water else
@@ -806,7 +814,8 @@ def main():
                                   "achieved = algorithmic bytes per launch x launches in the timed region / its duration" % chains)
                                  if chains > 1 else "one launch per step",
                          "frac_of_8TBs_nominal": achieved / 8000.0,
-                         "kernel": "constv_fused_step_batched_kernel" if args.ensemble else
+                         "kernel": "constv_settle_step_tiled_kernel" if (args.ensemble and water) else
+                                   "constv_fused_step_batched_kernel" if args.ensemble else
                                    "constv_drude_step_kernel" if drude else
                                    ("constv_settle_step_tiled_kernel" if args.rigid_water == "fused" else
                                     ("constv_part1_kernel + constv_settle_positions_kernel + constv_part2_mirror_kernel"
@@ -814,7 +823,7 @@ def main():
             "cpu_baseline": cpu,
             "reference_gpu": ref_gpu,
             "e2e": e2e,
-            "gpu_launches": int(K * (3 if args.rigid_water == "split" else chains)),
+            "gpu_launches": int(K * (M if (args.ensemble and water) else 3 if args.rigid_water == "split" else chains)),
             "eager_launches_in_region": int(eager_launches),
             "clocks": clocks,
             "kinetic_energy_kj_mol": ke_total, "temperature_K": temperature,
