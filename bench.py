@@ -523,9 +523,8 @@ def main():
                 if q:
                     cs.wait_event(fork)
                 for k in range(first, first + count):
-                    if args.ensemble and water:  # rigid-water ensemble: one launch per slab, slabs spread over the streams
-                        for h in handles[(k % replicas) * M + bounds[q]:(k % replicas) * M + bounds[q + 1]]:
-                            _capi.check(lib.constv_step_fused_settle(h, None, 0, cs.cuda_stream))
+                    if args.ensemble and water:  # rigid-water ensemble: one batched launch per sub-group and stream
+                        _capi.check(lib.constv_step_fused_settle_batched(subgroups[k % replicas][q], bounds[q + 1] - bounds[q], cs.cuda_stream))
                     elif args.ensemble:
                         _capi.check(lib.constv_step_fused_batched(subgroups[k % replicas][q], bounds[q + 1] - bounds[q], cs.cuda_stream))
                     elif drude:
@@ -541,8 +540,7 @@ def main():
             return
         for k in range(first, first + count):
             if args.ensemble and water:
-                for h in handles[(k % replicas) * M:(k % replicas + 1) * M]:
-                    _capi.check(lib.constv_step_fused_settle(h, None, 0, sptr))
+                _capi.check(lib.constv_step_fused_settle_batched(groups[k % replicas], M, sptr))
             elif args.ensemble:
                 _capi.check(lib.constv_step_fused_batched(groups[k % replicas], M, sptr))
             elif drude:
@@ -785,7 +783,7 @@ def main():
             "dtype": "f32" if args.precision == "single" else ("f32+f64" if args.precision == "mixed" else "f64"),
             "data": "synthetic",
             "config": {
-                "workload": (f"ensemble of {M * world} independent synthetic RIGID-WATER slabs of {shard.num_atoms} atoms, {M} per GPU, one constraint-solving step launch per slab spread over {chains} stream(s) (BASELINE configs[4] with the example's constraints)"
+                "workload": (f"ensemble of {M * world} independent synthetic RIGID-WATER slabs of {shard.num_atoms} atoms, {M} per GPU, advanced by {chains} batched constraint-solving launch(es) per step (BASELINE configs[4] with the example's constraints)"
                              if (args.ensemble and water) else
                              f"ensemble of {M * world} independent synthetic slabs of {shard.num_atoms} atoms, {M} per GPU advanced by one batched launch per step (BASELINE configs[4])"
                              if args.ensemble else
@@ -814,7 +812,7 @@ def main():
                                   "achieved = algorithmic bytes per launch x launches in the timed region / its duration" % chains)
                                  if chains > 1 else "one launch per step",
                          "frac_of_8TBs_nominal": achieved / 8000.0,
-                         "kernel": "constv_settle_step_tiled_kernel" if (args.ensemble and water) else
+                         "kernel": "constv_settle_step_tiled_batched_kernel" if (args.ensemble and water) else
                                    "constv_fused_step_batched_kernel" if args.ensemble else
                                    "constv_drude_step_kernel" if drude else
                                    ("constv_settle_step_tiled_kernel" if args.rigid_water == "fused" else
@@ -823,7 +821,7 @@ def main():
             "cpu_baseline": cpu,
             "reference_gpu": ref_gpu,
             "e2e": e2e,
-            "gpu_launches": int(K * (M if (args.ensemble and water) else 3 if args.rigid_water == "split" else chains)),
+            "gpu_launches": int(K * (3 if args.rigid_water == "split" else chains)),
             "eager_launches_in_region": int(eager_launches),
             "clocks": clocks,
             "kinetic_energy_kj_mol": ke_total, "temperature_K": temperature,

@@ -342,6 +342,11 @@ CONSTV_API int constv_step_fused_settle(constv_slab* slab, const void* random4, 
 CONSTV_API int constv_step_fused_settle_chain(constv_slab* slab, int32_t chain, const void* random4,
                                               uint32_t random_index, void* stream);
 
+/* One launch (per group of 8) that advances n independent rigid-molecule slabs -- an ensemble of Contexts -- by
+ * one step each; all slabs must share device and precision, be in identity slot order, unchained, and take the
+ * staged kernel.  Philox noise only. */
+CONSTV_API int constv_step_fused_settle_batched(constv_slab* const* slabs, int32_t n, void* stream);
+
 /* The solver alone on pos_delta, thread <-> molecule: what applyConstraints does for these molecules, for
  * the split path constv_step_part1 | constv_settle_positions | constv_step_part2_mirror. */
 CONSTV_API int constv_settle_positions(constv_slab* slab, void* stream);

@@ -39,7 +39,7 @@ SYMBOLS = [
     "constv_drude_get_parameters", "constv_drude_step_part1", "constv_drude_step_part2",
     "constv_drude_step_fused", "constv_drude_hardwall",
     "constv_settle_find_clusters", "constv_settle_configure", "constv_step_fused_settle", "constv_settle_positions",
-    "constv_step_fused_settle_chain", "constv_drude_step_fused_chain",
+    "constv_step_fused_settle_chain", "constv_drude_step_fused_chain", "constv_step_fused_settle_batched",
 ]
 
 
@@ -119,6 +119,7 @@ def load() -> C.CDLL:
         "constv_settle_positions": [vp, vp],
         "constv_step_fused_settle_chain": [vp, i32, vp, u32, vp],
         "constv_drude_step_fused_chain": [vp, i32, vp, u32, vp],
+        "constv_step_fused_settle_batched": [C.POINTER(vp), i32, vp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)

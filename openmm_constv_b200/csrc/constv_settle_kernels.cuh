@@ -351,6 +351,148 @@ template <int PREC, int BLOCK, bool INDEXED> struct SettleStage {
 // same; what changes is that the Philox key is the ORIGINAL index atomIndex[slot], that an atom's images sit
 // wherever invAtomOrder says (a scattered 16-byte store each, as in the reference, constVLangevin.cu:155-158),
 // and that the image slots are zeroed by extra tiles in slot order (coalesced) instead of by their partners.
+// One tile of the staged step for one slab (`tile` in the slab's own tile space), for the batched ensemble
+// kernel.  The caller owns the loop over tiles and the barrier between two tiles (the stage and the step box are
+// rewritten by the next tile).  Same text as the body of constv_settle_step_tiled_kernel.
+template <int PREC, int BLOCK, bool INDEXED, bool STREAM>
+__device__ __forceinline__ void settle_tiled_tile(const SlabDev& d, const SettleSegments& seg, SettleStage<PREC, BLOCK, INDEXED>& st,
+                                                  StepBox& box, const float4* __restrict__ random, const unsigned int randomIndex,
+                                                  const int tile) {
+    using Real = typename Prec<PREC>::Real;
+    using Mixed = typename Prec<PREC>::Mixed;
+    constexpr bool kSplit = Prec<PREC>::kSplitPos;
+    const int R = d.numReal;
+    const size_t P = (size_t) d.padded;
+    const int realTiles = seg.tileStart[seg.count];
+    constexpr int kZeroSpan = 12;  // a zeroing tile covers 12 * BLOCK image slots
+    // a chain (constv_set_chains) advances tiles [rangeLo, rangeHi) of the tile space with its own counters;
+    // the whole step = [0, realTiles + zeroTiles)
+    const unsigned int holders = (unsigned int) (d.rangeHi - d.rangeLo);
+    const StepScalars<Mixed> s = scalars_of<Mixed>(d);
+    const Real* __restrict__ posq = static_cast<const Real*>(d.posq);
+    const Real* __restrict__ corrA = static_cast<const Real*>(d.corr);
+    const Mixed* __restrict__ velm = static_cast<const Mixed*>(d.velm);
+    const long long* __restrict__ force = d.force;
+    const Real* qbase = d.imageCharge ? static_cast<const Real*>(d.imageCharge) : posq + 4 * (size_t) R + 3;
+    const size_t qstride = d.imageCharge ? 1 : 4;
+    const int j = (int) threadIdx.x;
+
+    if (INDEXED && tile >= realTiles) {  // a tile of image slots: zero them, coalesced
+        publish_step(box, d.counters);
+        __syncthreads();
+        const unsigned long long step = box.step;
+        const unsigned int ticket = take_ticket(d.counters, holders);
+#pragma unroll
+        for (int i = 0; i < kZeroSpan; i++) {
+            const int slot = R + ((tile - realTiles) * kZeroSpan + i) * BLOCK + j;
+            if (slot < d.numAtoms) {
+                if (d.zeroVelm) store4x<STREAM>(static_cast<Mixed*>(d.velm), (size_t) slot, Vec4<Mixed>{0, 0, 0, 0});
+                if (d.zeroForce) {
+                    __stcs(d.force + slot, 0LL);
+                    __stcs(d.force + P + slot, 0LL);
+                    __stcs(d.force + 2 * P + slot, 0LL);
+                }
+            }
+        }
+        close_step(d.counters, ticket, holders, step);
+        return;
+    }
+    int q = 0;
+#pragma unroll
+    for (int k = 1; k < kSettleMaxSegments; k++)
+        if (k < seg.count && tile >= seg.tileStart[k]) q = k;
+    const int per = seg.atomsPerItem[q];
+    const int firstItem = (tile - seg.tileStart[q]) * BLOCK;
+    const int items = min(BLOCK, seg.itemStart[q + 1] - seg.itemStart[q] - firstItem);
+    const int base = seg.slotStart[q] + firstItem * per;
+    const int slotsInTile = items * per;
+    const float2 prm = seg.params[q];
+
+    // stage in: coalesced
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int idx = j + i * BLOCK;
+        if (idx < slotsInTile) {
+            const size_t slot = (size_t) (base + idx);
+            st.v[idx] = load4x<STREAM>(velm, slot);
+            st.p[idx] = load4x<STREAM>(posq, slot);
+            if (kSplit) st.c[idx] = load4x<STREAM>(corrA, slot);
+            st.f[0][idx] = load_force(force + slot);
+            st.f[1][idx] = load_force(force + P + slot);
+            st.f[2][idx] = load_force(force + 2 * P + slot);
+            if (INDEXED) st.orig[idx] = d.atomIndex[slot];
+            else st.q1[idx] = qbase[qstride * slot];
+        }
+    }
+    publish_step(box, d.counters);
+    __syncthreads();
+    const unsigned long long step = box.step;
+    const unsigned int ticket = take_ticket(d.counters, holders);
+
+    // compute item j from the stage
+    if (j < items) {
+        Vec4<Mixed> v[3], delta[3];
+        Vec4<Real> p[3], c[3];
+        bool moved[3] = {false, false, false};
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            if (k < per) {
+                const int idx = per * j + k;
+                v[k] = st.v[idx];
+                p[k] = st.p[idx];
+                c[k] = kSplit ? st.c[idx] : Vec4<Real>{0, 0, 0, 0};
+                delta[k] = Vec4<Mixed>{0, 0, 0, 0};
+                moved[k] = v[k].w != 0;
+                if (moved[k]) {
+                    float4 xi;
+                    const int a = INDEXED ? st.orig[idx] : base + idx;
+                    if (random != nullptr) xi = __ldcs(random + (size_t) randomIndex + base + idx);
+                    else xi = (s.noisescale != 0) ? gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) a, step)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                    part1_update(v[k], delta[k], st.f[0][idx], st.f[1][idx], st.f[2][idx], xi.x, xi.y, xi.z, s);
+                }
+            }
+        if (per == 3) {
+            Mixed pos[3][3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) drude_pos_load<PREC>(p[k], c[k], pos[k]);
+            settle_molecule<Mixed>(pos[0], pos[1], pos[2], delta[0], delta[1], delta[2], rcp_rn(v[0].w), rcp_rn(v[1].w),
+                                   rcp_rn(v[2].w), prm.x, prm.y);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            if (k < per && moved[k]) {
+                const int idx = per * j + k;
+                part2_update<PREC>(p[k], c[k], v[k], delta[k], s.invDt);
+                st.v[idx] = v[k];
+                st.p[idx] = p[k];
+                if (kSplit) st.c[idx] = c[k];
+            }
+    }
+    __syncthreads();
+
+    // stage out: own record (coalesced), rewritten images, and (identity order) zeroed images
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int idx = j + i * BLOCK;
+        if (idx < slotsInTile) {
+            const Vec4<Mixed> v = st.v[idx];
+            const Vec4<Real> p = st.p[idx];
+            const Vec4<Real> c = kSplit ? st.c[idx] : Vec4<Real>{0, 0, 0, 0};
+            if (INDEXED) {
+                DrudeAtom<PREC> rec;
+                rec.v = v; rec.p = p; rec.c = c;
+                drude_emit<PREC, true, STREAM>(d, base + idx, st.orig[idx], v.w != 0, rec);
+            } else {
+                emit_atom<PREC, STREAM>(d, s.zshift, base + idx, v.w != 0, v, p, c, st.q1[idx]);
+            }
+        }
+    }
+    close_step(d.counters, ticket, holders, step);
+}
+
+// The single-slab kernel keeps its own copy of the tile body (below) rather than calling settle_tiled_tile: the
+// call, though inlined, cost a spill under the 64-register cap and 8 % of the step.
 template <int PREC, int BLOCK, bool INDEXED, bool STREAM>
 __global__ void __launch_bounds__(BLOCK, INDEXED ? 0 : (PREC == PREC_SINGLE ? 8 : 4))  // 64 registers, no spills: 8 CTAs per SM
 constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ SettleSegments seg,
@@ -499,6 +641,34 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
     }
 }
 
+
+// An ensemble of slabs (identity slot order, Philox noise) in ONE launch: the CTA looks its tile up in the table
+// of slabs and runs it with that slab's descriptor, runs and step counter (one ticket per tile, on the tile's own
+// slab: every slab's counter advances exactly once).
+template <int CAP> struct SettleBatchParams {
+    int numSlabs, totalTiles;
+    int tileBase[CAP];
+    SlabDev slab[CAP];
+    SettleSegments seg[CAP];
+};
+
+template <int PREC, int BLOCK, int CAP>
+__global__ void __launch_bounds__(BLOCK, PREC == PREC_SINGLE ? 8 : 4)
+constv_settle_step_tiled_batched_kernel(const __grid_constant__ SettleBatchParams<CAP> b) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    SettleStage<PREC, BLOCK, false>& st = *reinterpret_cast<SettleStage<PREC, BLOCK, false>*>(smemRaw);
+    __shared__ StepBox box;
+    pdl_wait();
+    pdl_launch();
+    for (int tile = (int) blockIdx.x; tile < b.totalTiles; tile += (int) gridDim.x) {
+        int k = 0;
+#pragma unroll
+        for (int q = 1; q < CAP; q++)
+            if (q < b.numSlabs && tile >= b.tileBase[q]) k = q;
+        settle_tiled_tile<PREC, BLOCK, false, true>(b.slab[k], b.seg[k], st, box, nullptr, 0u, tile - b.tileBase[k]);
+        if (tile + (int) gridDim.x < b.totalTiles) __syncthreads();
+    }
+}
 
 // ---- kinetic energy of a system with rigid molecules ------------------------------------------------------
 // OpenMM's integration.computeKineticEnergy (CudaConstVKernels.cpp:175-177) projects the half-step-shifted
