@@ -188,7 +188,13 @@ class ConstVLangevinIntegrator:
     def step(self, steps: int) -> None:
         if self._context is None:
             raise OpenMMException("This Integrator is not bound to a context!")
-        for _ in range(int(steps)):
+        steps = int(steps)
+        if steps > 1 and self._kernel.can_execute_many(self._context):
+            # nothing changes between the steps (no force callback, no constraint hand-off, Philox noise): the
+            # reference's loop body (ConstVLangevinIntegrator.cpp:80-83) is n x execute, issued in one call
+            self._kernel.execute_many(self._context, self, steps)
+            return
+        for _ in range(steps):
             self._context.updateContextState()
             self._context.calcForcesAndEnergy(True, False)
             self._kernel.execute(self._context, self)
@@ -304,6 +310,23 @@ class IntegrateConstVLangevinStepKernel:
             check(lib.constv_step_part2_mirror(slab, st))
         context.time += integrator.getStepSize()
         context.step_count += 1
+
+    def can_execute_many(self, context: "SlabContext") -> bool:
+        return (type(self) is IntegrateConstVLangevinStepKernel and context.force_fn is None
+                and context.apply_constraints is None and context.random_pool is None
+                and not getattr(self, "fused_constraints", False) and context.getSystem().getNumConstraints() == 0)
+
+    def execute_many(self, context: "SlabContext", integrator: ConstVLangevinIntegrator, steps: int) -> None:
+        """``steps`` x execute in one C-ABI call (constv_step_fused_multi; on a chained slab the library forks
+        onto its own streams)."""
+        lib, slab, st = self._lib, self._slab, context.stream_ptr()
+        check(lib.constv_set_parameters(slab, integrator._temperature, integrator._friction, integrator.getStepSize()))
+        if context.atoms_were_reordered:
+            check(lib.constv_update_inverse_order(slab, st))
+            context.atoms_were_reordered = False
+        check(lib.constv_step_fused_multi(slab, steps, st))
+        context.time += steps * integrator.getStepSize()
+        context.step_count += steps
 
     def computeKineticEnergy(self, context: "SlabContext", integrator: ConstVLangevinIntegrator) -> float:
         ke = C.c_double(0.0)
