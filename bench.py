@@ -4,32 +4,43 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one fused integrator step over one synthetic slab of ``--atoms`` particles per GPU
-(default 1,000,000 = 500k real + 500k image: BASELINE.json configs[2]).  Metric: atom-steps/s,
-whole job (sum over ranks / max-over-ranks device time).  Multi-GPU is the range partition of
-SURVEY.md 8e: every rank owns a contiguous real-atom range plus its images and there is NO
-data-path collective (weak scaling: per-GPU shard fixed, so N=8 with --atoms 2000000 is the 16M
-slab of configs[3]); the only collective is the scalar kinetic-energy all-reduce, issued once after
-the timed region as a report, never per step.
+One "step" = one fused integrator step over this rank's shard of ONE seeded global synthetic slab of
+``--atoms`` particles per GPU (default 1,000,000 = 500k real + 500k image per GPU: BASELINE.json
+configs[2] at N = 1).  Metric: atom-steps/s, whole job (atoms of all ranks / max-over-ranks device time).
+Multi-GPU is the range partition of SURVEY.md 8e: the global slab is ``--gpus`` lateral tiles
+(slab.slab_tile), rank r owns partition.shard_range(R_total, r, N) = tile r and its images, and there is NO
+data-path collective (weak scaling); the only collective is the scalar kinetic-energy all-reduce, issued
+once outside the timed region as a report, never per step.
+
+How the K steps are timed (the same at --steps 20 and at --steps 100000):
+  * every launch inside the timed region comes from a CUDA graph: whole regions of K steps when K is small,
+    else 120-step chunks plus one tail graph -- never an eager launch (``eager_launches_in_region`` = 0);
+  * after W warm-up steps and enough untimed regions to have replayed every graph once and to have kept the
+    GPU busy for >= 30 ms, the K-step region is run ``repeats`` (>= 9) times back to back, a CUDA event
+    between regions (recorded on the launching stream); ms_per_step = MEDIAN region time / K, min and max
+    reported; for N > 1 the MAX over ranks of each rank's median;
+  * clocks and throttle reasons are sampled every 10 ms over the whole repeat loop (the number of repeats is
+    raised until the loop lasts ~0.4 s);
+  * L2: a 1M-atom slab is 56 MB < B200's 126 MB L2, so the steps rotate over ``replicas`` copies of the slab
+    whose footprint exceeds 2x L2: every step streams its slab from HBM.
 
 Chains (default 2): the slab is cut into contiguous ranges of real atoms, each with its own device step
-counter and its own stream (constv_set_chains / constv_step_fused_chain), so that the drain of one
-range's step k overlaps the ramp-up of another range's step k+1; results are bit-identical to one launch
-per step (tests/test_gpu_parity.py::test_chains_are_bit_identical_to_the_single_launch).  --chains 1 is
-the single launch per step.
-
-L2 policy: a 1M-atom slab is 58 MB, smaller than B200's 126 MB L2, so the timed loop rotates over
-``replicas`` independent copies of the slab whose total footprint exceeds 2x L2: every step streams
-its slab from HBM.
+counter and stream (constv_set_chains / constv_step_fused_chain), so that the drain of one range's step k
+overlaps the ramp-up of another's step k+1; bit-identical to one launch per step.  A host that runs other
+kernels between two steps (OpenMM) cannot use that overlap: ``also.single_launch`` is the same workload with
+one launch per step and ``also.plugin_path`` steps through CudaIntegrateConstVLangevinStepKernel::execute
+(plugin/tests/BenchPluginPath.cpp), a cache-sweeping kernel between two steps.
 
 The JSON line carries, besides the base contract's keys:
-  roofline      algorithmic bytes of one launch / average launch duration (CUDA events around the
-                timed region on the launching stream / launches), against MEASURED_PEAKS.json
-  cpu_baseline  the oracle (kind "port": the reference has no CPU implementation of this path)
-                timed on this box's host cores on a bounded sample of the same workload
-  e2e           the same metric through the C ABI with HOST buffers (constv_step_host): per step
-                H2D of the real atoms' forces from pinned memory, the fused step, D2H of posq
+  roofline      algorithmic bytes of one launch / average launch duration, against MEASURED_PEAKS.json
+  cpu_baseline  the reference's kernel source compiled for the host (oracle/_ref, kind "reference"; else the
+                oracle port) timed on this box's host cores on a bounded sample of the same workload
+  e2e           the same metric through the C ABI with HOST buffers: per step H2D of the real atoms' forces
+                from pinned memory, the fused step, D2H of the kinetic energy (full_state: + posq)
   clocks        SM clock / throttle reasons sampled during the timed region
+  also          (last key, so that it survives a truncated log) single_launch, plugin_path, the 16M-atom slab
+                of configs[3] over these N GPUs, the 64 x 100k ensemble of configs[4], partition_parity,
+                e2e_full_state
 """
 from __future__ import annotations
 
@@ -51,20 +62,26 @@ T_KELVIN, FRICTION, DT = 300.0, 1.0, 0.001  # example/nacl_1m_spce/nacl_constv.p
 DRUDE_FRICTION_CM, DRUDE_T, DRUDE_FRICTION, DRUDE_WALL = 5.0, 1.0, 20.0, 0.02  # usual Drude-oscillator settings
 L2_BYTES = 126 * 1024 * 1024
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback
+GRAPH_CHUNK_STEPS = 120
+SLAB_SEED = 12345
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100_000)
-    ap.add_argument("--warmup", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=10_000)
+    ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--atoms", type=int, default=1_000_000, help="particles (real+image) per GPU")
+    ap.add_argument("--slab", default="", choices=["", "16M"],
+                    help="16M = BASELINE configs[3] as the headline: ONE 16M-atom slab range-partitioned over the N GPUs "
+                         "(strong scaling: 16M/N atoms per GPU)")
     ap.add_argument("--precision", default="single", choices=["single", "mixed", "double"])
     ap.add_argument("--ensemble", type=int, default=0,
-                    help="BASELINE configs[4]: M independent slabs of --atoms particles per GPU advanced by ONE batched "
-                         "launch per step (64 slabs of 100k atoms over 8 GPUs = --ensemble 8 --atoms 100000)")
+                    help="BASELINE configs[4] as the headline: M independent slabs of --atoms particles per GPU advanced by "
+                         "batched launches (64 slabs of 100k atoms over 8 GPUs = --ensemble 8 --atoms 100000)")
     ap.add_argument("--replicas", type=int, default=0, help="slab copies rotated through (0 = auto: > 2x L2)")
+    ap.add_argument("--repeats", type=int, default=0, help="timed K-step regions (0 = auto: >= 9, ~0.4 s in total)")
     ap.add_argument("--pairs-per-thread", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--variant", type=int, default=0, help="0 auto (one-shot LDG kernel), 1 LDG kernel, 2 TMA ring kernel")
@@ -73,19 +90,14 @@ def parse_args():
     ap.add_argument("--tma-ctas", type=int, default=0)
     ap.add_argument("--chains", type=int, default=2,
                     help="cut the slab into this many independent real-atom ranges, each advanced on its own stream "
-                         "(constv_set_chains): the drain of one range's step overlaps the ramp of another's; for --ensemble, "
-                         "the slabs of a step are advanced by this many batched launches on as many streams")
+                         "(constv_set_chains); for --ensemble, the slabs of a step are advanced by this many batched launches")
     ap.add_argument("--rigid-water", default="", choices=["", "fused", "split"],
-                    help="BASELINE configs[0-1] shape: the slab's water molecules are rigid (constraints=AllBonds on SPC/E, "
-                         "example/nacl_1m_spce/nacl_constv.py:56).  fused = constv_step_fused_settle, one kernel per step; "
-                         "split = the reference's structure, part 1 | constraint solver on posDelta | part 2 + image rewrite "
-                         "(three launches; implies --chains 1).")
+                    help="BASELINE configs[0-1] shape: rigid SPC/E water (constraints=AllBonds, nacl_constv.py:56).  fused = "
+                         "constv_step_fused_settle, one kernel per step; split = part 1 | solver | part 2 + image rewrite")
     ap.add_argument("--drude", action="store_true",
-                    help="ConstVDrudeLangevinIntegrator on a slab of polarizable 4-site water (SURVEY.md 8f.4): one fused kernel "
-                         "per step (per chain), timed beside the reference's own four Drude kernels on the same GPU.")
+                    help="ConstVDrudeLangevinIntegrator on polarizable 4-site water (SURVEY.md 8f.4), one fused kernel per step")
     ap.add_argument("--reordered", action="store_true",
-                    help="the state behind OpenMM after cu.reorderAtoms(): whole molecules (and their images) have traded "
-                         "slots inside spatial windows; the step addresses images through atomIndex / invAtomOrder "
+                    help="the state behind OpenMM after cu.reorderAtoms(): slots addressed through atomIndex / invAtomOrder "
                          "(constVLangevin.cu:142-158).  Implies --chains 1.")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cache-image-charge", action="store_true")
@@ -96,6 +108,8 @@ def parse_args():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-ref-gpu", action="store_true", help="do not time the reference's own CUDA kernels beside ours")
+    ap.add_argument("--skip-also", action="store_true", help="headline only: no single-launch / plugin / 16M / ensemble / parity legs")
+    ap.add_argument("--only", default="", help="experiments: comma list of `also` legs to run (single,plugin,slab16m,ensemble,parity)")
     return ap.parse_args()
 
 
@@ -121,10 +135,33 @@ def traffic_from_profile(atoms, chains):
     return None
 
 
+def auto_replicas(bytes_per_step_working_set):
+    """Copies to rotate through so that no step finds its data in L2: footprint > 2x L2."""
+    if bytes_per_step_working_set >= 2 * L2_BYTES:
+        return 1
+    return int(np.ceil(2.0 * L2_BYTES / bytes_per_step_working_set)) + 1
+
+
+def workload_config(atoms_per_gpu, n_gpus, precision, slab16m=False):
+    """The `config` object: identical in the B200 arm and the reference arm (what is computed, not how)."""
+    total = 16_000_000 if slab16m else atoms_per_gpu * n_gpus
+    per = total // n_gpus
+    rec = per * (56 if precision == "single" else 104 if precision == "mixed" else 88)
+    reps = auto_replicas(rec)
+    name = ("synthetic 16M-atom slab (BASELINE configs[3])" if slab16m else
+            "synthetic slab (BASELINE configs[2] per GPU)")
+    return {"workload": f"{name}: {total} atoms ({total // 2} real + {total // 2} image), {per} per GPU over {n_gpus} GPU(s) by "
+                        f"contiguous real-atom range, ConstV Langevin step only, injected forces",
+            "atoms_per_gpu": per, "total_atoms": total, "precision": precision,
+            "T_K": T_KELVIN, "friction_per_ps": FRICTION, "dt_ps": DT,
+            "l2": f"steps rotate over {reps} replica(s) of the per-GPU slab ({reps * rec / 1e6:.0f} MB > 126 MB L2): inputs larger than L2, "
+                  f"every step streams from memory"}
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons during the timed region (NVML; nvidia-smi fallback)."""
 
-    def __init__(self, index, period=0.05):
+    def __init__(self, index, period=0.01):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
@@ -139,6 +176,7 @@ class ClockSampler(threading.Thread):
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception:
             self.nvml = None
+            self.period = max(period, 0.05)
 
     def sample(self):
         if self.nvml is not None:
@@ -181,77 +219,24 @@ class ClockSampler(threading.Thread):
         if not self.samples:
             self.sample()
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_min_mhz": float(np.min(self.samples)) if self.samples else None,
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-# ---- CPU legs (the only place bench.py touches oracle/) ---------------------------------------------
+# ---- CPU legs (the only place bench.py times anything under oracle/) -----------------------------------
 
-def cpu_oracle_rate(slab, seconds, steps_cap=None, window=None, replicas=1):
-    """Times the oracle's single-pass fused step (oracle_step_range_f32) with all host threads,
-    rotating over `replicas` copies of the slab exactly as the GPU arm does (so neither side runs
-    out of its last-level cache).  Returns (atom_steps_per_s, steps, threads, atoms_per_step, s)."""
-    import oracle
+def _cpu_rate(step_range_fn, slab, seconds, steps_cap, window, replicas, threads):
     copies = [slab.copy() for _ in range(max(1, replicas))]
-    s = copies[0]
-    prm = oracle.params(T_KELVIN, FRICTION, DT).astype(np.float32 if s.precision == "single" else np.float64)
-    dt = (np.float32 if s.precision == "single" else np.float64)(DT)
-    xi = oracle.fill_noise(s.padded, 1, 0)
-    R = s.num_real
+    R = slab.num_real
     w = R if window is None else max(1, min(R, window))
-    threads = oracle.num_threads()
-    per_pass = (R + w - 1) // w
-
-    def one(k):
-        c = copies[(k // per_pass) % len(copies)]
-        lo = (k % per_pass) * w
-        hi = min(R, lo + w)
-        oracle.step_range(c.precision, c.num_atoms, c.num_cells, c.zmax, c.posq, c.corr, c.velm,
-                          c.force.reshape(-1), prm, dt, xi, 0, lo, hi)
-        return (hi - lo) * c.num_cells
-
-    for k in range(2):
-        one(k)
-    done, atoms = 0, 0
-    t0 = time.perf_counter()
-    while True:
-        atoms += one(done)
-        done += 1
-        el = time.perf_counter() - t0
-        if (steps_cap is not None and done >= steps_cap) or (steps_cap is None and el >= seconds):
-            break
-    el = time.perf_counter() - t0
-    return atoms / el, done, threads, atoms / done, el
-
-
-def cpu_reference_rate(slab, seconds, steps_cap=None, window=None, replicas=1):
-    """Times the REFERENCE'S OWN kernel source compiled for the host (oracle/_ref/
-    libconstv_ref_host.so: constVLangevin.cu unmodified, CUDA execution model emulated, one OpenMP
-    thread per contiguous range of atoms; part 1, part 2 and the image rewrite as three passes,
-    the launch sequence of CudaConstVKernels.cpp:146-166) on all host threads, rotating over
-    `replicas` copies of the slab like the GPU arm.  Same return value as cpu_oracle_rate."""
-    import oracle
-    from oracle import ref
-    copies = [slab.copy() for _ in range(max(1, replicas))]
-    s = copies[0]
-    m = np.float32 if s.precision == "single" else np.float64
-    prm = oracle.params(T_KELVIN, FRICTION, DT).astype(m)
-    dt = m(DT)
-    xi = oracle.fill_noise(s.padded, 1, 0)
-    inv = np.arange(s.padded, dtype=np.int32)
-    deltas = [np.zeros((s.padded, 4), m) for _ in copies]
-    R = s.num_real
-    w = R if window is None else max(1, min(R, window))
-    threads = ref.host_num_threads()
     per_pass = (R + w - 1) // w
 
     def one(k):
         j = (k // per_pass) % len(copies)
-        c = copies[j]
         lo = (k % per_pass) * w
         hi = min(R, lo + w)
-        ref.host_step_range(c.precision, c.num_atoms, c.num_cells, c.zmax, c.posq, c.corr, c.velm,
-                            c.force.reshape(-1), deltas[j], prm, dt, xi, 0, inv, lo, hi)
-        return (hi - lo) * c.num_cells
+        step_range_fn(copies[j], j, lo, hi)
+        return (hi - lo) * slab.num_cells
 
     for k in range(2):
         one(k)
@@ -265,6 +250,46 @@ def cpu_reference_rate(slab, seconds, steps_cap=None, window=None, replicas=1):
             break
     el = time.perf_counter() - t0
     return atoms / el, done, threads, atoms / done, el
+
+
+def cpu_oracle_rate(slab, seconds, steps_cap=None, window=None, replicas=1):
+    """Times the oracle's single-pass fused step (oracle_step_range_f32) with all host threads, rotating over
+    `replicas` copies of the slab exactly as the GPU arm does (so neither side runs out of its last-level
+    cache).  Returns (atom_steps_per_s, steps, threads, atoms_per_step, seconds)."""
+    import oracle
+    m = np.float32 if slab.precision == "single" else np.float64
+    prm = oracle.params(T_KELVIN, FRICTION, DT).astype(m)
+    dt = m(DT)
+    xi = oracle.fill_noise(slab.padded, 1, 0)
+
+    def fn(c, j, lo, hi):
+        oracle.step_range(c.precision, c.num_atoms, c.num_cells, c.zmax, c.posq, c.corr, c.velm,
+                          c.force.reshape(-1), prm, dt, xi, 0, lo, hi)
+
+    return _cpu_rate(fn, slab, seconds, steps_cap, window, replicas, oracle.num_threads())
+
+
+def cpu_reference_rate(slab, seconds, steps_cap=None, window=None, replicas=1):
+    """Times the REFERENCE'S OWN kernel source compiled for the host (oracle/_ref/libconstv_ref_host.so:
+    constVLangevin.cu unmodified, CUDA execution model emulated, one OpenMP thread per contiguous range of
+    atoms; part 1, part 2 and the image rewrite as three passes, the launch sequence of
+    CudaConstVKernels.cpp:146-166) on all host threads, rotating over `replicas` copies like the GPU arm."""
+    import oracle
+    from oracle import ref
+    m = np.float32 if slab.precision == "single" else np.float64
+    prm = oracle.params(T_KELVIN, FRICTION, DT).astype(m)
+    dt = m(DT)
+    xi = oracle.fill_noise(slab.padded, 1, 0)
+    inv = np.arange(slab.padded, dtype=np.int32)
+    deltas = {}
+
+    def fn(c, j, lo, hi):
+        if j not in deltas:
+            deltas[j] = np.zeros((c.padded, 4), m)
+        ref.host_step_range(c.precision, c.num_atoms, c.num_cells, c.zmax, c.posq, c.corr, c.velm,
+                            c.force.reshape(-1), deltas[j], prm, dt, xi, 0, inv, lo, hi)
+
+    return _cpu_rate(fn, slab, seconds, steps_cap, window, replicas, ref.host_num_threads())
 
 
 def host_thread_count():
@@ -275,8 +300,8 @@ def host_thread_count():
 
 
 def cpu_leg():
-    """(rate function, kind): the reference's own source when oracle/_ref travelled with the tree,
-    else the oracle port."""
+    """(rate function, kind): the reference's own source when oracle/_ref travelled with the tree, else the
+    oracle port."""
     import oracle
     from oracle import ref
     n = host_thread_count()
@@ -288,19 +313,23 @@ def cpu_leg():
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's C++ host code needs OpenMM and ships no CPU platform for
-    this path, but its kernel source is self-contained: the reference arm times
-    that source compiled for the host (oracle/_ref, kind "reference") on all host threads, and
-    reports the faster single-pass oracle port beside it.  Without oracle/_ref the port is timed."""
+    """--impl reference: the reference's C++ host code needs OpenMM and ships no CPU platform for this path
+    (SURVEY.md 0.1, 8c), but its kernel source is self-contained: the reference arm times that source compiled
+    for the host (oracle/_ref, kind "reference") on all host threads, and reports the faster single-pass oracle
+    port beside it.  Without oracle/_ref the port is timed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     from openmm_constv_b200 import slab as slabmod
     rate_fn, kind = cpu_leg()
-    total_atoms = args.atoms * max(1, args.gpus)  # the whole job's slab, as the GPU arm partitions it
-    s = slabmod.make_slab(total_atoms // 2, args.precision, seed=12345)
+    n_gpus = max(1, args.gpus)
+    config = workload_config(args.atoms, n_gpus, args.precision, args.slab == "16M")
+    total_atoms = config["total_atoms"]
+    # the whole job's slab, as the GPU arm partitions it; the CPU walks it in windows
+    tiles = [slabmod.slab_tile(total_atoms // 2, n_gpus, t, args.precision, seed=SLAB_SEED) for t in range(n_gpus)]
+    s = slabmod.concat_slabs(tiles) if n_gpus > 1 else tiles[0]
+    reps = auto_replicas(s.posq.nbytes + s.velm.nbytes + s.force.nbytes + (s.corr.nbytes if s.corr is not None else 0))
     # bound the run: calibrate, then size the per-step window so warmup+steps stay under ~90 s
-    reps = 6 if total_atoms <= 2_000_000 else 2
     rate, _, threads, _, _ = rate_fn(s, 1.0, replicas=reps)
     total = max(1, args.steps + args.warmup)
     window_atoms = min(total_atoms, max(65536, int(rate * 90.0 / total)))
@@ -310,7 +339,7 @@ def run_reference_arm(args):
     what = ("the reference's constVLangevin.cu compiled for the host (part 1, part 2, image rewrite)" if kind == "reference"
             else "the fused oracle step")
     sample = (f"{done} steps, each {what} over a window of {int(per_step)} atoms walking through "
-              f"{reps} replicas of the {total_atoms}-atom slab (like the GPU arm's L2 rotation), injected noise pool")
+              f"{reps} replica(s) of the {total_atoms}-atom slab (like the GPU arm's L2 rotation), injected noise pool")
     port = None
     if kind == "reference":
         prate, pdone, _, _, pel = cpu_oracle_rate(s, min(10.0, args.cpu_seconds), window=window, replicas=reps)
@@ -319,12 +348,11 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": "atom-steps/s", "value": rate, "unit": "atom-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * el / done, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * el / done, "higher_is_better": True, "scaling": "strong" if args.slab == "16M" else "weak",
         "vs_baseline": None, "dtype": "f32" if args.precision == "single" else "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic slab, {total_atoms} atoms ({total_atoms // 2} real + images), fused ConstV Langevin step only",
-                   "atoms_per_step": int(per_step), "precision": args.precision,
-                   "note": "the reference ships no CPU platform for this path; its kernel source compiled for the host is timed"
-                           if kind == "reference" else "oracle/_ref absent: oracle port timed"},
+        "config": config,
+        "note": ("the reference ships no CPU platform for this path; its kernel source compiled for the host is timed"
+                 if kind == "reference" else "oracle/_ref absent: oracle port timed"),
         "cpu_baseline": {"value": rate, "unit": "atom-steps/s", "cores": threads, "kind": kind, "sample": sample, "port": port},
         "e2e": {"value": rate, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -333,15 +361,298 @@ def run_reference_arm(args):
     return 0
 
 
-def time_reference_gpu(torch, ctxs, shard, stream, steps, max_blocks, use_graph):
-    """The reference's own kernels (constVLangevin.cu compiled by nvcc for sm_100a, oracle/_ref)
-    on the same rotating slab replicas: per step the three launches of CudaConstVKernels.cpp:146-166
-    (part 1 reading a pre-filled float4 Gaussian pool, part 2, image rewrite), 128-thread blocks,
-    grid capped at `max_blocks` (0 = uncapped).  The pool refill (OpenMM's RNG kernel) and the
-    reordering kernel are NOT charged to the reference.  Returns ms per step."""
+# ---- the B200 arm ------------------------------------------------------------------------------------------
+
+class Env:
+    """Process-wide handles of one rank."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        from openmm_constv_b200 import _capi, integrator as hostapi, partition, slab as slabmod
+        self.torch, self.dist = torch, dist
+        self.capi, self.hostapi, self.partition, self.slabmod = _capi, hostapi, partition, slabmod
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the ConstV step path has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.lib = _capi.load()
+        self.stream = torch.cuda.Stream(device=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def min_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return float(t.item())
+
+
+class Workload:
+    """`replicas` rotating groups of `M` slabs on this rank, and how one step of them is launched."""
+
+    def __init__(self, env, args, shard, *, kind="langevin", M=1, replicas=0, chains=1, water=None, drude=None,
+                 reorder_perm=None, variant=0, precision=None, per_slab_forces=False):
+        torch, lib, capi, hostapi = env.torch, env.lib, env.capi, env.hostapi
+        self.env, self.args, self.shard, self.kind, self.M = env, args, shard, kind, M
+        self.water, self.drude = water, drude
+        precision = precision or shard.precision
+        rec_bytes = shard.posq.nbytes + shard.velm.nbytes + shard.force.nbytes + (shard.corr.nbytes if shard.corr is not None else 0)
+        self.rec_bytes = rec_bytes
+        self.replicas = replicas or auto_replicas(rec_bytes * M)
+        flags = capi.FLAGS_DEFAULT
+        if not args.no_cache_image_charge:
+            flags |= capi.FLAG_CACHE_IMAGE_CHARGE
+        if args.keep_in_l2:
+            flags |= capi.FLAG_KEEP_IN_L2
+        self.ctxs = []
+        for r in range(self.replicas * M):
+            sysm = hostapi.SlabSystem()
+            sysm.addParticles(shard.masses)
+            sysm.setDefaultPeriodicBoxVectors((shard.box[0], 0, 0), (0, shard.box[1], 0), (0, 0, shard.num_cells * shard.zmax))
+            if water:
+                sysm.addConstraints(*water[2])
+            if drude:
+                dforce = hostapi.DrudeForce()
+                for a, b in drude[1]:
+                    dforce.addParticle(int(a), int(b))
+                sysm.addForce(dforce)
+                it = hostapi.ConstVDrudeLangevinIntegrator(args.temperature, DRUDE_FRICTION_CM, DRUDE_T, DRUDE_FRICTION, DT, shard.num_cells)
+                it.setMaxDrudeDistance(DRUDE_WALL)
+            else:
+                it = hostapi.ConstVLangevinIntegrator(args.temperature, FRICTION, DT, shard.num_cells)
+            it.setRandomNumberSeed(2024 + (r % M))
+            ctx = hostapi.SlabContext(sysm, it, precision=precision, device=env.local_rank, flags=flags,
+                                      global_atom_offset=shard.global_atom_offset, padded=shard.padded)
+            ctx.load_slab(shard)
+            if per_slab_forces and (r % M):  # ensemble: every slab sits at its own applied voltage = its own forces
+                ctx.force.copy_(torch.from_numpy(env.slabmod.new_forces(shard, r % M)))
+            if reorder_perm is not None:
+                ctx.set_atom_order(reorder_perm)
+                capi.check(lib.constv_update_inverse_order(it._kernel.handle, ctx.stream_ptr()))
+            if args.pairs_per_thread or args.ctas_per_sm:
+                it._kernel.set_launch_shape(args.pairs_per_thread, args.ctas_per_sm)
+            it._kernel.set_kernel_variant(variant, args.tma_block, args.tma_stages, args.tma_ctas)
+            if drude:
+                capi.check(lib.constv_drude_set_parameters(it._kernel.handle, args.temperature, DRUDE_FRICTION_CM, DRUDE_T,
+                                                           DRUDE_FRICTION, DRUDE_WALL, DT))
+            else:
+                capi.check(lib.constv_set_parameters(it._kernel.handle, args.temperature, FRICTION, DT))
+            self.ctxs.append((ctx, it))
+        self.handles = [it._kernel.handle for _, it in self.ctxs]
+        self.groups = [(C.c_void_p * M)(*self.handles[g * M:(g + 1) * M]) for g in range(self.replicas)]
+        self.side_streams = []
+        self.set_chains(chains)
+        torch.cuda.synchronize()
+
+    def set_chains(self, chains):
+        env, lib, capi, M = self.env, self.env.lib, self.env.capi, self.M
+        want = max(1, chains)
+        if M == 1:
+            got = C.c_int32(0)
+            for h in self.handles:
+                capi.check(lib.constv_set_chains(h, want))
+            capi.check(lib.constv_get_chains(self.handles[0], C.byref(got)))
+            self.chains = got.value
+        else:
+            self.chains = min(want, M)
+        while len(self.side_streams) < self.chains - 1:
+            self.side_streams.append(env.torch.cuda.Stream(device=env.dev))
+        # ensemble: sub-group q of every replica's M slabs = one batched launch on stream q
+        ch = self.chains
+        self.bounds = [M * q // ch for q in range(ch + 1)]
+        self.subgroups = [[(C.c_void_p * (self.bounds[q + 1] - self.bounds[q]))(
+            *self.handles[g * M + self.bounds[q]:g * M + self.bounds[q + 1]]) for q in range(ch)] for g in range(self.replicas)]
+
+    @property
+    def launches_per_step(self):
+        return 3 if self.kind == "settle_split" else self.chains
+
+    def launch_steps(self, first, count):
+        env, lib, capi = self.env, self.env.lib, self.env.capi
+        stream, torch = env.stream, env.torch
+        check, kind, M, reps = capi.check, self.kind, self.M, self.replicas
+        sptr = stream.cuda_stream
+        if self.chains > 1:  # fork: chain q's steps on stream q, in step order; join back into `stream`
+            fork = torch.cuda.Event()
+            fork.record(stream)
+            for q, cs in enumerate([stream] + self.side_streams[:self.chains - 1]):
+                if q:
+                    cs.wait_event(fork)
+                for k in range(first, first + count):
+                    if M > 1 and kind == "settle":
+                        check(lib.constv_step_fused_settle_batched(self.subgroups[k % reps][q], self.bounds[q + 1] - self.bounds[q], cs.cuda_stream))
+                    elif M > 1:
+                        check(lib.constv_step_fused_batched(self.subgroups[k % reps][q], self.bounds[q + 1] - self.bounds[q], cs.cuda_stream))
+                    elif kind == "drude":
+                        check(lib.constv_drude_step_fused_chain(self.handles[k % reps], q, None, 0, cs.cuda_stream))
+                    elif kind == "settle":
+                        check(lib.constv_step_fused_settle_chain(self.handles[k % reps], q, None, 0, cs.cuda_stream))
+                    else:
+                        check(lib.constv_step_fused_chain(self.handles[k % reps], q, None, 0, cs.cuda_stream))
+            for cs in self.side_streams[:self.chains - 1]:
+                join = torch.cuda.Event()
+                join.record(cs)
+                stream.wait_event(join)
+            return
+        for k in range(first, first + count):
+            if M > 1 and kind == "settle":
+                check(lib.constv_step_fused_settle_batched(self.groups[k % reps], M, sptr))
+            elif M > 1:
+                check(lib.constv_step_fused_batched(self.groups[k % reps], M, sptr))
+            elif kind == "drude":
+                check(lib.constv_drude_step_fused(self.handles[k % reps], None, 0, sptr))
+            elif kind == "settle":
+                check(lib.constv_step_fused_settle(self.handles[k % reps], None, 0, sptr))
+            elif kind == "settle_split":
+                h = self.handles[k % reps]
+                check(lib.constv_step_part1(h, None, 0, sptr))
+                check(lib.constv_settle_positions(h, sptr))
+                check(lib.constv_step_part2_mirror(h, sptr))
+            else:
+                check(lib.constv_step_fused(self.handles[k % reps], None, 0, sptr))
+
+    def algorithmic_bytes(self):
+        sm = self.env.slabmod
+        water, drude = self.water, self.drude
+        gather = water is not None and self.args.variant == 1  # only the gather kernel reads the item / molecule lists
+        return self.M * sm.algorithmic_bytes_per_step(self.shard, rigid_molecules=len(water[0]) if gather else 0,
+                                                      drude=drude is not None, drude_pairs=len(drude[1]) if drude else 0)
+
+    def reload(self):
+        for ctx, _ in self.ctxs:
+            ctx.load_slab(self.shard)
+
+    def close(self):
+        self.env.torch.cuda.synchronize()
+        for ctx, _ in self.ctxs:
+            ctx.close()
+        self.ctxs = []
+
+
+def time_steps(env, wl, K, W, use_graph=True, repeats=0, target_s=0.4, sample_clocks=False):
+    """W warm-up steps, then the K-step region `repeats` times back to back (see the module docstring).
+    Returns {"ms": median region time (max over ranks), "ms_min", "ms_max", "repeats", "eager_launches",
+    "graph": description, "clocks": ...}."""
+    torch, stream, capi = env.torch, env.stream, env.capi
+    reps = wl.replicas
+    chunk = reps * max(1, GRAPH_CHUNK_STEPS // reps)
+    graphs = {}
+
+    def graph_for(offset, count):
+        key = (offset % reps, count)
+        if key not in graphs:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                wl.launch_steps(key[0], count)
+            graphs[key] = g
+        return graphs[key]
+
+    def plan(start, n):
+        """The launches of steps [start, start+n): graphs only (eager only with --no-graph)."""
+        if not use_graph:
+            return [("eager", start, n)]
+        out, done = [], 0
+        while n - done >= chunk and n > 2 * chunk:
+            out.append(graph_for(start + done, chunk))
+            done += chunk
+        if n - done:
+            out.append(graph_for(start + done, n - done))
+        return out
+
+    def run(p):
+        for g in p:
+            if isinstance(g, tuple):
+                wl.launch_steps(g[1], g[2])
+            else:
+                g.replay()
+
+    with torch.cuda.stream(stream):
+        wl.launch_steps(0, reps)  # first touch: refreshes image-charge snapshots outside capture
+        stream.synchronize()
+        pos = 0
+        run(plan(pos, W))
+        pos += W
+        # one synchronous region: an estimate of its duration (also replays its graphs once)
+        first = plan(pos, K)
+        stream.synchronize()
+        t0 = time.perf_counter()
+        run(first)
+        stream.synchronize()
+        est = max(1e-5, time.perf_counter() - t0)
+        pos += K
+        n_rep = repeats or int(min(400, max(9, np.ceil(target_s / est))))
+        period = reps // int(np.gcd(K, reps))  # distinct graph offsets a sequence of regions walks through
+        n_pre = int(max(period, min(200, np.ceil(0.03 / est))))
+        plans = [plan(pos + r * K, K) for r in range(n_pre + n_rep)]
+        stream.synchronize()
+        env.barrier()
+        torch.cuda.synchronize()
+        sampler = None
+        if sample_clocks:
+            sampler = ClockSampler(env.local_rank)
+            sampler.start()
+        launches0 = capi.launch_count()
+        events = [torch.cuda.Event(enable_timing=True) for _ in range(n_rep + 1)]
+        for r in range(n_pre):  # untimed: every graph replayed once, clocks up, and the GPU busy while the host queues ahead
+            run(plans[r])
+        events[0].record(stream)
+        for r in range(n_rep):
+            run(plans[n_pre + r])
+            events[r + 1].record(stream)
+        stream.synchronize()
+        torch.cuda.synchronize()
+        eager = capi.launch_count() - launches0
+        clocks = sampler.stop() if sampler else None
+        env.barrier()
+    ms = np.asarray([events[r].elapsed_time(events[r + 1]) for r in range(n_rep)])
+    med = float(np.median(ms))
+    out = {"ms": env.max_over_ranks(med), "ms_min": env.min_over_ranks(float(ms.min())), "ms_max": env.max_over_ranks(float(ms.max())),
+           "ms_this_rank": med, "repeats": n_rep, "untimed_regions": n_pre + 1, "eager_launches": int(eager),
+           "graph": (f"{len(graphs)} CUDA graphs ({K}-step regions" + (f" as {chunk}-step chunks + tail" if K > 2 * chunk else "") + "), PDL")
+                    if use_graph else "eager, PDL",
+           "clocks": clocks}
+    graphs.clear()
+    return out
+
+
+def rate_record(atoms_job, K, t, alg_bytes, launches_per_step, peak, kernel, extra=None):
+    """A compact result of one timed leg; alg_bytes = algorithmic bytes per step ON ONE GPU."""
+    ms_step = t["ms"] / K
+    achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+    rec = {"atom_steps_per_s": atoms_job * K / (t["ms"] * 1e-3), "us_per_step": 1e3 * ms_step,
+           "GBps_per_gpu": achieved, "frac_measured_peak": achieved / peak, "frac_8TBs": achieved / 8000.0,
+           "launches_per_step": launches_per_step, "repeats": t["repeats"], "us_min_max": [1e3 * t["ms_min"] / K, 1e3 * t["ms_max"] / K],
+           "eager_launches": t["eager_launches"], "kernel": kernel}
+    if extra:
+        rec.update(extra)
+    return rec
+
+
+def time_reference_gpu(env, wl, steps, max_blocks, use_graph):
+    """The reference's own kernels (constVLangevin.cu compiled by nvcc for sm_100a, oracle/_ref) on the same
+    rotating slab replicas: per step the three launches of CudaConstVKernels.cpp:146-166 (part 1 reading a
+    pre-filled float4 Gaussian pool, part 2, image rewrite), 128-thread blocks, grid capped at `max_blocks`
+    (0 = uncapped).  The pool refill (OpenMM's RNG kernel) and the reordering kernel are NOT charged to the
+    reference.  Returns ms per step."""
     import oracle
     from oracle import ref
-    dev = ctxs[0][0].device
+    torch, stream, shard, ctxs = env.torch, env.stream, wl.shard, wl.ctxs
+    dev = env.dev
     m = np.float32 if shard.precision == "single" else np.float64
     prm = oracle.params(T_KELVIN, FRICTION, DT).astype(m)
     r = ref.CudaReference(shard.precision, prm, m(DT), dev, max_blocks=max_blocks)
@@ -359,75 +670,292 @@ def time_reference_gpu(torch, ctxs, shard, stream, steps, max_blocks, use_graph)
     with torch.cuda.stream(stream):
         launch(0, n)
         stream.synchronize()
-        graph, chunk = None, 0
-        if use_graph and steps >= 2 * n:
-            chunk = n * max(1, min(20, steps // n))
+        chunk = n * max(1, min(20, steps // n))
+        graph = None
+        if use_graph:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=stream):
                 launch(0, chunk)
+        reps = max(1, steps // chunk)
 
-        def run(nsteps):
-            done = 0
-            if graph is not None:
-                while done + chunk <= nsteps:
+        def run():
+            for _ in range(reps):
+                if graph is not None:
                     graph.replay()
-                    done += chunk
-            launch(done, nsteps - done)
+                else:
+                    launch(0, chunk)
 
-        run(max(3, steps // 10))
+        run()
         stream.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        run(steps)
-        e1.record(stream)
+        times = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            run()
+            e1.record(stream)
+            stream.synchronize()
+            times.append(e0.elapsed_time(e1) / (reps * chunk))
+    return float(np.median(times))
+
+
+def time_reference_gpu_drude(env, wl, steps):
+    import oracle
+    from oracle import ref as refmod
+    torch, stream, shard, ctxs, drude = env.torch, env.stream, wl.shard, wl.ctxs, wl.drude
+    args = wl.args
+    R = shard.num_real
+    m = np.float32 if args.precision == "single" else np.float64
+    scal = oracle.drude_params(args.temperature, DRUDE_FRICTION_CM, DRUDE_T, DRUDE_FRICTION, DRUDE_WALL, DT)
+    rr = refmod.CudaDrudeReference(args.precision, scal, m(DT), env.dev, drude[0], drude[1], R, shard.padded, max_blocks=0)
+    pool = torch.randn((R + 8, 4), dtype=torch.float32, device=env.dev)
+    inv = torch.arange(shard.padded, dtype=torch.int32, device=env.dev)
+    sptr = stream.cuda_stream
+    n = len(ctxs)
+
+    def ref_launch(first, count):
+        for k in range(first, first + count):
+            c = ctxs[k % n][0]
+            rr.drude_step(shard.num_atoms, shard.num_cells, shard.zmax, c.posq, c.corr, c.velm, c.force, c.pos_delta,
+                          pool, 0, inv, stream=sptr)
+
+    with torch.cuda.stream(stream):
+        ref_launch(0, n)
         stream.synchronize()
-    return e0.elapsed_time(e1) / steps
+        rchunk = n * max(1, min(20, steps // n))
+        rgraph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(rgraph, stream=stream):
+            ref_launch(0, rchunk)
+        reps = max(1, steps // rchunk)
+        for _ in range(3):
+            rgraph.replay()
+        stream.synchronize()
+        times = []
+        for _ in range(5):
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record(stream)
+            for _ in range(reps):
+                rgraph.replay()
+            r1.record(stream)
+            stream.synchronize()
+            times.append(r0.elapsed_time(r1) / (reps * rchunk))
+    return float(np.median(times)), reps * rchunk
 
 
-# ---- the B200 arm -------------------------------------------------------------------------------------
+def run_e2e(env, wl, args, atoms_job):
+    """e2e: host buffers through constv_step_host*.  Per step: H2D of the step's input (the real atoms'
+    fixed-point forces, pinned memory), the fused step, the kinetic-energy reduction, and D2H of the step's
+    result.  `value` reads back the scalar a StateDataReporter asks for every step (kinetic energy);
+    `full_state` also reads back posq of all atoms (what a DCD frame needs)."""
+    torch, lib, capi, stream, slabmod = env.torch, env.lib, env.capi, env.stream, env.slabmod
+    shard = wl.shard
+    R = shard.num_real
+    sptr = stream.cuda_stream
+    ctx0, it0 = wl.ctxs[0]
+    n_e2e = max(3, args.e2e_steps)
+    host_force = [torch.from_numpy(np.ascontiguousarray(slabmod.new_forces(shard, j)[:, :R])).pin_memory() for j in range(2)]
+    esize = 4 if args.precision != "double" else 8
+    host_posq = torch.empty((shard.num_atoms, 4), dtype=torch.float32 if esize == 4 else torch.float64).pin_memory()
+    h2d = host_force[0].numel() * 8
+    ke_host = C.c_double(0.0)
+    h = it0._kernel.handle
+
+    def e2e_sync(with_posq):
+        out = host_posq.data_ptr() if with_posq else None
+        for j in range(3):
+            capi.check(lib.constv_step_host(h, host_force[j % 2].data_ptr(), out, None, C.byref(ke_host), sptr))
+        best = []
+        for _ in range(3):
+            env.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for j in range(n_e2e):
+                capi.check(lib.constv_step_host(h, host_force[j % 2].data_ptr(), out, None, C.byref(ke_host), sptr))
+            e1.record(stream)
+            stream.synchronize()
+            best.append(e0.elapsed_time(e1))
+        return env.max_over_ranks(float(np.median(best)))
+
+    def e2e_pipelined(buffers, code, nsteps):
+        """submit step k+1, then collect step k: the upload of k+1 overlaps the kernels and the read-back of
+        k.  Every step still uploads its own forces and returns its own energy."""
+        ticket = C.c_uint64(0)
+
+        def loop(n):
+            prev = None
+            for j in range(n):
+                capi.check(lib.constv_step_host_submit(h, buffers[j % 2].data_ptr(), code, C.byref(ticket), sptr))
+                if prev is not None:
+                    capi.check(lib.constv_step_host_collect(h, prev, C.byref(ke_host)))
+                prev = ticket.value
+            capi.check(lib.constv_step_host_collect(h, prev, C.byref(ke_host)))
+
+        loop(4)
+        ts = []
+        for _ in range(5):  # PCIe transfers are noisy on a shared host: median of five passes
+            env.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            loop(nsteps)
+            e1.record(stream)
+            stream.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return env.max_over_ranks(float(np.median(ts)))
+
+    with torch.cuda.stream(stream):
+        ms_ke = e2e_sync(False)
+        ms_full = e2e_sync(True)
+        n_pipe = 4 * n_e2e
+        ms_pipe = e2e_pipelined(host_force, capi.FORCE_FIXED64, n_pipe)
+        host_force32 = [(torch.randn((3, R), dtype=torch.float32) * 1000.0).pin_memory() for _ in range(2)]
+        ms_pipe32 = e2e_pipelined(host_force32, capi.FORCE_FLOAT32, n_pipe)
+    return {"value": atoms_job * n_pipe / (ms_pipe * 1e-3), "unit": "atom-steps/s",
+            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8, "steps": n_pipe,
+            "ms_per_step": ms_pipe / n_pipe,
+            "what": "constv_step_host_submit/_collect, two tickets in flight: every step uploads its real-atom forces (int64 fixed "
+                    "point, OpenMM's buffer format, pinned memory) and reads back its kinetic energy; PCIe-bound; median of 5 passes",
+            "float32_forces": {"value": atoms_job * n_pipe / (ms_pipe32 * 1e-3), "ms_per_step": ms_pipe32 / n_pipe,
+                               "h2d_bytes_per_step": int(h2d // 2), "d2h_bytes_per_step": 8},
+            "synchronous": {"value": atoms_job * n_e2e / (ms_ke * 1e-3), "ms_per_step": ms_ke / n_e2e,
+                            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8},
+            "full_state": {"value": atoms_job * n_e2e / (ms_full * 1e-3), "ms_per_step": ms_full / n_e2e,
+                           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(host_posq.numel() * esize + 8),
+                           "what": "synchronous constv_step_host, plus D2H of posq for all atoms"}}
+
+
+def run_plugin_path(args, atoms):
+    """Steps through the C++ plugin class against the OpenMM shim (plugin/tests/BenchPluginPath.cpp)."""
+    exe = os.path.join(ROOT, "openmm_constv_b200", "plugin", "bin", "BenchPluginPath")
+    if not os.path.exists(exe):
+        return {"unavailable": "plugin/bin/BenchPluginPath has not been built"}
+    out = {}
+    for mode in ("identity", "reordered"):
+        cmd = [exe, "--atoms", str(atoms), "--steps", "300", "--precision", args.precision] + (["--reordered"] if mode == "reordered" else [])
+        try:
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+            line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+            out[mode] = json.loads(line[-1]) if line else {"error": (res.stderr or res.stdout)[-300:]}
+        except Exception as exc:  # noqa: BLE001
+            out[mode] = {"error": str(exc)[-300:]}
+    return out
+
+
+def run_partition_parity(env, steps=8, tile_real=20000):
+    """One small seeded slab, range-partitioned over the ranks (over 2 shards on this GPU when N = 1): after
+    `steps` Philox steps every shard's posq / velm / force must equal, bit for bit, the same slots of the
+    UNPARTITIONED slab advanced on this GPU, and that must equal the CPU oracle fed the Gaussians the device
+    publishes for (seed, step) (rank 0).  The oracle is used as the checker only."""
+    torch, lib, capi, hostapi, slabmod, partition = env.torch, env.lib, env.capi, env.hostapi, env.slabmod, env.partition
+    parts = max(2, env.world)
+    R = tile_real * parts
+    tiles = [slabmod.slab_tile(R, parts, t, "single", seed=777) for t in range(parts)]
+    full = slabmod.concat_slabs(tiles)
+    mine = [env.rank] if env.world > 1 else list(range(parts))
+
+    def advance(s, offset):
+        sysm = hostapi.SlabSystem()
+        sysm.addParticles(s.masses)
+        sysm.setDefaultPeriodicBoxVectors((s.box[0], 0, 0), (0, s.box[1], 0), (0, 0, 2 * s.zmax))
+        it = hostapi.ConstVLangevinIntegrator(T_KELVIN, FRICTION, DT)
+        it.setRandomNumberSeed(4242)
+        ctx = hostapi.SlabContext(sysm, it, precision="single", device=env.local_rank, global_atom_offset=offset, padded=s.padded)
+        ctx.load_slab(s)
+        return ctx, it
+
+    ok = True
+    with torch.cuda.stream(env.stream):
+        ctx_full, it_full = advance(full, 0)
+        # rank 0: the unpartitioned GPU trajectory against the oracle, step by step
+        oracle_ok = None
+        if env.rank == 0:
+            import oracle
+            ref = full.copy()
+            prm = oracle.params(T_KELVIN, FRICTION, DT).astype(np.float32)
+            inv = np.arange(full.padded, dtype=np.int32)
+            delta = np.zeros((full.padded, 4), np.float32)
+            noise = torch.zeros((full.padded, 4), dtype=torch.float32, device=env.dev)
+            oracle_ok = True
+            for k in range(steps):
+                capi.check(lib.constv_generate_noise(it_full._kernel.handle, k, noise.data_ptr(), ctx_full.stream_ptr()))
+                xi = noise.cpu().numpy()
+                it_full.step(1)
+                oracle.step("single", full.num_atoms, 2, full.zmax, ref.posq, None, ref.velm, ref.force.reshape(-1),
+                            delta, prm, np.float32(DT), xi, 0, inv, True, True)
+            oracle_ok = (np.array_equal(ctx_full.posq.cpu().numpy().view(np.uint32), ref.posq.view(np.uint32))
+                         and np.array_equal(ctx_full.velm.cpu().numpy().view(np.uint32), ref.velm.view(np.uint32))
+                         and np.array_equal(ctx_full.force.cpu().numpy(), ref.force))
+            ok = ok and oracle_ok
+        else:
+            it_full.step(steps)
+        Rf = full.num_real
+        for t in mine:
+            lo, hi = partition.shard_range(Rf, t, parts)
+            shard = slabmod.slice_slab(full, lo, hi)
+            assert shard.global_atom_offset == tiles[t].global_atom_offset == lo
+            assert np.array_equal(shard.posq, tiles[t].posq) and np.array_equal(shard.force, tiles[t].force)
+            ctx, it = advance(tiles[t], lo)
+            capi.check(lib.constv_set_chains(it._kernel.handle, 2))
+            it.step(steps)
+            torch.cuda.synchronize()
+            r = hi - lo
+            for cell in range(2):
+                a = slice(cell * r, (cell + 1) * r)
+                b = slice(cell * Rf + lo, cell * Rf + hi)
+                ok = ok and bool(torch.equal(ctx.posq[a].view(torch.int32), ctx_full.posq[b].view(torch.int32)))
+                ok = ok and bool(torch.equal(ctx.velm[a].view(torch.int32), ctx_full.velm[b].view(torch.int32)))
+                ok = ok and bool(torch.equal(ctx.force[:, a], ctx_full.force[:, b]))
+            ctx.close()
+        ctx_full.close()
+    all_ok = env.min_over_ranks(1.0 if ok else 0.0) == 1.0
+    return {"result": "bit-exact" if all_ok else "MISMATCH", "shards": parts, "ranks": env.world, "steps": steps,
+            "atoms": full.num_atoms, "vs": "unpartitioned slab on the GPU == CPU oracle (rank 0); every shard == its slots of the unpartitioned slab"}
+
 
 def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
 
-    import torch
-    import torch.distributed as dist
-    from openmm_constv_b200 import _capi, integrator as hostapi, partition, slab as slabmod
+    env = Env()
+    torch, lib, capi, slabmod, partition = env.torch, env.lib, env.capi, env.slabmod, env.partition
+    world, rank = env.world, env.rank
+    peak, peak_src = peaks()
+    only = set(filter(None, args.only.split(",")))
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the ConstV step path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    lib = _capi.load()
+    def want(leg):
+        return (not args.skip_also) and (not only or leg in only)
 
-    # ---- workload: this rank's shard of the range-partitioned slab ------------------------------
-    R = args.atoms // 2
-    water = None
-    drude = None
+    # ---- workload: this rank's shard = its tile of the ONE global slab -------------------------------------
+    slab16m = args.slab == "16M"
+    config = workload_config(args.atoms, world, args.precision, slab16m)
+    R_total = config["total_atoms"] // 2
+    R = R_total // world
+    plain = not (args.drude or args.rigid_water or args.ensemble or args.reordered)
+    water = drude = None
+    kind = "langevin"
     if args.drude:
         if args.ensemble or args.rigid_water:
             raise SystemExit("--drude, --rigid-water and --ensemble are separate configurations")
         if args.variant == 1:
             args.chains = 1
-        shard, d_normal, d_pairs = slabmod.make_drude_slab(R, args.precision, seed=12345 + rank)
+        shard, d_normal, d_pairs = slabmod.slab_tile(R_total, world, rank, args.precision, seed=SLAB_SEED, maker=slabmod.make_drude_slab)
         drude = (d_normal, d_pairs)
+        kind = "drude"
     elif args.rigid_water:
         if args.ensemble and args.rigid_water != "fused":
             raise SystemExit("--ensemble takes --rigid-water fused only")
         if args.rigid_water == "split" or args.variant == 1:
             args.chains = 1
-        shard, w_atoms, w_params, w_cons = slabmod.make_water_slab(R, args.precision, seed=12345 + rank)
+        shard, w_atoms, w_params, w_cons = slabmod.slab_tile(R_total, world, rank, args.precision, seed=SLAB_SEED, maker=slabmod.make_water_slab)
         water = (w_atoms, w_params, w_cons)
+        kind = "settle" if args.rigid_water == "fused" else "settle_split"
     else:
-        shard = slabmod.make_slab(R, args.precision, seed=12345 + rank)
-    shard.global_atom_offset = partition.shard_range(R * world, rank, world)[0]
+        shard = slabmod.slab_tile(R_total, world, rank, args.precision, seed=SLAB_SEED)
+    lo, hi = partition.shard_range(R_total, rank, world)
+    assert (lo, hi) == (shard.global_atom_offset, shard.global_atom_offset + shard.num_real), "tile != partition range"
+    if args.ensemble:
+        shard.global_atom_offset = 0  # independent slabs: each is its own system
     reorder_perm = None
     if args.reordered:
         if args.ensemble:
@@ -437,400 +965,187 @@ def main():
         n_mol = shard.meta["n_pairs"] if drude else shard.meta["n_water"] // 3
         reorder_perm = slabmod.molecule_permutation(shard, shard.meta["n_ion"], per, n_mol, seed=7 + rank)
         shard, _ = slabmod.permute_slab(shard, reorder_perm)
-    # the staged rigid-water kernel finds its slots arithmetically; only the gather kernel (--variant 1) reads lists
-    alg_bytes = slabmod.algorithmic_bytes_per_step(shard, rigid_molecules=len(water[0]) if (water and args.variant == 1) else 0,
-                                                   drude=drude is not None, drude_pairs=len(drude[1]) if drude else 0)
-    rec_bytes = shard.posq.nbytes + shard.velm.nbytes + shard.force.nbytes + (shard.corr.nbytes if shard.corr is not None else 0)
-    M = max(1, args.ensemble)  # slabs advanced per step on this GPU (1 = the plain slab configs)
-    replicas = args.replicas or max(2, int(np.ceil(2.0 * L2_BYTES / (rec_bytes * M))) + 1)
+    M = max(1, args.ensemble)
+    wl = Workload(env, args, shard, kind=kind, M=M, replicas=args.replicas, chains=args.chains, water=water, drude=drude,
+                  reorder_perm=reorder_perm, variant=args.variant, per_slab_forces=bool(args.ensemble))
+    chains = wl.chains
+    n_replicas = wl.replicas
+    alg_bytes = wl.algorithmic_bytes()
 
-    flags = _capi.FLAGS_DEFAULT
-    if not args.no_cache_image_charge:
-        flags |= _capi.FLAG_CACHE_IMAGE_CHARGE
-    if args.keep_in_l2:
-        flags |= _capi.FLAG_KEEP_IN_L2
-
-    ctxs = []
-    for r in range(replicas * M):
-        sysm = hostapi.SlabSystem()
-        sysm.addParticles(shard.masses)
-        sysm.setDefaultPeriodicBoxVectors((shard.box[0], 0, 0), (0, shard.box[1], 0), (0, 0, shard.num_cells * shard.zmax))
-        if water:
-            sysm.addConstraints(*water[2])
-        if drude:
-            dforce = hostapi.DrudeForce()
-            for a, b in drude[1]:
-                dforce.addParticle(int(a), int(b))
-            sysm.addForce(dforce)
-            it = hostapi.ConstVDrudeLangevinIntegrator(args.temperature, DRUDE_FRICTION_CM, DRUDE_T, DRUDE_FRICTION, DT, shard.num_cells)
-            it.setMaxDrudeDistance(DRUDE_WALL)
-        else:
-            it = hostapi.ConstVLangevinIntegrator(args.temperature, FRICTION, DT, shard.num_cells)
-        it.setRandomNumberSeed(2024 + (r % M))
-        ctx = hostapi.SlabContext(sysm, it, precision=args.precision, device=local_rank, flags=flags,
-                                  global_atom_offset=shard.global_atom_offset, padded=shard.padded)
-        ctx.load_slab(shard)
-        if reorder_perm is not None:
-            ctx.set_atom_order(reorder_perm)
-            _capi.check(lib.constv_update_inverse_order(it._kernel.handle, ctx.stream_ptr()))
-        if args.pairs_per_thread or args.ctas_per_sm:
-            it._kernel.set_launch_shape(args.pairs_per_thread, args.ctas_per_sm)
-        it._kernel.set_kernel_variant(args.variant, args.tma_block, args.tma_stages, args.tma_ctas)
-        if drude:
-            _capi.check(lib.constv_drude_set_parameters(it._kernel.handle, args.temperature, DRUDE_FRICTION_CM, DRUDE_T,
-                                                        DRUDE_FRICTION, DRUDE_WALL, DT))
-        else:
-            _capi.check(lib.constv_set_parameters(it._kernel.handle, args.temperature, FRICTION, DT))
-        ctxs.append((ctx, it))
-    handles = [it._kernel.handle for _, it in ctxs]
-
-    stream = torch.cuda.Stream(device=dev)
-    sptr = stream.cuda_stream
-
-    # ---- kinetic energy report: the ONE collective of the partition (on demand, never per step),
-    # taken on the initial state (the timed loop below keeps the injected forces constant, so the
-    # state it ends in is not physical)
-    ke_dev = torch.zeros(1, dtype=torch.float64, device=dev)
-    ctxs[0][1]._kernel.kinetic_energy_device(0.0, ke_dev)
+    # ---- kinetic energy report: the ONE collective of the partition (on demand, never per step), on the
+    # initial state (the timed loops keep the injected forces constant, so the state they end in is not physical)
+    ke_dev = torch.zeros(1, dtype=torch.float64, device=env.dev)
+    wl.ctxs[0][1]._kernel.kinetic_energy_device(0.0, ke_dev)
     torch.cuda.synchronize()
     partition.allreduce_scalar_sum(ke_dev)  # NCCL over NVLink when world > 1
     ke_total = float(ke_dev.item())
-    n_massive = int(np.sum(shard.velm[:R, 3] != 0)) * world
-    temperature = partition.temperature_from_kinetic_energy(ke_total, n_massive, slabmod.BOLTZ)
+    cnt = torch.tensor([float(np.sum(shard.velm[:shard.num_real, 3] != 0))], dtype=torch.float64, device=env.dev)
+    partition.allreduce_scalar_sum(cnt)
+    temperature = partition.temperature_from_kinetic_energy(ke_total, int(cnt.item()), slabmod.BOLTZ)
 
-    groups = [(C.c_void_p * M)(*handles[g * M:(g + 1) * M]) for g in range(replicas)]
-
-    chains = 1
-    if args.chains > 1 and not args.ensemble:
-        got = C.c_int32(0)
-        for h in handles:
-            _capi.check(lib.constv_set_chains(h, args.chains))
-        _capi.check(lib.constv_get_chains(handles[0], C.byref(got)))
-        chains = got.value
-    elif args.chains > 1:
-        chains = min(args.chains, M)
-    side_streams = [torch.cuda.Stream(device=dev) for _ in range(chains - 1)]
-    # ensemble: sub-group q of every replica's M slabs = one batched launch on stream q
-    bounds = [M * q // chains for q in range(chains + 1)]
-    subgroups = [[(C.c_void_p * (bounds[q + 1] - bounds[q]))(*handles[g * M + bounds[q]:g * M + bounds[q + 1]])
-                  for q in range(chains)] for g in range(replicas)]
-
-    def launch_steps(first, count):
-        if chains > 1:  # fork: chain q's steps on stream q, in step order; join back into `stream`
-            fork = torch.cuda.Event()
-            fork.record(stream)
-            for q, cs in enumerate([stream] + side_streams):
-                if q:
-                    cs.wait_event(fork)
-                for k in range(first, first + count):
-                    if args.ensemble and water:  # rigid-water ensemble: one batched launch per sub-group and stream
-                        _capi.check(lib.constv_step_fused_settle_batched(subgroups[k % replicas][q], bounds[q + 1] - bounds[q], cs.cuda_stream))
-                    elif args.ensemble:
-                        _capi.check(lib.constv_step_fused_batched(subgroups[k % replicas][q], bounds[q + 1] - bounds[q], cs.cuda_stream))
-                    elif drude:
-                        _capi.check(lib.constv_drude_step_fused_chain(handles[k % replicas], q, None, 0, cs.cuda_stream))
-                    elif args.rigid_water == "fused":
-                        _capi.check(lib.constv_step_fused_settle_chain(handles[k % replicas], q, None, 0, cs.cuda_stream))
-                    else:
-                        _capi.check(lib.constv_step_fused_chain(handles[k % replicas], q, None, 0, cs.cuda_stream))
-            for cs in side_streams:
-                join = torch.cuda.Event()
-                join.record(cs)
-                stream.wait_event(join)
-            return
-        for k in range(first, first + count):
-            if args.ensemble and water:
-                _capi.check(lib.constv_step_fused_settle_batched(groups[k % replicas], M, sptr))
-            elif args.ensemble:
-                _capi.check(lib.constv_step_fused_batched(groups[k % replicas], M, sptr))
-            elif drude:
-                _capi.check(lib.constv_drude_step_fused(handles[k % replicas], None, 0, sptr))
-            elif args.rigid_water == "fused":
-                _capi.check(lib.constv_step_fused_settle(handles[k % replicas], None, 0, sptr))
-            elif args.rigid_water == "split":
-                h = handles[k % replicas]
-                _capi.check(lib.constv_step_part1(h, None, 0, sptr))
-                _capi.check(lib.constv_settle_positions(h, sptr))
-                _capi.check(lib.constv_step_part2_mirror(h, sptr))
-            else:
-                _capi.check(lib.constv_step_fused(handles[k % replicas], None, 0, sptr))
-
-    # ---- optional CUDA graph: `chunk` consecutive steps per replay --------------------------------
+    # ---- the headline ------------------------------------------------------------------------------------------
     K, W = args.steps, max(args.warmup, 3)
-    use_graph = (not args.no_graph) and K >= 2 * replicas
-    graph, chunk = None, 0
-    with torch.cuda.stream(stream):
-        launch_steps(0, replicas)  # first touch, refreshes image-charge snapshots outside capture
-        stream.synchronize()
-        if use_graph:
-            chunk = replicas * max(1, min(20, K // replicas))
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=stream):
-                launch_steps(0, chunk)
+    use_graph = not args.no_graph
+    t = time_steps(env, wl, K, W, use_graph=use_graph, repeats=args.repeats, sample_clocks=True)
+    ms_step = t["ms"] / K
+    atoms_job = shard.num_atoms * M * world
+    value = atoms_job / (ms_step * 1e-3)
+    kernel_name = ("constv_settle_step_tiled_batched_kernel" if (args.ensemble and water) else
+                   "constv_fused_step_batched_kernel" if args.ensemble else
+                   "constv_drude_step_kernel" if drude else
+                   "constv_settle_step_tiled_kernel" if kind == "settle" else
+                   "constv_part1_kernel + constv_settle_positions_kernel + constv_part2_mirror_kernel" if kind == "settle_split" else
+                   "constv_fused_step_indexed_kernel" if args.reordered else "constv_fused_step_kernel")
 
-        def run(nsteps):
-            done = 0
-            if graph is not None:
-                while done + chunk <= nsteps:
-                    graph.replay()
-                    done += chunk
-            launch_steps(done, nsteps - done)
+    also = {}
+    # ---- one launch per step on the same slab (what a host with other kernels between two steps gets at best)
+    if plain and chains > 1 and want("single"):
+        wl.set_chains(1)
+        t1 = time_steps(env, wl, K, W, use_graph=use_graph, repeats=args.repeats)
+        also["single_launch"] = rate_record(atoms_job, K, t1, alg_bytes, 1, peak, "constv_fused_step_kernel")
+        wl.set_chains(chains)
 
-        run(W)
-        stream.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        launches0 = _capi.launch_count()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        run(K)
-        ev1.record(stream)
-        stream.synchronize()
-        torch.cuda.synchronize()
-        clocks = sampler.stop()
-        if world > 1:
-            dist.barrier()
-    ms = ev0.elapsed_time(ev1)
-    eager_launches = _capi.launch_count() - launches0
-
-    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_max = float(tmax.item())
-    launch_ms_for_ref = ms_max / K
-    atoms_per_step_job = shard.num_atoms * M * world
-    value = atoms_per_step_job * K / (ms_max * 1e-3)
-
-    # ---- e2e: host buffers through constv_step_host -------------------------------------------------
-    # Per step: H2D of the step's input (the real atoms' fixed-point forces, pinned memory), the fused
-    # step, the kinetic-energy reduction, and D2H of the step's result.  `value` reads back the scalar
-    # a StateDataReporter asks for every step (kinetic energy); `full_state` also reads back posq of
-    # all atoms (what a DCD frame needs) and is reported beside it.
+    # ---- e2e -------------------------------------------------------------------------------------------------------
     e2e = None
-    if not args.skip_e2e and not args.ensemble and not args.rigid_water and not drude:
-        ctx0, it0 = ctxs[0]
-        n_e2e = max(3, args.e2e_steps)
-        host_force = [torch.from_numpy(np.ascontiguousarray(slabmod.new_forces(shard, j)[:, :R])).pin_memory() for j in range(2)]
-        esize = 4 if args.precision != "double" else 8
-        host_posq = torch.empty((shard.num_atoms, 4), dtype=torch.float32 if esize == 4 else torch.float64).pin_memory()
-        h2d = host_force[0].numel() * 8
-        ke_host = C.c_double(0.0)
+    if not args.skip_e2e and plain:
+        wl.set_chains(1)
+        e2e = run_e2e(env, wl, args, atoms_job)
+        wl.set_chains(chains)
+        also["e2e_full_state"] = {"atom_steps_per_s": e2e["full_state"]["value"], "ms_per_step": e2e["full_state"]["ms_per_step"],
+                                  "d2h_bytes_per_step": e2e["full_state"]["d2h_bytes_per_step"]}
 
-        def e2e_run(with_posq):
-            out = host_posq.data_ptr() if with_posq else None
-            for j in range(3):
-                _capi.check(lib.constv_step_host(it0._kernel.handle, host_force[j % 2].data_ptr(), out, None, C.byref(ke_host), sptr))
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            for j in range(n_e2e):
-                _capi.check(lib.constv_step_host(it0._kernel.handle, host_force[j % 2].data_ptr(), out, None, C.byref(ke_host), sptr))
-            e1.record(stream)
-            stream.synchronize()
-            ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-            return float(ems.item())
-
-        def e2e_pipelined(buffers, code, nsteps):
-            """submit step k+1, then collect step k: the upload of k+1 overlaps the kernels and the
-            read-back of k.  Every step still uploads its own forces and returns its own energy."""
-            h = it0._kernel.handle
-            ticket = C.c_uint64(0)
-
-            def loop(n):
-                prev = None
-                for j in range(n):
-                    _capi.check(lib.constv_step_host_submit(h, buffers[j % 2].data_ptr(), code, C.byref(ticket), sptr))
-                    if prev is not None:
-                        _capi.check(lib.constv_step_host_collect(h, prev, C.byref(ke_host)))
-                    prev = ticket.value
-                _capi.check(lib.constv_step_host_collect(h, prev, C.byref(ke_host)))
-
-            loop(4)
-            best = float("inf")
-            for _ in range(3):  # PCIe transfers are noisy on a shared host: best of three passes
-                if world > 1:
-                    dist.barrier()
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-                loop(nsteps)
-                e1.record(stream)
-                stream.synchronize()
-                best = min(best, e0.elapsed_time(e1))
-            ems = torch.tensor([best], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-            return float(ems.item())
-
-        ms_ke = e2e_run(False)
-        ms_full = e2e_run(True)
-        n_pipe = 4 * n_e2e
-        ms_pipe = e2e_pipelined(host_force, _capi.FORCE_FIXED64, n_pipe)
-        host_force32 = [(torch.randn((3, R), dtype=torch.float32) * 1000.0).pin_memory() for _ in range(2)]
-        ms_pipe32 = e2e_pipelined(host_force32, _capi.FORCE_FLOAT32, n_pipe)
-        e2e = {"value": atoms_per_step_job * n_pipe / (ms_pipe * 1e-3), "unit": "atom-steps/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8, "steps": n_pipe,
-               "ms_per_step": ms_pipe / n_pipe,
-               "what": "constv_step_host_submit/_collect, two tickets in flight: every step uploads its real-atom forces "
-                       "(int64 fixed point, OpenMM's buffer format, pinned memory) and reads back its kinetic energy; the "
-                       "upload of step k+1 overlaps the kernels of step k; PCIe-bound",
-               "float32_forces": {"value": atoms_per_step_job * n_pipe / (ms_pipe32 * 1e-3), "ms_per_step": ms_pipe32 / n_pipe,
-                                  "h2d_bytes_per_step": int(h2d // 2), "d2h_bytes_per_step": 8,
-                                  "what": "same with float32 host forces converted to fixed point on the device"},
-               "synchronous": {"value": atoms_per_step_job * n_e2e / (ms_ke * 1e-3), "ms_per_step": ms_ke / n_e2e,
-                               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
-                               "what": "constv_step_host: upload, fused step, kinetic energy, read-back, one step at a time"},
-               "full_state": {"value": atoms_per_step_job * n_e2e / (ms_full * 1e-3), "ms_per_step": ms_full / n_e2e,
-                              "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(host_posq.numel() * esize + 8),
-                              "what": "synchronous, plus D2H of posq for all atoms"}}
-
-    # ---- the reference's own CUDA kernels on this GPU (information beside the headline) ---------------
+    # ---- the reference's own CUDA kernels on this GPU (information beside the headline) ---------------------
     ref_gpu = None
-    if rank == 0 and world == 1 and not args.skip_ref_gpu and not args.ensemble and not args.rigid_water:
+    if rank == 0 and world == 1 and not args.skip_ref_gpu and not args.ensemble and not args.rigid_water and not args.reordered:
         from oracle import ref as refmod
-        if refmod.available("cuda"):
-            for ctx, _ in ctxs:
-                ctx.load_slab(shard)
-            sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            n_ref = max(60, min(K, 6000))
-            ms_cap = time_reference_gpu(torch, ctxs, shard, stream, n_ref, 6 * sms, graph is not None)
-            ms_unc = time_reference_gpu(torch, ctxs, shard, stream, n_ref, 0, graph is not None)
+        if refmod.available("cuda") and not drude:
+            wl.reload()
+            sms = torch.cuda.get_device_properties(env.dev).multi_processor_count
+            n_ref = max(60, min(K, 2400))
+            ms_cap = time_reference_gpu(env, wl, n_ref, 6 * sms, use_graph)
+            ms_unc = time_reference_gpu(env, wl, n_ref, 0, use_graph)
             best = min(ms_cap, ms_unc)
             ref_gpu = {"value": shard.num_atoms / (best * 1e-3), "unit": "atom-steps/s", "ms_per_step": best,
                        "ms_per_step_grid_6_blocks_per_sm": ms_cap, "ms_per_step_grid_uncapped": ms_unc, "steps": n_ref,
                        "launches_per_step": 3,
-                       "what": "the reference's constVLangevin.cu compiled by nvcc for sm_100a (oracle/_ref): part 1 (reads a "
-                               "pre-filled Gaussian pool; refill not charged), part 2, image rewrite; 128-thread blocks; same "
-                               "rotating replicas, same CUDA-graph launch; value = the faster of OpenMM's capped grid "
-                               "(6 blocks/SM, recalled) and an uncapped grid",
-                       "speedup_of_fused_step": best / launch_ms_for_ref}
-
-    if rank == 0 and world == 1 and not args.skip_ref_gpu and drude:
-        from oracle import ref as refmod
-        import oracle
-        if refmod.available("cuda") and hasattr(refmod.cuda(), "constv_ref_drude_cuda_part1_single"):
-            for ctx, _ in ctxs:
-                ctx.load_slab(shard)
-            m = np.float32 if args.precision == "single" else np.float64
-            scal = oracle.drude_params(args.temperature, DRUDE_FRICTION_CM, DRUDE_T, DRUDE_FRICTION, DRUDE_WALL, DT)
-            rr = refmod.CudaDrudeReference(args.precision, scal, m(DT), dev, drude[0], drude[1], R, shard.padded, max_blocks=0)
-            pool = torch.randn((R + 8, 4), dtype=torch.float32, device=dev)
-            inv = torch.arange(shard.padded, dtype=torch.int32, device=dev)
-            n_ref = max(60, min(K, 6000))
-
-            def ref_launch(first, count):
-                for k in range(first, first + count):
-                    c = ctxs[k % replicas][0]
-                    rr.drude_step(shard.num_atoms, shard.num_cells, shard.zmax, c.posq, c.corr, c.velm, c.force, c.pos_delta,
-                                  pool, 0, inv, stream=sptr)
-
-            with torch.cuda.stream(stream):
-                ref_launch(0, replicas)
-                stream.synchronize()
-                rchunk = replicas * max(1, min(20, n_ref // replicas))
-                rgraph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(rgraph, stream=stream):
-                    ref_launch(0, rchunk)
-                for _ in range(3):
-                    rgraph.replay()
-                stream.synchronize()
-                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                reps = max(1, n_ref // rchunk)
-                r0.record(stream)
-                for _ in range(reps):
-                    rgraph.replay()
-                r1.record(stream)
-                stream.synchronize()
-            ms_ref = r0.elapsed_time(r1) / (reps * rchunk)
-            ref_gpu = {"value": shard.num_atoms / (ms_ref * 1e-3), "unit": "atom-steps/s", "ms_per_step": ms_ref, "steps": reps * rchunk,
+                       "what": "the reference's constVLangevin.cu compiled by nvcc for sm_100a (oracle/_ref): part 1 (pre-filled Gaussian "
+                               "pool; refill not charged), part 2, image rewrite; 128-thread blocks; same rotating replicas and CUDA-graph "
+                               "launch; the faster of OpenMM's capped grid (6 blocks/SM, recalled) and an uncapped grid; median of 5",
+                       "speedup_of_fused_step": best / ms_step}
+        elif refmod.available("cuda") and hasattr(refmod.cuda(), "constv_ref_drude_cuda_part1_single"):
+            wl.reload()
+            ms_ref, n_ref = time_reference_gpu_drude(env, wl, max(60, min(K, 2400)))
+            ref_gpu = {"value": shard.num_atoms / (ms_ref * 1e-3), "unit": "atom-steps/s", "ms_per_step": ms_ref, "steps": n_ref,
                        "launches_per_step": 4,
-                       "what": "the reference's constVDrudeLangevin.cu + constVLangevin.cu compiled by nvcc for sm_100a (oracle/_ref): "
-                               "Drude part 1 (pre-filled Gaussian pool; refill not charged), part 2, hard wall, image rewrite; 128-thread "
-                               "blocks, uncapped grid; same rotating replicas, same CUDA-graph launch",
-                       "speedup_of_fused_step": ms_ref / launch_ms_for_ref}
+                       "what": "the reference's constVDrudeLangevin.cu + constVLangevin.cu compiled by nvcc for sm_100a (oracle/_ref): Drude "
+                               "part 1, part 2, hard wall, image rewrite; 128-thread blocks, uncapped grid; same replicas and graph launch",
+                       "speedup_of_fused_step": ms_ref / ms_step}
 
-    # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------
+    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.skip_cpu and not args.ensemble and not args.rigid_water and not drude:
-        rate_fn, kind = cpu_leg()
-        rate, done, threads, per_step, el = rate_fn(shard, args.cpu_seconds, replicas=replicas)
+    if rank == 0 and world == 1 and not args.skip_cpu and plain:
+        rate_fn, ckind = cpu_leg()
+        rate, done, threads, per_step, el = rate_fn(shard, args.cpu_seconds, replicas=wl.replicas)
         what = ("steps of the reference's constVLangevin.cu compiled for the host (part 1, part 2, image rewrite; oracle/_ref)"
-                if kind == "reference" else "fused oracle steps")
-        cpu = {"value": rate, "unit": "atom-steps/s", "cores": threads, "kind": kind,
-               "sample": f"{done} full {what} rotating over {replicas} replicas of the same {shard.num_atoms}-atom slab in {el:.1f} s, all host threads, injected noise pool",
+                if ckind == "reference" else "fused oracle steps")
+        cpu = {"value": rate, "unit": "atom-steps/s", "cores": threads, "kind": ckind,
+               "sample": f"{done} full {what} rotating over {wl.replicas} replicas of the same {shard.num_atoms}-atom slab in {el:.1f} s, all host threads, injected noise pool",
                "host_cpus": os.cpu_count()}
-        if kind == "reference":
-            prate, pdone, _, _, pel = cpu_oracle_rate(shard, args.cpu_seconds / 2, replicas=replicas)
+        if ckind == "reference":
+            prate, pdone, _, _, pel = cpu_oracle_rate(shard, args.cpu_seconds / 2, replicas=wl.replicas)
             cpu["port"] = {"value": prate, "unit": "atom-steps/s", "kind": "port", "cores": threads,
                            "sample": f"{pdone} single-pass oracle steps in {pel:.1f} s (a tuned CPU port, for scale)"}
+    wl.close()
+    del wl
+    torch.cuda.empty_cache()
+
+    # ---- behind the plugin class: CudaIntegrateConstVLangevinStepKernel::execute against the shim -----------
+    if rank == 0 and world == 1 and plain and want("plugin"):
+        also["plugin_path"] = run_plugin_path(args, shard.num_atoms)
+
+    # ---- BASELINE configs[3]: the 16M-atom slab over these N GPUs -----------------------------------------------
+    if plain and not slab16m and want("slab16m"):
+        Rt = 8_000_000
+        tiles16 = 8  # the 16M slab is always the same 8 tiles; a rank of an N-GPU job holds 8/N consecutive ones
+        if tiles16 % world == 0:
+            mine = [slabmod.slab_tile(Rt, tiles16, tt, args.precision, seed=SLAB_SEED + 100) for tt in
+                    range(rank * tiles16 // world, (rank + 1) * tiles16 // world)]
+            sh16 = slabmod.concat_slabs(mine) if len(mine) > 1 else mine[0]
+            sh16.global_atom_offset = mine[0].global_atom_offset
+            assert (sh16.global_atom_offset, sh16.global_atom_offset + sh16.num_real) == partition.shard_range(Rt, rank, world)
+            del mine
+            w16 = Workload(env, args, sh16, chains=args.chains)
+            k16 = max(20, min(K, 600))
+            t16 = time_steps(env, w16, k16, 5, use_graph=use_graph, repeats=args.repeats)
+            also["slab_16M"] = rate_record(sh16.num_atoms * world, k16, t16, w16.algorithmic_bytes(), w16.chains, peak, "constv_fused_step_kernel",
+                                           {"atoms_per_gpu": sh16.num_atoms, "n_gpus": world, "scaling": "strong", "replicas": w16.replicas})
+            w16.close()
+            del w16, sh16
+            torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[4]: 64 independent 100k-atom slabs, batched per GPU -----------------------------------
+    if plain and not slab16m and want("ensemble"):
+        n_slabs = 64
+        if n_slabs % world == 0:
+            per_gpu = n_slabs // world
+            she = slabmod.make_slab(50_000, args.precision, seed=SLAB_SEED + 200 + rank)
+            we = Workload(env, args, she, M=per_gpu, chains=min(4, per_gpu), per_slab_forces=True)
+            ke_ = max(20, min(K, 600))
+            te = time_steps(env, we, ke_, 5, use_graph=use_graph, repeats=args.repeats)
+            rec = rate_record(she.num_atoms * n_slabs, ke_, te, we.algorithmic_bytes(), we.chains, peak, "constv_fused_step_batched_kernel",
+                              {"slabs": n_slabs, "slabs_per_gpu": per_gpu, "atoms_per_slab": she.num_atoms, "n_gpus": world, "replicas": we.replicas})
+            also["ensemble_64x100k"] = rec
+            we.close()
+            del we, she
+            torch.cuda.empty_cache()
+
+    # ---- the partition, checked: shards == unpartitioned == oracle, bit for bit -----------------------------------
+    if want("parity"):
+        also["partition_parity"] = run_partition_parity(env)
 
     if rank == 0:
-        peak, peak_src = peaks()
-        launch_ms = ms_max / K
-        alg_bytes *= M
-        achieved = alg_bytes / (launch_ms * 1e-3) / 1e9  # = (alg_bytes / chains) x (K x chains launches) / time
+        achieved = alg_bytes / (ms_step * 1e-3) / 1e9  # = (alg_bytes / chains) x (K x chains launches) / time
         line = {
             "metric": "atom-steps/s", "value": value, "unit": "atom-steps/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": launch_ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
+            "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if slab16m else "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == "single" else ("f32+f64" if args.precision == "mixed" else "f64"),
             "data": "synthetic",
-            "config": {
-                "workload": (f"ensemble of {M * world} independent synthetic RIGID-WATER slabs of {shard.num_atoms} atoms, {M} per GPU, advanced by {chains} batched constraint-solving launch(es) per step (BASELINE configs[4] with the example's constraints)"
-                             if (args.ensemble and water) else
-                             f"ensemble of {M * world} independent synthetic slabs of {shard.num_atoms} atoms, {M} per GPU advanced by one batched launch per step (BASELINE configs[4])"
-                             if args.ensemble else
-                             f"synthetic slab with RIGID water ({len(water[0])} SPC/E molecules, constraints solved {'inside the step kernel' if args.rigid_water == 'fused' else 'by a separate launch between part 1 and part 2'}), {shard.num_atoms} atoms per GPU, ConstV Langevin step incl. constraints (BASELINE configs[0-1] shape); range partition over {world} GPU(s)"
-                             if water else
-                             f"synthetic slab of polarizable water ({len(drude[1])} Drude pairs, {len(drude[0])} ordinary particles), {shard.num_atoms} atoms per GPU, fused ConstVDrudeLangevinIntegrator step incl. hard wall (SURVEY 8f.4); range partition over {world} GPU(s)"
-                             if drude else
-                             f"synthetic slab, {shard.num_atoms} atoms per GPU ({R} real + {shard.num_atoms - R} image), fused ConstV Langevin step only (BASELINE configs[2]); range partition over {world} GPU(s)"),
-                "atoms_per_gpu": shard.num_atoms, "total_atoms": atoms_per_step_job, "precision": args.precision,
-                "pair_classes": shard.pair_classes(), "rng": "in-kernel Philox4x32-10",
-                "l2": f"rotating {replicas} replicas of the per-step working set ({replicas * M * rec_bytes / 1e6:.0f} MB) > 126 MB L2: every step streams from HBM",
-                "launch": ("CUDA graph of %d steps, PDL" % chunk) if graph is not None else "eager, PDL",
-                "chains": chains, "reordered_slots": bool(args.reordered),
-                "image_charge": "re-read from posq" if args.no_cache_image_charge else "side array",
-                "kernel_variant": {"variant": args.variant, "tma_block": args.tma_block, "tma_stages": args.tma_stages,
-                                   "tma_ctas": args.tma_ctas, "pairs_per_thread": args.pairs_per_thread, "ctas_per_sm": args.ctas_per_sm},
-                "T_K": args.temperature, "friction_per_ps": FRICTION, "dt_ps": DT,
-            },
-            "steps_per_s": K / (ms_max * 1e-3),
+            "config": config,
+            "variant": {"kind": kind + ("/ensemble" if args.ensemble else "") + ("/reordered" if args.reordered else ""),
+                        "slabs_per_gpu": M, "pair_classes": shard.pair_classes(), "rng": "in-kernel Philox4x32-10",
+                        "replicas": n_replicas,
+                        "launch": t["graph"], "chains": chains,
+                        "image_charge": "re-read from posq" if args.no_cache_image_charge else "side array",
+                        "kernel_variant": {"variant": args.variant, "tma_block": args.tma_block, "tma_stages": args.tma_stages,
+                                           "tma_ctas": args.tma_ctas, "pairs_per_thread": args.pairs_per_thread, "ctas_per_sm": args.ctas_per_sm}},
+            "timing": {"repeats": t["repeats"], "statistic": "median of the repeats' K-step region times, max over ranks",
+                       "us_per_step_min": 1e3 * t["ms_min"] / K, "us_per_step_max": 1e3 * t["ms_max"] / K,
+                       "untimed_regions_before": t["untimed_regions"]},
+            "steps_per_s": 1.0 / (ms_step * 1e-3),
             "atom_steps_per_s_per_gpu": value / world,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None if args.ensemble else traffic_from_profile(shard.num_atoms, chains), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes / chains, "launches_per_step": chains,
+                         "algorithmic_bytes_per_launch": alg_bytes / max(1, chains if kind != "settle_split" else 1),
+                         "launches_per_step": 3 if kind == "settle_split" else chains,
                          "algorithmic_bytes_per_step": alg_bytes,
-                         "note": ("a step is %d launches, one per chain (contiguous range of real atoms) on its own stream; "
-                                  "achieved = algorithmic bytes per launch x launches in the timed region / its duration" % chains)
-                                 if chains > 1 else "one launch per step",
-                         "frac_of_8TBs_nominal": achieved / 8000.0,
-                         "kernel": "constv_settle_step_tiled_batched_kernel" if (args.ensemble and water) else
-                                   "constv_fused_step_batched_kernel" if args.ensemble else
-                                   "constv_drude_step_kernel" if drude else
-                                   ("constv_settle_step_tiled_kernel" if args.rigid_water == "fused" else
-                                    ("constv_part1_kernel + constv_settle_positions_kernel + constv_part2_mirror_kernel"
-                                     if args.rigid_water == "split" else "constv_fused_step_kernel"))},
+                         "note": ("a step is %d launches, one per chain (contiguous range of real atoms) on its own stream; achieved = "
+                                  "algorithmic bytes per launch x launches in a region / its duration; per GPU" % chains)
+                                 if chains > 1 else "one launch per step; per GPU",
+                         "frac_of_8TBs_nominal": achieved / 8000.0, "kernel": kernel_name},
             "cpu_baseline": cpu,
             "reference_gpu": ref_gpu,
             "e2e": e2e,
-            "gpu_launches": int(K * (3 if args.rigid_water == "split" else chains)),
-            "eager_launches_in_region": int(eager_launches),
-            "clocks": clocks,
+            "gpu_launches": int(K * (3 if kind == "settle_split" else chains)),
+            "gpu_launches_all_repeats": int(K * (3 if kind == "settle_split" else chains) * t["repeats"]),
+            "eager_launches_in_region": int(t["eager_launches"]),
+            "clocks": t["clocks"],
             "kinetic_energy_kj_mol": ke_total, "temperature_K": temperature,
+            "also": also,
         }
         print(json.dumps(line), flush=True)
-    for ctx, _ in ctxs:
-        ctx.close()
     if world > 1:
-        dist.destroy_process_group()
+        env.dist.destroy_process_group()
     return 0
 
 

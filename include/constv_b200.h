@@ -37,7 +37,7 @@ extern "C" {
 
 #define CONSTV_API __attribute__((visibility("default")))
 
-#define CONSTV_VERSION 110 /* 0.1.1: + chains, Drude integrator, rigid molecules */
+#define CONSTV_VERSION 120 /* 0.1.2: + constv_mirror, constv_generate_philox_words */
 
 typedef struct constv_slab constv_slab; /* one Context's worth of integrator state (opaque) */
 
@@ -156,6 +156,15 @@ CONSTV_API int constv_step_part1(constv_slab* slab, const void* random4, uint32_
  * constv_step_part1 and this call (integration.applyConstraints, Kernels.cpp:153). */
 CONSTV_API int constv_step_part2_mirror(constv_slab* slab, void* stream);
 
+/* Replaces the updateImageParticlePositions launch alone, Kernels.cpp:165-166 (and :346-347 for the Drude
+ * integrator) / Langevin.cu:138-164: every charged real atom's images are rewritten from its current posq;
+ * identity order or, with an atom_index bound, through invAtomOrder.  No velocity, force or step-counter
+ * change.  The reference runs this pass AFTER integration.computeVirtualSites() (Kernels.cpp:161, :342): a
+ * host whose System has virtual sites calls the step entry point, computeVirtualSites, then constv_mirror,
+ * so that the image of a charged virtual site follows the site's new position (the rewrite is idempotent
+ * for every other atom). */
+CONSTV_API int constv_mirror(constv_slab* slab, void* stream);
+
 /* The whole of execute (Kernels.cpp:139-172) for a system without constraints in ONE kernel:
  * part 1, part 2, the image rewrite and the image zeroing, each atom record crossing HBM once;
  * pos_delta never leaves registers.  Same random4 / Philox convention as constv_step_part1. */
@@ -183,6 +192,12 @@ CONSTV_API int constv_kinetic_energy_device(constv_slab* slab, double time_shift
  * device array out4 (the stream that stands in for integration.prepareRandomNumbers/getRandom,
  * Kernels.cpp:146,148).  For parity tests and for checkpoint verification. */
 CONSTV_API int constv_generate_noise(constv_slab* slab, uint64_t step, void* out4, void* stream);
+
+/* Debug / parity entry: the raw Philox4x32-10 block (four uint32 words) behind those Gaussians, for slots
+ * [0, N): counter = (atom lo, atom hi, step lo, step hi) with atom = global_atom_offset + original atom
+ * index, key = (seed lo, seed hi).  words4 = device uint32[4*N].  Integer work: bit-exact against the
+ * Random123 known-answer vectors and the oracle (tests/test_gpu_philox.py). */
+CONSTV_API int constv_generate_philox_words(constv_slab* slab, uint64_t step, void* words4, void* stream);
 
 /* ---- bookkeeping (cu.getTime/setTime, getStepCount/setStepCount, Kernels.cpp:170-171) -------- */
 

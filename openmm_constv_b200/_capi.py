@@ -40,6 +40,7 @@ SYMBOLS = [
     "constv_drude_step_fused", "constv_drude_hardwall",
     "constv_settle_find_clusters", "constv_settle_configure", "constv_step_fused_settle", "constv_settle_positions",
     "constv_step_fused_settle_chain", "constv_drude_step_fused_chain", "constv_step_fused_settle_batched",
+    "constv_mirror", "constv_generate_philox_words",
 ]
 
 
@@ -120,6 +121,8 @@ def load() -> C.CDLL:
         "constv_step_fused_settle_chain": [vp, i32, vp, u32, vp],
         "constv_drude_step_fused_chain": [vp, i32, vp, u32, vp],
         "constv_step_fused_settle_batched": [C.POINTER(vp), i32, vp],
+        "constv_mirror": [vp, vp],
+        "constv_generate_philox_words": [vp, u64, vp, vp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)

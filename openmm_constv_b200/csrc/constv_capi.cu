@@ -318,7 +318,7 @@ int launchPart2(constv_slab* s, const SlabDev& d, cudaStream_t st) {
                       (bool) (s->cfg.flags & CONSTV_FLAG_PDL), st, d);
     int rc = launch(constv_part2_indexed_kernel<PREC, kBlock>, gridFor(s, s->cfg.num_atoms, kBlock, s->ctasPerSM), kBlock, false, st, d);
     if (rc) return rc;
-    return launch(constv_mirror_indexed_kernel<PREC, kBlock>, gridFor(s, s->numReal, kBlock, s->ctasPerSM), kBlock, false, st, d);
+    return launch(constv_mirror_indexed_kernel<PREC, kBlock, true>, gridFor(s, s->numReal, kBlock, s->ctasPerSM), kBlock, false, st, d);
 }
 
 template <int PREC>
@@ -747,6 +747,19 @@ int constv_step_part2_mirror(constv_slab* s, void* stream) {
     return rc;
 }
 
+int constv_mirror(constv_slab* s, void* stream) {
+    GUARD(s);
+    if (!s->posq) return fail(CONSTV_ERR_STATE, "device arrays are not bound (constv_bind_arrays / constv_alloc_arrays)");
+    if (s->cfg.precision == CONSTV_PRECISION_MIXED && !s->corr) return fail(CONSTV_ERR_STATE, "mixed precision needs posq_correction");
+    int rc;
+    if ((s->cfg.flags & CONSTV_FLAG_CACHE_IMAGE_CHARGE) && !s->imageChargeValid)
+        if ((rc = constv_refresh_image_charges(s, stream))) return rc;
+    const SlabDev d = makeDev(s);
+    DISPATCH_PREC(s->cfg.precision, launch(constv_mirror_indexed_kernel<PR, kBlock, false>, gridFor(s, s->numReal, kBlock, 0), kBlock, false,
+                                           (cudaStream_t) stream, d));
+    return rc;
+}
+
 int constv_step_fused_batched(constv_slab* const* slabs, int32_t n, void* stream) {
     if (!slabs || n <= 0) return fail(CONSTV_ERR_INVALID, "constv_step_fused_batched: empty batch");
     constv_slab* lead = slabs[0];
@@ -826,6 +839,15 @@ int constv_generate_noise(constv_slab* s, uint64_t step, void* out4, void* strea
     return launch(constv_noise_kernel, gridFor(s, n, 256, 8), 256, false, (cudaStream_t) stream, n,
                   (const int*) s->atomIndex, (unsigned long long) s->cfg.seed,
                   (unsigned long long) s->cfg.global_atom_offset, (unsigned long long) step, static_cast<float4*>(out4));
+}
+
+int constv_generate_philox_words(constv_slab* s, uint64_t step, void* words4, void* stream) {
+    GUARD(s);
+    if (!words4) return fail(CONSTV_ERR_INVALID, "null output");
+    const int n = s->cfg.num_atoms;
+    return launch(constv_philox_words_kernel, gridFor(s, n, 256, 8), 256, false, (cudaStream_t) stream, n,
+                  (const int*) s->atomIndex, (unsigned long long) s->cfg.seed,
+                  (unsigned long long) s->cfg.global_atom_offset, (unsigned long long) step, static_cast<uint4*>(words4));
 }
 
 int constv_get_step_count(constv_slab* s, uint64_t* count) {

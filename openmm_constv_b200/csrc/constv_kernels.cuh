@@ -907,8 +907,11 @@ constv_part2_indexed_kernel(const __grid_constant__ SlabDev d) {
     }
 }
 
-// ... then the image rewrite per original real index, as Langevin.cu:138-164 does
-template <int PREC, int BLOCK>
+// ... then the image rewrite per original real index, as Langevin.cu:138-164 does.  ADVANCE = this launch
+// closes a split step (advances the step counter); false = the image rewrite alone (constv_mirror: the pass
+// the reference runs after integration.computeVirtualSites(), CudaConstVKernels.cpp:161-166).  With
+// atomIndex == nullptr invAtomOrder is the identity the library initialised it to: same kernel, same bits.
+template <int PREC, int BLOCK, bool ADVANCE>
 __global__ void __launch_bounds__(BLOCK)
 constv_mirror_indexed_kernel(const __grid_constant__ SlabDev d) {
     using Real = typename Prec<PREC>::Real;
@@ -934,7 +937,7 @@ constv_mirror_indexed_kernel(const __grid_constant__ SlabDev d) {
         }
     }
     // no thread of this launch reads the counter (part 1 did): one thread advances it
-    if (blockIdx.x == 0 && threadIdx.x == 0) d.counters->step = __ldcg(&d.counters->step) + 1;
+    if (ADVANCE && blockIdx.x == 0 && threadIdx.x == 0) d.counters->step = __ldcg(&d.counters->step) + 1;
 }
 
 // ---- small kernels -----------------------------------------------------------------------------
@@ -975,6 +978,18 @@ __global__ void constv_noise_kernel(const int numAtoms, const int* __restrict__ 
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < numAtoms; slot += gridDim.x * blockDim.x) {
         const int a = atomIndex ? atomIndex[slot] : slot;
         out[slot] = gaussian4<true>(seed, globalAtomOffset + (unsigned long long) a, step);
+    }
+}
+
+// the raw Philox block of (seed; atom, step): what gaussian4 turns into four Gaussians
+__global__ void constv_philox_words_kernel(const int numAtoms, const int* __restrict__ atomIndex,
+                                           const unsigned long long seed, const unsigned long long globalAtomOffset,
+                                           const unsigned long long step, uint4* __restrict__ out) {
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < numAtoms; slot += gridDim.x * blockDim.x) {
+        const unsigned long long atom = globalAtomOffset + (unsigned long long) (atomIndex ? atomIndex[slot] : slot);
+        out[slot] = philox4x32_10(make_uint4((unsigned int) atom, (unsigned int) (atom >> 32), (unsigned int) step,
+                                             (unsigned int) (step >> 32)),
+                                  make_uint2((unsigned int) seed, (unsigned int) (seed >> 32)));
     }
 }
 

@@ -11,6 +11,13 @@
 %import(module="simtk.openmm") "swig/OpenMMSwigHeaders.i"
 %include "swig/typemaps.i"
 
+/* std::vector<double> / std::vector<int> wrappers under the reference's names (constvplugin.i:12-16) */
+%include "std_vector.i"
+namespace std {
+  %template(vectord) vector<double>;
+  %template(vectori) vector<int>;
+};
+
 %{
 #include "OpenMM.h"
 #include "OpenMMDrude.h"
@@ -22,15 +29,13 @@ import simtk.openmm as mm
 import simtk.unit as unit
 %}
 
-/* getters that carry units on the Python side */
+/* getters that carry units on the Python side: exactly the reference's seven (constvplugin.i:35-61);
+ * getCellSize / getNumCells / getRandomNumberSeed return bare numbers there and here */
 %pythonappend OpenMM::ConstVLangevinIntegrator::getTemperature() const %{
    val = unit.Quantity(val, unit.kelvin)
 %}
 %pythonappend OpenMM::ConstVLangevinIntegrator::getFriction() const %{
    val = unit.Quantity(val, 1/unit.picosecond)
-%}
-%pythonappend OpenMM::ConstVLangevinIntegrator::getCellSize() const %{
-   val = unit.Quantity(val, unit.nanometer) if val >= 0 else val
 %}
 
 %pythonappend OpenMM::ConstVDrudeLangevinIntegrator::getTemperature() const %{

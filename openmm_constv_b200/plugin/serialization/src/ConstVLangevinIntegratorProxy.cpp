@@ -18,16 +18,16 @@ void ConstVLangevinIntegratorProxy::serialize(const void* object, SerializationN
     node.setDoubleProperty("temperature", integrator.getTemperature());
     node.setDoubleProperty("friction", integrator.getFriction());
     node.setIntProperty("randomSeed", integrator.getRandomNumberSeed());
-    // version 2
+    // what the reference drops: extra attributes its reader ignores (it rejects any version but 1)
     node.setIntProperty("numCells", integrator.getNumCells());
     node.setDoubleProperty("cellSize", integrator.getCellSize());
 }
 
 void* ConstVLangevinIntegratorProxy::deserialize(const SerializationNode& node) const {
     const int version = node.getIntProperty("version");
-    if (version < kOldestReadable || version > kWritten)
+    if (version < kOldestReadable || version > kNewestReadable)
         throw OpenMMException("Unsupported version number");
-    // a version 1 file carries neither numCells nor cellSize: the reference's defaults apply
+    // a file written by the reference carries neither numCells nor cellSize: the reference's defaults apply
     ConstVLangevinIntegrator* integrator = new ConstVLangevinIntegrator(
         node.getDoubleProperty("temperature"), node.getDoubleProperty("friction"), node.getDoubleProperty("stepSize"),
         node.getIntProperty("numCells", 2), node.getDoubleProperty("cellSize", -1.0));

@@ -9,6 +9,14 @@ class OPENMM_EXPORT CudaContext {
 public:
     CudaContext(const System& system, int deviceIndex, const std::string& precision, CudaPlatform::PlatformData& platformData);
     ~CudaContext();
+    // OpenMM's hook for code that caches slot-dependent state: execute() runs after every re-sort.  The context
+    // owns (and deletes) the listeners, as OpenMM's does.
+    class ReorderListener {
+    public:
+        virtual void execute() = 0;
+        virtual ~ReorderListener() {}
+    };
+    void addReorderListener(ReorderListener* listener) { reorderListeners.push_back(listener); }
     void setAsCurrent();
     CudaPlatform::PlatformData& getPlatformData() { return platformData; }
     int getDeviceIndex() const { return deviceIndex; }
@@ -41,6 +49,7 @@ private:
     double time;
     CudaArray *posq, *posqCorrection, *velm, *force, *atomIndex;
     std::vector<int> atomIndexHost, pendingOrder;
+    std::vector<ReorderListener*> reorderListeners;
     CudaIntegrationUtilities* integration;
 };
 }

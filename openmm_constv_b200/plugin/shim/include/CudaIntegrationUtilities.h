@@ -16,7 +16,9 @@ public:
     // The shim has no SHAKE/SETTLE/CCMA: applyConstraints only counts calls (systems under test
     // carry no constraints); a hook lets tests observe the hand-off.
     void applyConstraints(double tol);
-    void computeVirtualSites() {}
+    // two-particle-average sites only (host round trip: the shim is test scaffolding)
+    void computeVirtualSites();
+    int virtualSiteCalls = 0;
     void initRandomNumberGenerator(unsigned int seed) { randomSeed = seed; }
     int prepareRandomNumbers(int numValues);
     double computeKineticEnergy(double timeShift);
@@ -24,6 +26,7 @@ public:
     double lastConstraintTol = 0;
 private:
     CudaContext& context;
+    const System& system;
     CudaArray* posDelta;
     CudaArray* random;
     CudaArray* stepSize;

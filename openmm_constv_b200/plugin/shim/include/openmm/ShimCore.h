@@ -85,10 +85,35 @@ private:
     std::vector<Entry> particles;
 };
 
+// Virtual sites as OpenMM declares them (openmm/VirtualSite.h); the shim implements the two-particle average.
+class OPENMM_EXPORT VirtualSite {
+public:
+    virtual ~VirtualSite() {}
+    int getNumParticles() const { return (int) particles.size(); }
+    int getParticle(int particle) const { return particles.at(particle); }
+protected:
+    void setParticles(const std::vector<int>& p) { particles = p; }
+private:
+    std::vector<int> particles;
+};
+
+class OPENMM_EXPORT TwoParticleAverageSite : public VirtualSite {
+public:
+    TwoParticleAverageSite(int particle1, int particle2, double weight1, double weight2) : weight1(weight1), weight2(weight2) {
+        setParticles({particle1, particle2});
+    }
+    double getWeight(int particle) const { return particle == 0 ? weight1 : weight2; }
+private:
+    double weight1, weight2;
+};
+
 class OPENMM_EXPORT System {
 public:
     System();
     ~System();
+    void setVirtualSite(int index, VirtualSite* virtualSite);  // takes ownership
+    bool isVirtualSite(int index) const { return index < (int) virtualSites.size() && virtualSites[index] != NULL; }
+    const VirtualSite& getVirtualSite(int index) const;
     int addParticle(double mass) { masses.push_back(mass); return (int) masses.size() - 1; }
     int getNumParticles() const { return (int) masses.size(); }
     double getParticleMass(int index) const { return masses.at(index); }
@@ -106,6 +131,7 @@ private:
     std::vector<double> masses;
     std::vector<Constraint> constraints;
     std::vector<Force*> forces;
+    std::vector<VirtualSite*> virtualSites;
     Vec3 box[3];
 };
 

@@ -8,6 +8,7 @@
 #include <iostream>
 #include <random>
 #include <sstream>
+#include <type_traits>
 
 #include "CudaContext.h"
 #include "openmm/serialization/XmlSerializer.h"
@@ -95,6 +96,18 @@ System::System() {
 
 System::~System() {
     for (Force* f : forces) delete f;
+    for (VirtualSite* v : virtualSites) delete v;
+}
+
+void System::setVirtualSite(int index, VirtualSite* virtualSite) {
+    if ((int) virtualSites.size() <= index) virtualSites.resize(index + 1, NULL);
+    delete virtualSites[index];
+    virtualSites[index] = virtualSite;
+}
+
+const VirtualSite& System::getVirtualSite(int index) const {
+    if (!isVirtualSite(index)) throw OpenMMException("This particle is not a virtual site");
+    return *virtualSites[index];
 }
 
 int System::addConstraint(int p1, int p2, double distance) {
@@ -155,7 +168,7 @@ void CudaArray::downloadBytes(void* data) const { CUCHECK(cudaMemcpy(data, (void
 // ---- CudaIntegrationUtilities -----------------------------------------------------------------------
 
 CudaIntegrationUtilities::CudaIntegrationUtilities(CudaContext& context, const System& system)
-    : context(context), lastStepSize(0), randomSeed(0) {
+    : context(context), system(system), lastStepSize(0), randomSeed(0) {
     const int P = context.getPaddedNumAtoms();
     const int mixed = (context.getUseDoublePrecision() || context.getUseMixedPrecision()) ? 8 : 4;
     posDelta = new CudaArray(context, P, 4 * mixed, "posDelta");
@@ -187,6 +200,45 @@ void CudaIntegrationUtilities::applyConstraints(double tol) {
 }
 
 int CudaIntegrationUtilities::prepareRandomNumbers(int numValues) { return 0; }
+
+void CudaIntegrationUtilities::computeVirtualSites() {
+    virtualSiteCalls++;
+    const int n = context.getNumAtoms(), P = context.getPaddedNumAtoms();
+    bool any = false;
+    for (int i = 0; i < n && !any; i++) any = system.isVirtualSite(i);
+    if (!any) return;
+    const vector<int>& order = context.getAtomIndex();
+    vector<int> slotOf(P);
+    for (int s = 0; s < P; s++) slotOf[order[s]] = s;
+    auto place = [&](auto* p, auto* c) {
+        for (int i = 0; i < n; i++) {
+            if (!system.isVirtualSite(i)) continue;
+            const TwoParticleAverageSite* site = dynamic_cast<const TwoParticleAverageSite*>(&system.getVirtualSite(i));
+            if (site == NULL) throw OpenMMException("the shim implements TwoParticleAverageSite only");
+            const int s0 = slotOf[i], s1 = slotOf[site->getParticle(0)], s2 = slotOf[site->getParticle(1)];
+            for (int k = 0; k < 3; k++) {
+                const double a = (double) p[4 * s1 + k] + (c ? (double) c[4 * s1 + k] : 0.0);
+                const double b = (double) p[4 * s2 + k] + (c ? (double) c[4 * s2 + k] : 0.0);
+                const double v = site->getWeight(0) * a + site->getWeight(1) * b;
+                p[4 * s0 + k] = (std::remove_reference_t<decltype(p[0])>) v;
+                if (c) c[4 * s0 + k] = (std::remove_reference_t<decltype(c[0])>) (v - (double) p[4 * s0 + k]);
+            }
+        }
+    };
+    if (context.getUseDoublePrecision()) {
+        vector<double> p(4 * (size_t) P);
+        context.getPosq().downloadBytes(p.data());
+        place(p.data(), (double*) NULL);
+        context.getPosq().uploadBytes(p.data());
+    } else {
+        vector<float> p(4 * (size_t) P), c(4 * (size_t) P, 0.f);
+        context.getPosq().downloadBytes(p.data());
+        if (context.getUseMixedPrecision()) context.getPosqCorrection().downloadBytes(c.data());
+        place(p.data(), context.getUseMixedPrecision() ? c.data() : (float*) NULL);
+        context.getPosq().uploadBytes(p.data());
+        if (context.getUseMixedPrecision()) context.getPosqCorrection().uploadBytes(c.data());
+    }
+}
 
 double CudaIntegrationUtilities::computeKineticEnergy(double timeShift) {
     const int P = context.getPaddedNumAtoms(), n = context.getNumAtoms();
@@ -249,6 +301,7 @@ CudaContext::CudaContext(const System& system, int deviceIndex, const string& pr
 }
 
 CudaContext::~CudaContext() {
+    for (ReorderListener* l : reorderListeners) delete l;
     delete integration;
     delete posq;
     delete posqCorrection;
@@ -287,6 +340,7 @@ void CudaContext::reorderAtoms() {
     atomIndex->upload(atomIndexHost);
     pendingOrder.clear();
     atomsWereReordered = true;
+    for (ReorderListener* l : reorderListeners) l->execute();
 }
 
 CudaPlatform::CudaPlatform() {

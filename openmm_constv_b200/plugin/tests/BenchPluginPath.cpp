@@ -1,0 +1,204 @@
+// Times the drop-in path: one CudaIntegrateConstVLangevinStepKernel::execute per step, created through the
+// platform's kernel factory exactly as ConstVLangevinIntegrator::initialize does, with a cache-sweeping
+// device operation between two steps standing in for the force kernels a host (OpenMM) runs there.  Unlike
+// bench.py's headline there is no CUDA graph, no second stream and nothing of the next step to overlap with:
+// this is what a Context stepping through the plugin gets.
+//
+//   BenchPluginPath [--atoms N] [--steps S] [--precision single|mixed|double] [--reordered] [--sweep-mb M]
+//
+// Reported (one JSON line): the MARGINAL cost of execute() inside the stream of sweeps,
+//   us_per_step = (T[sweep + execute loop] - T[sweep-only loop]) / steps        (median of 5 passes each),
+// i.e. launch gap + ramp + transfer + drain of the step kernel, for two sweeps:
+//   flush   a 256 MB memset: nothing of the slab is left in the 126 MB L2 (the conservative case)
+//   forces  a device-to-device copy into the force buffer (24 B per atom), what the cheapest possible force
+//           kernel does; posq / velm may then still be L2 hits
+// --reordered applies one slot permutation of the kind cu.reorderAtoms() produces (whole molecules trade
+// places inside windows of 1024 molecules) so that execute() addresses images through atomIndex /
+// invAtomOrder (constVLangevin.cu:142-158).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "CudaContext.h"
+#include "CudaPlatform.h"
+#include "openmm/ConstVKernels.h"
+#include "openmm/ConstVLangevinIntegrator.h"
+#include "openmm/Context.h"
+#include "openmm/OpenMMException.h"
+#include "openmm/Platform.h"
+#include "openmm/System.h"
+#include "openmm/internal/ContextImpl.h"
+
+using namespace OpenMM;
+using std::vector;
+
+extern "C" void registerConstVCudaKernelFactories();
+
+#define CU(x)                                                                              \
+    do {                                                                                   \
+        cudaError_t e_ = (x);                                                              \
+        if (e_ != cudaSuccess) {                                                           \
+            std::fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e_));                  \
+            std::exit(2);                                                                  \
+        }                                                                                  \
+    } while (0)
+
+static double median(vector<double> v) {
+    std::sort(v.begin(), v.end());
+    return v[v.size() / 2];
+}
+
+int main(int argc, char** argv) {
+    int atoms = 1000000, steps = 300;
+    size_t sweepMB = 256;
+    std::string precision = "single";
+    bool reordered = false;
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        if (a == "--atoms" && i + 1 < argc) atoms = std::atoi(argv[++i]);
+        else if (a == "--steps" && i + 1 < argc) steps = std::atoi(argv[++i]);
+        else if (a == "--precision" && i + 1 < argc) precision = argv[++i];
+        else if (a == "--sweep-mb" && i + 1 < argc) sweepMB = (size_t) std::atoi(argv[++i]);
+        else if (a == "--reordered") reordered = true;
+        else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
+    }
+    try {
+        registerConstVCudaKernelFactories();
+        // the example's composition (nacl_1m_eq.pdb): ~1 % ions, 82 % SPC/E water, 17 % massless neutral wall atoms
+        const int R = atoms / 2;
+        const int nWall = (int) std::lround(R * (1280.0 / 7494.0));
+        const int nIon = (int) std::lround(R * (76.0 / 7494.0));
+        const int nWater = (R - nWall - nIon) / 3 * 3;
+        const int nIonAll = R - nWall - nWater;
+        vector<double> mass(2 * (size_t) R, 0.0), charge(2 * (size_t) R, 0.0);
+        for (int i = 0; i < nIonAll; i++) { mass[i] = i % 2 ? 35.45 : 22.98977; charge[i] = i % 2 ? -1.0 : 1.0; }
+        for (int i = 0; i < nWater; i++) {
+            mass[nIonAll + i] = i % 3 ? 1.008 : 15.9994;
+            charge[nIonAll + i] = i % 3 ? 0.4238 : -0.8476;
+        }
+        for (int i = 0; i < R; i++) charge[R + i] = -charge[i];
+        const double zmax = 4.2183, scale = std::sqrt(R / 7494.0), lx = 3.9352 * scale, ly = 4.26 * scale;
+        System system;
+        for (double m : mass) system.addParticle(m);
+        system.setDefaultPeriodicBoxVectors(Vec3(lx, 0, 0), Vec3(0, ly, 0), Vec3(0, 0, 2 * zmax));
+        ConstVLangevinIntegrator integrator(300.0, 1.0, 0.001);
+        integrator.setRandomNumberSeed(2024);
+        Platform& platform = Platform::getPlatformByName("CUDA");
+        std::map<std::string, std::string> properties;
+        properties["Precision"] = precision;
+        Context context(system, integrator, platform, properties);
+        std::mt19937_64 gen(12345);
+        std::uniform_real_distribution<double> uni(0.0, 1.0);
+        vector<Vec3> pos(2 * (size_t) R);
+        for (int i = 0; i < R; i++) {
+            const bool wall = i >= nIonAll + nWater;
+            const double z = wall ? ((i & 1) ? zmax : 0.0) : (0.05 + 0.9 * uni(gen)) * zmax;
+            pos[i] = Vec3(uni(gen) * lx, uni(gen) * ly, z);
+            pos[R + i] = Vec3(pos[i][0], pos[i][1], charge[i] != 0 ? -z : -z + 0.001);
+        }
+        context.setPositions(pos);
+        context.setCharges(charge);
+        context.setVelocitiesToTemperature(300.0, 7);
+
+        CudaContext& cu = *static_cast<CudaPlatform::PlatformData*>(context.getImpl().getPlatformData())->contexts[0];
+        const int P = cu.getPaddedNumAtoms();
+        // injected forces in OpenMM's fixed-point layout, images included (so that the zeroing is real work)
+        vector<long long> force(3 * (size_t) P, 0);
+        std::normal_distribution<double> normal(0.0, 1000.0);
+        for (int k = 0; k < 3; k++)
+            for (int i = 0; i < 2 * R; i++) force[(size_t) k * P + i] = (long long) std::llround(normal(gen) * 4294967296.0);
+        cu.getForce().uploadBytes(force.data());
+        void* spareForce = NULL;
+        CU(cudaMalloc(&spareForce, 24 * (size_t) P));
+        CU(cudaMemcpy(spareForce, force.data(), 24 * (size_t) P, cudaMemcpyHostToDevice));
+        void* sweep = NULL;
+        CU(cudaMalloc(&sweep, sweepMB << 20));
+
+        // the kernel, made and initialised the way ConstVLangevinIntegrator::initialize does it
+        Kernel kernel = platform.createKernel(IntegrateConstVLangevinStepKernel::Name(), context.getImpl());
+        IntegrateConstVLangevinStepKernel& step = kernel.getAs<IntegrateConstVLangevinStepKernel>();
+        step.initialize(system, integrator);
+        step.execute(context.getImpl(), integrator);
+        if (reordered) {
+            vector<int> order(2 * (size_t) R);
+            for (int i = 0; i < 2 * R; i++) order[i] = i;
+            const int nMol = nWater / 3, window = 1024;
+            std::mt19937 pgen(7);
+            for (int lo = 0; lo < nMol; lo += window) {
+                const int hi = std::min(nMol, lo + window);
+                vector<int> w(hi - lo);
+                for (int j = 0; j < hi - lo; j++) w[j] = lo + j;
+                std::shuffle(w.begin(), w.end(), pgen);
+                for (int j = 0; j < hi - lo; j++)
+                    for (int k = 0; k < 3; k++)
+                        for (int cell = 0; cell < 2; cell++)
+                            order[(size_t) cell * R + nIonAll + 3 * (lo + j) + k] = cell * R + nIonAll + 3 * w[j] + k;
+            }
+            cu.setPendingReorder(order);
+            step.execute(context.getImpl(), integrator);  // cu.reorderAtoms() at its end applies the permutation
+            cu.getForce().uploadBytes(force.data());
+        }
+        for (int i = 0; i < 5; i++) step.execute(context.getImpl(), integrator);
+        CU(cudaDeviceSynchronize());
+
+        cudaStream_t stream = 0;
+        cudaEvent_t e0, e1;
+        CU(cudaEventCreate(&e0));
+        CU(cudaEventCreate(&e1));
+        auto pass = [&](int mode, bool withStep) {
+            CU(cudaEventRecord(e0, stream));
+            for (int i = 0; i < steps; i++) {
+                if (mode == 0) CU(cudaMemsetAsync(sweep, 0, sweepMB << 20, stream));
+                else CU(cudaMemcpyAsync((void*) cu.getForce().getDevicePointer(), spareForce, 24 * (size_t) P, cudaMemcpyDeviceToDevice, stream));
+                if (withStep) step.execute(context.getImpl(), integrator);
+            }
+            CU(cudaEventRecord(e1, stream));
+            CU(cudaEventSynchronize(e1));
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            return (double) ms * 1e3 / steps;
+        };
+        double us[2], sweepUs[2];
+        for (int mode = 0; mode < 2; mode++) {
+            vector<double> with, without;
+            pass(mode, true);
+            for (int r = 0; r < 5; r++) {
+                without.push_back(pass(mode, false));
+                with.push_back(pass(mode, true));
+            }
+            sweepUs[mode] = median(without);
+            us[mode] = median(with) - sweepUs[mode];
+        }
+
+        // algorithmic bytes of one step (DESIGN.md "bytes per pair"), numCells = 2
+        const double rb = precision == "double" ? 8 : 4, mb = precision == "single" ? 4 : 8;
+        const double posB = 4 * rb * (precision == "mixed" ? 2 : 1), velB = 4 * mb;
+        const long long massive = nIonAll + nWater, charged = nIonAll + nWater;
+        double bytes = (double) R * (velB + posB) + (double) massive * (24 + velB + posB) + (double) charged * (rb + posB) +
+                       (double) R * (velB + 24);
+        if (reordered) bytes += 8.0 * R + 4.0 * charged;  // atomIndex of both slots, invAtomOrder of the image
+        std::printf("{\"path\": \"CudaIntegrateConstVLangevinStepKernel::execute via the kernel factory (OpenMM shim)\", "
+                    "\"atoms\": %d, \"precision\": \"%s\", \"reordered_slots\": %s, \"steps\": %d, \"launches_per_step\": 1, "
+                    "\"algorithmic_bytes_per_step\": %.0f, "
+                    "\"flush\": {\"us_per_step\": %.3f, \"GBps\": %.1f, \"frac_8TBs\": %.4f, \"sweep\": \"%zu MB memset between steps, %.1f us\"}, "
+                    "\"forces\": {\"us_per_step\": %.3f, \"GBps\": %.1f, \"frac_8TBs\": %.4f, \"sweep\": \"D2D copy into the force buffer between steps, %.1f us\"}, "
+                    "\"statistic\": \"marginal cost: median of 5 (sweep+execute) passes minus median of 5 sweep-only passes\"}\n",
+                    atoms, precision.c_str(), reordered ? "true" : "false", steps, bytes,
+                    us[0], bytes / us[0] * 1e-3, bytes / us[0] * 1e-3 / 8000.0, sweepMB, sweepUs[0],
+                    us[1], bytes / us[1] * 1e-3, bytes / us[1] * 1e-3 / 8000.0, sweepUs[1]);
+        kernel = Kernel();
+        cudaFree(spareForce);
+        cudaFree(sweep);
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "exception: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

@@ -264,6 +264,120 @@ static void testReorderedAtoms() {
     CHECK(identical(v1, v2));
 }
 
+// A re-sort that happens BETWEEN two steps (OpenMM re-sorts inside setPositions, loadCheckpoint and the
+// minimizer) leaves cu.getAtomsWereReordered() false by the time execute() runs, because every later
+// reorderAtoms() call that does not re-sort clears the flag.  The kernel must still notice (it listens for
+// re-sorts instead of polling the flag as the reference does, CudaConstVKernels.cpp:139-142).
+static void testReorderBetweenSteps() {
+    const int numReal = 100, n = 2 * numReal;
+    vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = (i * 77 + 13) % n;
+    vector<Vec3> ref, refVel;
+    runNoisy(21, 12, false, NULL, ref, refVel);
+
+    System system;
+    vector<Vec3> positions;
+    vector<double> charges;
+    buildNoisySlab(system, positions, charges, numReal, false);
+    ConstVLangevinIntegrator integrator(300.0, 5.0, 0.002);
+    integrator.setRandomNumberSeed(21);
+    integrator.setConstraintTolerance(3e-6);
+    Platform& platform = Platform::getPlatformByName("CUDA");
+    Context context(system, integrator, platform, properties);
+    context.setPositions(positions);
+    context.setCharges(charges);
+    context.setVelocitiesToTemperature(300.0, 4);
+    CudaContext& cu = cudaContextOf(context);
+    integrator.step(6);
+    cu.setPendingReorder(order);
+    cu.reorderAtoms();  // the re-sort, outside any step
+    cu.reorderAtoms();  // a later call that re-sorts nothing: the flag is false again
+    CHECK(!cu.getAtomsWereReordered());
+    integrator.step(6);
+    State state = context.getState(State::Positions | State::Velocities);
+    CHECK(identical(ref, state.getPositions()));
+    CHECK(identical(refVel, state.getVelocities()));
+}
+
+// The noise of step k is a function of (seed, atom, k) with k = OpenMM's own step count: a state carried into
+// a NEW Context together with its step count (what loadCheckpoint does) continues the trajectory bit for bit
+// instead of replaying the noise of steps 0, 1, ...
+static void testStepCountDrivesTheNoise() {
+    const int numReal = 100;
+    vector<Vec3> ref, refVel;
+    runNoisy(33, 10, false, NULL, ref, refVel);  // 5 + 5 steps in one Context
+
+    System system;
+    vector<Vec3> positions;
+    vector<double> charges;
+    buildNoisySlab(system, positions, charges, numReal, false);
+    Platform& platform = Platform::getPlatformByName("CUDA");
+    vector<Vec3> midPos, midVel;
+    {
+        ConstVLangevinIntegrator integrator(300.0, 5.0, 0.002);
+        integrator.setRandomNumberSeed(33);
+        Context context(system, integrator, platform, properties);
+        context.setPositions(positions);
+        context.setCharges(charges);
+        context.setVelocitiesToTemperature(300.0, 4);
+        integrator.step(4);
+        State state = context.getState(State::Positions | State::Velocities);
+        midPos = state.getPositions();
+        midVel = state.getVelocities();
+    }
+    ConstVLangevinIntegrator integrator(300.0, 5.0, 0.002);
+    integrator.setRandomNumberSeed(33);
+    Context context(system, integrator, platform, properties);
+    context.setPositions(midPos);
+    context.setCharges(charges);
+    context.setVelocities(midVel);
+    cudaContextOf(context).setStepCount(4);
+    cudaContextOf(context).setTime(4 * 0.002);
+    integrator.step(6);
+    State state = context.getState(State::Positions | State::Velocities);
+    CHECK(identical(ref, state.getPositions()));
+    CHECK(identical(refVel, state.getVelocities()));
+    CHECK_EQ(10, cudaContextOf(context).getStepCount());
+}
+
+// A charged virtual site (the M site of a 4-site water): the reference places the sites after part 2 and
+// rewrites the images after that (part 2, computeVirtualSites, updateImageParticlePositions:
+// CudaConstVKernels.cpp:158-166), so the site's image mirrors the position the site has at the END of the step.
+static void testVirtualSiteImage() {
+    System system;
+    addSlabParticles(system, {16.0, 1.0, 0.0});  // atom 2: massless site halfway between atoms 0 and 1
+    system.setVirtualSite(2, new TwoParticleAverageSite(0, 1, 0.5, 0.5));
+    ConstVLangevinIntegrator integrator(300.0, 2.0, 0.004);
+    integrator.setRandomNumberSeed(9);
+    HarmonicWellForce* wells = new HarmonicWellForce();
+    wells->addParticle(0, Vec3(1.0, 1.0, 0.8), 20.0);
+    wells->addParticle(1, Vec3(1.2, 1.1, 1.1), 20.0);
+    system.addForce(wells);
+    Platform& platform = Platform::getPlatformByName("CUDA");
+    Context context(system, integrator, platform, properties);
+    vector<Vec3> positions = {Vec3(1.0, 1.0, 0.8), Vec3(1.2, 1.1, 1.1), Vec3(1.1, 1.05, 0.95),
+                              Vec3(1.0, 1.0, -0.8), Vec3(1.2, 1.1, -1.1), Vec3(0, 0, 0)};
+    context.setPositions(positions);
+    context.setCharges({0.0, 0.52, -1.04, 0.0, -0.52, 1.04});
+    for (int k = 0; k < 25; k++) {
+        integrator.step(1);
+        State state = context.getState(State::Positions);
+        const vector<Vec3>& p = state.getPositions();
+        const double tol = precision == "single" ? 1e-6 : 1e-12;
+        for (int c = 0; c < 3; c++)  // the shim placed the site from this step's positions
+            CHECK_CLOSE(0.5 * (p[0][c] + p[1][c]), p[2][c], tol);
+        // ... and the image of the site is the mirror of THAT position, bit for bit, not of last step's
+        CHECK_EQ(bitsOf(p[2][0]), bitsOf(p[5][0]));
+        CHECK_EQ(bitsOf(p[2][1]), bitsOf(p[5][1]));
+        if (precision != "mixed")
+            CHECK_EQ(bitsOf(mirroredZ(p[2][2], 2.0)), bitsOf(p[5][2]));
+        else
+            CHECK_CLOSE(-p[2][2] + 4.0, p[5][2], 1e-12);
+        CHECK(p[2][2] != positions[2][2] || k == 0);
+    }
+    CHECK_EQ(25, cudaContextOf(context).getIntegrationUtilities().virtualSiteCalls);
+}
+
 // With constraints in the System the step is split around integration.applyConstraints(tol)
 // (CudaConstVKernels.cpp:146-166).  The shim's solver is a no-op, so the split path must reproduce
 // the fused path exactly, and the solver must have been handed posDelta once per step.
@@ -438,6 +552,9 @@ int main(int argc, char* argv[]) {
         testMasslessAndNeutralParticles();
         testRandomSeed();
         testReorderedAtoms();
+        testReorderBetweenSteps();
+        testStepCountDrivesTheNoise();
+        testVirtualSiteImage();
         testConstraintHandOff();
         testRigidWater();
         testKineticEnergy();

@@ -51,6 +51,17 @@ static void testReadsVersion1() {
     delete integ;
 }
 
+static void testReadsVersion2() {
+    // what round 1 of this plugin wrote
+    std::stringstream v2(
+        "<Integrator type=\"ConstVLangevinIntegrator\" version=\"2\" stepSize=\".002\" constraintTolerance=\"1e-05\" "
+        "temperature=\"300\" friction=\"1\" randomSeed=\"7\" numCells=\"4\" cellSize=\"2.5\"/>\n");
+    ConstVLangevinIntegrator* integ = XmlSerializer::deserialize<ConstVLangevinIntegrator>(v2);
+    CHECK_EQ(4, integ->getNumCells());
+    CHECK_EQ(2.5, integ->getCellSize());
+    delete integ;
+}
+
 static void testRejectsUnknownVersion() {
     std::stringstream v3(
         "<Integrator type=\"ConstVLangevinIntegrator\" version=\"3\" stepSize=\".002\" constraintTolerance=\"1e-05\" "
@@ -64,7 +75,9 @@ static void testWrittenDocument() {
     XmlSerializer::serialize<ConstVLangevinIntegrator>(&integ, "Integrator", buffer);
     const std::string text = buffer.str();
     CHECK(text.find("type=\"ConstVLangevinIntegrator\"") != std::string::npos);
-    CHECK(text.find("version=\"2\"") != std::string::npos);
+    // version 1: the only one the reference's reader accepts (its ConstVLangevinIntegratorProxy.cpp:55-56), so a
+    // document written here loads in the reference plugin; numCells / cellSize ride along as extra attributes
+    CHECK(text.find("version=\"1\"") != std::string::npos);
     for (const char* key : {"stepSize=", "constraintTolerance=", "temperature=", "friction=", "randomSeed=", "numCells=", "cellSize="})
         CHECK(text.find(key) != std::string::npos);
 }
@@ -104,6 +117,7 @@ int main() {
         registerConstVSerializationProxies();  // and calling it again is harmless
         testRoundTrip();
         testReadsVersion1();
+        testReadsVersion2();
         testRejectsUnknownVersion();
         testWrittenDocument();
         testDrudeRoundTrip();

@@ -82,8 +82,9 @@ def padded_atoms(n: int) -> int:
 def make_slab(num_real: int, precision: str = "single", num_cells: int = 2, seed: int = 12345,
               temperature: float = 300.0, wall_fraction: float = WALL_FRACTION,
               ion_fraction: float = ION_FRACTION, force_sigma: float = 1000.0,
-              image_force_garbage: bool = True, zmax: float = EXAMPLE_ZMAX) -> Slab:
-    """Build a seeded slab with ``num_real`` real atoms and ``num_cells - 1`` image cells."""
+              image_force_garbage: bool = True, zmax: float = EXAMPLE_ZMAX, x_offset: float = 0.0) -> Slab:
+    """Build a seeded slab with ``num_real`` real atoms and ``num_cells - 1`` image cells.
+    ``x_offset`` shifts the slab along x (a lateral tile of a wider electrode, see ``slab_tile``)."""
     assert precision in PRECISIONS
     assert num_cells >= 2 and num_cells % 2 == 0
     rng = np.random.Generator(np.random.Philox(seed))
@@ -110,7 +111,7 @@ def make_slab(num_real: int, precision: str = "single", num_cells: int = 2, seed
     # walls: mass 0, charge 0 (spce.xml:28,42-44), split between z = 0 and z = zmax
 
     pos = np.empty((R, 3), np.float64)
-    pos[:, 0] = rng.random(R) * lx
+    pos[:, 0] = x_offset + rng.random(R) * lx
     pos[:, 1] = rng.random(R) * ly
     pos[:, 2] = (0.05 + 0.9 * rng.random(R)) * zmax
     wall = slice(n_ion + n_water, R)
@@ -336,6 +337,67 @@ def slice_slab(slab: Slab, lo: int, hi: int) -> Slab:
     force[:, :n] = slab.force[:, src]
     return Slab(slab.precision, nc, r, n, P, slab.zmax, slab.box, posq, corr, velm, force,
                 slab.masses[src].copy(), slab.global_atom_offset + lo, dict(slab.meta))
+
+
+def tile_real_atoms(num_real_total: int, tiles: int) -> int:
+    """Real atoms per lateral tile of a tiled slab (``slab_tile``); the total must divide evenly and a tile must
+    be a multiple of 32 atoms so that tile boundaries are partition boundaries (``partition.shard_range``)."""
+    if tiles < 1 or num_real_total % tiles != 0 or (tiles > 1 and (num_real_total // tiles) % 32 != 0):
+        raise ValueError(f"{num_real_total} real atoms do not cut into {tiles} tiles of a multiple of 32 atoms")
+    return num_real_total // tiles
+
+
+def slab_tile(num_real_total: int, tiles: int, t: int, precision: str = "single", seed: int = 12345,
+              maker=None, **kw):
+    """Lateral tile ``t`` of the seeded global slab of ``num_real_total`` real atoms made of ``tiles`` tiles.
+
+    The multi-GPU workloads are ONE global slab: an electrode ``tiles`` times as wide in x as the example's
+    aspect, tile ``t`` occupying x in [t*lx, (t+1)*lx) with its own ions, water and wall atoms (seed + t), so
+    that every contiguous real-atom range of one tile has the composition of the whole.  Its real atoms are
+    numbered [t*Rt, (t+1)*Rt) in the global slab (``global_atom_offset``), which is exactly
+    ``partition.shard_range(num_real_total, t, tiles)``: a rank of a ``tiles``-GPU job builds only its own
+    tile, and ``concat_slabs`` of all tiles is the unpartitioned slab (``slice_slab`` of which is the tile).
+    ``maker`` = ``make_slab`` (default), ``make_water_slab`` or ``make_drude_slab``; returns what it returns.
+    """
+    rt = tile_real_atoms(num_real_total, tiles)
+    maker = maker or make_slab
+    scale = np.sqrt(max(rt, 1) / EXAMPLE_REAL_ATOMS)
+    out = maker(rt, precision, seed=seed + t, x_offset=t * EXAMPLE_LX * scale, **kw)
+    s = out[0] if isinstance(out, tuple) else out
+    s.global_atom_offset = t * rt
+    s.meta["tile"] = (t, tiles)
+    return out
+
+
+def concat_slabs(tiles: list) -> Slab:
+    """The unpartitioned slab whose real atoms are the tiles' real atoms in order (and likewise each image
+    cell): the inverse of ``slice_slab`` over consecutive ranges."""
+    first = tiles[0]
+    nc = first.num_cells
+    R = sum(t.num_real for t in tiles)
+    N = R * nc
+    P = padded_atoms(N)
+    posq = np.zeros((P, 4), first.posq.dtype)
+    corr = None if first.corr is None else np.zeros((P, 4), first.corr.dtype)
+    velm = np.zeros((P, 4), first.velm.dtype)
+    force = np.zeros((3, P), np.int64)
+    masses = np.zeros(N, np.float64)
+    lo = 0
+    for t in tiles:
+        r = t.num_real
+        for cell in range(nc):
+            dst = slice(cell * R + lo, cell * R + lo + r)
+            src = slice(cell * r, (cell + 1) * r)
+            posq[dst] = t.posq[src]
+            if corr is not None:
+                corr[dst] = t.corr[src]
+            velm[dst] = t.velm[src]
+            force[:, dst] = t.force[:, src]
+            masses[dst] = t.masses[src]
+        lo += r
+    box = (sum(t.box[0] for t in tiles), first.box[1], first.box[2])
+    return Slab(first.precision, nc, R, N, P, first.zmax, box, posq, corr, velm, force, masses,
+                first.global_atom_offset, dict(first.meta))
 
 
 def new_forces(slab: Slab, step_index: int, force_sigma: float = 1000.0) -> np.ndarray:

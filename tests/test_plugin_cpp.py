@@ -117,3 +117,67 @@ def test_constvplugin_python_module_drude():
     assert integ.getKernelNames() == ["IntegrateConstVDrudeLangevinStep"]
     text = open(os.path.join(PLUGIN, "python", "constvplugin.i")).read()
     assert "class ConstVDrudeLangevinIntegrator : public Integrator" in text
+
+
+def _surfaces():
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("make_swig_surface", os.path.join(ROOT, "tests", "golden", "make_swig_surface.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ours = mod.swig_surface(open(os.path.join(PLUGIN, "python", "constvplugin.i")).read())
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_swig_surface.json")))
+    return ours, ref
+
+
+def test_swig_interface_matches_the_reference_surface():
+    """constvplugin.i declares the reference's module surface (python/constvplugin.i: module name, vector
+    templates, the two classes with their constructors, defaults, accessors and the SEVEN unit-decorated
+    getters) and nothing that changes the behaviour of a reference call.  The only additions are
+    get/setRandomNumberSeed on the Drude class, which the reference's C++ class has but its .i forgot."""
+    ours, ref = _surfaces()
+    assert ours["module"] == ref["module"] == "constvplugin"
+    assert ours["templates"] == ref["templates"]
+    assert ours["unit_getters"] == ref["unit_getters"]  # in particular: getCellSize is NOT decorated
+    assert set(ours["classes"]) == set(ref["classes"])
+    for name, rc in ref["classes"].items():
+        oc = ours["classes"][name]
+        assert oc["base"] == rc["base"]
+        assert [(t, d) for t, _, d in oc["constructor"]] == [(t, d) for t, _, d in rc["constructor"]]
+        for method, sig in rc["methods"].items():
+            assert oc["methods"][method] == sig, (name, method)
+        extra = set(oc["methods"]) - set(rc["methods"])
+        assert extra <= {"getRandomNumberSeed", "setRandomNumberSeed"}, extra
+    if os.path.exists("/root/reference/python/constvplugin.i"):  # the fixture is what the reference says today
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("mss", os.path.join(ROOT, "tests", "golden", "make_swig_surface.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        assert mod.swig_surface(open("/root/reference/python/constvplugin.i").read()) == ref
+
+
+def test_ctypes_module_has_the_swig_surface():
+    """The ctypes constvplugin module (what runs without SWIG/OpenMM) offers every class, constructor default
+    and method the .i declares, decorates exactly the getters the .i decorates, and nothing else."""
+    ours, _ = _surfaces()
+    sys.path.insert(0, os.path.join(PLUGIN, "python"))
+    try:
+        import constvplugin
+    finally:
+        sys.path.pop(0)
+    import inspect
+    for name, info in ours["classes"].items():
+        cls = getattr(constvplugin, name)
+        params = list(inspect.signature(cls.__init__).parameters.values())[1:]
+        assert len(params) == len(info["constructor"])
+        for p, (typ, _, default) in zip(params, info["constructor"]):
+            if default is None:
+                assert p.default is inspect.Parameter.empty
+            else:
+                assert p.default == (int(default) if typ == "int" else float(default))
+        for method in info["methods"]:
+            assert callable(getattr(cls, method)), (name, method)
+        decorated = {m for m in info["methods"] if f"{name}::{m}" in ours["unit_getters"]}
+        # a getter is decorated in the ctypes module iff the class overrides it (constvplugin.py wraps the host getters)
+        overridden = {m for m in info["methods"] if m.startswith("get") and m in cls.__dict__}
+        assert overridden == decorated, (name, overridden, decorated)
