@@ -810,13 +810,16 @@ def run_e2e(env, wl, args, atoms_job):
         ms_pipe = e2e_pipelined(host_force, capi.FORCE_FIXED64, n_pipe)
         host_force32 = [(torch.randn((3, R), dtype=torch.float32) * 1000.0).pin_memory() for _ in range(2)]
         ms_pipe32 = e2e_pipelined(host_force32, capi.FORCE_FLOAT32, n_pipe)
-    return {"value": atoms_job * n_pipe / (ms_pipe * 1e-3), "unit": "atom-steps/s",
-            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8, "steps": n_pipe,
-            "ms_per_step": ms_pipe / n_pipe,
-            "what": "constv_step_host_submit/_collect, two tickets in flight: every step uploads its real-atom forces (int64 fixed "
-                    "point, OpenMM's buffer format, pinned memory) and reads back its kinetic energy; PCIe-bound; median of 5 passes",
-            "float32_forces": {"value": atoms_job * n_pipe / (ms_pipe32 * 1e-3), "ms_per_step": ms_pipe32 / n_pipe,
-                               "h2d_bytes_per_step": int(h2d // 2), "d2h_bytes_per_step": 8},
+    return {"value": atoms_job * n_pipe / (ms_pipe32 * 1e-3), "unit": "atom-steps/s",
+            "h2d_bytes_per_step": int(h2d // 2), "d2h_bytes_per_step": 8, "steps": n_pipe,
+            "ms_per_step": ms_pipe32 / n_pipe,
+            "what": "constv_step_host_submit/_collect with HOST buffers, two tickets in flight: every step uploads the real atoms' forces "
+                    "from pinned memory (float32 x, y, z planes, 12 B per real atom; converted to OpenMM's fixed point on the device as "
+                    "OpenMM's force kernels do), runs the fused step and the kinetic-energy reduction and reads the energy back; "
+                    "PCIe-bound; median of 5 passes",
+            "fixed64_forces": {"value": atoms_job * n_pipe / (ms_pipe * 1e-3), "ms_per_step": ms_pipe / n_pipe,
+                               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
+                               "what": "same with the host forces already in OpenMM's int64 fixed-point buffer format (24 B per real atom)"},
             "synchronous": {"value": atoms_job * n_e2e / (ms_ke * 1e-3), "ms_per_step": ms_ke / n_e2e,
                             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8},
             "full_state": {"value": atoms_job * n_e2e / (ms_full * 1e-3), "ms_per_step": ms_full / n_e2e,
@@ -829,13 +832,22 @@ def run_plugin_path(args, atoms):
     exe = os.path.join(ROOT, "openmm_constv_b200", "plugin", "bin", "BenchPluginPath")
     if not os.path.exists(exe):
         return {"unavailable": "plugin/bin/BenchPluginPath has not been built"}
-    out = {}
+    out = {"what": "us per CudaIntegrateConstVLangevinStepKernel::execute (one launch per step, no graph), a sweep between two steps: "
+                   "forces = D2D copy into the force buffer (24 B/atom), copy = D2D copy 128 MB -> 128 MB, read = a kernel reading "
+                   "256 MB; bracketed = events around execute(), marginal = loop time with minus without the step"}
     for mode in ("identity", "reordered"):
         cmd = [exe, "--atoms", str(atoms), "--steps", "300", "--precision", args.precision] + (["--reordered"] if mode == "reordered" else [])
         try:
             res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
             line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
-            out[mode] = json.loads(line[-1]) if line else {"error": (res.stderr or res.stdout)[-300:]}
+            if line:
+                r = json.loads(line[-1])
+                out[mode] = {"algorithmic_bytes_per_step": r["algorithmic_bytes_per_step"]}
+                for sweep in ("forces", "copy", "read"):
+                    out[mode][sweep] = {"marginal_us": r[sweep]["marginal_us"], "bracketed_us": r[sweep]["bracketed_us"],
+                                        "bracketed_frac_8TBs": r[sweep]["bracketed_frac_8TBs"]}
+            else:
+                out[mode] = {"error": (res.stderr or res.stdout)[-300:]}
         except Exception as exc:  # noqa: BLE001
             out[mode] = {"error": str(exc)[-300:]}
     return out

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -16,6 +17,7 @@
 #include "constv_kernels.cuh"
 #include "constv_drude_kernels.cuh"
 #include "constv_settle_kernels.cuh"
+#include "constv_settle_ws_kernels.cuh"
 
 using namespace constv;
 
@@ -79,6 +81,13 @@ struct constv_slab {
     double time = 0;
     // launch shape
     int ilp = 1;
+    int fusedBlock = 256;    // threads per CTA of the fused step (128 | 256); experiments: CONSTV_FUSED_BLOCK
+    // fused step: the Philox blocks are drawn and the image zeroing stores issued while the tile's loads are in flight
+    // (in-process A/B on a B200, profiles/r02_ab_fused.jsonl: 13.76 -> 13.46 us with one launch per step, 12.27 ->
+    // 11.64 us with two chains).  CONSTV_FUSED_EARLY=0 / CONSTV_FUSED_ZERO=0|2 restore the round-1 order.
+    bool fusedEarly = true;
+    int zeroWhen = 1;         // 0 with the dependent stores, 1 right behind the loads, 2 after the step-counter barrier
+    bool settleWs = true;     // rigid-water step: the warp-specialised TMA pipeline (CONSTV_SETTLE_WS=0: the LDG-staged kernel)
     int ctasPerSM = 0;   // 0 = one-shot grid (one tile per CTA); > 0 = persistent grid of that many CTAs per SM
     int variant = 0;     // 0 auto (= the one-shot LDG kernel, the faster one as measured), 1 LDG, 2 TMA ring
     int tmaBlock = 256;  // pairs per chunk = threads per CTA of the TMA kernel
@@ -176,6 +185,7 @@ SlabDev makeDev(const constv_slab* s) {
     d.tileBase = 0;
     d.rangeLo = 0;
     d.rangeHi = s->numReal;
+    d.zeroWhen = s->zeroWhen;
     return d;
 }
 
@@ -229,20 +239,25 @@ int gridFor(const constv_slab* s, long long work, int perBlock, int ctasPerSM) {
 
 // ---- dispatch over (precision, ILP) --------------------------------------------------------------
 
-template <int PREC, bool STREAM>
+template <int PREC, bool STREAM, bool EARLY>
 int launchFusedS(constv_slab* s, const SlabDev& d, const float4* random, unsigned randomIndex, cudaStream_t st) {
     const bool pdl = s->cfg.flags & CONSTV_FLAG_PDL;
+    if (s->fusedBlock == 128)
+        return launch(constv_fused_step_kernel<PREC, 128, 1, STREAM, EARLY>, gridFor(s, d.rangeHi - d.rangeLo, 128, s->ctasPerSM), 128, pdl, st, d, random, randomIndex);
     switch (s->ilp) {
-        case 1: return launch(constv_fused_step_kernel<PREC, kBlock, 1, STREAM>, gridFor(s, d.rangeHi - d.rangeLo, kBlock * 1, s->ctasPerSM), kBlock, pdl, st, d, random, randomIndex);
-        case 4: return launch(constv_fused_step_kernel<PREC, kBlock, 4, STREAM>, gridFor(s, d.rangeHi - d.rangeLo, kBlock * 4, s->ctasPerSM), kBlock, pdl, st, d, random, randomIndex);
-        default: return launch(constv_fused_step_kernel<PREC, kBlock, 2, STREAM>, gridFor(s, d.rangeHi - d.rangeLo, kBlock * 2, s->ctasPerSM), kBlock, pdl, st, d, random, randomIndex);
+        case 1: return launch(constv_fused_step_kernel<PREC, kBlock, 1, STREAM, EARLY>, gridFor(s, d.rangeHi - d.rangeLo, kBlock * 1, s->ctasPerSM), kBlock, pdl, st, d, random, randomIndex);
+        case 4: return launch(constv_fused_step_kernel<PREC, kBlock, 4, STREAM, EARLY>, gridFor(s, d.rangeHi - d.rangeLo, kBlock * 4, s->ctasPerSM), kBlock, pdl, st, d, random, randomIndex);
+        default: return launch(constv_fused_step_kernel<PREC, kBlock, 2, STREAM, EARLY>, gridFor(s, d.rangeHi - d.rangeLo, kBlock * 2, s->ctasPerSM), kBlock, pdl, st, d, random, randomIndex);
     }
 }
 
 template <int PREC>
 int launchFused(constv_slab* s, const SlabDev& d, const float4* random, unsigned randomIndex, cudaStream_t st) {
-    return (s->cfg.flags & CONSTV_FLAG_KEEP_IN_L2) ? launchFusedS<PREC, false>(s, d, random, randomIndex, st)
-                                                   : launchFusedS<PREC, true>(s, d, random, randomIndex, st);
+    if (s->fusedEarly)
+        return (s->cfg.flags & CONSTV_FLAG_KEEP_IN_L2) ? launchFusedS<PREC, false, true>(s, d, random, randomIndex, st)
+                                                       : launchFusedS<PREC, true, true>(s, d, random, randomIndex, st);
+    return (s->cfg.flags & CONSTV_FLAG_KEEP_IN_L2) ? launchFusedS<PREC, false, false>(s, d, random, randomIndex, st)
+                                                   : launchFusedS<PREC, true, false>(s, d, random, randomIndex, st);
 }
 
 template <int PREC, int BLOCK, int STAGES>
@@ -404,6 +419,10 @@ int constv_create(const constv_config* config, constv_slab** out) {
     s->cfg = *config;
     if (s->cfg.boltz == 0) s->cfg.boltz = kBoltzDefault;
     s->numReal = config->num_atoms / config->num_cells;
+    if (const char* e = std::getenv("CONSTV_FUSED_BLOCK")) s->fusedBlock = std::atoi(e) == 128 ? 128 : 256;
+    if (const char* e = std::getenv("CONSTV_FUSED_EARLY")) s->fusedEarly = std::atoi(e) != 0;
+    if (const char* e = std::getenv("CONSTV_FUSED_ZERO")) s->zeroWhen = std::atoi(e);
+    if (const char* e = std::getenv("CONSTV_SETTLE_WS")) s->settleWs = std::atoi(e) != 0;
     DeviceGuard guard(config->device);
     if (guard.rc) { delete s; return guard.rc; }
     int dev = 0;
@@ -1017,7 +1036,7 @@ int constv_set_launch_shape(constv_slab* s, int32_t pairs_per_thread, int32_t ct
 
 int constv_set_kernel_variant(constv_slab* s, int32_t variant, int32_t block_size, int32_t stages, int32_t ctas_per_sm) {
     if (!s) return fail(CONSTV_ERR_INVALID, "null slab");
-    if (variant < 0 || variant > 2) return fail(CONSTV_ERR_INVALID, "variant must be 0 (auto), 1 (LDG) or 2 (TMA)");
+    if (variant < 0 || variant > 3) return fail(CONSTV_ERR_INVALID, "variant must be 0 (auto), 1 (LDG / gather), 2 (TMA ring) or 3 (LDG-staged rigid-water / Drude kernels)");
     s->variant = variant;
     if (block_size) s->tmaBlock = block_size;
     if (stages) s->tmaStages = stages;

@@ -63,7 +63,7 @@ struct SlabDev {
     int tileBase;                // batched launch: first tile of this slab in the global tile space
     int rangeLo, rangeHi;        // real atoms [rangeLo, rangeHi) this launch advances (a chain, see
                                  // constv_set_chains; the whole slab = [0, numReal)); `counters` is the chain's
-    int pad_;
+    int zeroWhen;                // fused step: when the image zeroing stores are issued (see fused_tile)
 };
 
 // ---- small vector helpers ----------------------------------------------------------------------
@@ -343,7 +343,28 @@ template <int PREC> struct PairIn {
 // What one real atom leaves in HBM at the end of a step (identity slot order): its own record (when
 // it moved), the rewritten images (charged atoms only, Langevin.cu:143) and the zeroed image
 // velocities / forces.  i = slot of the real atom, q1 = charge of its cell-1 image.
+// image invariants of real atom i (identity slot order): velm = 0 (velocity and inverse mass), force = 0.
+// Depends on nothing the step reads, so a kernel may issue it before its loads have returned.
 template <int PREC, bool STREAM>
+__device__ __forceinline__ void emit_zero(const SlabDev& d, const int i) {
+    using Mixed = typename Prec<PREC>::Mixed;
+    const int R = d.numReal;
+    const size_t P = (size_t) d.padded;
+    Mixed* __restrict__ velm = static_cast<Mixed*>(d.velm);
+    long long* __restrict__ force = d.force;
+#pragma unroll 1
+    for (int cell = 1; cell < d.numCells; cell++) {
+        const size_t slot = (size_t) i + (size_t) R * cell;
+        if (d.zeroVelm) store4x<STREAM>(velm, slot, Vec4<Mixed>{0, 0, 0, 0});
+        if (d.zeroForce) {
+            __stcs(force + slot, 0LL);
+            __stcs(force + P + slot, 0LL);
+            __stcs(force + 2 * P + slot, 0LL);
+        }
+    }
+}
+
+template <int PREC, bool STREAM, bool ZERO = true>
 __device__ __forceinline__ void emit_atom(const SlabDev& d, const double zshift, const int i, const bool moved,
                                           const Vec4<typename Prec<PREC>::Mixed>& v, const Vec4<typename Prec<PREC>::Real>& p,
                                           const Vec4<typename Prec<PREC>::Real>& c, const typename Prec<PREC>::Real q1) {
@@ -379,21 +400,12 @@ __device__ __forceinline__ void emit_atom(const SlabDev& d, const double zshift,
             }
         }
     }
-    // image invariants: velm = 0 (velocity and inverse mass), force = 0
-#pragma unroll 1
-    for (int cell = 1; cell < d.numCells; cell++) {
-        const size_t slot = (size_t) i + (size_t) R * cell;
-        if (d.zeroVelm) store4x<STREAM>(velm, slot, Vec4<Mixed>{0, 0, 0, 0});
-        if (d.zeroForce) {
-            __stcs(force + slot, 0LL);
-            __stcs(force + P + slot, 0LL);
-            __stcs(force + 2 * P + slot, 0LL);
-        }
-    }
+    if (ZERO) emit_zero<PREC, STREAM>(d, i);
 }
 
 // Part 1 + part 2 + image rewrite + image zeroing for pair i; all stores go straight to global.
-template <int PREC, bool STREAM>
+// ZERO = false: the caller has already issued emit_zero for this pair.
+template <int PREC, bool STREAM, bool ZERO = true>
 __device__ __forceinline__ void process_pair(const SlabDev& d, const StepScalars<typename Prec<PREC>::Mixed>& s,
                                              const int i, PairIn<PREC>& in, const bool havePool, float4 xi,
                                              const unsigned long long step) {
@@ -408,14 +420,20 @@ __device__ __forceinline__ void process_pair(const SlabDev& d, const StepScalars
         part1_update(in.v, delta, in.fx, in.fy, in.fz, xi.x, xi.y, xi.z, s);
         part2_update<PREC>(in.p, in.c, in.v, delta, s.invDt);
     }
-    emit_atom<PREC, STREAM>(d, s.zshift, i, moved, in.v, in.p, in.c, in.q1);
+    emit_atom<PREC, STREAM, ZERO>(d, s.zshift, i, moved, in.v, in.p, in.c, in.q1);
 }
 
 // LDG variant: all loads of a tile (ILP pairs per thread) are issued before the first use so that
 // each thread keeps ILP*(60..100) bytes in flight.
 // `stepOf()` is called once, after the tile's loads have been issued: it returns the step index (the
 // Philox counter) and is where the caller synchronises the CTA on the published counter.
-template <int PREC, int BLOCK, int ILP, bool STREAM, typename StepFn>
+// EARLY: everything that does not depend on the tile's loads is done while they are in flight -- the image
+// zeroing stores are issued right behind the loads, and the Philox block of every pair (a function of seed,
+// atom index and step only; ~130 of the ~270 instructions of a pair) is drawn as soon as the step counter is
+// known, for massless atoms too (their draw is discarded).  What remains once the records arrive is part 1,
+// part 2 and the dependent stores.  Same arithmetic, same bits; it shortens the serial load -> compute ->
+// store path of a CTA, which is what a launch of only 1-2 waves of CTAs (1M atoms) is made of.
+template <int PREC, int BLOCK, int ILP, bool STREAM, bool EARLY, typename StepFn>
 __device__ __forceinline__ void fused_tile(const SlabDev& d, const int base, const int end, StepFn stepOf,
                                            const float4* __restrict__ random, const unsigned int randomIndex) {
     using Real = typename Prec<PREC>::Real;
@@ -453,16 +471,35 @@ __device__ __forceinline__ void fused_tile(const SlabDev& d, const int base, con
             if (random) xi[j] = __ldcs(random + (size_t) randomIndex + i);
         }
     }
+    const int zeroWhen = d.zeroWhen;  // experiment: 0 with the dependent stores, 1 right behind the loads, 2 after the barrier
+    if (zeroWhen == 1) {
+#pragma unroll
+        for (int j = 0; j < ILP; j++)
+            if (valid[j]) emit_zero<PREC, STREAM>(d, base + j * BLOCK + (int) threadIdx.x);
+    }
     const unsigned long long step = stepOf();
+    if (zeroWhen == 2) {
+#pragma unroll
+        for (int j = 0; j < ILP; j++)
+            if (valid[j]) emit_zero<PREC, STREAM>(d, base + j * BLOCK + (int) threadIdx.x);
+    }
+    if (EARLY && random == nullptr && s.noisescale != 0) {
+#pragma unroll
+        for (int j = 0; j < ILP; j++)
+            if (valid[j])
+                xi[j] = gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) (base + j * BLOCK + (int) threadIdx.x), step);
+    }
 #pragma unroll
     for (int j = 0; j < ILP; j++) {
         if (!valid[j]) continue;
-        process_pair<PREC, STREAM>(d, s, base + j * BLOCK + (int) threadIdx.x, in[j], random != nullptr, xi[j], step);
+        // with EARLY the noise is in xi[j] already (zero when the noise scale is zero: the reference's 0 * xi)
+        process_pair<PREC, STREAM, false>(d, s, base + j * BLOCK + (int) threadIdx.x, in[j], EARLY || random != nullptr, xi[j], step);
+        if (zeroWhen == 0) emit_zero<PREC, STREAM>(d, base + j * BLOCK + (int) threadIdx.x);
     }
 }
 
-template <int PREC, int BLOCK, int ILP, bool STREAM>
-__global__ void __launch_bounds__(BLOCK)
+template <int PREC, int BLOCK, int ILP, bool STREAM, bool EARLY = true>
+__global__ void __launch_bounds__(BLOCK, (PREC == PREC_SINGLE && ILP == 1) ? 2048 / BLOCK : 1)  // single: 32 registers, 2048 threads per SM
 constv_fused_step_kernel(const __grid_constant__ SlabDev d, const float4* __restrict__ random,
                          const unsigned int randomIndex) {
     __shared__ StepBox box;
@@ -477,7 +514,7 @@ constv_fused_step_kernel(const __grid_constant__ SlabDev d, const float4* __rest
     for (long long base = lo + (long long) blockIdx.x * kTile; base < hi; base += (long long) gridDim.x * kTile) {
         unsigned int ticket = 0;
         unsigned long long step = 0;
-        fused_tile<PREC, BLOCK, ILP, STREAM>(d, (int) base, hi, [&]() {
+        fused_tile<PREC, BLOCK, ILP, STREAM, EARLY>(d, (int) base, hi, [&]() {
             publish_step(box, d.counters);
             __syncthreads();
             step = box.step;
@@ -655,7 +692,7 @@ constv_fused_step_batched_kernel(const __grid_constant__ BatchParams<CAP> b) {
         const unsigned int holders = (unsigned int) ((d.numReal + BLOCK - 1) / BLOCK);
         unsigned int ticket = 0;
         unsigned long long step = 0;
-        fused_tile<PREC, BLOCK, 1, true>(d, (tile - d.tileBase) * BLOCK, d.numReal, [&]() {
+        fused_tile<PREC, BLOCK, 1, true, true>(d, (tile - d.tileBase) * BLOCK, d.numReal, [&]() {
             publish_step(box, d.counters);
             __syncthreads();
             step = box.step;
@@ -723,7 +760,9 @@ constv_fused_step_indexed_kernel(const __grid_constant__ SlabDev d, const float4
             __stcs(force + 2 * P + slot, 0LL);
         }
     };
-    auto updateReal = [&](int slot, int a, Vec4<Mixed> v, Vec4<Real> p, Vec4<Real> c, long long fx, long long fy, long long fz) {
+    // haveXi: the caller drew this atom's Philox block already (while the record was in flight)
+    auto updateReal = [&](int slot, int a, Vec4<Mixed> v, Vec4<Real> p, Vec4<Real> c, long long fx, long long fy, long long fz,
+                          bool haveXi, float4 xi) {
         const bool charged = p.w != -p.w;
         size_t t1 = 0;
         Real q1 = 0;
@@ -732,10 +771,9 @@ constv_fused_step_indexed_kernel(const __grid_constant__ SlabDev d, const float4
             q1 = d.imageCharge ? static_cast<const Real*>(d.imageCharge)[a] : posq[4 * t1 + 3];
         }
         if (v.w != 0) {
-            float4 xi;
             if (random) xi = __ldcs(random + (size_t) randomIndex + slot);
-            else xi = (s.noisescale != 0) ? gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) a, step)
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+            else if (!haveXi) xi = (s.noisescale != 0) ? gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) a, step)
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
             Vec4<Mixed> delta;
             part1_update(v, delta, fx, fy, fz, xi.x, xi.y, xi.z, s);
             part2_update<PREC>(p, c, v, delta, s.invDt);
@@ -760,19 +798,27 @@ constv_fused_step_indexed_kernel(const __grid_constant__ SlabDev d, const float4
     };
 
     if (inRange) {
+        // What needs the atom indices only is done first, while the low slot's record is still in flight (the
+        // index loads were issued ahead of it): the zeroing of the image slots this thread owns and the Philox
+        // block of the low slot's atom (drawn for a massless atom too, and discarded).
+        if (a1 >= R) zeroSlot(i + R);
+        float4 xi0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool drawn = a0 < R && random == nullptr;
+        if (drawn && s.noisescale != 0) xi0 = gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) a0, step);
         if (a0 >= R) zeroSlot(i);
-        else updateReal(i, a0, v, p, c, fx, fy, fz);
+        else updateReal(i, a0, v, p, c, fx, fy, fz, drawn, xi0);
 #pragma unroll 1
         for (int cell = 1; cell < d.numCells; cell++) {
             const int slot = i + R * cell;
             const int a = cell == 1 ? a1 : d.atomIndex[slot];
             if (a >= R) {
-                zeroSlot(slot);
+                if (cell > 1) zeroSlot(slot);
             } else {  // a real atom in a high slot
                 Vec4<Real> c2{0, 0, 0, 0};
                 if (kSplit) c2 = load4x<true>(corrA, (size_t) slot);
                 updateReal(slot, a, load4x<true>(velm, (size_t) slot), load4x<true>(posq, (size_t) slot), c2,
-                           load_force(force + slot), load_force(force + P + slot), load_force(force + 2 * P + slot));
+                           load_force(force + slot), load_force(force + P + slot), load_force(force + 2 * P + slot),
+                           false, make_float4(0.f, 0.f, 0.f, 0.f));
             }
         }
     }

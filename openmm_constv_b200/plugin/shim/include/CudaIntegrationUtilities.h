@@ -19,6 +19,7 @@ public:
     // two-particle-average sites only (host round trip: the shim is test scaffolding)
     void computeVirtualSites();
     int virtualSiteCalls = 0;
+    int hasVirtualSites = -1;
     void initRandomNumberGenerator(unsigned int seed) { randomSeed = seed; }
     int prepareRandomNumbers(int numValues);
     double computeKineticEnergy(double timeShift);

@@ -204,9 +204,11 @@ int CudaIntegrationUtilities::prepareRandomNumbers(int numValues) { return 0; }
 void CudaIntegrationUtilities::computeVirtualSites() {
     virtualSiteCalls++;
     const int n = context.getNumAtoms(), P = context.getPaddedNumAtoms();
-    bool any = false;
-    for (int i = 0; i < n && !any; i++) any = system.isVirtualSite(i);
-    if (!any) return;
+    if (hasVirtualSites < 0) {  // scanned once: OpenMM builds its site lists at context creation
+        hasVirtualSites = 0;
+        for (int i = 0; i < n && !hasVirtualSites; i++) hasVirtualSites = system.isVirtualSite(i) ? 1 : 0;
+    }
+    if (!hasVirtualSites) return;
     const vector<int>& order = context.getAtomIndex();
     vector<int> slotOf(P);
     for (int s = 0; s < P; s++) slotOf[order[s]] = s;

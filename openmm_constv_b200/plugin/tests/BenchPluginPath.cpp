@@ -6,12 +6,17 @@
 //
 //   BenchPluginPath [--atoms N] [--steps S] [--precision single|mixed|double] [--reordered] [--sweep-mb M]
 //
-// Reported (one JSON line): the MARGINAL cost of execute() inside the stream of sweeps,
-//   us_per_step = (T[sweep + execute loop] - T[sweep-only loop]) / steps        (median of 5 passes each),
-// i.e. launch gap + ramp + transfer + drain of the step kernel, for two sweeps:
-//   flush   a 256 MB memset: nothing of the slab is left in the 126 MB L2 (the conservative case)
-//   forces  a device-to-device copy into the force buffer (24 B per atom), what the cheapest possible force
+// Reported (one JSON line), for three sweeps between two steps --
+//   forces  a device-to-device copy into the force buffer (24 B per atom): what the cheapest possible force
 //           kernel does; posq / velm may then still be L2 hits
+//   copy    a device-to-device copy of 128 MB onto another 128 MB: reads and writes more than the 126 MB L2
+//           holds, like the force evaluation of a large system; nothing of the slab survives in L2
+//   read    a kernel that only READS 256 MB: the L2 ends up full of clean lines of something else
+// -- two numbers per step:
+//   marginal   (T[sweep + execute loop] - T[sweep-only loop]) / steps, medians of 5 passes: launch gap, ramp,
+//              transfer and drain of the step kernel PLUS what the step costs its neighbour (the write-back of
+//              the step's 37 MB of dirty lines happens while the next sweep runs and slows it down)
+//   bracketed  CUDA events around each execute(): the step's own duration and launch gap
 // --reordered applies one slot permutation of the kind cu.reorderAtoms() produces (whole molecules trade
 // places inside windows of 1024 molecules) so that execute() addresses images through atomIndex /
 // invAtomOrder (constVLangevin.cu:142-158).
@@ -40,6 +45,7 @@ using namespace OpenMM;
 using std::vector;
 
 extern "C" void registerConstVCudaKernelFactories();
+extern "C" void benchSweepRead(const void* p, size_t bytes, unsigned int* sink, cudaStream_t stream);
 
 #define CU(x)                                                                              \
     do {                                                                                   \
@@ -120,6 +126,9 @@ int main(int argc, char** argv) {
         CU(cudaMemcpy(spareForce, force.data(), 24 * (size_t) P, cudaMemcpyHostToDevice));
         void* sweep = NULL;
         CU(cudaMalloc(&sweep, sweepMB << 20));
+        CU(cudaMemset(sweep, 0, sweepMB << 20));
+        unsigned int* sink = NULL;
+        CU(cudaMalloc(&sink, 4));
 
         // the kernel, made and initialised the way ConstVLangevinIntegrator::initialize does it
         Kernel kernel = platform.createKernel(IntegrateConstVLangevinStepKernel::Name(), context.getImpl());
@@ -152,11 +161,19 @@ int main(int argc, char** argv) {
         cudaEvent_t e0, e1;
         CU(cudaEventCreate(&e0));
         CU(cudaEventCreate(&e1));
+        // sweeps: 0 forces = D2D copy into the force buffer (24 B per atom); 1 copy = D2D copy of half the sweep buffer
+        // onto the other half (reads and writes > L2, like a force evaluation of a large system);
+        // 2 read = a kernel that only reads the sweep buffer
+        const size_t half = (sweepMB << 20) / 2;
+        auto sweepOp = [&](int mode) {
+            if (mode == 0) CU(cudaMemcpyAsync((void*) cu.getForce().getDevicePointer(), spareForce, 24 * (size_t) P, cudaMemcpyDeviceToDevice, stream));
+            else if (mode == 1) CU(cudaMemcpyAsync((char*) sweep + half, sweep, half, cudaMemcpyDeviceToDevice, stream));
+            else benchSweepRead(sweep, sweepMB << 20, sink, stream);
+        };
         auto pass = [&](int mode, bool withStep) {
             CU(cudaEventRecord(e0, stream));
             for (int i = 0; i < steps; i++) {
-                if (mode == 0) CU(cudaMemsetAsync(sweep, 0, sweepMB << 20, stream));
-                else CU(cudaMemcpyAsync((void*) cu.getForce().getDevicePointer(), spareForce, 24 * (size_t) P, cudaMemcpyDeviceToDevice, stream));
+                sweepOp(mode);
                 if (withStep) step.execute(context.getImpl(), integrator);
             }
             CU(cudaEventRecord(e1, stream));
@@ -165,8 +182,31 @@ int main(int argc, char** argv) {
             CU(cudaEventElapsedTime(&ms, e0, e1));
             return (double) ms * 1e3 / steps;
         };
-        double us[2], sweepUs[2];
-        for (int mode = 0; mode < 2; mode++) {
+        // the step alone between two events (its own duration + launch gap; what it costs its neighbours is not in it)
+        vector<cudaEvent_t> ev(2 * (size_t) steps);
+        for (auto& e : ev) CU(cudaEventCreate(&e));
+        auto bracketed = [&](int mode) {
+            for (int i = 0; i < steps; i++) {
+                sweepOp(mode);
+                CU(cudaEventRecord(ev[2 * i], stream));
+                step.execute(context.getImpl(), integrator);
+                CU(cudaEventRecord(ev[2 * i + 1], stream));
+            }
+            CU(cudaEventSynchronize(ev[2 * (size_t) steps - 1]));
+            vector<double> t;
+            for (int i = 0; i < steps; i++) {
+                float ms = 0;
+                CU(cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]));
+                t.push_back(ms * 1e3);
+            }
+            std::sort(t.begin(), t.end());
+            double sum = 0;
+            int n = 0;
+            for (int i = steps / 10; i < steps - steps / 10; i++, n++) sum += t[i];  // mean of the middle 80 %
+            return sum / n;
+        };
+        double us[3], sweepUs[3], alone[3];
+        for (int mode = 0; mode < 3; mode++) {
             vector<double> with, without;
             pass(mode, true);
             for (int r = 0; r < 5; r++) {
@@ -175,6 +215,7 @@ int main(int argc, char** argv) {
             }
             sweepUs[mode] = median(without);
             us[mode] = median(with) - sweepUs[mode];
+            alone[mode] = bracketed(mode);
         }
 
         // algorithmic bytes of one step (DESIGN.md "bytes per pair"), numCells = 2
@@ -184,18 +225,25 @@ int main(int argc, char** argv) {
         double bytes = (double) R * (velB + posB) + (double) massive * (24 + velB + posB) + (double) charged * (rb + posB) +
                        (double) R * (velB + 24);
         if (reordered) bytes += 8.0 * R + 4.0 * charged;  // atomIndex of both slots, invAtomOrder of the image
+        const char* names[3] = {"forces", "copy", "read"};
+        const char* what[3] = {"D2D copy into the force buffer (24 B/atom) between steps", "D2D copy of 128 MB onto 128 MB between steps",
+                               "a kernel reading 256 MB between steps"};
         std::printf("{\"path\": \"CudaIntegrateConstVLangevinStepKernel::execute via the kernel factory (OpenMM shim)\", "
                     "\"atoms\": %d, \"precision\": \"%s\", \"reordered_slots\": %s, \"steps\": %d, \"launches_per_step\": 1, "
-                    "\"algorithmic_bytes_per_step\": %.0f, "
-                    "\"flush\": {\"us_per_step\": %.3f, \"GBps\": %.1f, \"frac_8TBs\": %.4f, \"sweep\": \"%zu MB memset between steps, %.1f us\"}, "
-                    "\"forces\": {\"us_per_step\": %.3f, \"GBps\": %.1f, \"frac_8TBs\": %.4f, \"sweep\": \"D2D copy into the force buffer between steps, %.1f us\"}, "
-                    "\"statistic\": \"marginal cost: median of 5 (sweep+execute) passes minus median of 5 sweep-only passes\"}\n",
-                    atoms, precision.c_str(), reordered ? "true" : "false", steps, bytes,
-                    us[0], bytes / us[0] * 1e-3, bytes / us[0] * 1e-3 / 8000.0, sweepMB, sweepUs[0],
-                    us[1], bytes / us[1] * 1e-3, bytes / us[1] * 1e-3 / 8000.0, sweepUs[1]);
+                    "\"algorithmic_bytes_per_step\": %.0f, ",
+                    atoms, precision.c_str(), reordered ? "true" : "false", steps, bytes);
+        for (int mode = 0; mode < 3; mode++)
+            std::printf("\"%s\": {\"marginal_us\": %.3f, \"marginal_frac_8TBs\": %.4f, \"bracketed_us\": %.3f, \"bracketed_frac_8TBs\": %.4f, "
+                        "\"sweep\": \"%s, %.1f us\"}, ",
+                        names[mode], us[mode], bytes / us[mode] * 1e-3 / 8000.0, alone[mode], bytes / alone[mode] * 1e-3 / 8000.0, what[mode],
+                        sweepUs[mode]);
+        std::printf("\"statistic\": \"marginal = median of 5 (sweep+execute) passes minus median of 5 sweep-only passes, per step; "
+                    "bracketed = CUDA events around each execute(), mean of the middle 80 %% of the steps\"}\n");
+        for (auto& e : ev) cudaEventDestroy(e);
         kernel = Kernel();
         cudaFree(spareForce);
         cudaFree(sweep);
+        cudaFree(sink);
     } catch (const std::exception& e) {
         std::fprintf(stderr, "exception: %s\n", e.what());
         return 1;

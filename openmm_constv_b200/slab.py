@@ -281,6 +281,57 @@ def make_water_slab(num_real: int, precision: str = "single", num_cells: int = 2
     return s, np.ascontiguousarray(atoms), np.ascontiguousarray(params), (p1, p2, dist)
 
 
+def example_system(path: str, precision: str = "mixed", num_cells: int = 2):
+    """The reference's example workload, example/nacl_1m_spce (BASELINE.json configs[0-1]): 38 Na+, 38 Cl-,
+    2046 SPC/E waters and 1280 massless neutral wall carbons between two electrodes, from the fixture
+    tests/golden/nacl_1m_spce_system.npz (the real atoms as `forcefield.createSystem(topology,
+    constraints=AllBonds)` sees them; written by tests/golden/make_example_system.py from the PDB and spce.xml).
+
+    The image particles are added here exactly as the example's script adds them (nacl_constv.py:60-95): one
+    per real atom, appended after all real atoms, mass 0, charge -q, at (x, y, -z) -- a neutral atom's image at
+    (x, y, -z + 0.001 nm) so that it does not sit on its partner (:82-85).  Velocities start at zero (the
+    script never sets them); forces are left zero for the caller to inject.  Default precision is the
+    script's ('CudaPrecision': 'mixed', :150).
+
+    Returns ``(slab, cluster_atoms, cluster_params, constraints)`` like ``make_water_slab``."""
+    assert precision in PRECISIONS and num_cells == 2
+    d = np.load(path)
+    pos = d["pos_mA"].astype(np.float64) / 1.0e4  # thousandths of an Angstrom -> nm
+    mass, charge = d["mass"].astype(np.float64), d["charge"].astype(np.float64)
+    R = len(mass)
+    N, P = 2 * R, padded_atoms(2 * R)
+    real, mixed = REAL[precision], MIXED[precision]
+    zmax = float(d["zmax_nm"])
+    posq64 = np.zeros((P, 4), np.float64)
+    posq64[:R, :3], posq64[:R, 3] = pos, charge
+    posq64[R:N, 0], posq64[R:N, 1] = pos[:, 0], pos[:, 1]
+    posq64[R:N, 2] = np.where(charge != -charge, -pos[:, 2], -pos[:, 2] + 0.001)
+    posq64[R:N, 3] = -charge
+    posq = posq64.astype(real)
+    corr = None
+    if precision == "mixed":
+        corr = np.zeros((P, 4), real)
+        corr[:, :3] = (posq64[:, :3] - posq[:, :3].astype(np.float64)).astype(real)
+    velm = np.zeros((P, 4), mixed)
+    velm[:R, 3] = np.where(mass > 0, 1.0 / np.where(mass > 0, mass, 1.0), 0.0).astype(mixed)
+    masses = np.zeros(N, np.float64)
+    masses[:R] = mass
+    p1, p2, dist = d["constraint_p1"], d["constraint_p2"], d["constraint_distance"]
+    # the rigid molecules: apex = the atom with two bonds to the others (O), as constv_settle_find_clusters finds them
+    n_mol = len(p1) // 3
+    oxy = p1[:n_mol * 2:2]
+    assert np.array_equal(p1[1:n_mol * 2:2], oxy)
+    atoms = np.stack([oxy, p2[:n_mol * 2:2], p2[1:n_mol * 2:2]], axis=1).astype(np.int32)
+    assert np.array_equal(p1[2 * n_mol:], atoms[:, 1]) and np.array_equal(p2[2 * n_mol:], atoms[:, 2])
+    params = np.stack([dist[:n_mol * 2:2], dist[2 * n_mol:]], axis=1).astype(np.float32)
+    box = tuple(float(x) for x in d["box_nm"])
+    slab = Slab(precision, 2, R, N, P, zmax, box, posq, corr, velm, np.zeros((3, P), np.int64), masses, 0,
+                {"seed": 0, "n_ion": int(np.sum(np.abs(charge) == 1.0)), "n_water": 3 * n_mol,
+                 "n_wall": int(np.sum(mass == 0)), "n_molecules": n_mol, "temperature": 300.0,
+                 "source": "example/nacl_1m_spce"})
+    return slab, np.ascontiguousarray(atoms), np.ascontiguousarray(params), (p1.copy(), p2.copy(), dist.copy())
+
+
 def permute_slab(slab: Slab, perm) -> tuple:
     """A copy of ``slab`` whose slot ``k`` holds original atom ``perm[k]`` (what OpenMM's ``reorderAtoms``
     leaves behind), plus the padded ``atom_index`` array (padding slots stay in place)."""

@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""In-process A/B timing of kernel variants (experiments; not part of the product or of bench.py's line).
+
+Box-to-box and minute-to-minute differences on the shared B200 pool are as large as the effects being
+measured (the same binary: 10.8 vs 11.9 us per step in two sessions), so variants are built side by side in
+ONE process -- the environment knobs (CONSTV_FUSED_EARLY, CONSTV_FUSED_ZERO, CONSTV_FUSED_BLOCK,
+CONSTV_SETTLE_WS) are read when a slab is created -- and timed in alternation, several rounds; the table
+printed at the end is the median over rounds.
+
+    python scripts/ab_variants.py fused      # the unconstrained fused step, 1 and 2 chains
+    python scripts/ab_variants.py settle     # the rigid-water step: TMA pipeline vs LDG-staged kernel
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+which = sys.argv[1] if len(sys.argv) > 1 else "fused"
+atoms = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
+sys.argv = ["bench.py", "--atoms", str(atoms)]
+import bench  # noqa: E402
+
+args = bench.parse_args()
+env = bench.Env()
+peak, _ = bench.peaks()
+R = atoms // 2
+K, W, ROUNDS = 1500, 30, 4
+
+if which == "fused":
+    variants = [("early0_zero0", {"CONSTV_FUSED_EARLY": "0", "CONSTV_FUSED_ZERO": "0"}),
+                ("early1_zero0", {"CONSTV_FUSED_EARLY": "1", "CONSTV_FUSED_ZERO": "0"}),
+                ("early0_zero2", {"CONSTV_FUSED_EARLY": "0", "CONSTV_FUSED_ZERO": "2"}),
+                ("early1_zero2", {"CONSTV_FUSED_EARLY": "1", "CONSTV_FUSED_ZERO": "2"}),
+                ("early1_zero1", {"CONSTV_FUSED_EARLY": "1", "CONSTV_FUSED_ZERO": "1"})]
+    shard = env.slabmod.slab_tile(R, 1, 0, "single", seed=bench.SLAB_SEED)
+    kind, water = "langevin", None
+    chain_counts = (1, 2)
+else:
+    variants = [("tma_pipeline", {"CONSTV_SETTLE_WS": "1"}), ("ldg_staged", {"CONSTV_SETTLE_WS": "0"})]
+    shard, w_atoms, w_params, w_cons = env.slabmod.slab_tile(R, 1, 0, "single", seed=bench.SLAB_SEED, maker=env.slabmod.make_water_slab)
+    kind, water = "settle", (w_atoms, w_params, w_cons)
+    chain_counts = (1, 2)
+
+wls = []
+for name, knobs in variants:
+    os.environ.update(knobs)
+    wls.append((name, bench.Workload(env, args, shard, kind=kind, chains=1, water=water)))
+alg = wls[0][1].algorithmic_bytes()
+results = {}
+for rnd in range(ROUNDS):
+    for name, wl in wls:
+        for ch in chain_counts:
+            wl.set_chains(ch)
+            t = bench.time_steps(env, wl, K, W, repeats=7)
+            results.setdefault((name, wl.chains), []).append(1e3 * t["ms"] / K)
+for (name, ch), us in sorted(results.items()):
+    med = float(np.median(us))
+    print(json.dumps({"variant": name, "chains": ch, "us_per_step": round(med, 3), "rounds": [round(x, 3) for x in us],
+                      "GBps": round(alg / med * 1e-3, 1), "frac_measured_peak": round(alg / med * 1e-3 / peak, 4),
+                      "frac_8TBs": round(alg / med * 1e-3 / 8000.0, 4), "atoms": atoms}), flush=True)
