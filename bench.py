@@ -13,12 +13,14 @@ data-path collective (weak scaling); the only collective is the scalar kinetic-e
 once outside the timed region as a report, never per step.
 
 How the K steps are timed (the same at --steps 20 and at --steps 100000):
-  * every launch inside the timed region comes from a CUDA graph: whole regions of K steps when K is small,
-    else 120-step chunks plus one tail graph -- never an eager launch (``eager_launches_in_region`` = 0);
-  * after W warm-up steps and enough untimed regions to have replayed every graph once and to have kept the
-    GPU busy for >= 30 ms, the K-step region is run ``repeats`` (>= 9) times back to back, a CUDA event
-    between regions (recorded on the launching stream); ms_per_step = MEDIAN region time / K, min and max
-    reported; for N > 1 the MAX over ranks of each rank's median;
+  * every launch inside the timed region comes from a CUDA graph -- never an eager launch
+    (``eager_launches_in_region`` = 0).  Small K (the driver's --steps 20): ONE graph holds a train of K-step
+    regions with an event-record node between regions, so a region is exactly K steps between two events on the
+    launching stream and costs no graph relaunch.  Large K: 120-step chunk graphs plus one tail graph, stream
+    events between regions;
+  * after W warm-up steps and untimed regions that upload every graph and keep the GPU busy, the K-step region
+    is run ``repeats`` (>= 9) times back to back; ms_per_step = MEDIAN region time / K, min and max reported;
+    for N > 1 the MAX over ranks of each rank's median;
   * clocks and throttle reasons are sampled every 10 ms over the whole repeat loop (the number of repeats is
     raised until the loop lasts ~0.4 s);
   * L2: a 1M-atom slab is 56 MB < B200's 126 MB L2, so the steps rotate over ``replicas`` copies of the slab
@@ -581,6 +583,15 @@ def time_steps(env, wl, K, W, use_graph=True, repeats=0, target_s=0.4, sample_cl
             else:
                 g.replay()
 
+    lps = wl.launches_per_step
+    in_graph_error = None
+    if use_graph and K * lps <= 400:
+        try:
+            return time_steps_in_graph(env, wl, K, W, repeats, target_s, sample_clocks)
+        except Exception as exc:  # noqa: BLE001 -- e.g. a runtime without external events: stream events between graph launches
+            in_graph_error = str(exc)[:200]
+            torch.cuda.synchronize()
+
     with torch.cuda.stream(stream):
         wl.launch_steps(0, reps)  # first touch: refreshes image-charge snapshots outside capture
         stream.synchronize()
@@ -626,8 +637,67 @@ def time_steps(env, wl, K, W, use_graph=True, repeats=0, target_s=0.4, sample_cl
            "graph": (f"{len(graphs)} CUDA graphs ({K}-step regions" + (f" as {chunk}-step chunks + tail" if K > 2 * chunk else "") + "), PDL")
                     if use_graph else "eager, PDL",
            "clocks": clocks}
+    if in_graph_error:
+        out["graph"] += "; in-graph events unavailable: " + in_graph_error
     graphs.clear()
     return out
+
+
+def time_steps_in_graph(env, wl, K, W, repeats, target_s, sample_clocks):
+    """Short regions (K x launches per step <= 400 kernels, e.g. the driver's --steps 20): the timed regions AND the
+    event records between them are nodes of one CUDA graph -- [event][K steps][event][K steps] ... -- so that a region
+    boundary costs an event node, not the relaunch of a graph (measured: ~7 us per 20-step graph relaunch, 3 % of a
+    230 us region).  Events are created external=True (cudaEventRecordExternal), which is what makes an event recorded
+    by a graph node usable with elapsed_time.  The graph holds `per` + 1 regions; the first interval of every replay
+    (the GPU was idle before it) is discarded."""
+    torch, stream, capi = env.torch, env.stream, env.capi
+    lps = wl.launches_per_step
+    with torch.cuda.stream(stream):
+        wl.launch_steps(0, wl.replicas)  # first touch: refreshes image-charge snapshots outside capture
+        stream.synchronize()
+        warm = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(warm, stream=stream):
+            wl.launch_steps(0, W)
+        warm.replay()
+        stream.synchronize()
+        t0 = time.perf_counter()
+        warm.replay()
+        stream.synchronize()
+        est = max(2e-6, (time.perf_counter() - t0) / W) * K  # rough: includes the launch of a small graph
+        n_rep = repeats or int(min(400, max(9, np.ceil(target_s / est))))
+        per = int(max(2, min(n_rep, 8000 // (K * lps))))
+        replays = int(np.ceil(n_rep / per))
+        events = [torch.cuda.Event(enable_timing=True, external=True) for _ in range(per + 2)]
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            events[0].record(stream)
+            for r in range(per + 1):
+                wl.launch_steps(W + r * K, K)
+                events[r + 1].record(stream)
+        graph.replay()  # untimed: uploads the graph, warms clocks and caches
+        stream.synchronize()
+        env.barrier()
+        torch.cuda.synchronize()
+        sampler = None
+        if sample_clocks:
+            sampler = ClockSampler(env.local_rank)
+            sampler.start()
+        launches0 = capi.launch_count()
+        ms = []
+        for _ in range(replays):
+            graph.replay()
+            stream.synchronize()
+            ms.extend(events[r + 1].elapsed_time(events[r + 2]) for r in range(per))
+        eager = capi.launch_count() - launches0
+        clocks = sampler.stop() if sampler else None
+        env.barrier()
+    ms = np.asarray(ms)
+    med = float(np.median(ms))
+    return {"ms": env.max_over_ranks(med), "ms_min": env.min_over_ranks(float(ms.min())), "ms_max": env.max_over_ranks(float(ms.max())),
+            "ms_this_rank": med, "repeats": int(len(ms)), "untimed_regions": per + 1 + replays, "eager_launches": int(eager),
+            "graph": f"one CUDA graph of {per + 1} regions of {K} steps with an (external) event record node between regions, replayed "
+                     f"{replays}x; the first region of every replay is untimed; PDL",
+            "clocks": clocks}
 
 
 def rate_record(atoms_job, K, t, alg_bytes, launches_per_step, peak, kernel, extra=None):

@@ -87,7 +87,8 @@ struct constv_slab {
     // 11.64 us with two chains).  CONSTV_FUSED_EARLY=0 / CONSTV_FUSED_ZERO=0|2 restore the round-1 order.
     bool fusedEarly = true;
     int zeroWhen = 1;         // 0 with the dependent stores, 1 right behind the loads, 2 after the step-counter barrier
-    bool settleWs = true;     // rigid-water step: the warp-specialised TMA pipeline (CONSTV_SETTLE_WS=0: the LDG-staged kernel)
+    bool settleWs = false;    // rigid-water step: the warp-specialised TMA pipeline instead of the LDG-staged kernel (CONSTV_SETTLE_WS=1, or kernel variant 4)
+    int wsGroups = 4;         // its consumer groups in single precision (CONSTV_WS_GROUPS=3..5: experiments)
     int ctasPerSM = 0;   // 0 = one-shot grid (one tile per CTA); > 0 = persistent grid of that many CTAs per SM
     int variant = 0;     // 0 auto (= the one-shot LDG kernel, the faster one as measured), 1 LDG, 2 TMA ring
     int tmaBlock = 256;  // pairs per chunk = threads per CTA of the TMA kernel
@@ -423,6 +424,7 @@ int constv_create(const constv_config* config, constv_slab** out) {
     if (const char* e = std::getenv("CONSTV_FUSED_EARLY")) s->fusedEarly = std::atoi(e) != 0;
     if (const char* e = std::getenv("CONSTV_FUSED_ZERO")) s->zeroWhen = std::atoi(e);
     if (const char* e = std::getenv("CONSTV_SETTLE_WS")) s->settleWs = std::atoi(e) != 0;
+    if (const char* e = std::getenv("CONSTV_WS_GROUPS")) { const int g = std::atoi(e); if (g >= 3 && g <= 5) s->wsGroups = g; }
     DeviceGuard guard(config->device);
     if (guard.rc) { delete s; return guard.rc; }
     int dev = 0;
@@ -436,7 +438,7 @@ int constv_create(const constv_config* config, constv_slab** out) {
         return fail(CONSTV_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(err));
     };
     if ((e = cudaMalloc(&s->invAtomOrder, sizeof(int) * (size_t) P)) != cudaSuccess) return cleanup(e, "cudaMalloc(invAtomOrder)");
-    if ((e = cudaMalloc(&s->imageCharge, realSize(config->precision) * (size_t) (config->num_atoms - s->numReal))) != cudaSuccess) return cleanup(e, "cudaMalloc(imageCharge)");
+    if ((e = cudaMalloc(&s->imageCharge, realSize(config->precision) * ((size_t) (config->num_atoms - s->numReal) + 4))) != cudaSuccess) return cleanup(e, "cudaMalloc(imageCharge)");  // + 4: the TMA kernels read whole 4-slot windows
     if ((e = cudaMalloc(&s->counters, sizeof(DevCounters) * kMaxChains)) != cudaSuccess) return cleanup(e, "cudaMalloc(counters)");
     if ((e = cudaMemset(s->counters, 0, sizeof(DevCounters) * kMaxChains)) != cudaSuccess) return cleanup(e, "cudaMemset(counters)");
     s->chainLo[1] = s->numReal;
@@ -1036,7 +1038,7 @@ int constv_set_launch_shape(constv_slab* s, int32_t pairs_per_thread, int32_t ct
 
 int constv_set_kernel_variant(constv_slab* s, int32_t variant, int32_t block_size, int32_t stages, int32_t ctas_per_sm) {
     if (!s) return fail(CONSTV_ERR_INVALID, "null slab");
-    if (variant < 0 || variant > 3) return fail(CONSTV_ERR_INVALID, "variant must be 0 (auto), 1 (LDG / gather), 2 (TMA ring) or 3 (LDG-staged rigid-water / Drude kernels)");
+    if (variant < 0 || variant > 4) return fail(CONSTV_ERR_INVALID, "variant must be 0 (auto), 1 (LDG / gather), 2 (TMA ring), 3 (LDG-staged rigid-water kernel) or 4 (TMA-pipelined rigid-water kernel)");
     s->variant = variant;
     if (block_size) s->tmaBlock = block_size;
     if (stages) s->tmaStages = stages;

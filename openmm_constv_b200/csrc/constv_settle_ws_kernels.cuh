@@ -1,24 +1,29 @@
 // The constrained step (part 1 + SETTLE + part 2 + image rewrite + zeroing) as a
 // warp-specialised TMA pipeline for sm_100a: NO thread of the kernel issues a global load or store in the
 // common case -- every byte enters and leaves the SM as a bulk asynchronous copy (cp.async.bulk, SASS UBLKCP)
-// between global memory and a ring of stages in shared memory, tracked by mbarriers.
+// between global memory and two rings in shared memory, tracked by mbarriers.
 //
 // What it replaces: constv_settle_step_tiled_kernel (same tiles, same arithmetic, same bits), whose CTAs did
 // load -> barrier -> compute -> barrier -> store one after the other with 8 CTAs per SM to hide each phase
-// behind other CTAs' (profile r01: issue slots 46 % busy, 0.64 of the copy peak at 1M atoms, the barrier the
-// first stall reason).  Here ONE persistent CTA per SM runs three roles concurrently:
+// behind other CTAs'.  Here ONE persistent CTA per SM runs three roles concurrently:
 //
 //   producer (1 thread)    walks this CTA's tiles (round robin over the grid: the access front stays
 //                          sequential across the slab, walls -- the cheap tiles -- last), waits for a free
-//                          stage and issues the tile's 6-7 bulk loads: velm, posq, [posqCorrection], the three
-//                          force planes, the image charges (side array, or the image posq records themselves);
-//   consumers (NG groups   wait for the stage to fill, run part 1, the constraints and part 2 for "their" work
-//   of 128 threads)        item out of shared memory, write the new records back IN PLACE and the rewritten
-//                          image records next to them -- registers are never a staging area, so the solver
-//                          keeps its ~110 registers without costing occupancy;
+//                          INPUT stage and issues the tile's 6-7 bulk loads: velm, posq, [posqCorrection], the
+//                          three force planes, the image charges (side array);
+//   consumers (NG groups   wait for the stage to fill, pull "their" work item's records into registers and hand the
+//   of 128 threads)        stage straight back to the producer; run part 1, the constraints and part 2; then take
+//                          an OUTPUT buffer and leave the new records and the rewritten image records in it;
 //   storer (1 warp)        waits until a tile has been computed and issues its 6-10 bulk stores: own records,
 //                          image records, and the zeroing of the image velocities / forces straight out of a
-//                          block of zeros in shared memory; releases the stage once the copies have read it.
+//                          block of zeros in shared memory; releases the buffer once the copies have read it.
+//
+// Every group owns ONE input stage and ONE output buffer.  The input stage is busy for a load latency plus a few
+// hundred cycles and the output buffer for the time its copies take to leave -- neither for the ~9000 cycles the
+// group spends on the arithmetic of a tile, during which the next tile's records arrive and the last tile's copies
+// drain (first cut, profiles/r02_settle_ws_first_cut_ncu.txt: one ring of stages held from load to store starved
+// the consumers).  Private stages also make every mbarrier a strict two-party alternation, which the parity
+// protocol requires.
 //
 // A tile is up to 128 work items of one run of the slab = up to 384 consecutive slots.  Bulk copies need
 // 16-byte aligned addresses and sizes: the load window is widened to multiples of 4 slots (the few extra slots
@@ -28,7 +33,7 @@
 // per-slot store path in the storer warp.
 //
 // Requirements checked by the host (constv_settle_capi.inc: settleWsApplies): identity slot order, work items
-// in arithmetic runs, numCells == 2, in-kernel Philox noise.
+// in arithmetic runs, numCells == 2, in-kernel Philox noise, the image-charge side array.
 #pragma once
 
 #include "constv_settle_kernels.cuh"
@@ -39,27 +44,43 @@ constexpr int kWsItems = 128;                 // work items per tile = threads p
 constexpr int kWsSlots = 3 * kWsItems + 4;    // slots of a stage: a tile plus the alignment margin of the load window
 constexpr int kWsProducerWarps = 1, kWsStorerWarps = 1;
 
-template <int PREC, bool STAGE_IMAGE_POSQ> struct WsStage {
+template <int PREC> struct WsIn {             // what a tile reads
     using Real = typename Prec<PREC>::Real;
     using Mixed = typename Prec<PREC>::Mixed;
     static constexpr bool kSplit = Prec<PREC>::kSplitPos;
-    Vec4<Mixed> v[kWsSlots];                  // velm, rewritten in place
-    Vec4<Real> p[kWsSlots];                   // posq, rewritten in place
-    Vec4<Real> c[kSplit ? kWsSlots : 1];      // posqCorrection
-    long long f[3][kWsSlots];                 // force planes
+    Vec4<Mixed> v[kWsSlots];
+    Vec4<Real> p[kWsSlots];
+    Vec4<Real> c[kSplit ? kWsSlots : 1];
+    long long f[3][kWsSlots];
     Real q1[kWsSlots];                        // image charges (side array)
-    Vec4<Real> ip[kWsSlots];                  // image posq records: loaded when there is no side array (w is kept), stored
-    Vec4<Real> ic[kSplit ? kWsSlots : 1];     // image posqCorrection records, stored
+};
+
+template <int PREC> struct WsOut {            // what a tile writes (indexed by slot - base)
+    using Real = typename Prec<PREC>::Real;
+    using Mixed = typename Prec<PREC>::Mixed;
+    static constexpr bool kSplit = Prec<PREC>::kSplitPos;
+    Vec4<Mixed> v[3 * kWsItems];
+    Vec4<Real> p[3 * kWsItems];
+    Vec4<Real> c[kSplit ? 3 * kWsItems : 1];
+    Vec4<Real> ip[3 * kWsItems];              // image posq records
+    Vec4<Real> ic[kSplit ? 3 * kWsItems : 1]; // image posqCorrection records
     unsigned int counts[4];                   // [0] atoms that moved, [1] atoms that are charged (consumers -> storer)
 };
 
-template <int PREC> struct WsShape {
-    static constexpr int kGroups = PREC == PREC_SINGLE ? 4 : 2;
+// Consumer groups x ring depths.  The arithmetic of an item is one long dependent chain (~1400 instructions, 25
+// IEEE divisions / square roots) that wants ~100 registers: 4 groups (16 warps) in single precision, 2 otherwise.
+template <int PREC, int GROUPS> struct WsShape {
+    static constexpr int kGroups = GROUPS;
     static constexpr int kThreads = 32 * (kWsProducerWarps + kWsStorerWarps) + kWsItems * kGroups;
-    static constexpr size_t kStageBytes = (sizeof(WsStage<PREC, true>) + 127) / 128 * 128;
-    static constexpr size_t kZeroBytes = (kWsSlots * sizeof(Vec4<typename Prec<PREC>::Mixed>) + 127) / 128 * 128;
-    static constexpr int kStages = (int) ((227 * 1024 - kZeroBytes - 1024) / kStageBytes);
-    static constexpr size_t kSmemBytes = kZeroBytes + kStages * kStageBytes + 128;  // + alignment slack
+    static constexpr size_t kInBytes = (sizeof(WsIn<PREC>) + 127) / 128 * 128;
+    static constexpr size_t kOutBytes = (sizeof(WsOut<PREC>) + 127) / 128 * 128;
+    static constexpr size_t kZeroBytes = (3 * kWsItems * sizeof(Vec4<typename Prec<PREC>::Mixed>) + 127) / 128 * 128;
+    // one input stage and one output buffer PER GROUP: every mbarrier then has one party on each side in strict
+    // alternation, which is what the parity protocol needs (a waiter may be at most one phase ahead; on a ring shared
+    // by several groups nothing guarantees that).  One stage each way is also all a group needs: the next tile's
+    // records arrive and the last tile's copies leave while it spends ~9000 cycles on the current one.
+    static constexpr int kIn = GROUPS, kOut = GROUPS;
+    static constexpr size_t kSmemBytes = kZeroBytes + kIn * kInBytes + kOut * kOutBytes + 128;  // + alignment slack
 };
 
 __device__ __forceinline__ void mbar_arrive(unsigned int bar) {
@@ -98,22 +119,59 @@ __device__ __forceinline__ WsTile ws_tile_of(const SettleSegments& seg, const in
     return t;
 }
 
+// Part 1, the constraints and part 2 for one work item whose records are in registers (v, p, c, f); leaves the new
+// records in v / p / c and returns in `moved` which atoms moved.  Same operations as the LDG-staged kernel: same bits.
 template <int PREC>
-__global__ void __launch_bounds__(WsShape<PREC>::kThreads, 1)
+__device__ __forceinline__ void ws_compute_item(const SlabDev& d, const StepScalars<typename Prec<PREC>::Mixed>& sc, const WsTile& t,
+                                                const int j, const unsigned long long step,
+                                                Vec4<typename Prec<PREC>::Mixed> (&v)[3], Vec4<typename Prec<PREC>::Real> (&p)[3],
+                                                Vec4<typename Prec<PREC>::Real> (&c)[3], const long long (&f)[3][3], bool (&moved)[3]) {
+    using Mixed = typename Prec<PREC>::Mixed;
+    const bool three = t.per == 3;  // uniform over the tile
+    const unsigned long long a0 = d.globalAtomOffset + (unsigned long long) (t.base + t.per * j);
+    Vec4<Mixed> delta[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        if (k == 0 || three) {
+            delta[k] = Vec4<Mixed>{0, 0, 0, 0};
+            moved[k] = v[k].w != 0;
+            if (moved[k]) {
+                const float4 xi = (sc.noisescale != 0) ? gaussian4<false>(d.seed, a0 + k, step) : make_float4(0.f, 0.f, 0.f, 0.f);
+                part1_update(v[k], delta[k], f[k][0], f[k][1], f[k][2], xi.x, xi.y, xi.z, sc);
+            }
+        }
+    if (three) {
+        Mixed pos[3][3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) drude_pos_load<PREC>(p[k], c[k], pos[k]);
+        settle_molecule<Mixed>(pos[0], pos[1], pos[2], delta[0], delta[1], delta[2], rcp_rn(v[0].w), rcp_rn(v[1].w),
+                               rcp_rn(v[2].w), t.prm.x, t.prm.y);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        if ((k == 0 || three) && moved[k]) part2_update<PREC>(p[k], c[k], v[k], delta[k], sc.invDt);
+}
+
+template <int PREC, int GROUPS>
+__global__ void __launch_bounds__(WsShape<PREC, GROUPS>::kThreads, 1)
 constv_settle_step_ws_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ SettleSegments seg) {
     using Real = typename Prec<PREC>::Real;
     using Mixed = typename Prec<PREC>::Mixed;
-    using Shape = WsShape<PREC>;
-    using Stage = WsStage<PREC, true>;
+    using Shape = WsShape<PREC, GROUPS>;
+    using In = WsIn<PREC>;
+    using Out = WsOut<PREC>;
     constexpr bool kSplit = Prec<PREC>::kSplitPos;
-    constexpr int kStages = Shape::kStages, kGroups = Shape::kGroups;
-    static_assert(kStages >= kGroups + 1, "the ring must hold one tile per consumer group and one in flight");
+    constexpr int kIn = Shape::kIn, kOut = Shape::kOut, kGroups = Shape::kGroups;
+    static_assert(Shape::kSmemBytes <= 227 * 1024 - 1024, "stages of all groups must fit in shared memory");
 
     extern __shared__ unsigned char smemRawWs[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((size_t) smemRawWs + 127) & ~(size_t) 127);
     unsigned char* zeros = smem;
-    auto stageAt = [&](int s) -> Stage& { return *reinterpret_cast<Stage*>(smem + Shape::kZeroBytes + (size_t) s * Shape::kStageBytes); };
-    __shared__ __align__(8) unsigned long long fullBar[kStages], computedBar[kStages], emptyBar[kStages];
+    auto inAt = [&](int s) -> In& { return *reinterpret_cast<In*>(smem + Shape::kZeroBytes + (size_t) s * Shape::kInBytes); };
+    auto outAt = [&](int s) -> Out& {
+        return *reinterpret_cast<Out*>(smem + Shape::kZeroBytes + (size_t) kIn * Shape::kInBytes + (size_t) s * Shape::kOutBytes);
+    };
+    __shared__ __align__(8) unsigned long long fullIn[kIn], emptyIn[kIn], computedOut[kOut], emptyOut[kOut];
     __shared__ StepBox box;
 
     const int tid = (int) threadIdx.x;
@@ -126,12 +184,16 @@ constv_settle_step_ws_kernel(const __grid_constant__ SlabDev d, const __grid_con
     for (int i = tid; i < (int) (Shape::kZeroBytes / 16); i += Shape::kThreads) reinterpret_cast<uint4*>(zeros)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; s++) {
-            mbar_init(smem_u32(&fullBar[s]), 1);
-            mbar_init(smem_u32(&computedBar[s]), kWsItems);
-            mbar_init(smem_u32(&emptyBar[s]), 1);
-            stageAt(s).counts[0] = 0;
-            stageAt(s).counts[1] = 0;
+        for (int s = 0; s < kIn; s++) {
+            mbar_init(smem_u32(&fullIn[s]), 1);
+            mbar_init(smem_u32(&emptyIn[s]), kWsItems);
+        }
+#pragma unroll
+        for (int s = 0; s < kOut; s++) {
+            mbar_init(smem_u32(&computedOut[s]), kWsItems);
+            mbar_init(smem_u32(&emptyOut[s]), 1);
+            outAt(s).counts[0] = 0;
+            outAt(s).counts[1] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -146,7 +208,7 @@ constv_settle_step_ws_kernel(const __grid_constant__ SlabDev d, const __grid_con
     Real* __restrict__ corrA = static_cast<Real*>(d.corr);
     Mixed* __restrict__ velm = static_cast<Mixed*>(d.velm);
     long long* __restrict__ force = d.force;
-    const Real* __restrict__ charge = static_cast<const Real*>(d.imageCharge);  // may be null: image posq records are staged instead
+    const Real* __restrict__ charge = static_cast<const Real*>(d.imageCharge);  // the side array (the host checks it is there)
     const int firstTile = tileLo + (int) blockIdx.x, stride = (int) gridDim.x;
 
     if (warp == 0) {
@@ -154,16 +216,15 @@ constv_settle_step_ws_kernel(const __grid_constant__ SlabDev d, const __grid_con
         if (lane == 0) {
             int n = 0;
             for (int tile = firstTile; tile < tileHi; tile += stride, n++) {
-                const int s = n % kStages;
-                if (n >= kStages) mbar_wait(smem_u32(&emptyBar[s]), (unsigned int) ((n / kStages - 1) & 1));
+                const int s = n % kGroups, use = n / kGroups;  // the group's own stage, its use-th tile
+                if (use >= 1) mbar_wait(smem_u32(&emptyIn[s]), (unsigned int) ((use - 1) & 1));
                 const WsTile t = ws_tile_of(seg, tile);
                 const int lo = t.base & ~3;                                  // load window: multiples of 4 slots
                 const int hi = min((t.base + t.n + 3) & ~3, (int) P);
                 const unsigned int w = (unsigned int) (hi - lo);
-                Stage& st = stageAt(s);
-                const unsigned int bar = smem_u32(&fullBar[s]);
-                unsigned int bytes = w * (unsigned int) (sizeof(Vec4<Mixed>) + sizeof(Vec4<Real>) * (kSplit ? 2 : 1) + 24);
-                bytes += charge ? w * (unsigned int) sizeof(Real) : (unsigned int) t.n * (unsigned int) sizeof(Vec4<Real>);
+                In& st = inAt(s);
+                const unsigned int bar = smem_u32(&fullIn[s]);
+                const unsigned int bytes = w * (unsigned int) (sizeof(Vec4<Mixed>) + sizeof(Vec4<Real>) * (kSplit ? 2 : 1) + 24 + sizeof(Real));
                 mbar_expect_tx(bar, bytes);
                 bulk_g2s(smem_u32(st.v), velm + 4 * (size_t) lo, w * (unsigned int) sizeof(Vec4<Mixed>), bar);
                 bulk_g2s(smem_u32(st.p), posq + 4 * (size_t) lo, w * (unsigned int) sizeof(Vec4<Real>), bar);
@@ -171,19 +232,17 @@ constv_settle_step_ws_kernel(const __grid_constant__ SlabDev d, const __grid_con
                 bulk_g2s(smem_u32(st.f[0]), force + lo, w * 8u, bar);
                 bulk_g2s(smem_u32(st.f[1]), force + P + lo, w * 8u, bar);
                 bulk_g2s(smem_u32(st.f[2]), force + 2 * P + lo, w * 8u, bar);
-                if (charge) bulk_g2s(smem_u32(st.q1), charge + lo, w * (unsigned int) sizeof(Real), bar);
-                else bulk_g2s(smem_u32(st.ip + (t.base - lo)), posq + 4 * ((size_t) R + t.base), (unsigned int) t.n * (unsigned int) sizeof(Vec4<Real>), bar);
+                bulk_g2s(smem_u32(st.q1), charge + lo, w * (unsigned int) sizeof(Real), bar);
             }
         }
     } else if (warp == 1) {
         // ================================= storer =================================
         int n = 0;
         for (int tile = firstTile; tile < tileHi; tile += stride, n++) {
-            const int s = n % kStages;
-            mbar_wait(smem_u32(&computedBar[s]), (unsigned int) ((n / kStages) & 1));
+            const int s = n % kGroups, use = n / kGroups;
+            mbar_wait(smem_u32(&computedOut[s]), (unsigned int) (use & 1));
             const WsTile t = ws_tile_of(seg, tile);
-            const int off = t.base - (t.base & ~3);
-            Stage& st = stageAt(s);
+            Out& st = outAt(s);
             const unsigned int moved = st.counts[0], charged = st.counts[1];
             __syncwarp();
             if (lane == 0) {
@@ -191,13 +250,13 @@ constv_settle_step_ws_kernel(const __grid_constant__ SlabDev d, const __grid_con
                 st.counts[1] = 0;
                 const unsigned int nb = (unsigned int) t.n;
                 if (moved == nb) {  // every atom of the tile moved: its records go out as they lie
-                    bulk_s2g(velm + 4 * (size_t) t.base, smem_u32(st.v + off), nb * (unsigned int) sizeof(Vec4<Mixed>));
-                    bulk_s2g(posq + 4 * (size_t) t.base, smem_u32(st.p + off), nb * (unsigned int) sizeof(Vec4<Real>));
-                    if (kSplit) bulk_s2g(corrA + 4 * (size_t) t.base, smem_u32(st.c + off), nb * (unsigned int) sizeof(Vec4<Real>));
+                    bulk_s2g(velm + 4 * (size_t) t.base, smem_u32(st.v), nb * (unsigned int) sizeof(Vec4<Mixed>));
+                    bulk_s2g(posq + 4 * (size_t) t.base, smem_u32(st.p), nb * (unsigned int) sizeof(Vec4<Real>));
+                    if (kSplit) bulk_s2g(corrA + 4 * (size_t) t.base, smem_u32(st.c), nb * (unsigned int) sizeof(Vec4<Real>));
                 }
                 if (charged == nb) {  // every atom is charged: the whole range of image records is rewritten
-                    bulk_s2g(posq + 4 * ((size_t) R + t.base), smem_u32(st.ip + off), nb * (unsigned int) sizeof(Vec4<Real>));
-                    if (kSplit) bulk_s2g(corrA + 4 * ((size_t) R + t.base), smem_u32(st.ic + off), nb * (unsigned int) sizeof(Vec4<Real>));
+                    bulk_s2g(posq + 4 * ((size_t) R + t.base), smem_u32(st.ip), nb * (unsigned int) sizeof(Vec4<Real>));
+                    if (kSplit) bulk_s2g(corrA + 4 * ((size_t) R + t.base), smem_u32(st.ic), nb * (unsigned int) sizeof(Vec4<Real>));
                 }
                 if (d.zeroVelm) bulk_s2g(velm + 4 * ((size_t) R + t.base), smem_u32(zeros), nb * (unsigned int) sizeof(Vec4<Mixed>));
                 if (d.zeroForce) {
@@ -214,29 +273,28 @@ constv_settle_step_ws_kernel(const __grid_constant__ SlabDev d, const __grid_con
                 }
                 bulk_commit();
             }
-            // tiles that are not uniform: per-slot stores from the stage (generic proxy), one warp
+            // tiles that are not uniform: per-slot stores from the buffer (generic proxy), one warp
             if ((moved != 0 && moved != (unsigned int) t.n) || (charged != 0 && charged != (unsigned int) t.n)) {
                 for (int i = lane; i < t.n; i += 32) {
-                    const int idx = off + i;
-                    const Vec4<Mixed> v = st.v[idx];
-                    const Vec4<Real> p = st.p[idx];
+                    const Vec4<Mixed> v = st.v[i];
+                    const Vec4<Real> p = st.p[i];
                     if (moved != (unsigned int) t.n && v.w != 0) {
                         store4(velm, (size_t) (t.base + i), v);
                         store4(posq, (size_t) (t.base + i), p);
-                        if (kSplit) store4(corrA, (size_t) (t.base + i), st.c[idx]);
+                        if (kSplit) store4(corrA, (size_t) (t.base + i), st.c[i]);
                     }
                     if (charged != (unsigned int) t.n && p.w != -p.w) {
-                        store4(posq, (size_t) R + t.base + i, st.ip[idx]);
-                        if (kSplit) store4(corrA, (size_t) R + t.base + i, st.ic[idx]);
+                        store4(posq, (size_t) R + t.base + i, st.ip[i]);
+                        if (kSplit) store4(corrA, (size_t) R + t.base + i, st.ic[i]);
                     }
                 }
             }
             __syncwarp();
             if (lane == 0 && n >= 1) {
-                // a stage is free once the copies that read it have done so: release the PREVIOUS tile's stage and
+                // a buffer is free once the copies that read it have done so: release the PREVIOUS tile's buffer and
                 // leave this tile's copies in flight while the next tile is being waited for
                 bulk_wait_read<1>();
-                mbar_arrive(smem_u32(&emptyBar[(n - 1) % kStages]));
+                mbar_arrive(smem_u32(&emptyOut[(n - 1) % kGroups]));
             }
         }
         if (lane == 0) {
@@ -253,56 +311,54 @@ constv_settle_step_ws_kernel(const __grid_constant__ SlabDev d, const __grid_con
         int n = 0;
         for (int tile = firstTile; tile < tileHi; tile += stride, n++) {
             if (n % kGroups != group) continue;
-            const int s = n % kStages;
+            const int si = group, so = group, use = n / kGroups;
             const WsTile t = ws_tile_of(seg, tile);
             const int off = t.base - (t.base & ~3);
-            Stage& st = stageAt(s);
-            mbar_wait(smem_u32(&fullBar[s]), (unsigned int) ((n / kStages) & 1));
-            unsigned int nMoved = 0, nCharged = 0;
-            if (j < t.items) {
-                Vec4<Mixed> v[3], delta[3];
-                Vec4<Real> p[3], c[3];
-                bool moved[3] = {false, false, false};
+            const bool active = j < t.items;
+            const bool three = t.per == 3;  // uniform over the tile
+            Vec4<Mixed> v[3];
+            Vec4<Real> p[3], c[3];
+            long long f[3][3];
+            Real q1[3];
+            {   // records -> registers, and the input stage goes back to the producer
+                In& in = inAt(si);
+                mbar_wait(smem_u32(&fullIn[si]), (unsigned int) (use & 1));
+                if (active) {
+                    const int idx0 = off + t.per * j;
 #pragma unroll
-                for (int k = 0; k < 3; k++)
-                    if (k < t.per) {
-                        const int idx = off + t.per * j + k;
-                        v[k] = st.v[idx];
-                        p[k] = st.p[idx];
-                        c[k] = kSplit ? st.c[idx] : Vec4<Real>{0, 0, 0, 0};
-                        delta[k] = Vec4<Mixed>{0, 0, 0, 0};
-                        moved[k] = v[k].w != 0;
-                        if (moved[k]) {
-                            const int a = t.base + t.per * j + k;
-                            const float4 xi = (sc.noisescale != 0) ? gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) a, step)
-                                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-                            part1_update(v[k], delta[k], st.f[0][idx], st.f[1][idx], st.f[2][idx], xi.x, xi.y, xi.z, sc);
+                    for (int k = 0; k < 3; k++)
+                        if (k == 0 || three) {
+                            v[k] = in.v[idx0 + k];
+                            p[k] = in.p[idx0 + k];
+                            c[k] = kSplit ? in.c[idx0 + k] : Vec4<Real>{0, 0, 0, 0};
+                            f[k][0] = in.f[0][idx0 + k];
+                            f[k][1] = in.f[1][idx0 + k];
+                            f[k][2] = in.f[2][idx0 + k];
+                            q1[k] = in.q1[idx0 + k];
                         }
-                    }
-                if (t.per == 3) {
-                    Mixed pos[3][3];
-#pragma unroll
-                    for (int k = 0; k < 3; k++) drude_pos_load<PREC>(p[k], c[k], pos[k]);
-                    settle_molecule<Mixed>(pos[0], pos[1], pos[2], delta[0], delta[1], delta[2], rcp_rn(v[0].w), rcp_rn(v[1].w),
-                                           rcp_rn(v[2].w), t.prm.x, t.prm.y);
                 }
+                mbar_arrive(smem_u32(&emptyIn[si]));
+            }
+            bool moved[3] = {false, false, false};
+            if (active) ws_compute_item<PREC>(d, sc, t, j, step, v, p, c, f, moved);
+            // results -> an output buffer (free once the copies of the tile that used it before have read it)
+            Out& out = outAt(so);
+            if (use >= 1) mbar_wait(smem_u32(&emptyOut[so]), (unsigned int) ((use - 1) & 1));
+            unsigned int nMoved = 0, nCharged = 0;
+            if (active) {
+                const int o0 = t.per * j;
 #pragma unroll
                 for (int k = 0; k < 3; k++)
-                    if (k < t.per) {
-                        const int idx = off + t.per * j + k;
-                        if (moved[k]) {
-                            part2_update<PREC>(p[k], c[k], v[k], delta[k], sc.invDt);
-                            st.v[idx] = v[k];
-                            st.p[idx] = p[k];
-                            if (kSplit) st.c[idx] = c[k];
-                            nMoved++;
-                        }
+                    if (k == 0 || three) {
+                        out.v[o0 + k] = v[k];
+                        out.p[o0 + k] = p[k];
+                        if (kSplit) out.c[o0 + k] = c[k];
+                        nMoved += moved[k] ? 1u : 0u;
                         if (p[k].w != -p[k].w) {  // the image rewrite (Langevin.cu:143: neutral atoms are skipped)
-                            const Real q1 = charge ? st.q1[idx] : st.ip[idx].w;
                             ImageCursor<PREC> cur(p[k], c[k]);
                             cur.advance(1, sc.zshift);
-                            st.ip[idx] = cur.posq(q1);
-                            if (kSplit) st.ic[idx] = cur.corr();
+                            out.ip[o0 + k] = cur.posq(q1[k]);
+                            if (kSplit) out.ic[o0 + k] = cur.corr();
                             nCharged++;
                         }
                     }
@@ -310,11 +366,11 @@ constv_settle_step_ws_kernel(const __grid_constant__ SlabDev d, const __grid_con
             nMoved = __reduce_add_sync(0xffffffffu, nMoved);
             nCharged = __reduce_add_sync(0xffffffffu, nCharged);
             if (lane == 0) {
-                if (nMoved) atomicAdd(&st.counts[0], nMoved);
-                if (nCharged) atomicAdd(&st.counts[1], nCharged);
+                if (nMoved) atomicAdd(&out.counts[0], nMoved);
+                if (nCharged) atomicAdd(&out.counts[1], nCharged);
             }
-            fence_proxy_async_smem();  // this thread's writes to the stage, before the storer's bulk copies read them
-            mbar_arrive(smem_u32(&computedBar[s]));
+            fence_proxy_async_smem();  // this thread's writes to the buffer, before the storer's bulk copies read them
+            mbar_arrive(smem_u32(&computedOut[so]));
         }
     }
 }

@@ -46,6 +46,37 @@ def _raise_openmm(err: ConstVError):
     raise err
 
 
+class _ConstraintList:
+    """(particle1, particle2, distance) triples held as arrays; behaves like the list of tuples it replaces."""
+
+    def __init__(self, before, p1, p2, dist):
+        if isinstance(before, _ConstraintList):
+            p1, p2, dist = np.concatenate([before.p1, p1]), np.concatenate([before.p2, p2]), np.concatenate([before.dist, dist])
+        elif len(before):
+            b = list(before)
+            p1 = np.concatenate([np.asarray([x[0] for x in b], np.int32), p1])
+            p2 = np.concatenate([np.asarray([x[1] for x in b], np.int32), p2])
+            dist = np.concatenate([np.asarray([x[2] for x in b], np.float64), dist])
+        self.p1, self.p2, self.dist = p1, p2, dist
+
+    def __len__(self):
+        return len(self.p1)
+
+    def __getitem__(self, i):
+        return (int(self.p1[i]), int(self.p2[i]), float(self.dist[i]))
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def append(self, item):
+        self.p1 = np.append(self.p1, np.int32(item[0]))
+        self.p2 = np.append(self.p2, np.int32(item[1]))
+        self.dist = np.append(self.dist, np.float64(item[2]))
+
+    def arrays(self):
+        return self.p1, self.p2, self.dist
+
+
 class SlabSystem:
     """The slice of OpenMM::System the integrator reads: particle masses and the periodic box
     (CudaConstVKernels.cpp:79-89)."""
@@ -61,7 +92,14 @@ class SlabSystem:
         return len(self._constraints) - 1
 
     def addConstraints(self, particle1, particle2, distance) -> None:
-        self._constraints.extend((int(a), int(b), float(d)) for a, b, d in zip(particle1, particle2, distance))
+        """Many constraints at once (arrays).  A million-constraint water slab is listed in milliseconds instead of
+        through a Python loop; getConstraintParameters(i) answers the same either way."""
+        p1 = np.ascontiguousarray(particle1, np.int32).reshape(-1)
+        p2 = np.ascontiguousarray(particle2, np.int32).reshape(-1)
+        d = np.ascontiguousarray(distance, np.float64).reshape(-1)
+        if not (len(p1) == len(p2) == len(d)):
+            raise ValueError("addConstraints: arrays of different lengths")
+        self._constraints = _ConstraintList(self._constraints, p1, p2, d)
 
     def getNumConstraints(self) -> int:
         return len(self._constraints)
@@ -257,10 +295,14 @@ class IntegrateConstVLangevinStepKernel:
         nc = system.getNumConstraints() if hasattr(system, "getNumConstraints") else 0
         if nc == 0:
             return
-        cons = [system.getConstraintParameters(i) for i in range(nc)]
-        p1 = np.ascontiguousarray([c[0] for c in cons], np.int32)
-        p2 = np.ascontiguousarray([c[1] for c in cons], np.int32)
-        dist = np.ascontiguousarray([c[2] for c in cons], np.float64)
+        held = getattr(system, "_constraints", None)
+        if isinstance(held, _ConstraintList):
+            p1, p2, dist = (np.ascontiguousarray(a) for a in held.arrays())
+        else:
+            cons = [system.getConstraintParameters(i) for i in range(nc)]
+            p1 = np.ascontiguousarray([c[0] for c in cons], np.int32)
+            p2 = np.ascontiguousarray([c[1] for c in cons], np.int32)
+            dist = np.ascontiguousarray([c[2] for c in cons], np.float64)
         atoms = np.zeros((max(nc // 3, 1), 3), np.int32)
         params = np.zeros((max(nc // 3, 1), 2), np.float32)
         found, other = C.c_int32(0), C.c_int32(0)

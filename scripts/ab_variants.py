@@ -24,6 +24,7 @@ sys.argv = ["bench.py", "--atoms", str(atoms)]
 import bench  # noqa: E402
 
 args = bench.parse_args()
+args.replicas = 3 if atoms > 1_000_000 else 0
 env = bench.Env()
 peak, _ = bench.peaks()
 R = atoms // 2
@@ -39,13 +40,17 @@ if which == "fused":
     kind, water = "langevin", None
     chain_counts = (1, 2)
 else:
-    variants = [("tma_pipeline", {"CONSTV_SETTLE_WS": "1"}), ("ldg_staged", {"CONSTV_SETTLE_WS": "0"})]
+    variants = [("ldg_staged", {"CONSTV_SETTLE_WS": "0"})]
+    for g in (3, 4, 5):
+        variants.append((f"tma_g{g}", {"CONSTV_SETTLE_WS": "1", "CONSTV_WS_GROUPS": str(g)}))
     shard, w_atoms, w_params, w_cons = env.slabmod.slab_tile(R, 1, 0, "single", seed=bench.SLAB_SEED, maker=env.slabmod.make_water_slab)
     kind, water = "settle", (w_atoms, w_params, w_cons)
-    chain_counts = (1, 2)
+    chain_counts = (1,)
+    ROUNDS = 3
 
 wls = []
 for name, knobs in variants:
+    os.environ.pop("CONSTV_SETTLE_WS", None)
     os.environ.update(knobs)
     wls.append((name, bench.Workload(env, args, shard, kind=kind, chains=1, water=water)))
 alg = wls[0][1].algorithmic_bytes()

@@ -1,8 +1,8 @@
 """The rigid-water step as a warp-specialised TMA pipeline (csrc/constv_settle_ws_kernels.cuh: bulk asynchronous
 copies in and out of a shared-memory ring, producer / consumer groups / storer): same bits as the CPU oracle and
-as the LDG-staged kernel it replaces (kernel variant 3), for
+as the LDG-staged kernel (kernel variant 3; the pipeline is variant 4 and is not the default: it is slower), for
 
-  * every precision, with the image-charge side array and without it (the image posq records are staged instead),
+  * every precision, with the image-charge side array (without it the library falls back to the LDG-staged kernel),
   * runs that start on every alignment of the 4-slot load window and the 2-element force-plane window
     (1..9 ions before the water, odd and even numbers of real atoms), tiny slabs, several tiles per CTA,
   * tiles that are NOT uniformly massive / charged (massless or neutral atoms inside the ion run): the per-slot
@@ -33,7 +33,10 @@ def gpu():
     return integrator
 
 
-def make_context(gpu, s, cons, seed=77, flags=None, variant=0):
+WS = 4  # constv_set_kernel_variant: the TMA-pipelined rigid-water kernel (3 = the LDG-staged one, which 0 = auto picks)
+
+
+def make_context(gpu, s, cons, seed=77, flags=None, variant=WS):
     from openmm_constv_b200 import _capi
     sysm = gpu.SlabSystem()
     sysm.addParticles(s.masses)
@@ -95,12 +98,16 @@ def run_against_oracle(gpu, oracle, s0, atoms, params, cons, nsteps=3, flags=Non
 
 @pytest.mark.parametrize("precision", slabmod.PRECISIONS)
 @pytest.mark.parametrize("side_array", [False, True])
-@pytest.mark.parametrize("num_real", [7, 37, 6007, 60001])
+@pytest.mark.parametrize("num_real", [7, 37, 6007, 60001, 400003])
 def test_ws_step_bit_exact(gpu, oracle, precision, side_array, num_real):
+    """side_array False: the pipeline needs the image-charge side array, so the library falls back to the LDG-staged
+    kernel -- same bits either way.  400003 real atoms: every CTA walks several tiles (the stages are reused)."""
     from openmm_constv_b200 import _capi
+    if num_real > 100000 and precision != "single":
+        pytest.skip("the large case runs in single precision only")
     s0, atoms, params, cons = slabmod.make_water_slab(num_real, precision, seed=41)
     flags = _capi.FLAGS_DEFAULT | (_capi.FLAG_CACHE_IMAGE_CHARGE if side_array else 0)
-    run_against_oracle(gpu, oracle, s0, atoms, params, cons, flags=flags)
+    run_against_oracle(gpu, oracle, s0, atoms, params, cons, flags=flags, nsteps=3 if num_real < 100000 else 2)
 
 
 @pytest.mark.parametrize("n_ion", [1, 2, 3, 4, 5, 6, 7, 8, 9])
@@ -138,9 +145,10 @@ def test_ws_tiles_that_are_not_uniform(gpu, oracle, precision):
 
 
 def test_ws_without_image_zeroing(gpu, oracle):
-    """flags = 0: the reference's behaviour (no zeroing kernel exists there): image velm / forces are left alone."""
+    """No zeroing flags: the reference's behaviour (no zeroing kernel exists there): image velm / forces are left alone."""
+    from openmm_constv_b200 import _capi
     s0, atoms, params, cons = slabmod.make_water_slab(5003, "single", seed=44)
-    got = run_against_oracle(gpu, oracle, s0, atoms, params, cons, flags=0, zero=False)
+    got = run_against_oracle(gpu, oracle, s0, atoms, params, cons, flags=_capi.FLAG_CACHE_IMAGE_CHARGE, zero=False)
     assert np.any(got.force[:, s0.num_real:s0.num_atoms] != 0)
 
 
@@ -151,7 +159,7 @@ def test_ws_equals_the_ldg_staged_kernel(gpu, precision):
     from openmm_constv_b200 import _capi
     s0, atoms, params, cons = slabmod.make_water_slab(50021, precision, seed=45)
     out = []
-    for variant in (0, 3):
+    for variant in (WS, 3):
         ctx, it = make_context(gpu, s0, cons, seed=9, variant=variant, flags=_capi.FLAGS_DEFAULT | _capi.FLAG_CACHE_IMAGE_CHARGE)
         n0 = _capi.launch_count()
         it.step(6)
