@@ -88,6 +88,7 @@ struct constv_slab {
     bool fusedEarly = true;
     int zeroWhen = 1;         // 0 with the dependent stores, 1 right behind the loads, 2 after the step-counter barrier
     bool settleWs = false;    // rigid-water step: the warp-specialised TMA pipeline instead of the LDG-staged kernel (CONSTV_SETTLE_WS=1, or kernel variant 4)
+    bool settleEarly = true;  // LDG-staged rigid-water kernel: cp.async stage-in with the Philox draws made while the copies fly (CONSTV_SETTLE_EARLY=0)
     int wsGroups = 4;         // its consumer groups in single precision (CONSTV_WS_GROUPS=3..5: experiments)
     int ctasPerSM = 0;   // 0 = one-shot grid (one tile per CTA); > 0 = persistent grid of that many CTAs per SM
     int variant = 0;     // 0 auto (= the one-shot LDG kernel, the faster one as measured), 1 LDG, 2 TMA ring
@@ -424,6 +425,7 @@ int constv_create(const constv_config* config, constv_slab** out) {
     if (const char* e = std::getenv("CONSTV_FUSED_EARLY")) s->fusedEarly = std::atoi(e) != 0;
     if (const char* e = std::getenv("CONSTV_FUSED_ZERO")) s->zeroWhen = std::atoi(e);
     if (const char* e = std::getenv("CONSTV_SETTLE_WS")) s->settleWs = std::atoi(e) != 0;
+    if (const char* e = std::getenv("CONSTV_SETTLE_EARLY")) s->settleEarly = std::atoi(e) != 0;
     if (const char* e = std::getenv("CONSTV_WS_GROUPS")) { const int g = std::atoi(e); if (g >= 3 && g <= 5) s->wsGroups = g; }
     DeviceGuard guard(config->device);
     if (guard.rc) { delete s; return guard.rc; }

@@ -334,6 +334,19 @@ constv_settle_step_kernel(const __grid_constant__ SlabDev d, const __grid_consta
 // shared memory; after a barrier thread j computes item j from stage entries per*j + k (stride 3: free of
 // bank conflicts), writes the new velocity and position back, and after a second barrier every thread
 // emits "its" slots again: own record, rewritten images, zeroed images, all coalesced.
+// Ampere-style asynchronous copies global -> shared (SASS LDGSTS): no staging registers, and the thread goes on
+// to other work -- here the Philox draws of its work item -- while the records are in flight.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <int PREC, int BLOCK, bool INDEXED> struct SettleStage {
     using Real = typename Prec<PREC>::Real;
     using Mixed = typename Prec<PREC>::Mixed;
@@ -493,10 +506,14 @@ __device__ __forceinline__ void settle_tiled_tile(const SlabDev& d, const Settle
 
 // The single-slab kernel keeps its own copy of the tile body (below) rather than calling settle_tiled_tile: the
 // call, though inlined, cost a spill under the 64-register cap and 8 % of the step.
-template <int PREC, int BLOCK, bool INDEXED, bool STREAM>
-__global__ void __launch_bounds__(BLOCK, INDEXED ? 0 : (PREC == PREC_SINGLE ? 8 : 4))  // 64 registers, no spills: 8 CTAs per SM
+// EARLY (identity order, Philox noise): the stage is filled with asynchronous copies (cp.async) and, while they are in
+// flight, every thread reads the step counter and draws the Philox blocks of its work item's atoms (for massless atoms
+// too; discarded) -- ~390 of a molecule's ~1400 instructions leave the dependent chain that follows the barrier.
+template <int PREC, int BLOCK, bool INDEXED, bool STREAM, bool EARLY = false>
+__global__ void __launch_bounds__(BLOCK, INDEXED ? 0 : (PREC == PREC_SINGLE ? 8 : 4))  // 64 registers: 8 CTAs per SM
 constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ SettleSegments seg,
                                 const float4* __restrict__ random, const unsigned int randomIndex) {
+    static_assert(!(EARLY && INDEXED), "the early draw needs the atom index before the stage is filled");
     using Real = typename Prec<PREC>::Real;
     using Mixed = typename Prec<PREC>::Mixed;
     constexpr bool kSplit = Prec<PREC>::kSplitPos;
@@ -557,19 +574,49 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
         const float2 prm = seg.params[q];
 
         // stage in: coalesced
+        float4 xiEarly[3];
+        xiEarly[0] = xiEarly[1] = xiEarly[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (EARLY) {
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
-            const int idx = j + i * BLOCK;
-            if (idx < slotsInTile) {
-                const size_t slot = (size_t) (base + idx);
-                st.v[idx] = load4x<STREAM>(velm, slot);
-                st.p[idx] = load4x<STREAM>(posq, slot);
-                if (kSplit) st.c[idx] = load4x<STREAM>(corrA, slot);
-                st.f[0][idx] = load_force(force + slot);
-                st.f[1][idx] = load_force(force + P + slot);
-                st.f[2][idx] = load_force(force + 2 * P + slot);
-                if (INDEXED) st.orig[idx] = d.atomIndex[slot];
-                else st.q1[idx] = qbase[qstride * slot];
+            for (int i = 0; i < 3; i++) {
+                const int idx = j + i * BLOCK;
+                if (idx < slotsInTile) {
+                    const size_t slot = (size_t) (base + idx);
+                    if (sizeof(Vec4<Mixed>) == 16) cp_async16(&st.v[idx], velm + 4 * slot);
+                    else { cp_async16(&st.v[idx], velm + 4 * slot); cp_async16(reinterpret_cast<char*>(&st.v[idx]) + 16, velm + 4 * slot + 2); }
+                    if (sizeof(Vec4<Real>) == 16) cp_async16(&st.p[idx], posq + 4 * slot);
+                    else { cp_async16(&st.p[idx], posq + 4 * slot); cp_async16(reinterpret_cast<char*>(&st.p[idx]) + 16, posq + 4 * slot + 2); }
+                    if (kSplit) cp_async16(&st.c[idx], corrA + 4 * slot);
+                    cp_async8(&st.f[0][idx], force + slot);
+                    cp_async8(&st.f[1][idx], force + P + slot);
+                    cp_async8(&st.f[2][idx], force + 2 * P + slot);
+                    if (sizeof(Real) == 4) cp_async4(&st.q1[idx], qbase + qstride * slot);
+                    else cp_async8(&st.q1[idx], qbase + qstride * slot);
+                }
+            }
+            // while the copies fly: the step counter (every thread reads it; the ticket below is taken after) and the draws
+            const unsigned long long stepEarly = __ldcg(&d.counters->step);
+            if (j < items && s.noisescale != 0) {
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    if (k < per) xiEarly[k] = gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) (base + per * j + k), stepEarly);
+            }
+            cp_async_wait_all();
+        } else {
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const int idx = j + i * BLOCK;
+                if (idx < slotsInTile) {
+                    const size_t slot = (size_t) (base + idx);
+                    st.v[idx] = load4x<STREAM>(velm, slot);
+                    st.p[idx] = load4x<STREAM>(posq, slot);
+                    if (kSplit) st.c[idx] = load4x<STREAM>(corrA, slot);
+                    st.f[0][idx] = load_force(force + slot);
+                    st.f[1][idx] = load_force(force + P + slot);
+                    st.f[2][idx] = load_force(force + 2 * P + slot);
+                    if (INDEXED) st.orig[idx] = d.atomIndex[slot];
+                    else st.q1[idx] = qbase[qstride * slot];
+                }
             }
         }
         publish_step(box, d.counters);
@@ -594,7 +641,8 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
                     if (moved[k]) {
                         float4 xi;
                         const int a = INDEXED ? st.orig[idx] : base + idx;
-                        if (random != nullptr) xi = __ldcs(random + (size_t) randomIndex + base + idx);
+                        if (EARLY) xi = xiEarly[k];  // drawn before the barrier, from the same (seed; atom, step)
+                        else if (random != nullptr) xi = __ldcs(random + (size_t) randomIndex + base + idx);
                         else xi = (s.noisescale != 0) ? gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) a, step)
                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
                         part1_update(v[k], delta[k], st.f[0][idx], st.f[1][idx], st.f[2][idx], xi.x, xi.y, xi.z, s);

@@ -40,12 +40,12 @@ if which == "fused":
     kind, water = "langevin", None
     chain_counts = (1, 2)
 else:
-    variants = [("ldg_staged", {"CONSTV_SETTLE_WS": "0"})]
-    for g in (3, 4, 5):
-        variants.append((f"tma_g{g}", {"CONSTV_SETTLE_WS": "1", "CONSTV_WS_GROUPS": str(g)}))
+    variants = [("ldg_staged_round1_order", {"CONSTV_SETTLE_WS": "0", "CONSTV_SETTLE_EARLY": "0"}),
+                ("ldg_staged_cp_async_early_philox", {"CONSTV_SETTLE_WS": "0", "CONSTV_SETTLE_EARLY": "1"}),
+                ("tma_pipeline_g3", {"CONSTV_SETTLE_WS": "1", "CONSTV_WS_GROUPS": "3"})]
     shard, w_atoms, w_params, w_cons = env.slabmod.slab_tile(R, 1, 0, "single", seed=bench.SLAB_SEED, maker=env.slabmod.make_water_slab)
     kind, water = "settle", (w_atoms, w_params, w_cons)
-    chain_counts = (1,)
+    chain_counts = (1, 2)
     ROUNDS = 3
 
 wls = []
