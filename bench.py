@@ -412,6 +412,7 @@ class Workload:
         torch, lib, capi, hostapi = env.torch, env.lib, env.capi, env.hostapi
         self.env, self.args, self.shard, self.kind, self.M = env, args, shard, kind, M
         self.water, self.drude = water, drude
+        self.reordered = reorder_perm is not None
         precision = precision or shard.precision
         rec_bytes = shard.posq.nbytes + shard.velm.nbytes + shard.force.nbytes + (shard.corr.nbytes if shard.corr is not None else 0)
         self.rec_bytes = rec_bytes
@@ -532,8 +533,12 @@ class Workload:
         sm = self.env.slabmod
         water, drude = self.water, self.drude
         gather = water is not None and self.args.variant == 1  # only the gather kernel reads the item / molecule lists
-        return self.M * sm.algorithmic_bytes_per_step(self.shard, rigid_molecules=len(water[0]) if gather else 0,
-                                                      drude=drude is not None, drude_pairs=len(drude[1]) if drude else 0)
+        total = self.M * sm.algorithmic_bytes_per_step(self.shard, rigid_molecules=len(water[0]) if gather else 0,
+                                                       drude=drude is not None, drude_pairs=len(drude[1]) if drude else 0)
+        if self.reordered:  # atomIndex of the two slots a thread owns (8 B per real atom), invAtomOrder of each rewritten image (4 B)
+            c = self.shard.pair_classes()
+            total += 8 * self.shard.num_real + 4 * (c["massive_charged"] + c["massless_charged"]) * (self.shard.num_cells - 1)
+        return total
 
     def reload(self):
         for ctx, _ in self.ctxs:
@@ -903,8 +908,8 @@ def run_plugin_path(args, atoms):
     if not os.path.exists(exe):
         return {"unavailable": "plugin/bin/BenchPluginPath has not been built"}
     out = {"what": "us per CudaIntegrateConstVLangevinStepKernel::execute (one launch per step, no graph), a sweep between two steps: "
-                   "forces = D2D copy into the force buffer (24 B/atom), copy = D2D copy 128 MB -> 128 MB, read = a kernel reading "
-                   "256 MB; bracketed = events around execute(), marginal = loop time with minus without the step"}
+                   "forces = a kernel copying into the force buffer (24 B/atom), copy = a kernel copying 128 MB -> 128 MB, read = a "
+                   "kernel reading 256 MB; bracketed = events around execute(), marginal = loop time with minus without the step"}
     for mode in ("identity", "reordered"):
         cmd = [exe, "--atoms", str(atoms), "--steps", "300", "--precision", args.precision] + (["--reordered"] if mode == "reordered" else [])
         try:
@@ -1223,6 +1228,8 @@ def main():
             "eager_launches_in_region": int(t["eager_launches"]),
             "clocks": t["clocks"],
             "kinetic_energy_kj_mol": ke_total, "temperature_K": temperature,
+            "parity_note": ("the constraint solver (SETTLE) is OpenMM's, absent here: restated from the published algorithm, parity "
+                            "UNPINNED against OpenMM (DESIGN.md 5); kernel == oracle bit for bit") if water else None,
             "also": also,
         }
         print(json.dumps(line), flush=True)

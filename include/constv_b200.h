@@ -380,7 +380,10 @@ CONSTV_API int constv_set_launch_shape(constv_slab* slab, int32_t pairs_per_thre
 /* Which fused kernel constv_step_fused launches: 0 = automatic (currently the plain-load one-shot
  * kernel, which measured faster than the TMA ring on B200), 1 = the plain-load kernel, 2 = the
  * TMA-pipelined kernel (error unless the slab is eligible: identity order, Philox noise,
- * CONSTV_FLAG_CACHE_IMAGE_CHARGE, even P).
+ * CONSTV_FLAG_CACHE_IMAGE_CHARGE, even P).  For the rigid-molecule step (constv_step_fused_settle*): 0 = automatic
+ * (the LDG-staged kernel), 1 = the gather kernel, 3 = the LDG-staged kernel, 4 = the warp-specialised TMA pipeline
+ * (bulk copies in and out; identity order, Philox noise, CONSTV_FLAG_CACHE_IMAGE_CHARGE, num_cells == 2, else the
+ * LDG-staged kernel runs); same results bit for bit.
  * (block_size, stages) in {(128,6), (256,2), (256,3), (256,4), (512,2), (512,3)} shape the TMA ring, ctas_per_sm caps the persistent
  * grid (0 = as many as shared memory allows); 0 keeps the current block_size / stages. */
 CONSTV_API int constv_set_kernel_variant(constv_slab* slab, int32_t variant, int32_t block_size,

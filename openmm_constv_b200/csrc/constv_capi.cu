@@ -88,7 +88,9 @@ struct constv_slab {
     bool fusedEarly = true;
     int zeroWhen = 1;         // 0 with the dependent stores, 1 right behind the loads, 2 after the step-counter barrier
     bool settleWs = false;    // rigid-water step: the warp-specialised TMA pipeline instead of the LDG-staged kernel (CONSTV_SETTLE_WS=1, or kernel variant 4)
-    bool settleEarly = true;  // LDG-staged rigid-water kernel: cp.async stage-in with the Philox draws made while the copies fly (CONSTV_SETTLE_EARLY=0)
+    // LDG-staged rigid-water kernel: cp.async stage-in with the Philox draws made while the copies fly.  Measured SLOWER
+    // (17.0 vs 16.2 us at 1M atoms, 58.0 vs 55.5 us at 4M; profiles/r02_ab_settle_cp_async_early.jsonl): off; CONSTV_SETTLE_EARLY=1 turns it on.
+    bool settleEarly = false;
     int wsGroups = 4;         // its consumer groups in single precision (CONSTV_WS_GROUPS=3..5: experiments)
     int ctasPerSM = 0;   // 0 = one-shot grid (one tile per CTA); > 0 = persistent grid of that many CTAs per SM
     int variant = 0;     // 0 auto (= the one-shot LDG kernel, the faster one as measured), 1 LDG, 2 TMA ring

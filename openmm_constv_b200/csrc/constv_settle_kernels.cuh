@@ -506,9 +506,10 @@ __device__ __forceinline__ void settle_tiled_tile(const SlabDev& d, const Settle
 
 // The single-slab kernel keeps its own copy of the tile body (below) rather than calling settle_tiled_tile: the
 // call, though inlined, cost a spill under the 64-register cap and 8 % of the step.
-// EARLY (identity order, Philox noise): the stage is filled with asynchronous copies (cp.async) and, while they are in
-// flight, every thread reads the step counter and draws the Philox blocks of its work item's atoms (for massless atoms
-// too; discarded) -- ~390 of a molecule's ~1400 instructions leave the dependent chain that follows the barrier.
+// EARLY (identity order, Philox noise; an experiment, off by default): the stage is filled with asynchronous copies
+// (cp.async) and, while they are in flight, every thread reads the step counter and draws the Philox blocks of its work
+// item's atoms (for massless atoms too; discarded) -- ~390 of a molecule's ~1400 instructions leave the dependent chain
+// that follows the barrier.  Same bits; measured 5 % SLOWER than the plain order.
 template <int PREC, int BLOCK, bool INDEXED, bool STREAM, bool EARLY = false>
 __global__ void __launch_bounds__(BLOCK, INDEXED ? 0 : (PREC == PREC_SINGLE ? 8 : 4))  // 64 registers: 8 CTAs per SM
 constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ SettleSegments seg,

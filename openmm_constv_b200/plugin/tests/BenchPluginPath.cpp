@@ -7,9 +7,9 @@
 //   BenchPluginPath [--atoms N] [--steps S] [--precision single|mixed|double] [--reordered] [--sweep-mb M]
 //
 // Reported (one JSON line), for three sweeps between two steps --
-//   forces  a device-to-device copy into the force buffer (24 B per atom): what the cheapest possible force
+//   forces  a kernel that copies into the force buffer (24 B per atom): what the cheapest possible force
 //           kernel does; posq / velm may then still be L2 hits
-//   copy    a device-to-device copy of 128 MB onto another 128 MB: reads and writes more than the 126 MB L2
+//   copy    a kernel that copies 128 MB onto another 128 MB: reads and writes more than the 126 MB L2
 //           holds, like the force evaluation of a large system; nothing of the slab survives in L2
 //   read    a kernel that only READS 256 MB: the L2 ends up full of clean lines of something else
 // -- two numbers per step:
@@ -46,6 +46,7 @@ using std::vector;
 
 extern "C" void registerConstVCudaKernelFactories();
 extern "C" void benchSweepRead(const void* p, size_t bytes, unsigned int* sink, cudaStream_t stream);
+extern "C" void benchSweepCopy(void* dst, const void* src, size_t bytes, cudaStream_t stream);
 
 #define CU(x)                                                                              \
     do {                                                                                   \
@@ -166,8 +167,8 @@ int main(int argc, char** argv) {
         // 2 read = a kernel that only reads the sweep buffer
         const size_t half = (sweepMB << 20) / 2;
         auto sweepOp = [&](int mode) {
-            if (mode == 0) CU(cudaMemcpyAsync((void*) cu.getForce().getDevicePointer(), spareForce, 24 * (size_t) P, cudaMemcpyDeviceToDevice, stream));
-            else if (mode == 1) CU(cudaMemcpyAsync((char*) sweep + half, sweep, half, cudaMemcpyDeviceToDevice, stream));
+            if (mode == 0) benchSweepCopy((void*) cu.getForce().getDevicePointer(), spareForce, 24 * (size_t) P, stream);
+            else if (mode == 1) benchSweepCopy((char*) sweep + half, sweep, half, stream);
             else benchSweepRead(sweep, sweepMB << 20, sink, stream);
         };
         auto pass = [&](int mode, bool withStep) {
@@ -226,7 +227,7 @@ int main(int argc, char** argv) {
                        (double) R * (velB + 24);
         if (reordered) bytes += 8.0 * R + 4.0 * charged;  // atomIndex of both slots, invAtomOrder of the image
         const char* names[3] = {"forces", "copy", "read"};
-        const char* what[3] = {"D2D copy into the force buffer (24 B/atom) between steps", "D2D copy of 128 MB onto 128 MB between steps",
+        const char* what[3] = {"a kernel copying into the force buffer (24 B/atom) between steps", "a kernel copying 128 MB onto 128 MB between steps",
                                "a kernel reading 256 MB between steps"};
         std::printf("{\"path\": \"CudaIntegrateConstVLangevinStepKernel::execute via the kernel factory (OpenMM shim)\", "
                     "\"atoms\": %d, \"precision\": \"%s\", \"reordered_slots\": %s, \"steps\": %d, \"launches_per_step\": 1, "
