@@ -91,6 +91,7 @@ struct constv_slab {
     // LDG-staged rigid-water kernel: cp.async stage-in with the Philox draws made while the copies fly.  Measured SLOWER
     // (17.0 vs 16.2 us at 1M atoms, 58.0 vs 55.5 us at 4M; profiles/r02_ab_settle_cp_async_early.jsonl): off; CONSTV_SETTLE_EARLY=1 turns it on.
     bool settleEarly = false;
+    int indexedMinBlocks = 0; // reordered-slot fused kernel, single precision: 8 = capped at 32 registers (experiment: CONSTV_INDEXED_MINB=8)
     int wsGroups = 4;         // its consumer groups in single precision (CONSTV_WS_GROUPS=3..5: experiments)
     int ctasPerSM = 0;   // 0 = one-shot grid (one tile per CTA); > 0 = persistent grid of that many CTAs per SM
     int variant = 0;     // 0 auto (= the one-shot LDG kernel, the faster one as measured), 1 LDG, 2 TMA ring
@@ -320,6 +321,9 @@ bool tmaEligible(const constv_slab* s, const void* random4) {
 template <int PREC>
 int launchFusedIndexed(constv_slab* s, const SlabDev& d, const float4* random, unsigned randomIndex, cudaStream_t st) {
     // thread i owns slot i and its numCells-1 image-cell slots: a one-shot grid over the real-atom count
+    if (PREC == PREC_SINGLE && s->indexedMinBlocks == 8)
+        return launch(constv_fused_step_indexed_kernel<PREC_SINGLE, kBlock, 8>, gridFor(s, s->numReal, kBlock, 0), kBlock,
+                      (bool) (s->cfg.flags & CONSTV_FLAG_PDL), st, d, random, randomIndex);
     return launch(constv_fused_step_indexed_kernel<PREC, kBlock>, gridFor(s, s->numReal, kBlock, 0), kBlock,
                   (bool) (s->cfg.flags & CONSTV_FLAG_PDL), st, d, random, randomIndex);
 }
@@ -427,6 +431,7 @@ int constv_create(const constv_config* config, constv_slab** out) {
     if (const char* e = std::getenv("CONSTV_FUSED_EARLY")) s->fusedEarly = std::atoi(e) != 0;
     if (const char* e = std::getenv("CONSTV_FUSED_ZERO")) s->zeroWhen = std::atoi(e);
     if (const char* e = std::getenv("CONSTV_SETTLE_WS")) s->settleWs = std::atoi(e) != 0;
+    if (const char* e = std::getenv("CONSTV_INDEXED_MINB")) s->indexedMinBlocks = std::atoi(e);
     if (const char* e = std::getenv("CONSTV_SETTLE_EARLY")) s->settleEarly = std::atoi(e) != 0;
     if (const char* e = std::getenv("CONSTV_WS_GROUPS")) { const int g = std::atoi(e); if (g >= 3 && g <= 5) s->wsGroups = g; }
     DeviceGuard guard(config->device);

@@ -708,8 +708,8 @@ constv_fused_step_batched_kernel(const __grid_constant__ BatchParams<CAP> b) {
 // Behind OpenMM the slots are periodically re-sorted (cu.reorderAtoms(), Kernels.cpp:172); slot s
 // holds original atom atomIndex[s].  Thread i owns slot i and slots i + R*cell: a real atom is updated
 // (coalesced) and scatters its images through invAtomOrder; an image slot is zeroed (coalesced).
-template <int PREC, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, PREC == PREC_SINGLE ? 0 : 4)  // mixed/double: 64 registers, 4 CTAs per SM
+template <int PREC, int BLOCK, int MINB = (PREC == PREC_SINGLE ? 0 : 4)>
+__global__ void __launch_bounds__(BLOCK, MINB)  // mixed/double: 64 registers, 4 CTAs per SM; single: MINB = 8 caps it at 32 registers
 constv_fused_step_indexed_kernel(const __grid_constant__ SlabDev d, const float4* __restrict__ random,
                                  const unsigned int randomIndex) {
     using Real = typename Prec<PREC>::Real;

@@ -39,6 +39,13 @@ if which == "fused":
     shard = env.slabmod.slab_tile(R, 1, 0, "single", seed=bench.SLAB_SEED)
     kind, water = "langevin", None
     chain_counts = (1, 2)
+elif which == "reordered":
+    variants = [("indexed_40_registers", {"CONSTV_INDEXED_MINB": "0"}), ("indexed_capped_32_registers", {"CONSTV_INDEXED_MINB": "8"})]
+    shard = env.slabmod.slab_tile(R, 1, 0, "single", seed=bench.SLAB_SEED)
+    perm = env.slabmod.molecule_permutation(shard, shard.meta["n_ion"], 3, shard.meta["n_water"] // 3, seed=7)
+    shard, _ = env.slabmod.permute_slab(shard, perm)
+    kind, water = "langevin", None
+    chain_counts = (1,)
 else:
     variants = [("ldg_staged_round1_order", {"CONSTV_SETTLE_WS": "0", "CONSTV_SETTLE_EARLY": "0"}),
                 ("ldg_staged_cp_async_early_philox", {"CONSTV_SETTLE_WS": "0", "CONSTV_SETTLE_EARLY": "1"}),
@@ -52,7 +59,7 @@ wls = []
 for name, knobs in variants:
     os.environ.pop("CONSTV_SETTLE_WS", None)
     os.environ.update(knobs)
-    wls.append((name, bench.Workload(env, args, shard, kind=kind, chains=1, water=water)))
+    wls.append((name, bench.Workload(env, args, shard, kind=kind, chains=1, water=water, reorder_perm=perm if which == "reordered" else None)))
 alg = wls[0][1].algorithmic_bytes()
 results = {}
 for rnd in range(ROUNDS):
