@@ -471,7 +471,7 @@ __device__ __forceinline__ void fused_tile(const SlabDev& d, const int base, con
             if (random) xi[j] = __ldcs(random + (size_t) randomIndex + i);
         }
     }
-    const int zeroWhen = d.zeroWhen;  // experiment: 0 with the dependent stores, 1 right behind the loads, 2 after the barrier
+    const int zeroWhen = d.zeroWhen & 3;  // 0 with the dependent stores, 1 right behind the loads (default), 2 after the barrier
     if (zeroWhen == 1) {
 #pragma unroll
         for (int j = 0; j < ILP; j++)
