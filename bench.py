@@ -26,9 +26,10 @@ How the K steps are timed (the same at --steps 20 and at --steps 100000):
   * L2: a 1M-atom slab is 56 MB < B200's 126 MB L2, so the steps rotate over ``replicas`` copies of the slab
     whose footprint exceeds 2x L2: every step streams its slab from HBM.
 
-Chains (default 2): the slab is cut into contiguous ranges of real atoms, each with its own device step
+Chains (default 3): the slab is cut into contiguous ranges of real atoms, each with its own device step
 counter and stream (constv_set_chains / constv_step_fused_chain), so that the drain of one range's step k
-overlaps the ramp-up of another's step k+1; bit-identical to one launch per step.  A host that runs other
+overlaps the ramp-up of another's step k+1; bit-identical to one launch per step.  (Same box, the driver's
+arguments: 2 chains 11.48-11.56 us, 3 chains 11.28-11.29, 4 chains 11.32, 8 chains 11.27.)  A host that runs other
 kernels between two steps (OpenMM) cannot use that overlap: ``also.single_launch`` is the same workload with
 one launch per step and ``also.plugin_path`` steps through CudaIntegrateConstVLangevinStepKernel::execute
 (plugin/tests/BenchPluginPath.cpp), a cache-sweeping kernel between two steps.
@@ -90,7 +91,7 @@ def parse_args():
     ap.add_argument("--tma-block", type=int, default=0)
     ap.add_argument("--tma-stages", type=int, default=0)
     ap.add_argument("--tma-ctas", type=int, default=0)
-    ap.add_argument("--chains", type=int, default=2,
+    ap.add_argument("--chains", type=int, default=3,
                     help="cut the slab into this many independent real-atom ranges, each advanced on its own stream "
                          "(constv_set_chains); for --ensemble, the slabs of a step are advanced by this many batched launches")
     ap.add_argument("--rigid-water", default="", choices=["", "fused", "split"],

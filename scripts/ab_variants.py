@@ -30,7 +30,12 @@ peak, _ = bench.peaks()
 R = atoms // 2
 K, W, ROUNDS = 1500, 30, 4
 
-if which == "fused":
+if which == "chains":
+    variants = [("default", {})]
+    shard = env.slabmod.slab_tile(R, 1, 0, "single", seed=bench.SLAB_SEED)
+    kind, water = "langevin", None
+    chain_counts = (2, 3, 4, 6, 8)
+elif which == "fused":
     variants = [("early0_zero0", {"CONSTV_FUSED_EARLY": "0", "CONSTV_FUSED_ZERO": "0"}),
                 ("early1_zero0", {"CONSTV_FUSED_EARLY": "1", "CONSTV_FUSED_ZERO": "0"}),
                 ("early0_zero2", {"CONSTV_FUSED_EARLY": "0", "CONSTV_FUSED_ZERO": "2"}),
