@@ -127,12 +127,15 @@ def peaks():
 
 
 def traffic_from_profile(atoms, chains):
-    """dram bytes per launch from the committed ncu capture, if it was taken on this workload."""
+    """dram bytes per launch from the committed ncu capture, if it was taken on this workload: the capture's bytes per
+    STEP (what the slab's records cost in DRAM traffic does not depend on how many launches a step is cut into)
+    divided by this run's launches per step."""
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     try:
         rec = json.load(open(path))
-        if int(rec.get("atoms", -1)) == int(atoms) and int(rec.get("chains", 1)) == int(chains):
-            return rec["dram_bytes_per_launch"]
+        if int(rec.get("atoms", -1)) == int(atoms):
+            per_step = rec["dram_bytes_per_launch"] * int(rec.get("chains", 1))
+            return int(round(per_step / max(1, int(chains))))
     except Exception:
         pass
     return None
