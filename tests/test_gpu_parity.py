@@ -146,6 +146,51 @@ def test_reordered_slots(gpu, oracle, precision, split):
     ctx.close()
 
 
+@pytest.mark.parametrize("precision", slabmod.PRECISIONS)
+@pytest.mark.parametrize("num_cells", [2, 4])
+@pytest.mark.parametrize("reordered", [False, True])
+@pytest.mark.parametrize("side_array", [False, True])
+def test_mirror_alone(gpu, oracle, precision, num_cells, reordered, side_array):
+    """constv_mirror = the updateImageParticlePositions launch alone (CudaConstVKernels.cpp:165-166), what a host with
+    virtual sites calls after computeVirtualSites: someone moves real atoms (here: a scatter of new positions written
+    straight into posq, as the virtual-site kernel would), the images follow bit for bit, neutral atoms' images stay
+    put, and neither velocities, forces nor the step counter change."""
+    import torch
+    from openmm_constv_b200 import _capi
+    s0 = slabmod.make_slab(3001, precision, num_cells=num_cells, seed=15)
+    perm = np.random.default_rng(4).permutation(s0.num_atoms).astype(np.int32) if reordered else None
+    sp, atom_index = permute_slab(s0, perm) if reordered else (s0, identity_order(s0.padded))
+    flags = _capi.FLAGS_DEFAULT | (_capi.FLAG_CACHE_IMAGE_CHARGE if side_array else 0)
+    ctx, it = make_context(gpu, sp, flags=flags)
+    if reordered:
+        ctx.set_atom_order(perm)
+    it.step(2)
+    before = download(ctx, sp)
+    # move every third real atom (by ORIGINAL index) somewhere else
+    R = s0.num_real
+    inv = oracle.inverse_order(atom_index)
+    movers = inv[np.arange(0, R, 3)]
+    rng = np.random.default_rng(8)
+    new_xyz = (rng.random((len(movers), 3)) * [sp.box[0], sp.box[1], sp.zmax]).astype(before.posq.dtype)
+    moved = before.copy()
+    moved.posq[movers, :3] = new_xyz
+    if moved.corr is not None:
+        moved.corr[movers, :3] = (rng.random((len(movers), 3)) * 1e-8).astype(moved.corr.dtype)
+        ctx.corr.copy_(torch.from_numpy(moved.corr))
+    ctx.posq.copy_(torch.from_numpy(moved.posq))
+    _capi.check(_capi.load().constv_mirror(it._kernel.handle, ctx.stream_ptr()))
+    got = download(ctx, sp)
+    oracle.mirror(precision, R, num_cells, sp.zmax, moved.posq, moved.corr, inv)
+    assert_bits_equal(got.posq, moved.posq, "posq after the image rewrite")
+    if moved.corr is not None:
+        assert_bits_equal(got.corr, moved.corr, "posqCorrection after the image rewrite")
+    assert_bits_equal(got.velm, before.velm, "velm untouched")
+    assert np.array_equal(got.force, before.force)
+    assert it._kernel.get_step_count() == 2
+    assert not np.array_equal(got.posq, before.posq)
+    ctx.close()
+
+
 def test_trajectory_1000_steps_friction_zero(gpu, oracle):
     """north_star: reference-matching 1000-step trajectory with friction 0 (fp32).  Static injected
     forces; every 100 steps all arrays must still be bit-identical to the oracle's."""
