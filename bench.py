@@ -111,8 +111,8 @@ def parse_args():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-ref-gpu", action="store_true", help="do not time the reference's own CUDA kernels beside ours")
-    ap.add_argument("--skip-also", action="store_true", help="headline only: no single-launch / plugin / 16M / ensemble / parity legs")
-    ap.add_argument("--only", default="", help="experiments: comma list of `also` legs to run (single,plugin,slab16m,ensemble,parity)")
+    ap.add_argument("--skip-also", action="store_true", help="headline only: no single-launch / plugin / 16M / ensemble / rigid-water / Drude / parity legs")
+    ap.add_argument("--only", default="", help="experiments: comma list of `also` legs to run (single,plugin,slab16m,ensemble,rigid,drude,parity)")
     return ap.parse_args()
 
 
@@ -1083,7 +1083,7 @@ def main():
     value = atoms_job / (ms_step * 1e-3)
     kernel_name = ("constv_settle_step_tiled_batched_kernel" if (args.ensemble and water) else
                    "constv_fused_step_batched_kernel" if args.ensemble else
-                   "constv_drude_step_kernel" if drude else
+                   "constv_drude_step_balanced_kernel" if (drude and args.variant != 1) else "constv_drude_step_kernel" if drude else
                    "constv_settle_step_tiled_kernel" if kind == "settle" else
                    "constv_part1_kernel + constv_settle_positions_kernel + constv_part2_mirror_kernel" if kind == "settle_split" else
                    "constv_fused_step_indexed_kernel" if args.reordered else "constv_fused_step_kernel")
@@ -1189,6 +1189,31 @@ def main():
             we.close()
             del we, she
             torch.cuda.empty_cache()
+
+    # ---- the same slab size with the constrained / polarizable steps: one kernel per step each ----
+    # (own tile of one global slab per rank, two chains; the flags --rigid-water / --drude run them as the headline instead)
+    if plain and not slab16m and want("rigid"):
+        shw, w_atoms, w_params, w_cons = slabmod.slab_tile(R_total, world, rank, args.precision, seed=SLAB_SEED, maker=slabmod.make_water_slab)
+        ww = Workload(env, args, shw, kind="settle", chains=2, water=(w_atoms, w_params, w_cons))
+        kw_ = max(20, min(K, 1200))
+        tw = time_steps(env, ww, kw_, 5, use_graph=use_graph, repeats=args.repeats)
+        also["rigid_water"] = rate_record(shw.num_atoms * world, kw_, tw, ww.algorithmic_bytes(), ww.chains, peak, "constv_settle_step_tiled_kernel",
+                                          {"atoms_per_gpu": shw.num_atoms, "n_gpus": world, "rigid_molecules_per_gpu": int(len(w_atoms)),
+                                           "replicas": ww.replicas, "parity_note": "SETTLE restated from recall: CUDA == oracle bit for bit, "
+                                           "oracle unpinned against OpenMM's solver (DESIGN.md 5)"})
+        ww.close()
+        del ww, shw, w_atoms, w_params, w_cons
+        torch.cuda.empty_cache()
+    if plain and not slab16m and want("drude"):
+        shd, d_normal, d_pairs = slabmod.slab_tile(R_total, world, rank, args.precision, seed=SLAB_SEED, maker=slabmod.make_drude_slab)
+        wd = Workload(env, args, shd, kind="drude", chains=2, drude=(d_normal, d_pairs))
+        kd_ = max(20, min(K, 1200))
+        td = time_steps(env, wd, kd_, 5, use_graph=use_graph, repeats=args.repeats)
+        also["drude"] = rate_record(shd.num_atoms * world, kd_, td, wd.algorithmic_bytes(), wd.chains, peak, "constv_drude_step_balanced_kernel",
+                                    {"atoms_per_gpu": shd.num_atoms, "n_gpus": world, "pairs_per_gpu": int(len(d_pairs)), "replicas": wd.replicas})
+        wd.close()
+        del wd, shd, d_normal, d_pairs
+        torch.cuda.empty_cache()
 
     # ---- the partition, checked: shards == unpartitioned == oracle, bit for bit -----------------------------------
     if want("parity"):

@@ -37,7 +37,7 @@ extern "C" {
 
 #define CONSTV_API __attribute__((visibility("default")))
 
-#define CONSTV_VERSION 120 /* 0.1.2: + constv_mirror, constv_generate_philox_words */
+#define CONSTV_VERSION 121 /* 0.1.2: + constv_mirror, constv_generate_philox_words */
 
 typedef struct constv_slab constv_slab; /* one Context's worth of integrator state (opaque) */
 
@@ -383,7 +383,9 @@ CONSTV_API int constv_set_launch_shape(constv_slab* slab, int32_t pairs_per_thre
  * CONSTV_FLAG_CACHE_IMAGE_CHARGE, even P).  For the rigid-molecule step (constv_step_fused_settle*): 0 = automatic
  * (the LDG-staged kernel), 1 = the gather kernel, 3 = the LDG-staged kernel, 4 = the warp-specialised TMA pipeline
  * (bulk copies in and out; identity order, Philox noise, CONSTV_FLAG_CACHE_IMAGE_CHARGE, num_cells == 2, else the
- * LDG-staged kernel runs); same results bit for bit.
+ * LDG-staged kernel runs); same results bit for bit.  For the Drude step (constv_drude_step_fused*): 0 = automatic (the
+ * staged kernel whose warps draw chunks of work items), 1 = the thread-per-slot gather kernel, 5 = the staged kernel with
+ * one work item per thread (round 1's); same results bit for bit.
  * (block_size, stages) in {(128,6), (256,2), (256,3), (256,4), (512,2), (512,3)} shape the TMA ring, ctas_per_sm caps the persistent
  * grid (0 = as many as shared memory allows); 0 keeps the current block_size / stages. */
 CONSTV_API int constv_set_kernel_variant(constv_slab* slab, int32_t variant, int32_t block_size,

@@ -91,6 +91,9 @@ struct constv_slab {
     // LDG-staged rigid-water kernel: cp.async stage-in with the Philox draws made while the copies fly.  Measured SLOWER
     // (17.0 vs 16.2 us at 1M atoms, 58.0 vs 55.5 us at 4M; profiles/r02_ab_settle_cp_async_early.jsonl): off; CONSTV_SETTLE_EARLY=1 turns it on.
     bool settleEarly = false;
+    // staged Drude step: slots per thread.  2 | 3 = the balanced kernel (warps draw chunks of work items: 17.4 -> 15.2 us per step at 1M atoms
+    // with two chains, profiles/r02_ab_drude_balanced.jsonl); 1 = thread t takes work item t (CONSTV_DRUDE_SPT)
+    int drudeSlotsPerThread = 2;
     int indexedMinBlocks = 0; // reordered-slot fused kernel, single precision: 8 = capped at 32 registers (experiment: CONSTV_INDEXED_MINB=8)
     int wsGroups = 4;         // its consumer groups in single precision (CONSTV_WS_GROUPS=3..5: experiments)
     int ctasPerSM = 0;   // 0 = one-shot grid (one tile per CTA); > 0 = persistent grid of that many CTAs per SM
@@ -433,6 +436,7 @@ int constv_create(const constv_config* config, constv_slab** out) {
     if (const char* e = std::getenv("CONSTV_SETTLE_WS")) s->settleWs = std::atoi(e) != 0;
     if (const char* e = std::getenv("CONSTV_INDEXED_MINB")) s->indexedMinBlocks = std::atoi(e);
     if (const char* e = std::getenv("CONSTV_SETTLE_EARLY")) s->settleEarly = std::atoi(e) != 0;
+    if (const char* e = std::getenv("CONSTV_DRUDE_SPT")) s->drudeSlotsPerThread = std::min(3, std::max(1, std::atoi(e)));
     if (const char* e = std::getenv("CONSTV_WS_GROUPS")) { const int g = std::atoi(e); if (g >= 3 && g <= 5) s->wsGroups = g; }
     DeviceGuard guard(config->device);
     if (guard.rc) { delete s; return guard.rc; }
@@ -1047,7 +1051,9 @@ int constv_set_launch_shape(constv_slab* s, int32_t pairs_per_thread, int32_t ct
 
 int constv_set_kernel_variant(constv_slab* s, int32_t variant, int32_t block_size, int32_t stages, int32_t ctas_per_sm) {
     if (!s) return fail(CONSTV_ERR_INVALID, "null slab");
-    if (variant < 0 || variant > 4) return fail(CONSTV_ERR_INVALID, "variant must be 0 (auto), 1 (LDG / gather), 2 (TMA ring), 3 (LDG-staged rigid-water kernel) or 4 (TMA-pipelined rigid-water kernel)");
+    if (variant < 0 || variant > 5)
+        return fail(CONSTV_ERR_INVALID, "variant must be 0 (auto), 1 (LDG / gather), 2 (TMA ring), 3 (LDG-staged rigid-water kernel), 4 (TMA-pipelined "
+                                        "rigid-water kernel) or 5 (Drude step staged with one work item per thread)");
     s->variant = variant;
     if (block_size) s->tmaBlock = block_size;
     if (stages) s->tmaStages = stages;

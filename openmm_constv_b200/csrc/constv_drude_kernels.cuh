@@ -71,11 +71,12 @@ template <typename T> __device__ __forceinline__ const T& comp(const Vec4<T>& v,
 
 // Drude.cu:31-63.  f1/f2 = fixed-point forces of the Drude particle / the parent, r1/r2 = the pair's
 // two Gaussian float4s.  Writes the new velocities (w untouched) and posDelta = dt * v (w = 0).
+// f1, f2: the fixed-point force components already converted to `mixed` (from_fixed)
 template <typename M>
-__device__ __forceinline__ void drude_pair_part1(Vec4<M>& v1, Vec4<M>& v2, Vec4<M>& d1, Vec4<M>& d2,
-                                                 const long long (&f1)[3], const long long (&f2)[3],
-                                                 const float4 r1, const float4 r2,
-                                                 const StepScalars<M>& s, const DrudeScalars<M>& ds) {
+__device__ __forceinline__ void drude_pair_part1_converted(Vec4<M>& v1, Vec4<M>& v2, Vec4<M>& d1, Vec4<M>& d2,
+                                                           const M (&f1)[3], const M (&f2)[3],
+                                                           const float4 r1, const float4 r2,
+                                                           const StepScalars<M>& s, const DrudeScalars<M>& ds) {
     const M mass1 = rcp_rn(v1.w);
     const M mass2 = rcp_rn(v2.w);
     const M total = add_rn(mass1, mass2);
@@ -90,7 +91,7 @@ __device__ __forceinline__ void drude_pair_part1(Vec4<M>& v1, Vec4<M>& v2, Vec4<
     const float xi1[3] = {r1.x, r1.y, r1.z}, xi2[3] = {r2.x, r2.y, r2.z};
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        const M a = from_fixed(f1[k], M()), b = from_fixed(f2[k], M());
+        const M a = f1[k], b = f2[k];
         M cm = fma_rn(comp(v1, k), mass1fract, mul_rn(comp(v2, k), mass2fract));
         M rel = add_rn(comp(v2, k), -comp(v1, k));
         const M cmForce = add_rn(a, b);
@@ -104,6 +105,15 @@ __device__ __forceinline__ void drude_pair_part1(Vec4<M>& v1, Vec4<M>& v2, Vec4<
     }
     d1.w = 0;
     d2.w = 0;
+}
+template <typename M>
+__device__ __forceinline__ void drude_pair_part1(Vec4<M>& v1, Vec4<M>& v2, Vec4<M>& d1, Vec4<M>& d2,
+                                                 const long long (&f1)[3], const long long (&f2)[3],
+                                                 const float4 r1, const float4 r2,
+                                                 const StepScalars<M>& s, const DrudeScalars<M>& ds) {
+    const M a[3] = {from_fixed(f1[0], M()), from_fixed(f1[1], M()), from_fixed(f1[2], M())};
+    const M b[3] = {from_fixed(f2[0], M()), from_fixed(f2[1], M()), from_fixed(f2[2], M())};
+    drude_pair_part1_converted(v1, v2, d1, d2, a, b, r1, r2, s, ds);
 }
 
 // position of one particle as the `mixed` value the hard wall works on (Drude.cu:113-123) and back
@@ -605,6 +615,266 @@ constv_drude_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_c
         }
         close_step(d.counters, ticket, holders, step);
         if (tile + (int) gridDim.x < tileHi) __syncthreads();  // stage and box are rewritten by the next tile
+    }
+}
+
+// ---- the staged fused step, balanced ---------------------------------------------------------------------
+// In constv_drude_step_tiled_kernel thread t takes work item t, so a 128-slot tile of 4-site molecules
+// (32 pairs + 64 ordinary particles) is one warp of owners (~500 instructions), two warps of ordinary particles
+// (~200) and one idle warp: the three barriers of the tile make everybody wait for the owners, and fewer than half of
+// the resident warps compute at any time.  Here a CTA of BLOCK threads stages SPT * BLOCK slots (every thread loads
+// and later emits SPT slots, coalesced as before) and its warps draw CHUNKS of 32 work items from a counter in
+// shared memory -- owner chunks first, then ordinary ones -- until the tile is done: with SPT = 2 the same tile shape
+// gives two owner chunks and four ordinary chunks over four warps, 500 | 500 | 400 | 400 instructions.  Same
+// arithmetic per work item, same bits.  The stage differs too:
+//   * the three fixed-point force components are converted to `mixed` once, when staged (from_fixed is the first
+//     thing part 1 does with them), and travel with the image charge as ONE 4-vector: 16 bytes instead of 28 in
+//     single precision, one shared-memory load per work item instead of four;
+//   * records sit at position slot ^ ((slot >> 3) & 7): the work items of one kind are every 4th slot (O D H H), a
+//     stride that put 4 lanes of every quarter-warp on the same banks; the XOR keeps the coalesced phases (8
+//     consecutive slots stay in one aligned 128-byte window) conflict-free and spreads the strided ones;
+//   * a parent staged in the same tile leaves its position at its owner's entry of `partner` (checked against the
+//     parent's role, so a stale entry cannot pass): no dependent load of the pair list before the arithmetic.
+template <int PREC, int BLOCK, int SPT, bool INDEXED> struct DrudeStageB {
+    using Real = typename Prec<PREC>::Real;
+    using Mixed = typename Prec<PREC>::Mixed;
+    static constexpr int kTile = BLOCK * SPT;
+    Vec4<Mixed> v[kTile];
+    Vec4<Real> p[kTile];
+    Vec4<Real> c[Prec<PREC>::kSplitPos ? kTile : 1];
+    Vec4<Mixed> fq[kTile];       // force components as `mixed`, w = image charge of cell 1 (identity order)
+    int role[kTile];
+    int orig[INDEXED ? kTile : 1];
+    unsigned short list[kTile];     // work items: tile-local slot of each owner, then of each ordinary particle
+    unsigned short partner[kTile];  // [owner] = tile-local slot of its parent, when that parent is staged in this tile
+    int warpOwners[SPT * (BLOCK / 32)], warpNormals[SPT * (BLOCK / 32)];
+    int next;                    // next chunk of 32 work items
+};
+__device__ __forceinline__ int drude_swizzle(const int i) { return i ^ ((i >> 3) & 7); }
+
+template <int PREC, int BLOCK, int SPT, bool INDEXED, bool STREAM>
+__global__ void __launch_bounds__(BLOCK, (PREC == PREC_SINGLE ? 1024 : 512) / BLOCK)  // single: 64 registers, 32 warps per SM
+constv_drude_step_balanced_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ DrudeDev dd,
+                                  const float4* __restrict__ random, const unsigned int randomIndex) {
+    using Real = typename Prec<PREC>::Real;
+    using Mixed = typename Prec<PREC>::Mixed;
+    constexpr bool kSplit = Prec<PREC>::kSplitPos;
+    constexpr int kWarps = BLOCK / 32;
+    constexpr int kTile = BLOCK * SPT;
+    static_assert(kTile <= 65536 && (kTile & 63) == 0, "tile-local slots are 16-bit; the swizzle permutes aligned groups of 64");
+    __shared__ DrudeStageB<PREC, BLOCK, SPT, INDEXED> st;
+    __shared__ StepBox box;
+    pdl_wait();
+    pdl_launch();
+    const int R = d.numReal;
+    const size_t P = (size_t) d.padded;
+    const int realTiles = (R + kTile - 1) / kTile;
+    constexpr int kZeroSpan = 8;  // a zeroing tile covers 8 * BLOCK image slots
+    const int tileLo = d.rangeLo, tileHi = d.rangeHi;
+    const unsigned int holders = (unsigned int) (tileHi - tileLo);
+    const StepScalars<Mixed> s = scalars_of<Mixed>(d);
+    const DrudeScalars<Mixed> ds = drude_scalars_of<Mixed>(dd);
+    const int tid = (int) threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int tile = tileLo + (int) blockIdx.x; tile < tileHi; tile += (int) gridDim.x) {
+        if (INDEXED && tile >= realTiles) {  // a tile of image slots: zero them, coalesced
+            publish_step(box, d.counters);
+            __syncthreads();
+            const unsigned long long zstep = box.step;
+            const unsigned int zticket = take_ticket(d.counters, holders);
+#pragma unroll
+            for (int i = 0; i < kZeroSpan; i++) {
+                const int zslot = R + ((tile - realTiles) * kZeroSpan + i) * BLOCK + tid;
+                if (zslot < d.numAtoms) {
+                    if (d.zeroVelm) store4x<STREAM>(static_cast<Mixed*>(d.velm), (size_t) zslot, Vec4<Mixed>{0, 0, 0, 0});
+                    if (d.zeroForce) {
+                        __stcs(d.force + zslot, 0LL);
+                        __stcs(d.force + P + zslot, 0LL);
+                        __stcs(d.force + 2 * P + zslot, 0LL);
+                    }
+                }
+            }
+            close_step(d.counters, zticket, holders, zstep);
+            if (tile + (int) gridDim.x < tileHi) __syncthreads();
+            continue;
+        }
+        const int base = tile * kTile;
+        // 1. stage in: thread t loads slots base + t + i * BLOCK
+        unsigned int ownerMask[SPT], normalMask[SPT];
+#pragma unroll
+        for (int i = 0; i < SPT; i++) {
+            const int idx = tid + i * BLOCK, slot = base + idx, at = drude_swizzle(idx);
+            const bool inRange = slot < R;
+            // past the end of the real range: NORMAL, which no parent test below can mistake for "owned by slot x"
+            const int role = inRange ? dd.role[slot] : DRUDE_ROLE_NORMAL;
+            if (inRange) {
+                DrudeAtom<PREC> me;
+                drude_load<PREC, DRUDE_FUSED, INDEXED, STREAM>(d, slot, me);
+                if (INDEXED) st.orig[idx] = d.atomIndex ? d.atomIndex[slot] : slot;
+                st.v[at] = me.v;
+                st.p[at] = me.p;
+                if (kSplit) st.c[at] = me.c;
+                st.fq[at] = Vec4<Mixed>{from_fixed(me.f[0], Mixed()), from_fixed(me.f[1], Mixed()), from_fixed(me.f[2], Mixed()), (Mixed) me.q1};
+                if (role <= DRUDE_ROLE_PASSIVE) {  // a parent: tell the owner, if it is staged here
+                    const int owner = DRUDE_ROLE_PASSIVE - role - base;
+                    if (owner >= 0 && owner < kTile) st.partner[owner] = (unsigned short) idx;
+                }
+            }
+            st.role[idx] = role;
+            ownerMask[i] = __ballot_sync(0xffffffffu, role >= 0);
+            normalMask[i] = __ballot_sync(0xffffffffu, inRange && role == DRUDE_ROLE_NORMAL);
+            if (lane == 0) {
+                st.warpOwners[i * kWarps + warp] = __popc(ownerMask[i]);
+                st.warpNormals[i * kWarps + warp] = __popc(normalMask[i]);
+            }
+        }
+        if (tid == 0) st.next = 0;
+        publish_step(box, d.counters);
+        __syncthreads();
+        const unsigned long long step = box.step;
+        const unsigned int ticket = take_ticket(d.counters, holders);
+        // 2. compaction: owners first, then ordinary particles
+        int numOwners = 0, numNormals = 0;
+        {
+            int ownersBefore[SPT], normalsBefore[SPT];
+#pragma unroll
+            for (int i = 0; i < SPT; i++)
+#pragma unroll
+                for (int w = 0; w < kWarps; w++) {
+                    if (w == warp) { ownersBefore[i] = numOwners; normalsBefore[i] = numNormals; }
+                    numOwners += st.warpOwners[i * kWarps + w];
+                    numNormals += st.warpNormals[i * kWarps + w];
+                }
+            const unsigned int below = (1u << lane) - 1u;
+#pragma unroll
+            for (int i = 0; i < SPT; i++) {
+                const int idx = tid + i * BLOCK;
+                if ((ownerMask[i] >> lane) & 1u) st.list[ownersBefore[i] + __popc(ownerMask[i] & below)] = (unsigned short) idx;
+                if ((normalMask[i] >> lane) & 1u) st.list[numOwners + normalsBefore[i] + __popc(normalMask[i] & below)] = (unsigned short) idx;
+            }
+        }
+        __syncthreads();
+
+        // 3. the warps draw chunks of 32 work items
+        const int ownerChunks = (numOwners + 31) >> 5, chunks = ownerChunks + ((numNormals + 31) >> 5);
+        for (;;) {
+            int chunk = 0;
+            if (lane == 0) chunk = atomicAdd(&st.next, 1);
+            chunk = __shfl_sync(0xffffffffu, chunk, 0);
+            if (chunk >= chunks) break;
+            if (chunk < ownerChunks) {
+                const int item = chunk * 32 + lane;
+                if (item < numOwners) {
+                    const int a = (int) st.list[item];                // tile-local slot of the Drude particle
+                    const int aAt = drude_swizzle(a);
+                    const int pairIndex = st.role[a];
+                    int b = (int) st.partner[a];                      // tile-local slot of the parent, if staged here
+                    const bool partnerInTile = b < kTile && st.role[b] == DRUDE_ROLE_PASSIVE - (base + a);
+                    Vec4<Mixed> v1 = st.v[aAt], v2, delta1{0, 0, 0, 0}, delta2{0, 0, 0, 0};
+                    Vec4<Real> p1 = st.p[aAt], p2, c1 = kSplit ? st.c[aAt] : Vec4<Real>{0, 0, 0, 0}, c2{0, 0, 0, 0};
+                    const Vec4<Mixed> fq1 = st.fq[aAt];
+                    const Mixed f1[3] = {fq1.x, fq1.y, fq1.z};
+                    Mixed f2[3];
+                    Real q2 = 0;
+                    int orig2, far = 0, bAt = 0;
+                    if (partnerInTile) {
+                        bAt = drude_swizzle(b);
+                        v2 = st.v[bAt];
+                        p2 = st.p[bAt];
+                        if (kSplit) c2 = st.c[bAt];
+                        const Vec4<Mixed> fq2 = st.fq[bAt];
+                        f2[0] = fq2.x; f2[1] = fq2.y; f2[2] = fq2.z;
+                        orig2 = INDEXED ? st.orig[b] : base + b;
+                    } else {  // a pair that straddles two tiles: the owner handles its parent in global memory
+                        far = dd.pairs[pairIndex].y;
+                        DrudeAtom<PREC> rec;
+                        drude_load<PREC, DRUDE_FUSED, INDEXED, STREAM>(d, far, rec);
+                        v2 = rec.v; p2 = rec.p; c2 = rec.c; q2 = rec.q1;
+                        f2[0] = from_fixed(rec.f[0], Mixed()); f2[1] = from_fixed(rec.f[1], Mixed()); f2[2] = from_fixed(rec.f[2], Mixed());
+                        orig2 = (INDEXED && d.atomIndex) ? d.atomIndex[far] : far;
+                    }
+                    float4 xi1, xi2;
+                    if (random != nullptr) {
+                        const size_t at = (size_t) randomIndex + (size_t) dd.numNormal + 2 * (size_t) pairIndex;
+                        xi1 = __ldcs(random + at);
+                        xi2 = __ldcs(random + at + 1);
+                    } else {
+                        const int orig1 = INDEXED ? st.orig[a] : base + a;
+                        xi1 = gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) orig1, step);
+                        xi2 = gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) orig2, step);
+                    }
+                    drude_pair_part1_converted(v1, v2, delta1, delta2, f1, f2, xi1, xi2, s, ds);
+                    if (v1.w != 0) part2_update<PREC>(p1, c1, v1, delta1, s.invDt);
+                    if (v2.w != 0) part2_update<PREC>(p2, c2, v2, delta2, s.invDt);
+                    if (ds.maxDistance > 0)
+                        drude_hardwall<PREC>(v1, v2, p1, c1, p2, c2, s.dt, ds.maxDistance, ds.hardwallScale);
+                    st.v[aAt] = v1;
+                    st.p[aAt] = p1;
+                    if (kSplit) st.c[aAt] = c1;
+                    if (partnerInTile) {
+                        st.v[bAt] = v2;
+                        st.p[bAt] = p2;
+                        if (kSplit) st.c[bAt] = c2;
+                    } else if (INDEXED) {
+                        DrudeAtom<PREC> rec;
+                        rec.v = v2; rec.p = p2; rec.c = c2;
+                        drude_emit<PREC, true, STREAM>(d, far, orig2, true, rec);
+                    } else {
+                        emit_atom<PREC, STREAM>(d, d.zshift, far, true, v2, p2, c2, q2);
+                    }
+                }
+            } else {
+                const int item = (chunk - ownerChunks) * 32 + lane;
+                if (item < numNormals) {
+                    const int a = (int) st.list[numOwners + item];
+                    const int aAt = drude_swizzle(a);
+                    Vec4<Mixed> v = st.v[aAt];
+                    if (v.w != 0) {
+                        Vec4<Real> p = st.p[aAt], c = kSplit ? st.c[aAt] : Vec4<Real>{0, 0, 0, 0};
+                        const Vec4<Mixed> fq = st.fq[aAt];
+                        Vec4<Mixed> delta;
+                        float4 xi = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (random != nullptr) xi = __ldcs(random + (size_t) randomIndex + (size_t) base + a);
+                        else if (s.noisescale != 0)
+                            xi = gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) (INDEXED ? st.orig[a] : base + a), step);
+                        part1_update_converted(v, delta, fq.x, fq.y, fq.z, xi.x, xi.y, xi.z, s);
+                        part2_update<PREC>(p, c, v, delta, s.invDt);
+                        st.v[aAt] = v;
+                        st.p[aAt] = p;
+                        if (kSplit) st.c[aAt] = c;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // 4. every thread emits its own slots; a parent whose owner sits in another tile was emitted by that owner
+#pragma unroll
+        for (int i = 0; i < SPT; i++) {
+            const int idx = tid + i * BLOCK, slot = base + idx, at = drude_swizzle(idx);
+            const int role = st.role[idx];
+            bool mine = slot < R;
+            if (role <= DRUDE_ROLE_PASSIVE && mine) {
+                const int owner = DRUDE_ROLE_PASSIVE - role;
+                mine = owner >= base && owner < base + kTile;
+            }
+            if (mine) {
+                const Vec4<Mixed> v = st.v[at];
+                const Vec4<Real> p = st.p[at];
+                const Vec4<Real> c = kSplit ? st.c[at] : Vec4<Real>{0, 0, 0, 0};
+                // a pair's records are always written back (constVDrudeLangevin.cu:60-63 stores unconditionally)
+                const bool moved = role != DRUDE_ROLE_NORMAL || v.w != 0;
+                if (INDEXED) {
+                    DrudeAtom<PREC> rec;
+                    rec.v = v; rec.p = p; rec.c = c;
+                    drude_emit<PREC, true, STREAM>(d, slot, st.orig[idx], moved, rec);
+                } else {
+                    emit_atom<PREC, STREAM>(d, d.zshift, slot, moved, v, p, c, (Real) st.fq[at].w);
+                }
+            }
+        }
+        close_step(d.counters, ticket, holders, step);
+        if (tile + (int) gridDim.x < tileHi) __syncthreads();  // stage, partner entries and box are rewritten by the next tile
     }
 }
 

@@ -230,21 +230,27 @@ template <> __device__ __forceinline__ StepScalars<double> scalars_of<double>(co
 // nvcc applies to the reference's expression vscale*v + fscale*w*F + noisescale*sqrtInvMass*xi
 // (SASS of the reference kernel: FMUL t = fw*F; FFMA(vscale, v, t); FFMA(ns, xi, .)), so the
 // result equals the reference kernel's bit for bit (tests/test_gpu_reference.py).
+// fx, fy, fz: the fixed-point force components already converted to `mixed` (from_fixed)
 template <typename M>
-__device__ __forceinline__ void part1_update(Vec4<M>& v, Vec4<M>& delta, long long fx, long long fy,
-                                             long long fz, float xix, float xiy, float xiz,
-                                             const StepScalars<M>& s) {
+__device__ __forceinline__ void part1_update_converted(Vec4<M>& v, Vec4<M>& delta, const M fx, const M fy, const M fz,
+                                                       float xix, float xiy, float xiz, const StepScalars<M>& s) {
     const M w = v.w;
     const M sqrtInvMass = sqrt_rn(w);
     const M fw = mul_rn(s.fs, w);
     const M ns = mul_rn(s.noisescale, sqrtInvMass);
-    v.x = fma_rn(ns, (M) xix, fma_rn(s.vscale, v.x, mul_rn(fw, from_fixed(fx, M()))));
-    v.y = fma_rn(ns, (M) xiy, fma_rn(s.vscale, v.y, mul_rn(fw, from_fixed(fy, M()))));
-    v.z = fma_rn(ns, (M) xiz, fma_rn(s.vscale, v.z, mul_rn(fw, from_fixed(fz, M()))));
+    v.x = fma_rn(ns, (M) xix, fma_rn(s.vscale, v.x, mul_rn(fw, fx)));
+    v.y = fma_rn(ns, (M) xiy, fma_rn(s.vscale, v.y, mul_rn(fw, fy)));
+    v.z = fma_rn(ns, (M) xiz, fma_rn(s.vscale, v.z, mul_rn(fw, fz)));
     delta.x = mul_rn(s.dt, v.x);
     delta.y = mul_rn(s.dt, v.y);
     delta.z = mul_rn(s.dt, v.z);
     delta.w = 0;
+}
+template <typename M>
+__device__ __forceinline__ void part1_update(Vec4<M>& v, Vec4<M>& delta, long long fx, long long fy,
+                                             long long fz, float xix, float xiy, float xiz,
+                                             const StepScalars<M>& s) {
+    part1_update_converted(v, delta, from_fixed(fx, M()), from_fixed(fy, M()), from_fixed(fz, M()), xix, xiy, xiz, s);
 }
 
 // Langevin.cu:43-71 (__CUDA_ARCH__ >= 130 branch).  p/c are posq and posqCorrection.

@@ -51,6 +51,14 @@ elif which == "reordered":
     shard, _ = env.slabmod.permute_slab(shard, perm)
     kind, water = "langevin", None
     chain_counts = (1,)
+elif which == "drude":
+    # the staged Drude step: thread t <-> work item t (spt1) against the balanced kernel (csrc/constv_drude_kernels.cuh)
+    variants = [("item_per_thread", {"CONSTV_DRUDE_SPT": "1"}), ("balanced_2_slots_per_thread", {"CONSTV_DRUDE_SPT": "2"}),
+                ("balanced_3_slots_per_thread", {"CONSTV_DRUDE_SPT": "3"})]
+    shard, d_normal, d_pairs = env.slabmod.slab_tile(R, 1, 0, "single", seed=bench.SLAB_SEED, maker=env.slabmod.make_drude_slab)
+    kind, water, drude = "drude", None, (d_normal, d_pairs)
+    chain_counts = (1, 2, 3)
+    ROUNDS = 3
 else:
     variants = [("ldg_staged_round1_order", {"CONSTV_SETTLE_WS": "0", "CONSTV_SETTLE_EARLY": "0"}),
                 ("ldg_staged_cp_async_early_philox", {"CONSTV_SETTLE_WS": "0", "CONSTV_SETTLE_EARLY": "1"}),
@@ -64,7 +72,8 @@ wls = []
 for name, knobs in variants:
     os.environ.pop("CONSTV_SETTLE_WS", None)
     os.environ.update(knobs)
-    wls.append((name, bench.Workload(env, args, shard, kind=kind, chains=1, water=water, reorder_perm=perm if which == "reordered" else None)))
+    wls.append((name, bench.Workload(env, args, shard, kind=kind, chains=1, water=water, drude=drude if which == "drude" else None,
+                                     reorder_perm=perm if which == "reordered" else None)))
 alg = wls[0][1].algorithmic_bytes()
 results = {}
 for rnd in range(ROUNDS):

@@ -35,7 +35,7 @@ def test_library_exports_exactly_the_declared_symbols(capi):
     lib = capi.load()
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.constv_version() == 120
+    assert lib.constv_version() == 121
 
 
 def test_header_cites_the_reference_for_every_entry_point():

@@ -62,9 +62,10 @@ def mixed_scalars(oracle, precision, max_dist):
 @pytest.mark.parametrize("num_cells", [2, 4])
 @pytest.mark.parametrize("max_dist", [0.0, 0.02])
 @pytest.mark.parametrize("num_real", [41, 6007])
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 5])
 def test_drude_fused_step_bit_exact(gpu, oracle, precision, num_cells, max_dist, num_real, variant):
-    """variant 0 = the kernel staged through shared memory, variant 1 = the gather kernel."""
+    """variant 0 = the staged kernel whose warps draw chunks of work items (two slots per thread), 1 = the gather kernel,
+    5 = the staged kernel with one work item per thread."""
     import torch
     s0, normal, pairs = slabmod.make_drude_slab(num_real, precision, num_cells=num_cells, seed=11)
     nsteps, R = 4, s0.num_real
@@ -90,17 +91,20 @@ def test_drude_fused_step_bit_exact(gpu, oracle, precision, num_cells, max_dist,
 
 @pytest.mark.parametrize("precision", slabmod.PRECISIONS)
 @pytest.mark.parametrize("shift", [1, 37, 300])
-def test_drude_pairs_across_tiles(gpu, oracle, precision, shift):
-    """Pairs whose parent sits in another 128-slot tile than the Drude particle (here: every Drude particle
+@pytest.mark.parametrize("variant", [0, 5])
+def test_drude_pairs_across_tiles(gpu, oracle, precision, shift, variant):
+    """Pairs whose parent sits in another tile (128 or 256 slots) than the Drude particle (here: every Drude particle
     paired with the parent `shift` molecules further on; wall off, the geometry is meaningless): the owner
     handles such a parent in global memory and the parent's own thread stays silent."""
     s0, normal, pairs = slabmod.make_drude_slab(5003, precision, seed=19)
     pairs = np.stack([pairs[:, 0], np.roll(pairs[:, 1], -shift)], axis=1).astype(np.int32)
     pool = np.random.default_rng(10).standard_normal((2 * s0.num_real, 4)).astype(np.float32)
     ctx, it = make_drude_context(gpu, s0, pairs, 0.0, pool=pool)
+    it._kernel.set_kernel_variant(variant)
     ref = s0.copy()
     scalars = mixed_scalars(oracle, precision, 0.0)
-    far = np.sum(pairs[:, 0] // 128 != pairs[:, 1] // 128)
+    tile = 256 if variant == 0 else 128
+    far = np.sum(pairs[:, 0] // tile != pairs[:, 1] // tile)
     assert far > (0 if shift == 1 else len(pairs) // 2)
     for k in range(2):
         it.step(1)
@@ -147,9 +151,9 @@ def role_preserving_permutation(s, rng):
 
 
 @pytest.mark.parametrize("precision", slabmod.PRECISIONS)
-@pytest.mark.parametrize("split,variant", [(False, 0), (False, 1), (True, 0)])
+@pytest.mark.parametrize("split,variant", [(False, 0), (False, 1), (False, 5), (True, 0)])
 def test_drude_reordered_slots(gpu, oracle, precision, split, variant):
-    """variant 0 = the staged kernel with its extra tiles zeroing the image slots, variant 1 = thread per slot."""
+    """variant 0 | 5 = the staged kernels with their extra tiles zeroing the image slots, variant 1 = thread per slot."""
     s0, normal, pairs = slabmod.make_drude_slab(2501, precision, num_cells=2, seed=13)
     perm = role_preserving_permutation(s0, np.random.default_rng(4))
     sp, atom_index = H.permute_slab(s0, perm)
