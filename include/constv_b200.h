@@ -381,9 +381,10 @@ CONSTV_API int constv_set_launch_shape(constv_slab* slab, int32_t pairs_per_thre
  * kernel, which measured faster than the TMA ring on B200), 1 = the plain-load kernel, 2 = the
  * TMA-pipelined kernel (error unless the slab is eligible: identity order, Philox noise,
  * CONSTV_FLAG_CACHE_IMAGE_CHARGE, even P).  For the rigid-molecule step (constv_step_fused_settle*): 0 = automatic
- * (the LDG-staged kernel), 1 = the gather kernel, 3 = the LDG-staged kernel, 4 = the warp-specialised TMA pipeline
+ * (the staged kernel, its stage filled by asynchronous copies), 1 = the gather kernel, 3 = the staged kernel with its
+ * stage filled through registers (round 1's), 4 = the warp-specialised TMA pipeline
  * (bulk copies in and out; identity order, Philox noise, CONSTV_FLAG_CACHE_IMAGE_CHARGE, num_cells == 2, else the
- * LDG-staged kernel runs); same results bit for bit.  For the Drude step (constv_drude_step_fused*): 0 = automatic (the
+ * staged kernel runs); same results bit for bit.  For the Drude step (constv_drude_step_fused*): 0 = automatic (the
  * staged kernel whose warps draw chunks of work items), 1 = the thread-per-slot gather kernel, 5 = the staged kernel with
  * one work item per thread (round 1's); same results bit for bit.
  * (block_size, stages) in {(128,6), (256,2), (256,3), (256,4), (512,2), (512,3)} shape the TMA ring, ctas_per_sm caps the persistent

@@ -88,9 +88,6 @@ struct constv_slab {
     bool fusedEarly = true;
     int zeroWhen = 1;         // 0 with the dependent stores, 1 right behind the loads, 2 after the step-counter barrier
     bool settleWs = false;    // rigid-water step: the warp-specialised TMA pipeline instead of the LDG-staged kernel (CONSTV_SETTLE_WS=1, or kernel variant 4)
-    // LDG-staged rigid-water kernel: cp.async stage-in with the Philox draws made while the copies fly.  Measured SLOWER
-    // (17.0 vs 16.2 us at 1M atoms, 58.0 vs 55.5 us at 4M; profiles/r02_ab_settle_cp_async_early.jsonl): off; CONSTV_SETTLE_EARLY=1 turns it on.
-    bool settleEarly = false;
     // staged Drude step: slots per thread.  2 | 3 = the balanced kernel (warps draw chunks of work items: 17.4 -> 15.2 us per step at 1M atoms
     // with two chains, profiles/r02_ab_drude_balanced.jsonl); 1 = thread t takes work item t (CONSTV_DRUDE_SPT)
     int drudeSlotsPerThread = 2;
@@ -435,7 +432,6 @@ int constv_create(const constv_config* config, constv_slab** out) {
     if (const char* e = std::getenv("CONSTV_FUSED_ZERO")) s->zeroWhen = std::atoi(e);
     if (const char* e = std::getenv("CONSTV_SETTLE_WS")) s->settleWs = std::atoi(e) != 0;
     if (const char* e = std::getenv("CONSTV_INDEXED_MINB")) s->indexedMinBlocks = std::atoi(e);
-    if (const char* e = std::getenv("CONSTV_SETTLE_EARLY")) s->settleEarly = std::atoi(e) != 0;
     if (const char* e = std::getenv("CONSTV_DRUDE_SPT")) s->drudeSlotsPerThread = std::min(3, std::max(1, std::atoi(e)));
     if (const char* e = std::getenv("CONSTV_WS_GROUPS")) { const int g = std::atoi(e); if (g >= 3 && g <= 5) s->wsGroups = g; }
     DeviceGuard guard(config->device);

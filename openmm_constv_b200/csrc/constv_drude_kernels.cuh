@@ -699,34 +699,65 @@ constv_drude_step_balanced_kernel(const __grid_constant__ SlabDev d, const __gri
             continue;
         }
         const int base = tile * kTile;
-        // 1. stage in: thread t loads slots base + t + i * BLOCK
+        // 1. stage in: thread t takes slots base + t + i * BLOCK.  Every load of the thread is issued before the first
+        // use: the velocity and position records as asynchronous copies straight into the stage (cp.async, no registers),
+        // roles, forces and image charges through registers (the forces are converted on the way).
         unsigned int ownerMask[SPT], normalMask[SPT];
+        {
+            int role[SPT];
+            long long fr[SPT][3];
+            Real q1[SPT];
+            const Mixed* __restrict__ velm = static_cast<const Mixed*>(d.velm);
+            const Real* __restrict__ posq = static_cast<const Real*>(d.posq);
+            const Real* __restrict__ corrA = static_cast<const Real*>(d.corr);
+            // register loads first, unconditional (past the end of the real range they read the last real slot: discarded
+            // below), so that they form one block the compiler has no reason to split with the conversions
 #pragma unroll
-        for (int i = 0; i < SPT; i++) {
-            const int idx = tid + i * BLOCK, slot = base + idx, at = drude_swizzle(idx);
-            const bool inRange = slot < R;
-            // past the end of the real range: NORMAL, which no parent test below can mistake for "owned by slot x"
-            const int role = inRange ? dd.role[slot] : DRUDE_ROLE_NORMAL;
-            if (inRange) {
-                DrudeAtom<PREC> me;
-                drude_load<PREC, DRUDE_FUSED, INDEXED, STREAM>(d, slot, me);
-                if (INDEXED) st.orig[idx] = d.atomIndex ? d.atomIndex[slot] : slot;
-                st.v[at] = me.v;
-                st.p[at] = me.p;
-                if (kSplit) st.c[at] = me.c;
-                st.fq[at] = Vec4<Mixed>{from_fixed(me.f[0], Mixed()), from_fixed(me.f[1], Mixed()), from_fixed(me.f[2], Mixed()), (Mixed) me.q1};
-                if (role <= DRUDE_ROLE_PASSIVE) {  // a parent: tell the owner, if it is staged here
-                    const int owner = DRUDE_ROLE_PASSIVE - role - base;
-                    if (owner >= 0 && owner < kTile) st.partner[owner] = (unsigned short) idx;
+            for (int i = 0; i < SPT; i++) {
+                const int ls = min(base + tid + i * BLOCK, R - 1);
+                role[i] = dd.role[ls];
+                fr[i][0] = load_force(d.force + ls);
+                fr[i][1] = load_force(d.force + P + ls);
+                fr[i][2] = load_force(d.force + 2 * P + ls);
+                q1[i] = INDEXED ? (Real) 0 : (d.imageCharge ? static_cast<const Real*>(d.imageCharge)[ls] : posq[4 * ((size_t) R + ls) + 3]);
+            }
+#pragma unroll
+            for (int i = 0; i < SPT; i++) {
+                const int idx = tid + i * BLOCK, slot = base + idx, at = drude_swizzle(idx);
+                if (slot < R) {
+                    cp_async16(&st.v[at], velm + 4 * (size_t) slot);
+                    if (sizeof(Vec4<Mixed>) == 32) cp_async16(reinterpret_cast<char*>(&st.v[at]) + 16, velm + 4 * (size_t) slot + 2);
+                    cp_async16(&st.p[at], posq + 4 * (size_t) slot);
+                    if (sizeof(Vec4<Real>) == 32) cp_async16(reinterpret_cast<char*>(&st.p[at]) + 16, posq + 4 * (size_t) slot + 2);
+                    if (kSplit) cp_async16(&st.c[at], corrA + 4 * (size_t) slot);
+                    if (INDEXED) {
+                        if (d.atomIndex) cp_async4(&st.orig[idx], d.atomIndex + slot);
+                        else st.orig[idx] = slot;
+                    }
+                } else {
+                    role[i] = DRUDE_ROLE_NORMAL;  // which no parent test below can mistake for "owned by slot x"
                 }
             }
-            st.role[idx] = role;
-            ownerMask[i] = __ballot_sync(0xffffffffu, role >= 0);
-            normalMask[i] = __ballot_sync(0xffffffffu, inRange && role == DRUDE_ROLE_NORMAL);
-            if (lane == 0) {
-                st.warpOwners[i * kWarps + warp] = __popc(ownerMask[i]);
-                st.warpNormals[i * kWarps + warp] = __popc(normalMask[i]);
+#pragma unroll
+            for (int i = 0; i < SPT; i++) {
+                const int idx = tid + i * BLOCK, slot = base + idx, at = drude_swizzle(idx);
+                const bool inRange = slot < R;
+                if (inRange) {
+                    st.fq[at] = Vec4<Mixed>{from_fixed(fr[i][0], Mixed()), from_fixed(fr[i][1], Mixed()), from_fixed(fr[i][2], Mixed()), (Mixed) q1[i]};
+                    if (role[i] <= DRUDE_ROLE_PASSIVE) {  // a parent: tell the owner, if it is staged here
+                        const int owner = DRUDE_ROLE_PASSIVE - role[i] - base;
+                        if (owner >= 0 && owner < kTile) st.partner[owner] = (unsigned short) idx;
+                    }
+                }
+                st.role[idx] = role[i];
+                ownerMask[i] = __ballot_sync(0xffffffffu, role[i] >= 0);
+                normalMask[i] = __ballot_sync(0xffffffffu, inRange && role[i] == DRUDE_ROLE_NORMAL);
+                if (lane == 0) {
+                    st.warpOwners[i * kWarps + warp] = __popc(ownerMask[i]);
+                    st.warpNormals[i * kWarps + warp] = __popc(normalMask[i]);
+                }
             }
+            cp_async_wait_all();
         }
         if (tid == 0) st.next = 0;
         publish_step(box, d.counters);

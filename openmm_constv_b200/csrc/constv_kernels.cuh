@@ -132,6 +132,20 @@ __device__ __forceinline__ double from_fixed(long long f, double) { return __ll2
 __device__ __forceinline__ void pdl_wait()   { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ---- asynchronous copies global -> shared (cp.async, SASS LDGSTS) --------------------------------------
+// No staging registers: a thread can have all the records of its slots in flight at once whatever its register budget.
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---- counter-based Gaussian stream -------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  One block per (atom, step):
 //   counter = (atom_lo, atom_hi, step_lo, step_hi), key = (seed_lo, seed_hi)
@@ -543,7 +557,6 @@ constv_fused_step_kernel(const __grid_constant__ SlabDev d, const float4* __rest
 // padded_num_atoms even (16-byte aligned force planes).  Chunk starts are multiples of 4 pairs so
 // every bulk copy is 16-byte aligned and sized.
 
-__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned int bar, unsigned int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }

@@ -324,6 +324,7 @@ constv_settle_step_kernel(const __grid_constant__ SlabDev d, const __grid_consta
 }
 
 
+
 // ---- the same step, staged through shared memory (identity slot order, segmented item list) -----------
 // A molecule's three records are neighbours in memory, so a thread that gathers "its" three records makes
 // every warp-wide access a stride-48-byte pattern: half-filled sectors on the way in and, worse, on the
@@ -334,19 +335,6 @@ constv_settle_step_kernel(const __grid_constant__ SlabDev d, const __grid_consta
 // shared memory; after a barrier thread j computes item j from stage entries per*j + k (stride 3: free of
 // bank conflicts), writes the new velocity and position back, and after a second barrier every thread
 // emits "its" slots again: own record, rewritten images, zeroed images, all coalesced.
-// Ampere-style asynchronous copies global -> shared (SASS LDGSTS): no staging registers, and the thread goes on
-// to other work -- here the Philox draws of its work item -- while the records are in flight.
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
 template <int PREC, int BLOCK, bool INDEXED> struct SettleStage {
     using Real = typename Prec<PREC>::Real;
     using Mixed = typename Prec<PREC>::Mixed;
@@ -358,6 +346,57 @@ template <int PREC, int BLOCK, bool INDEXED> struct SettleStage {
     Real q1[INDEXED ? 1 : kSlots];   // identity order: charge of the cell-1 image, fetched with the record
     int orig[INDEXED ? kSlots : 1];  // reordered slots: original index of the atom in the slot
 };
+
+// Stage in slots [base, base + slotsInTile): thread j takes slots base + j + i * BLOCK (coalesced).
+// ASYNC: asynchronous copies global -> shared (cp.async, SASS LDGSTS) that never pass through registers.  Under the
+// 64-register cap the plain loads of the three slots of a thread were serialised by the compiler (load, wait, store
+// to shared memory, three times: three DRAM round trips per tile, 44 % of the stall samples of the kernel); the copies
+// are all in flight at once and are waited for once.  Measured (in-process A/B, profiles/r02_ab_settle_cp_async.jsonl):
+// 15.5 -> 14.7 us per step at 1M atoms with three chains, 52.7 -> 46.9 us at 4M with two (0.88 of the copy peak).
+template <int PREC, int BLOCK, bool INDEXED, bool STREAM, bool ASYNC>
+__device__ __forceinline__ void settle_stage_in(const SlabDev& d, SettleStage<PREC, BLOCK, INDEXED>& st, const int base,
+                                                const int slotsInTile, const int j) {
+    using Real = typename Prec<PREC>::Real;
+    using Mixed = typename Prec<PREC>::Mixed;
+    constexpr bool kSplit = Prec<PREC>::kSplitPos;
+    const size_t P = (size_t) d.padded;
+    const Real* __restrict__ posq = static_cast<const Real*>(d.posq);
+    const Real* __restrict__ corrA = static_cast<const Real*>(d.corr);
+    const Mixed* __restrict__ velm = static_cast<const Mixed*>(d.velm);
+    const long long* __restrict__ force = d.force;
+    const Real* qbase = d.imageCharge ? static_cast<const Real*>(d.imageCharge) : posq + 4 * (size_t) d.numReal + 3;
+    const size_t qstride = d.imageCharge ? 1 : 4;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int idx = j + i * BLOCK;
+        if (idx < slotsInTile) {
+            const size_t slot = (size_t) (base + idx);
+            if (ASYNC) {
+                cp_async16(&st.v[idx], velm + 4 * slot);
+                if (sizeof(Vec4<Mixed>) == 32) cp_async16(reinterpret_cast<char*>(&st.v[idx]) + 16, velm + 4 * slot + 2);
+                cp_async16(&st.p[idx], posq + 4 * slot);
+                if (sizeof(Vec4<Real>) == 32) cp_async16(reinterpret_cast<char*>(&st.p[idx]) + 16, posq + 4 * slot + 2);
+                if (kSplit) cp_async16(&st.c[idx], corrA + 4 * slot);
+                cp_async8(&st.f[0][idx], force + slot);
+                cp_async8(&st.f[1][idx], force + P + slot);
+                cp_async8(&st.f[2][idx], force + 2 * P + slot);
+                if (INDEXED) cp_async4(&st.orig[idx], d.atomIndex + slot);
+                else if (sizeof(Real) == 4) cp_async4(&st.q1[idx], qbase + qstride * slot);
+                else cp_async8(&st.q1[idx], qbase + qstride * slot);
+            } else {
+                st.v[idx] = load4x<STREAM>(velm, slot);
+                st.p[idx] = load4x<STREAM>(posq, slot);
+                if (kSplit) st.c[idx] = load4x<STREAM>(corrA, slot);
+                st.f[0][idx] = load_force(force + slot);
+                st.f[1][idx] = load_force(force + P + slot);
+                st.f[2][idx] = load_force(force + 2 * P + slot);
+                if (INDEXED) st.orig[idx] = d.atomIndex[slot];
+                else st.q1[idx] = qbase[qstride * slot];
+            }
+        }
+    }
+    if (ASYNC) cp_async_wait_all();
+}
 
 // INDEXED = reordered slots (behind OpenMM after cu.reorderAtoms()).  OpenMM swaps whole identical molecules,
 // so the real atoms keep slots [0, R) and a slot keeps its role: the tiles, the stage and the arithmetic are the
@@ -386,8 +425,6 @@ __device__ __forceinline__ void settle_tiled_tile(const SlabDev& d, const Settle
     const Real* __restrict__ corrA = static_cast<const Real*>(d.corr);
     const Mixed* __restrict__ velm = static_cast<const Mixed*>(d.velm);
     const long long* __restrict__ force = d.force;
-    const Real* qbase = d.imageCharge ? static_cast<const Real*>(d.imageCharge) : posq + 4 * (size_t) R + 3;
-    const size_t qstride = d.imageCharge ? 1 : 4;
     const int j = (int) threadIdx.x;
 
     if (INDEXED && tile >= realTiles) {  // a tile of image slots: zero them, coalesced
@@ -421,22 +458,7 @@ __device__ __forceinline__ void settle_tiled_tile(const SlabDev& d, const Settle
     const int slotsInTile = items * per;
     const float2 prm = seg.params[q];
 
-    // stage in: coalesced
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        const int idx = j + i * BLOCK;
-        if (idx < slotsInTile) {
-            const size_t slot = (size_t) (base + idx);
-            st.v[idx] = load4x<STREAM>(velm, slot);
-            st.p[idx] = load4x<STREAM>(posq, slot);
-            if (kSplit) st.c[idx] = load4x<STREAM>(corrA, slot);
-            st.f[0][idx] = load_force(force + slot);
-            st.f[1][idx] = load_force(force + P + slot);
-            st.f[2][idx] = load_force(force + 2 * P + slot);
-            if (INDEXED) st.orig[idx] = d.atomIndex[slot];
-            else st.q1[idx] = qbase[qstride * slot];
-        }
-    }
+    settle_stage_in<PREC, BLOCK, INDEXED, STREAM, true>(d, st, base, slotsInTile, j);
     publish_step(box, d.counters);
     __syncthreads();
     const unsigned long long step = box.step;
@@ -506,15 +528,11 @@ __device__ __forceinline__ void settle_tiled_tile(const SlabDev& d, const Settle
 
 // The single-slab kernel keeps its own copy of the tile body (below) rather than calling settle_tiled_tile: the
 // call, though inlined, cost a spill under the 64-register cap and 8 % of the step.
-// EARLY (identity order, Philox noise; an experiment, off by default): the stage is filled with asynchronous copies
-// (cp.async) and, while they are in flight, every thread reads the step counter and draws the Philox blocks of its work
-// item's atoms (for massless atoms too; discarded) -- ~390 of a molecule's ~1400 instructions leave the dependent chain
-// that follows the barrier.  Same bits; measured 5 % SLOWER than the plain order.
-template <int PREC, int BLOCK, bool INDEXED, bool STREAM, bool EARLY = false>
+// ASYNC: see settle_stage_in (false = the round-1 stage-in through registers, kernel variant 3).
+template <int PREC, int BLOCK, bool INDEXED, bool STREAM, bool ASYNC = true>
 __global__ void __launch_bounds__(BLOCK, INDEXED ? 0 : (PREC == PREC_SINGLE ? 8 : 4))  // 64 registers: 8 CTAs per SM
 constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ SettleSegments seg,
                                 const float4* __restrict__ random, const unsigned int randomIndex) {
-    static_assert(!(EARLY && INDEXED), "the early draw needs the atom index before the stage is filled");
     using Real = typename Prec<PREC>::Real;
     using Mixed = typename Prec<PREC>::Mixed;
     constexpr bool kSplit = Prec<PREC>::kSplitPos;
@@ -574,41 +592,25 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
         const int slotsInTile = items * per;
         const float2 prm = seg.params[q];
 
-        // stage in: coalesced
-        float4 xiEarly[3];
-        xiEarly[0] = xiEarly[1] = xiEarly[2] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (EARLY) {
+        // stage in (the text of settle_stage_in: calling it, though inlined, costs a spill under the 64-register cap)
 #pragma unroll
-            for (int i = 0; i < 3; i++) {
-                const int idx = j + i * BLOCK;
-                if (idx < slotsInTile) {
-                    const size_t slot = (size_t) (base + idx);
-                    if (sizeof(Vec4<Mixed>) == 16) cp_async16(&st.v[idx], velm + 4 * slot);
-                    else { cp_async16(&st.v[idx], velm + 4 * slot); cp_async16(reinterpret_cast<char*>(&st.v[idx]) + 16, velm + 4 * slot + 2); }
-                    if (sizeof(Vec4<Real>) == 16) cp_async16(&st.p[idx], posq + 4 * slot);
-                    else { cp_async16(&st.p[idx], posq + 4 * slot); cp_async16(reinterpret_cast<char*>(&st.p[idx]) + 16, posq + 4 * slot + 2); }
+        for (int i = 0; i < 3; i++) {
+            const int idx = j + i * BLOCK;
+            if (idx < slotsInTile) {
+                const size_t slot = (size_t) (base + idx);
+                if (ASYNC) {
+                    cp_async16(&st.v[idx], velm + 4 * slot);
+                    if (sizeof(Vec4<Mixed>) == 32) cp_async16(reinterpret_cast<char*>(&st.v[idx]) + 16, velm + 4 * slot + 2);
+                    cp_async16(&st.p[idx], posq + 4 * slot);
+                    if (sizeof(Vec4<Real>) == 32) cp_async16(reinterpret_cast<char*>(&st.p[idx]) + 16, posq + 4 * slot + 2);
                     if (kSplit) cp_async16(&st.c[idx], corrA + 4 * slot);
                     cp_async8(&st.f[0][idx], force + slot);
                     cp_async8(&st.f[1][idx], force + P + slot);
                     cp_async8(&st.f[2][idx], force + 2 * P + slot);
-                    if (sizeof(Real) == 4) cp_async4(&st.q1[idx], qbase + qstride * slot);
+                    if (INDEXED) cp_async4(&st.orig[idx], d.atomIndex + slot);
+                    else if (sizeof(Real) == 4) cp_async4(&st.q1[idx], qbase + qstride * slot);
                     else cp_async8(&st.q1[idx], qbase + qstride * slot);
-                }
-            }
-            // while the copies fly: the step counter (every thread reads it; the ticket below is taken after) and the draws
-            const unsigned long long stepEarly = __ldcg(&d.counters->step);
-            if (j < items && s.noisescale != 0) {
-#pragma unroll
-                for (int k = 0; k < 3; k++)
-                    if (k < per) xiEarly[k] = gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) (base + per * j + k), stepEarly);
-            }
-            cp_async_wait_all();
-        } else {
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                const int idx = j + i * BLOCK;
-                if (idx < slotsInTile) {
-                    const size_t slot = (size_t) (base + idx);
+                } else {
                     st.v[idx] = load4x<STREAM>(velm, slot);
                     st.p[idx] = load4x<STREAM>(posq, slot);
                     if (kSplit) st.c[idx] = load4x<STREAM>(corrA, slot);
@@ -620,6 +622,7 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
                 }
             }
         }
+        if (ASYNC) cp_async_wait_all();
         publish_step(box, d.counters);
         __syncthreads();
         const unsigned long long step = box.step;
@@ -642,8 +645,7 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
                     if (moved[k]) {
                         float4 xi;
                         const int a = INDEXED ? st.orig[idx] : base + idx;
-                        if (EARLY) xi = xiEarly[k];  // drawn before the barrier, from the same (seed; atom, step)
-                        else if (random != nullptr) xi = __ldcs(random + (size_t) randomIndex + base + idx);
+                        if (random != nullptr) xi = __ldcs(random + (size_t) randomIndex + base + idx);
                         else xi = (s.noisescale != 0) ? gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) a, step)
                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
                         part1_update(v[k], delta[k], st.f[0][idx], st.f[1][idx], st.f[2][idx], xi.x, xi.y, xi.z, s);

@@ -60,20 +60,19 @@ elif which == "drude":
     chain_counts = (1, 2, 3)
     ROUNDS = 3
 else:
-    variants = [("ldg_staged_round1_order", {"CONSTV_SETTLE_WS": "0", "CONSTV_SETTLE_EARLY": "0"}),
-                ("ldg_staged_cp_async_early_philox", {"CONSTV_SETTLE_WS": "0", "CONSTV_SETTLE_EARLY": "1"}),
-                ("tma_pipeline_g3", {"CONSTV_SETTLE_WS": "1", "CONSTV_WS_GROUPS": "3"})]
+    # "_variant" = constv_set_kernel_variant: 0 the default (cp.async stage-in), 3 the stage filled through registers (round 1)
+    variants = [("ldg_staged", {"_variant": 3}), ("cp_async_stage_in", {"_variant": 0})]
     shard, w_atoms, w_params, w_cons = env.slabmod.slab_tile(R, 1, 0, "single", seed=bench.SLAB_SEED, maker=env.slabmod.make_water_slab)
     kind, water = "settle", (w_atoms, w_params, w_cons)
-    chain_counts = (1, 2)
+    chain_counts = (1, 2, 3)
     ROUNDS = 3
 
 wls = []
 for name, knobs in variants:
     os.environ.pop("CONSTV_SETTLE_WS", None)
-    os.environ.update(knobs)
+    os.environ.update({k: v for k, v in knobs.items() if not k.startswith("_")})
     wls.append((name, bench.Workload(env, args, shard, kind=kind, chains=1, water=water, drude=drude if which == "drude" else None,
-                                     reorder_perm=perm if which == "reordered" else None)))
+                                     reorder_perm=perm if which == "reordered" else None, variant=knobs.get("_variant", 0))))
 alg = wls[0][1].algorithmic_bytes()
 results = {}
 for rnd in range(ROUNDS):

@@ -55,9 +55,10 @@ def bond_errors(s, atoms, params):
 @pytest.mark.parametrize("precision", slabmod.PRECISIONS)
 @pytest.mark.parametrize("num_cells", [2, 4])
 @pytest.mark.parametrize("num_real", [37, 6007])
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 3])
 def test_fused_settle_step_bit_exact(gpu, oracle, precision, num_cells, num_real, variant):
-    """variant 0 = the kernel staged through shared memory (tiles of 128 work items, coalesced both ways),
+    """variant 0 = the kernel staged through shared memory (tiles of 128 work items, coalesced both ways; the stage filled
+    by asynchronous copies), variant 3 = the same with the stage filled through registers,
     variant 1 = the gather kernel (a thread reads its three records itself)."""
     import torch
     s0, atoms, params, cons = slabmod.make_water_slab(num_real, precision, num_cells=num_cells, seed=31)

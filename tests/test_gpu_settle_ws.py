@@ -1,6 +1,6 @@
 """The rigid-water step as a warp-specialised TMA pipeline (csrc/constv_settle_ws_kernels.cuh: bulk asynchronous
 copies in and out of a shared-memory ring, producer / consumer groups / storer): same bits as the CPU oracle and
-as the LDG-staged kernel (kernel variant 3; the pipeline is variant 4 and is not the default: it is slower), for
+as the staged kernel (kernel variants 0 and 3; the pipeline is variant 4 and is not the default: it is slower), for
 
   * every precision, with the image-charge side array (without it the library falls back to the LDG-staged kernel),
   * runs that start on every alignment of the 4-slot load window and the 2-element force-plane window
@@ -33,7 +33,7 @@ def gpu():
     return integrator
 
 
-WS = 4  # constv_set_kernel_variant: the TMA-pipelined rigid-water kernel (3 = the LDG-staged one, which 0 = auto picks)
+WS = 4  # constv_set_kernel_variant: the TMA-pipelined rigid-water kernel (0 = auto = the staged kernel; 3 = the same, staged through registers)
 
 
 def make_context(gpu, s, cons, seed=77, flags=None, variant=WS):
