@@ -1191,10 +1191,11 @@ def main():
             torch.cuda.empty_cache()
 
     # ---- the same slab size with the constrained / polarizable steps: one kernel per step each ----
-    # (own tile of one global slab per rank, two chains; the flags --rigid-water / --drude run them as the headline instead)
+    # (own tile of one global slab per rank, six chains -- profiles/r02_ab_staged_chain_counts.jsonl; the flags --rigid-water /
+    # --drude run them as the headline instead)
     if plain and not slab16m and want("rigid"):
         shw, w_atoms, w_params, w_cons = slabmod.slab_tile(R_total, world, rank, args.precision, seed=SLAB_SEED, maker=slabmod.make_water_slab)
-        ww = Workload(env, args, shw, kind="settle", chains=2, water=(w_atoms, w_params, w_cons))
+        ww = Workload(env, args, shw, kind="settle", chains=6, water=(w_atoms, w_params, w_cons))
         kw_ = max(20, min(K, 1200))
         tw = time_steps(env, ww, kw_, 5, use_graph=use_graph, repeats=args.repeats)
         also["rigid_water"] = rate_record(shw.num_atoms * world, kw_, tw, ww.algorithmic_bytes(), ww.chains, peak, "constv_settle_step_tiled_kernel",
@@ -1206,7 +1207,7 @@ def main():
         torch.cuda.empty_cache()
     if plain and not slab16m and want("drude"):
         shd, d_normal, d_pairs = slabmod.slab_tile(R_total, world, rank, args.precision, seed=SLAB_SEED, maker=slabmod.make_drude_slab)
-        wd = Workload(env, args, shd, kind="drude", chains=2, drude=(d_normal, d_pairs))
+        wd = Workload(env, args, shd, kind="drude", chains=6, drude=(d_normal, d_pairs))
         kd_ = max(20, min(K, 1200))
         td = time_steps(env, wd, kd_, 5, use_graph=use_graph, repeats=args.repeats)
         also["drude"] = rate_record(shd.num_atoms * world, kd_, td, wd.algorithmic_bytes(), wd.chains, peak, "constv_drude_step_balanced_kernel",

@@ -51,6 +51,17 @@ elif which == "reordered":
     shard, _ = env.slabmod.permute_slab(shard, perm)
     kind, water = "langevin", None
     chain_counts = (1,)
+elif which in ("settle_chains", "drude_chains"):
+    variants = [("default", {})]
+    drude = None
+    if which == "drude_chains":
+        shard, d_normal, d_pairs = env.slabmod.slab_tile(R, 1, 0, "single", seed=bench.SLAB_SEED, maker=env.slabmod.make_drude_slab)
+        kind, water, drude = "drude", None, (d_normal, d_pairs)
+    else:
+        shard, w_atoms, w_params, w_cons = env.slabmod.slab_tile(R, 1, 0, "single", seed=bench.SLAB_SEED, maker=env.slabmod.make_water_slab)
+        kind, water = "settle", (w_atoms, w_params, w_cons)
+    chain_counts = (2, 3, 4, 6, 8, 12)
+    ROUNDS = 3
 elif which == "drude":
     # the staged Drude step: thread t <-> work item t (spt1) against the balanced kernel (csrc/constv_drude_kernels.cuh)
     variants = [("item_per_thread", {"CONSTV_DRUDE_SPT": "1"}), ("balanced_2_slots_per_thread", {"CONSTV_DRUDE_SPT": "2"}),
@@ -71,7 +82,7 @@ wls = []
 for name, knobs in variants:
     os.environ.pop("CONSTV_SETTLE_WS", None)
     os.environ.update({k: v for k, v in knobs.items() if not k.startswith("_")})
-    wls.append((name, bench.Workload(env, args, shard, kind=kind, chains=1, water=water, drude=drude if which == "drude" else None,
+    wls.append((name, bench.Workload(env, args, shard, kind=kind, chains=1, water=water, drude=drude if which in ("drude", "drude_chains") else None,
                                      reorder_perm=perm if which == "reordered" else None, variant=knobs.get("_variant", 0))))
 alg = wls[0][1].algorithmic_bytes()
 results = {}
