@@ -54,7 +54,7 @@ elif which == "reordered":
 elif which in ("settle_chains", "drude_chains"):
     variants = [("default", {})]
     drude = None
-    if which == "drude_chains":
+    if which.startswith("drude"):
         shard, d_normal, d_pairs = env.slabmod.slab_tile(R, 1, 0, "single", seed=bench.SLAB_SEED, maker=env.slabmod.make_drude_slab)
         kind, water, drude = "drude", None, (d_normal, d_pairs)
     else:
@@ -82,7 +82,7 @@ wls = []
 for name, knobs in variants:
     os.environ.pop("CONSTV_SETTLE_WS", None)
     os.environ.update({k: v for k, v in knobs.items() if not k.startswith("_")})
-    wls.append((name, bench.Workload(env, args, shard, kind=kind, chains=1, water=water, drude=drude if which in ("drude", "drude_chains") else None,
+    wls.append((name, bench.Workload(env, args, shard, kind=kind, chains=1, water=water, drude=drude if which.startswith("drude") else None,
                                      reorder_perm=perm if which == "reordered" else None, variant=knobs.get("_variant", 0))))
 alg = wls[0][1].algorithmic_bytes()
 results = {}
