@@ -431,7 +431,7 @@ template <int PREC, int BLOCK> struct DrudeStage {
 
 // INDEXED = reordered slots: same tiles and arithmetic (the real atoms keep slots [0, R) and a slot keeps its
 // role); the Philox key is atomIndex[slot], images are written wherever invAtomOrder says, and the image slots
-// are zeroed by extra tiles in slot order.
+// are zeroed in slot order (every thread zeroes the slots R * cell above its own: coalesced, whatever atoms they hold).
 template <int PREC, int BLOCK, bool INDEXED, bool STREAM>
 __global__ void __launch_bounds__(BLOCK, PREC == PREC_SINGLE ? 0 : 5)
 constv_drude_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ DrudeDev dd,
@@ -446,11 +446,8 @@ constv_drude_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_c
     pdl_launch();
     const int R = d.numReal;
     const size_t P = (size_t) d.padded;
-    const int realTiles = (R + BLOCK - 1) / BLOCK;
-    constexpr int kZeroSpan = 8;  // a zeroing tile covers 8 * BLOCK image slots
-    const int zeroTiles = INDEXED ? (d.numAtoms - R + kZeroSpan * BLOCK - 1) / (kZeroSpan * BLOCK) : 0;
     // a chain (constv_set_chains) advances tiles [rangeLo, rangeHi) of the tile space with its own counters;
-    // the whole step = [0, realTiles + zeroTiles)
+    // the whole step = [0, realTiles)
     const int tileLo = d.rangeLo, tileHi = d.rangeHi;
     const unsigned int holders = (unsigned int) (tileHi - tileLo);
     const StepScalars<Mixed> s = scalars_of<Mixed>(d);
@@ -458,27 +455,6 @@ constv_drude_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_c
     const int tid = (int) threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int tile = tileLo + (int) blockIdx.x; tile < tileHi; tile += (int) gridDim.x) {
-        if (INDEXED && tile >= realTiles) {  // a tile of image slots: zero them, coalesced
-            publish_step(box, d.counters);
-            __syncthreads();
-            const unsigned long long zstep = box.step;
-            const unsigned int zticket = take_ticket(d.counters, holders);
-#pragma unroll
-            for (int i = 0; i < kZeroSpan; i++) {
-                const int zslot = R + ((tile - realTiles) * kZeroSpan + i) * BLOCK + tid;
-                if (zslot < d.numAtoms) {
-                    if (d.zeroVelm) store4x<STREAM>(static_cast<Mixed*>(d.velm), (size_t) zslot, Vec4<Mixed>{0, 0, 0, 0});
-                    if (d.zeroForce) {
-                        __stcs(d.force + zslot, 0LL);
-                        __stcs(d.force + P + zslot, 0LL);
-                        __stcs(d.force + 2 * P + zslot, 0LL);
-                    }
-                }
-            }
-            close_step(d.counters, zticket, holders, zstep);
-            if (tile + (int) gridDim.x < tileHi) __syncthreads();
-            continue;
-        }
         const long long base = (long long) tile * BLOCK;
         const int slot = (int) base + tid;
         const bool inRange = slot < R;
@@ -609,6 +585,7 @@ constv_drude_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_c
                 DrudeAtom<PREC> rec;
                 rec.v = v; rec.p = p; rec.c = c;
                 drude_emit<PREC, true, STREAM>(d, slot, st.orig[tid], moved, rec);
+                emit_zero<PREC, STREAM>(d, slot);  // the image slots, in slot order: coalesced whatever atoms they hold
             } else {
                 emit_atom<PREC, STREAM>(d, d.zshift, slot, moved, v, p, c, q1);
             }
@@ -652,6 +629,9 @@ template <int PREC, int BLOCK, int SPT, bool INDEXED> struct DrudeStageB {
 };
 __device__ __forceinline__ int drude_swizzle(const int i) { return i ^ ((i >> 3) & 7); }
 
+// The zeroing stores of the image slots are issued in the stage-in phase, behind the loads (they depend on nothing):
+// 13.4 -> 13.0 us per step at 1M atoms with six chains, 19.4 -> 18.7 us with one launch per step
+// (profiles/r02_ab_staged_zero_timing.jsonl).
 template <int PREC, int BLOCK, int SPT, bool INDEXED, bool STREAM>
 __global__ void __launch_bounds__(BLOCK, (PREC == PREC_SINGLE ? 1024 : 512) / BLOCK)  // single: 64 registers, 32 warps per SM
 constv_drude_step_balanced_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ DrudeDev dd,
@@ -668,8 +648,6 @@ constv_drude_step_balanced_kernel(const __grid_constant__ SlabDev d, const __gri
     pdl_launch();
     const int R = d.numReal;
     const size_t P = (size_t) d.padded;
-    const int realTiles = (R + kTile - 1) / kTile;
-    constexpr int kZeroSpan = 8;  // a zeroing tile covers 8 * BLOCK image slots
     const int tileLo = d.rangeLo, tileHi = d.rangeHi;
     const unsigned int holders = (unsigned int) (tileHi - tileLo);
     const StepScalars<Mixed> s = scalars_of<Mixed>(d);
@@ -677,27 +655,6 @@ constv_drude_step_balanced_kernel(const __grid_constant__ SlabDev d, const __gri
     const int tid = (int) threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int tile = tileLo + (int) blockIdx.x; tile < tileHi; tile += (int) gridDim.x) {
-        if (INDEXED && tile >= realTiles) {  // a tile of image slots: zero them, coalesced
-            publish_step(box, d.counters);
-            __syncthreads();
-            const unsigned long long zstep = box.step;
-            const unsigned int zticket = take_ticket(d.counters, holders);
-#pragma unroll
-            for (int i = 0; i < kZeroSpan; i++) {
-                const int zslot = R + ((tile - realTiles) * kZeroSpan + i) * BLOCK + tid;
-                if (zslot < d.numAtoms) {
-                    if (d.zeroVelm) store4x<STREAM>(static_cast<Mixed*>(d.velm), (size_t) zslot, Vec4<Mixed>{0, 0, 0, 0});
-                    if (d.zeroForce) {
-                        __stcs(d.force + zslot, 0LL);
-                        __stcs(d.force + P + zslot, 0LL);
-                        __stcs(d.force + 2 * P + zslot, 0LL);
-                    }
-                }
-            }
-            close_step(d.counters, zticket, holders, zstep);
-            if (tile + (int) gridDim.x < tileHi) __syncthreads();
-            continue;
-        }
         const int base = tile * kTile;
         // 1. stage in: thread t takes slots base + t + i * BLOCK.  Every load of the thread is issued before the first
         // use: the velocity and position records as asynchronous copies straight into the stage (cp.async, no registers),
@@ -734,6 +691,7 @@ constv_drude_step_balanced_kernel(const __grid_constant__ SlabDev d, const __gri
                         if (d.atomIndex) cp_async4(&st.orig[idx], d.atomIndex + slot);
                         else st.orig[idx] = slot;
                     }
+                    emit_zero<PREC, STREAM>(d, slot);
                 } else {
                     role[i] = DRUDE_ROLE_NORMAL;  // which no parent test below can mistake for "owned by slot x"
                 }
@@ -851,7 +809,7 @@ constv_drude_step_balanced_kernel(const __grid_constant__ SlabDev d, const __gri
                         rec.v = v2; rec.p = p2; rec.c = c2;
                         drude_emit<PREC, true, STREAM>(d, far, orig2, true, rec);
                     } else {
-                        emit_atom<PREC, STREAM>(d, d.zshift, far, true, v2, p2, c2, q2);
+                        emit_atom<PREC, STREAM, false>(d, d.zshift, far, true, v2, p2, c2, q2);  // its image slots are zeroed by the thread that staged it
                     }
                 }
             } else {
@@ -900,7 +858,7 @@ constv_drude_step_balanced_kernel(const __grid_constant__ SlabDev d, const __gri
                     rec.v = v; rec.p = p; rec.c = c;
                     drude_emit<PREC, true, STREAM>(d, slot, st.orig[idx], moved, rec);
                 } else {
-                    emit_atom<PREC, STREAM>(d, d.zshift, slot, moved, v, p, c, (Real) st.fq[at].w);
+                    emit_atom<PREC, STREAM, false>(d, d.zshift, slot, moved, v, p, c, (Real) st.fq[at].w);
                 }
             }
         }

@@ -402,7 +402,8 @@ __device__ __forceinline__ void settle_stage_in(const SlabDev& d, SettleStage<PR
 // so the real atoms keep slots [0, R) and a slot keeps its role: the tiles, the stage and the arithmetic are the
 // same; what changes is that the Philox key is the ORIGINAL index atomIndex[slot], that an atom's images sit
 // wherever invAtomOrder says (a scattered 16-byte store each, as in the reference, constVLangevin.cu:155-158),
-// and that the image slots are zeroed by extra tiles in slot order (coalesced) instead of by their partners.
+// and that the image slots are zeroed in slot order (every thread zeroes the slots R * cell above its own: coalesced,
+// whatever atoms they hold) instead of by their partners.
 // One tile of the staged step for one slab (`tile` in the slab's own tile space), for the batched ensemble
 // kernel.  The caller owns the loop over tiles and the barrier between two tiles (the stage and the step box are
 // rewritten by the next tile).  Same text as the body of constv_settle_step_tiled_kernel.
@@ -415,10 +416,8 @@ __device__ __forceinline__ void settle_tiled_tile(const SlabDev& d, const Settle
     constexpr bool kSplit = Prec<PREC>::kSplitPos;
     const int R = d.numReal;
     const size_t P = (size_t) d.padded;
-    const int realTiles = seg.tileStart[seg.count];
-    constexpr int kZeroSpan = 12;  // a zeroing tile covers 12 * BLOCK image slots
     // a chain (constv_set_chains) advances tiles [rangeLo, rangeHi) of the tile space with its own counters;
-    // the whole step = [0, realTiles + zeroTiles)
+    // the whole step = [0, realTiles)
     const unsigned int holders = (unsigned int) (d.rangeHi - d.rangeLo);
     const StepScalars<Mixed> s = scalars_of<Mixed>(d);
     const Real* __restrict__ posq = static_cast<const Real*>(d.posq);
@@ -427,26 +426,6 @@ __device__ __forceinline__ void settle_tiled_tile(const SlabDev& d, const Settle
     const long long* __restrict__ force = d.force;
     const int j = (int) threadIdx.x;
 
-    if (INDEXED && tile >= realTiles) {  // a tile of image slots: zero them, coalesced
-        publish_step(box, d.counters);
-        __syncthreads();
-        const unsigned long long step = box.step;
-        const unsigned int ticket = take_ticket(d.counters, holders);
-#pragma unroll
-        for (int i = 0; i < kZeroSpan; i++) {
-            const int slot = R + ((tile - realTiles) * kZeroSpan + i) * BLOCK + j;
-            if (slot < d.numAtoms) {
-                if (d.zeroVelm) store4x<STREAM>(static_cast<Mixed*>(d.velm), (size_t) slot, Vec4<Mixed>{0, 0, 0, 0});
-                if (d.zeroForce) {
-                    __stcs(d.force + slot, 0LL);
-                    __stcs(d.force + P + slot, 0LL);
-                    __stcs(d.force + 2 * P + slot, 0LL);
-                }
-            }
-        }
-        close_step(d.counters, ticket, holders, step);
-        return;
-    }
     int q = 0;
 #pragma unroll
     for (int k = 1; k < kSettleMaxSegments; k++)
@@ -518,6 +497,7 @@ __device__ __forceinline__ void settle_tiled_tile(const SlabDev& d, const Settle
                 DrudeAtom<PREC> rec;
                 rec.v = v; rec.p = p; rec.c = c;
                 drude_emit<PREC, true, STREAM>(d, base + idx, st.orig[idx], v.w != 0, rec);
+                emit_zero<PREC, STREAM>(d, base + idx);  // the image slots, in slot order: coalesced whatever atoms they hold
             } else {
                 emit_atom<PREC, STREAM>(d, s.zshift, base + idx, v.w != 0, v, p, c, st.q1[idx]);
             }
@@ -529,13 +509,17 @@ __device__ __forceinline__ void settle_tiled_tile(const SlabDev& d, const Settle
 // The single-slab kernel keeps its own copy of the tile body (below) rather than calling settle_tiled_tile: the
 // call, though inlined, cost a spill under the 64-register cap and 8 % of the step.
 // ASYNC: see settle_stage_in (false = the round-1 stage-in through registers, kernel variant 3).
+// Reordered slots: the zeroing stores of the image slots are issued in the stage-in phase, behind the tile's loads (they
+// depend on nothing): 18.7 -> 18.3 us per step at 1M atoms; in identity order they stay with the dependent stores at the
+// end of the tile (issued early: 13.7 -> 14.0 us with six chains; profiles/r02_ab_staged_zero_timing.jsonl).
 template <int PREC, int BLOCK, bool INDEXED, bool STREAM, bool ASYNC = true>
-__global__ void __launch_bounds__(BLOCK, INDEXED ? 0 : (PREC == PREC_SINGLE ? 8 : 4))  // 64 registers: 8 CTAs per SM
+__global__ void __launch_bounds__(BLOCK, PREC == PREC_SINGLE ? 8 : (INDEXED ? 0 : 4))  // single precision: 64 registers, 8 CTAs per SM
 constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ SettleSegments seg,
                                 const float4* __restrict__ random, const unsigned int randomIndex) {
     using Real = typename Prec<PREC>::Real;
     using Mixed = typename Prec<PREC>::Mixed;
     constexpr bool kSplit = Prec<PREC>::kSplitPos;
+    constexpr bool ZEARLY = INDEXED;
     extern __shared__ __align__(16) unsigned char smemRaw[];
     SettleStage<PREC, BLOCK, INDEXED>& st = *reinterpret_cast<SettleStage<PREC, BLOCK, INDEXED>*>(smemRaw);
     __shared__ StepBox box;
@@ -543,11 +527,8 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
     pdl_launch();
     const int R = d.numReal;
     const size_t P = (size_t) d.padded;
-    const int realTiles = seg.tileStart[seg.count];
-    constexpr int kZeroSpan = 12;  // a zeroing tile covers 12 * BLOCK image slots
-    const int zeroTiles = INDEXED ? (d.numAtoms - R + kZeroSpan * BLOCK - 1) / (kZeroSpan * BLOCK) : 0;
     // a chain (constv_set_chains) advances tiles [rangeLo, rangeHi) of the tile space with its own counters;
-    // the whole step = [0, realTiles + zeroTiles)
+    // the whole step = [0, realTiles)
     const int tileLo = d.rangeLo, tileHi = d.rangeHi;
     const unsigned int holders = (unsigned int) (tileHi - tileLo);
     const StepScalars<Mixed> s = scalars_of<Mixed>(d);
@@ -560,27 +541,6 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
     const int j = (int) threadIdx.x;
 
     for (int tile = tileLo + (int) blockIdx.x; tile < tileHi; tile += (int) gridDim.x) {
-        if (INDEXED && tile >= realTiles) {  // a tile of image slots: zero them, coalesced
-            publish_step(box, d.counters);
-            __syncthreads();
-            const unsigned long long step = box.step;
-            const unsigned int ticket = take_ticket(d.counters, holders);
-#pragma unroll
-            for (int i = 0; i < kZeroSpan; i++) {
-                const int slot = R + ((tile - realTiles) * kZeroSpan + i) * BLOCK + j;
-                if (slot < d.numAtoms) {
-                    if (d.zeroVelm) store4x<STREAM>(static_cast<Mixed*>(d.velm), (size_t) slot, Vec4<Mixed>{0, 0, 0, 0});
-                    if (d.zeroForce) {
-                        __stcs(d.force + slot, 0LL);
-                        __stcs(d.force + P + slot, 0LL);
-                        __stcs(d.force + 2 * P + slot, 0LL);
-                    }
-                }
-            }
-            close_step(d.counters, ticket, holders, step);
-            if (tile + (int) gridDim.x < tileHi) __syncthreads();
-            continue;
-        }
         int q = 0;
 #pragma unroll
         for (int k = 1; k < kSettleMaxSegments; k++)
@@ -620,6 +580,7 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
                     if (INDEXED) st.orig[idx] = d.atomIndex[slot];
                     else st.q1[idx] = qbase[qstride * slot];
                 }
+                if (ZEARLY) emit_zero<PREC, STREAM>(d, base + idx);  // the image slots, in slot order: coalesced whatever atoms they hold
             }
         }
         if (ASYNC) cp_async_wait_all();
@@ -683,7 +644,7 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
                     rec.v = v; rec.p = p; rec.c = c;
                     drude_emit<PREC, true, STREAM>(d, base + idx, st.orig[idx], v.w != 0, rec);
                 } else {
-                    emit_atom<PREC, STREAM>(d, s.zshift, base + idx, v.w != 0, v, p, c, st.q1[idx]);
+                    emit_atom<PREC, STREAM, !ZEARLY>(d, s.zshift, base + idx, v.w != 0, v, p, c, st.q1[idx]);
                 }
             }
         }

@@ -51,7 +51,7 @@ elif which == "reordered":
     shard, _ = env.slabmod.permute_slab(shard, perm)
     kind, water = "langevin", None
     chain_counts = (1,)
-elif which in ("settle_chains", "drude_chains"):
+elif which in ("settle_chains", "drude_chains", "settle_reordered", "drude_reordered"):
     variants = [("default", {})]
     drude = None
     if which.startswith("drude"):
@@ -61,6 +61,13 @@ elif which in ("settle_chains", "drude_chains"):
         shard, w_atoms, w_params, w_cons = env.slabmod.slab_tile(R, 1, 0, "single", seed=bench.SLAB_SEED, maker=env.slabmod.make_water_slab)
         kind, water = "settle", (w_atoms, w_params, w_cons)
     chain_counts = (2, 3, 4, 6, 8, 12)
+    if which.endswith("reordered"):
+        chain_counts = (1,)
+    if which.endswith("reordered"):
+        per = 4 if which.startswith("drude") else 3
+        n_mol = shard.meta["n_pairs"] if which.startswith("drude") else shard.meta["n_water"] // 3
+        perm = env.slabmod.molecule_permutation(shard, shard.meta["n_ion"], per, n_mol, seed=7)
+        shard, _ = env.slabmod.permute_slab(shard, perm)
     ROUNDS = 3
 elif which == "drude":
     # the staged Drude step: thread t <-> work item t (spt1) against the balanced kernel (csrc/constv_drude_kernels.cuh)
@@ -83,7 +90,7 @@ for name, knobs in variants:
     os.environ.pop("CONSTV_SETTLE_WS", None)
     os.environ.update({k: v for k, v in knobs.items() if not k.startswith("_")})
     wls.append((name, bench.Workload(env, args, shard, kind=kind, chains=1, water=water, drude=drude if which.startswith("drude") else None,
-                                     reorder_perm=perm if which == "reordered" else None, variant=knobs.get("_variant", 0))))
+                                     reorder_perm=perm if which.endswith("reordered") else None, variant=knobs.get("_variant", 0))))
 alg = wls[0][1].algorithmic_bytes()
 results = {}
 for rnd in range(ROUNDS):
