@@ -89,6 +89,28 @@ def test_drude_fused_step_bit_exact(gpu, oracle, precision, num_cells, max_dist,
     ctx.close()
 
 
+@pytest.mark.parametrize("num_real", [253, 255, 256, 257, 259, 511, 513, 767, 769, 1023, 1025, 1279])
+def test_drude_sizes_around_the_tile_boundaries(gpu, oracle, num_real):
+    """The balanced kernel stages 256 slots per CTA (two per thread): real ranges that end just before, on and just after a
+    tile boundary, with the 4-site molecules starting at every residue of 4 (the ion count varies with the size); hard
+    wall on, the reference's pool addressing."""
+    import torch
+    s0, normal, pairs = slabmod.make_drude_slab(num_real, "single", seed=100 + num_real)
+    nsteps, R = 3, s0.num_real
+    pool = np.random.default_rng(num_real).standard_normal((nsteps * R + 7, 4)).astype(np.float32)
+    ctx, it = make_drude_context(gpu, s0, pairs, 0.02, pool=pool)
+    ref = s0.copy()
+    scalars = mixed_scalars(oracle, "single", 0.02)
+    for k in range(nsteps):
+        f = slabmod.new_forces(s0, k)
+        ctx.force.copy_(torch.from_numpy(f))
+        ref.force[:] = f
+        it.step(1)
+        oracle_drude_step(oracle, ref, normal, pairs, scalars, pool, random_index=k * R)
+        assert_slab_bits_equal(download(ctx, s0), ref)
+    ctx.close()
+
+
 @pytest.mark.parametrize("precision", slabmod.PRECISIONS)
 @pytest.mark.parametrize("shift", [1, 37, 300])
 @pytest.mark.parametrize("variant", [0, 5])
