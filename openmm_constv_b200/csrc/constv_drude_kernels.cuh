@@ -632,8 +632,11 @@ __device__ __forceinline__ int drude_swizzle(const int i) { return i ^ ((i >> 3)
 // The zeroing stores of the image slots are issued in the stage-in phase, behind the loads (they depend on nothing):
 // 13.4 -> 13.0 us per step at 1M atoms with six chains, 19.4 -> 18.7 us with one launch per step
 // (profiles/r02_ab_staged_zero_timing.jsonl).
+// Mixed precision (what the reference's example runs): 5 CTAs per SM at 96 registers measured 27.8 -> 24.5 us per step at 1M
+// atoms with six chains against 4 CTAs at 120 registers (31.6 -> 32.9 us with one launch per step;
+// profiles/r02_ab_staged_mixed_ctas_per_sm.jsonl).
 template <int PREC, int BLOCK, int SPT, bool INDEXED, bool STREAM>
-__global__ void __launch_bounds__(BLOCK, (PREC == PREC_SINGLE ? 1024 : 512) / BLOCK)  // single: 64 registers, 32 warps per SM
+__global__ void __launch_bounds__(BLOCK, PREC == PREC_SINGLE ? 1024 / BLOCK : (PREC == PREC_MIXED ? 5 : 4))  // single: 64 registers, 32 warps per SM
 constv_drude_step_balanced_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ DrudeDev dd,
                                   const float4* __restrict__ random, const unsigned int randomIndex) {
     using Real = typename Prec<PREC>::Real;

@@ -20,7 +20,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 which = sys.argv[1] if len(sys.argv) > 1 else "fused"
 atoms = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
-sys.argv = ["bench.py", "--atoms", str(atoms)]
+PRECISION = sys.argv[3] if len(sys.argv) > 3 else "single"
+sys.argv = ["bench.py", "--atoms", str(atoms), "--precision", PRECISION]
 import bench  # noqa: E402
 
 args = bench.parse_args()
@@ -32,7 +33,7 @@ K, W, ROUNDS = 1500, 30, 4
 
 if which == "chains":
     variants = [("default", {})]
-    shard = env.slabmod.slab_tile(R, 1, 0, "single", seed=bench.SLAB_SEED)
+    shard = env.slabmod.slab_tile(R, 1, 0, PRECISION, seed=bench.SLAB_SEED)
     kind, water = "langevin", None
     chain_counts = (2, 3, 4, 6, 8)
 elif which == "fused":
@@ -41,12 +42,12 @@ elif which == "fused":
                 ("early0_zero2", {"CONSTV_FUSED_EARLY": "0", "CONSTV_FUSED_ZERO": "2"}),
                 ("early1_zero2", {"CONSTV_FUSED_EARLY": "1", "CONSTV_FUSED_ZERO": "2"}),
                 ("early1_zero1", {"CONSTV_FUSED_EARLY": "1", "CONSTV_FUSED_ZERO": "1"})]
-    shard = env.slabmod.slab_tile(R, 1, 0, "single", seed=bench.SLAB_SEED)
+    shard = env.slabmod.slab_tile(R, 1, 0, PRECISION, seed=bench.SLAB_SEED)
     kind, water = "langevin", None
     chain_counts = (1, 2)
 elif which == "reordered":
     variants = [("indexed_40_registers", {"CONSTV_INDEXED_MINB": "0"}), ("indexed_capped_32_registers", {"CONSTV_INDEXED_MINB": "8"})]
-    shard = env.slabmod.slab_tile(R, 1, 0, "single", seed=bench.SLAB_SEED)
+    shard = env.slabmod.slab_tile(R, 1, 0, PRECISION, seed=bench.SLAB_SEED)
     perm = env.slabmod.molecule_permutation(shard, shard.meta["n_ion"], 3, shard.meta["n_water"] // 3, seed=7)
     shard, _ = env.slabmod.permute_slab(shard, perm)
     kind, water = "langevin", None
@@ -55,10 +56,10 @@ elif which in ("settle_chains", "drude_chains", "settle_reordered", "drude_reord
     variants = [("default", {})]
     drude = None
     if which.startswith("drude"):
-        shard, d_normal, d_pairs = env.slabmod.slab_tile(R, 1, 0, "single", seed=bench.SLAB_SEED, maker=env.slabmod.make_drude_slab)
+        shard, d_normal, d_pairs = env.slabmod.slab_tile(R, 1, 0, PRECISION, seed=bench.SLAB_SEED, maker=env.slabmod.make_drude_slab)
         kind, water, drude = "drude", None, (d_normal, d_pairs)
     else:
-        shard, w_atoms, w_params, w_cons = env.slabmod.slab_tile(R, 1, 0, "single", seed=bench.SLAB_SEED, maker=env.slabmod.make_water_slab)
+        shard, w_atoms, w_params, w_cons = env.slabmod.slab_tile(R, 1, 0, PRECISION, seed=bench.SLAB_SEED, maker=env.slabmod.make_water_slab)
         kind, water = "settle", (w_atoms, w_params, w_cons)
     chain_counts = (2, 3, 4, 6, 8, 12)
     if which.endswith("reordered"):
@@ -73,14 +74,14 @@ elif which == "drude":
     # the staged Drude step: thread t <-> work item t (spt1) against the balanced kernel (csrc/constv_drude_kernels.cuh)
     variants = [("item_per_thread", {"CONSTV_DRUDE_SPT": "1"}), ("balanced_2_slots_per_thread", {"CONSTV_DRUDE_SPT": "2"}),
                 ("balanced_3_slots_per_thread", {"CONSTV_DRUDE_SPT": "3"})]
-    shard, d_normal, d_pairs = env.slabmod.slab_tile(R, 1, 0, "single", seed=bench.SLAB_SEED, maker=env.slabmod.make_drude_slab)
+    shard, d_normal, d_pairs = env.slabmod.slab_tile(R, 1, 0, PRECISION, seed=bench.SLAB_SEED, maker=env.slabmod.make_drude_slab)
     kind, water, drude = "drude", None, (d_normal, d_pairs)
     chain_counts = (1, 2, 3)
     ROUNDS = 3
 else:
     # "_variant" = constv_set_kernel_variant: 0 the default (cp.async stage-in), 3 the stage filled through registers (round 1)
     variants = [("ldg_staged", {"_variant": 3}), ("cp_async_stage_in", {"_variant": 0})]
-    shard, w_atoms, w_params, w_cons = env.slabmod.slab_tile(R, 1, 0, "single", seed=bench.SLAB_SEED, maker=env.slabmod.make_water_slab)
+    shard, w_atoms, w_params, w_cons = env.slabmod.slab_tile(R, 1, 0, PRECISION, seed=bench.SLAB_SEED, maker=env.slabmod.make_water_slab)
     kind, water = "settle", (w_atoms, w_params, w_cons)
     chain_counts = (1, 2, 3)
     ROUNDS = 3
