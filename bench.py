@@ -42,8 +42,9 @@ The JSON line carries, besides the base contract's keys:
                 from pinned memory, the fused step, D2H of the kinetic energy (full_state: + posq)
   clocks        SM clock / throttle reasons sampled during the timed region
   also          (last key, so that it survives a truncated log) single_launch, plugin_path, the 16M-atom slab
-                of configs[3] over these N GPUs, the 64 x 100k ensemble of configs[4], partition_parity,
-                e2e_full_state
+                of configs[3] over these N GPUs, the 64 x 100k ensemble of configs[4], the same slab size with
+                rigid SPC/E water solved inside the step (rigid_water) and with polarizable water (drude),
+                partition_parity, e2e_full_state
 """
 from __future__ import annotations
 
