@@ -912,17 +912,22 @@ def run_plugin_path(args, atoms):
     exe = os.path.join(ROOT, "openmm_constv_b200", "plugin", "bin", "BenchPluginPath")
     if not os.path.exists(exe):
         return {"unavailable": "plugin/bin/BenchPluginPath has not been built"}
-    out = {"what": "us per CudaIntegrateConstVLangevinStepKernel::execute (one launch per step, no graph), a sweep between two steps: "
+    out = {"what": "us per CudaIntegrateConstVLangevinStepKernel::execute (one launch per step, no graph; rigid_water_* = the same System with "
+                   "SPC/E constraints, solved inside the step), a sweep between two steps: "
                    "forces = a kernel copying into the force buffer (24 B/atom), copy = a kernel copying 128 MB -> 128 MB, read = a "
                    "kernel reading 256 MB; bracketed = events around execute(), marginal = loop time with minus without the step"}
-    for mode in ("identity", "reordered"):
-        cmd = [exe, "--atoms", str(atoms), "--steps", "300", "--precision", args.precision] + (["--reordered"] if mode == "reordered" else [])
+    for mode in ("identity", "reordered", "rigid_water_identity", "rigid_water_reordered"):
+        cmd = [exe, "--atoms", str(atoms), "--steps", "300", "--precision", args.precision] + (["--reordered"] if mode.endswith("reordered") else []) + \
+              (["--rigid-water"] if mode.startswith("rigid_water") else [])
         try:
             res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
             line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
             if line:
                 r = json.loads(line[-1])
                 out[mode] = {"algorithmic_bytes_per_step": r["algorithmic_bytes_per_step"]}
+                if "max_constraint_error_nm" in r:  # sanity of the timed steps: a few ulp of the largest coordinate (the injected forces
+                    out[mode]["max_constraint_error_nm"] = r["max_constraint_error_nm"]  # are constant: the molecules drift far)
+                    out[mode]["max_abs_coordinate_nm"] = r.get("max_abs_coordinate_nm")
                 for sweep in ("forces", "copy", "read"):
                     out[mode][sweep] = {"marginal_us": r[sweep]["marginal_us"], "bracketed_us": r[sweep]["bracketed_us"],
                                         "bracketed_frac_8TBs": r[sweep]["bracketed_frac_8TBs"]}

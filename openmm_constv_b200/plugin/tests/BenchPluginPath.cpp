@@ -66,7 +66,7 @@ int main(int argc, char** argv) {
     int atoms = 1000000, steps = 300;
     size_t sweepMB = 256;
     std::string precision = "single";
-    bool reordered = false;
+    bool reordered = false, rigidWater = false;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         if (a == "--atoms" && i + 1 < argc) atoms = std::atoi(argv[++i]);
@@ -74,6 +74,7 @@ int main(int argc, char** argv) {
         else if (a == "--precision" && i + 1 < argc) precision = argv[++i];
         else if (a == "--sweep-mb" && i + 1 < argc) sweepMB = (size_t) std::atoi(argv[++i]);
         else if (a == "--reordered") reordered = true;
+        else if (a == "--rigid-water") rigidWater = true;  // constraints=AllBonds + rigidWater (nacl_constv.py:56): solved inside the step
         else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }
     try {
@@ -95,6 +96,14 @@ int main(int argc, char** argv) {
         System system;
         for (double m : mass) system.addParticle(m);
         system.setDefaultPeriodicBoxVectors(Vec3(lx, 0, 0), Vec3(0, ly, 0), Vec3(0, 0, 2 * zmax));
+        const double dOH = 0.1, theta = 109.47 * M_PI / 180.0, dHH = 2 * dOH * std::sin(0.5 * theta);  // SPC/E
+        if (rigidWater)
+            for (int k = 0; k < nWater / 3; k++) {
+                const int o = nIonAll + 3 * k;
+                system.addConstraint(o, o + 1, dOH);
+                system.addConstraint(o, o + 2, dOH);
+                system.addConstraint(o + 1, o + 2, dHH);
+            }
         ConstVLangevinIntegrator integrator(300.0, 1.0, 0.001);
         integrator.setRandomNumberSeed(2024);
         Platform& platform = Platform::getPlatformByName("CUDA");
@@ -108,7 +117,12 @@ int main(int argc, char** argv) {
             const bool wall = i >= nIonAll + nWater;
             const double z = wall ? ((i & 1) ? zmax : 0.0) : (0.05 + 0.9 * uni(gen)) * zmax;
             pos[i] = Vec3(uni(gen) * lx, uni(gen) * ly, z);
-            pos[R + i] = Vec3(pos[i][0], pos[i][1], charge[i] != 0 ? -z : -z + 0.001);
+            const int w = i - nIonAll;
+            if (rigidWater && w >= 0 && w < nWater && w % 3 != 0) {  // the hydrogens on the SPC/E geometry around their oxygen
+                const Vec3& o = pos[i - w % 3];
+                pos[i] = w % 3 == 1 ? Vec3(o[0] + dOH, o[1], o[2]) : Vec3(o[0] + dOH * std::cos(theta), o[1] + dOH * std::sin(theta), o[2]);
+            }
+            pos[R + i] = Vec3(pos[i][0], pos[i][1], charge[i] != 0 ? -pos[i][2] : -pos[i][2] + 0.001);
         }
         context.setPositions(pos);
         context.setCharges(charge);
@@ -230,14 +244,32 @@ int main(int argc, char** argv) {
         const char* what[3] = {"a kernel copying into the force buffer (24 B/atom) between steps", "a kernel copying 128 MB onto 128 MB between steps",
                                "a kernel reading 256 MB between steps"};
         std::printf("{\"path\": \"CudaIntegrateConstVLangevinStepKernel::execute via the kernel factory (OpenMM shim)\", "
-                    "\"atoms\": %d, \"precision\": \"%s\", \"reordered_slots\": %s, \"steps\": %d, \"launches_per_step\": 1, "
+                    "\"atoms\": %d, \"precision\": \"%s\", \"reordered_slots\": %s, \"rigid_water\": %s, \"steps\": %d, \"launches_per_step\": 1, "
                     "\"algorithmic_bytes_per_step\": %.0f, ",
-                    atoms, precision.c_str(), reordered ? "true" : "false", steps, bytes);
+                    atoms, precision.c_str(), reordered ? "true" : "false", rigidWater ? "true" : "false", steps, bytes);
         for (int mode = 0; mode < 3; mode++)
             std::printf("\"%s\": {\"marginal_us\": %.3f, \"marginal_frac_8TBs\": %.4f, \"bracketed_us\": %.3f, \"bracketed_frac_8TBs\": %.4f, "
                         "\"sweep\": \"%s, %.1f us\"}, ",
                         names[mode], us[mode], bytes / us[mode] * 1e-3 / 8000.0, alone[mode], bytes / alone[mode] * 1e-3 / 8000.0, what[mode],
                         sweepUs[mode]);
+        if (rigidWater) {  // sanity of what was timed: the constraints hold after all those steps (original order, whatever the slots)
+            State state = context.getState(State::Positions);
+            const vector<Vec3>& x = state.getPositions();
+            double worst = 0;
+            for (int k = 0; k < nWater / 3; k++) {
+                const int o = nIonAll + 3 * k;
+                const Vec3 a = x[o + 1] - x[o], b = x[o + 2] - x[o], c = x[o + 2] - x[o + 1];
+                worst = std::max(worst, std::fabs(std::sqrt(a.dot(a)) - dOH));
+                worst = std::max(worst, std::fabs(std::sqrt(b.dot(b)) - dOH));
+                worst = std::max(worst, std::fabs(std::sqrt(c.dot(c)) - dHH));
+            }
+            // the injected forces are constant and large (sigma 1000 kJ/mol/nm for thousands of steps), so the molecules drift far:
+            // the error to expect is a few units in the last place of the largest coordinate
+            double far = 0;
+            for (int i = 0; i < R; i++)
+                for (int k = 0; k < 3; k++) far = std::max(far, std::fabs(x[i][k]));
+            std::printf("\"max_constraint_error_nm\": %.3g, \"max_abs_coordinate_nm\": %.3g, ", worst, far);
+        }
         std::printf("\"statistic\": \"marginal = median of 5 (sweep+execute) passes minus median of 5 sweep-only passes, per step; "
                     "bracketed = CUDA events around each execute(), mean of the middle 80 %% of the steps\"}\n");
         for (auto& e : ev) cudaEventDestroy(e);
