@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Writes profiles/r02_sass_excerpts.txt: for the hot kernels of libconstv_b200.so (sm_100a cubin) the register
 count from the build log and the SASS lines that show HOW memory is moved -- vector widths and cache operators of
-LDG / STG, bulk asynchronous copies (UBLKCP = cp.async.bulk), mbarrier traffic (SYNCS), MUFU of the Box-Muller,
+LDG / STG, asynchronous copies (LDGSTS = cp.async, UBLKCP = cp.async.bulk), mbarrier traffic (SYNCS), MUFU of the Box-Muller,
 programmatic dependent launch (ACQBULK / PREEXIT).  Needs cuobjdump (CUDA toolkit); no GPU."""
 import collections
 import os
@@ -15,10 +15,12 @@ KERNELS = [
     ("constv_fused_step_indexed_kernel<single, 256> (reordered slots)", "constv_fused_step_indexed_kernelILi0ELi256E"),
     ("constv_fused_step_tma_kernel<single, 256, 4 stages> (TMA ring variant of the fused step)", "constv_fused_step_tma_kernelILi0ELi256ELi4ELb1E"),
     ("constv_settle_step_ws_kernel<single, 4 consumer groups> (rigid-water step, warp-specialised TMA pipeline)", "constv_settle_step_ws_kernelILi0ELi4E"),
-    ("constv_settle_step_tiled_kernel<single, 128, identity, evict-first> (rigid-water step, LDG-staged)", "constv_settle_step_tiled_kernelILi0ELi128ELb0ELb1E"),
-    ("constv_drude_step_tiled_kernel<single, 128, identity, evict-first>", "constv_drude_step_tiled_kernelILi0ELi128ELb0ELb1E"),
+    ("constv_settle_step_tiled_kernel<single, 128, identity, evict-first, cp.async stage-in> (rigid-water step, the default)", "constv_settle_step_tiled_kernelILi0ELi128ELb0ELb1ELb1E"),
+    ("constv_settle_step_tiled_kernel<single, 128, identity, evict-first, stage-in through registers> (round 1's, kernel variant 3)", "constv_settle_step_tiled_kernelILi0ELi128ELb0ELb1ELb0E"),
+    ("constv_drude_step_balanced_kernel<single, 128 threads, 2 slots per thread, identity, evict-first> (Drude step, the default)", "constv_drude_step_balanced_kernelILi0ELi128ELi2ELb0ELb1E"),
+    ("constv_drude_step_tiled_kernel<single, 128, identity, evict-first> (round 1's, kernel variant 5)", "constv_drude_step_tiled_kernelILi0ELi128ELb0ELb1E"),
 ]
-PAT = re.compile(r"\b(LDG|STG|LDS|STS|UBLKCP|UTMALDG|UTMASTG|SYNCS|MUFU|ACQBULK|PREEXIT|BAR|ATOMG|ATOMS|RED|LDL|STL|ERRBAR|MEMBAR|FENCE)\b[.\w]*")
+PAT = re.compile(r"\b(LDGSTS|LDGDEPBAR|DEPBAR|LDG|STG|LDS|STS|UBLKCP|UTMALDG|UTMASTG|SYNCS|MUFU|ACQBULK|PREEXIT|BAR|ATOMG|ATOMS|RED|LDL|STL|ERRBAR|MEMBAR|FENCE)\b[.\w]*")
 
 
 def main():
