@@ -440,7 +440,7 @@ constv_drude_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_c
     using Mixed = typename Prec<PREC>::Mixed;
     constexpr bool kSplit = Prec<PREC>::kSplitPos;
     constexpr int kWarps = BLOCK / 32;
-    __shared__ DrudeStage<PREC, BLOCK> st;
+    __shared__ __align__(16) DrudeStage<PREC, BLOCK> st;  // 16-byte vector accesses into its records
     __shared__ StepBox box;
     pdl_wait();
     pdl_launch();
@@ -645,7 +645,7 @@ constv_drude_step_balanced_kernel(const __grid_constant__ SlabDev d, const __gri
     constexpr int kWarps = BLOCK / 32;
     constexpr int kTile = BLOCK * SPT;
     static_assert(kTile <= 65536 && (kTile & 63) == 0, "tile-local slots are 16-bit; the swizzle permutes aligned groups of 64");
-    __shared__ DrudeStageB<PREC, BLOCK, SPT, INDEXED> st;
+    __shared__ __align__(16) DrudeStageB<PREC, BLOCK, SPT, INDEXED> st;  // 16-byte vector accesses and cp.async into its records
     __shared__ StepBox box;
     pdl_wait();
     pdl_launch();
