@@ -69,6 +69,10 @@ struct constv_slab {
     int* invAtomOrder = nullptr;
     void* imageCharge = nullptr;
     bool imageChargeValid = false;
+    // reordered slots: image slot and image charge per real SLOT, for the staged kernels (constv_image_by_slot_kernel)
+    int* imageSlotBySlot = nullptr;
+    void* imageChargeBySlot = nullptr;
+    bool imageBySlotValid = false;
     DevCounters* counters = nullptr;
     double* kePartials = nullptr;
     double* keOut = nullptr;
@@ -168,6 +172,9 @@ SlabDev makeDev(const constv_slab* s) {
     d.atomIndex = s->atomIndex;
     d.invAtomOrder = s->invAtomOrder;
     d.imageCharge = ((s->cfg.flags & CONSTV_FLAG_CACHE_IMAGE_CHARGE) && s->imageChargeValid) ? s->imageCharge : nullptr;
+    const bool bySlot = d.imageCharge && s->atomIndex && s->imageBySlotValid;
+    d.imageSlotBySlot = bySlot ? s->imageSlotBySlot : nullptr;
+    d.imageChargeBySlot = bySlot ? s->imageChargeBySlot : nullptr;
     d.counters = s->counters;
     d.numAtoms = s->cfg.num_atoms;
     d.numReal = s->numReal;
@@ -448,6 +455,8 @@ int constv_create(const constv_config* config, constv_slab** out) {
     };
     if ((e = cudaMalloc(&s->invAtomOrder, sizeof(int) * (size_t) P)) != cudaSuccess) return cleanup(e, "cudaMalloc(invAtomOrder)");
     if ((e = cudaMalloc(&s->imageCharge, realSize(config->precision) * ((size_t) (config->num_atoms - s->numReal) + 4))) != cudaSuccess) return cleanup(e, "cudaMalloc(imageCharge)");  // + 4: the TMA kernels read whole 4-slot windows
+    if ((e = cudaMalloc(&s->imageSlotBySlot, sizeof(int) * ((size_t) (config->num_atoms - s->numReal) + 4))) != cudaSuccess) return cleanup(e, "cudaMalloc(imageSlotBySlot)");
+    if ((e = cudaMalloc(&s->imageChargeBySlot, realSize(config->precision) * ((size_t) (config->num_atoms - s->numReal) + 4))) != cudaSuccess) return cleanup(e, "cudaMalloc(imageChargeBySlot)");
     if ((e = cudaMalloc(&s->counters, sizeof(DevCounters) * kMaxChains)) != cudaSuccess) return cleanup(e, "cudaMalloc(counters)");
     if ((e = cudaMemset(s->counters, 0, sizeof(DevCounters) * kMaxChains)) != cudaSuccess) return cleanup(e, "cudaMemset(counters)");
     s->chainLo[1] = s->numReal;
@@ -483,6 +492,8 @@ int constv_destroy(constv_slab* s) {
     cudaFree(s->settle.atoms);
     cudaFree(s->settle.params);
     cudaFree(s->imageCharge);
+    cudaFree(s->imageSlotBySlot);
+    cudaFree(s->imageChargeBySlot);
     cudaFree(s->counters);
     cudaFree(s->kePartials);
     cudaFree(s->keOut);
@@ -522,6 +533,7 @@ int constv_bind_arrays(constv_slab* s, void* posq, void* posq_correction, void* 
     s->posDelta = pos_delta;
     s->atomIndex = atom_index;
     s->imageChargeValid = false;
+    s->imageBySlotValid = false;
     return CONSTV_OK;
 }
 
@@ -607,6 +619,7 @@ int constv_update_inverse_order(constv_slab* s, void* stream) {
     const int n = s->cfg.num_atoms;
     int rc = launch(constv_inverse_order_kernel, gridFor(s, n, 256, 8), 256, false, (cudaStream_t) stream, n,
                     (const int*) s->atomIndex, s->invAtomOrder);
+    s->imageBySlotValid = false;  // the per-slot image tables follow the order: rebuilt before the next staged step
     return rc;
 }
 
@@ -622,6 +635,23 @@ int constv_refresh_image_charges(constv_slab* s, void* stream) {
         rc = launch(constv_image_charge_kernel<float>, gridFor(s, n, 256, 8), 256, false, (cudaStream_t) stream,
                     s->numReal, s->cfg.num_cells, (const float*) s->posq, (const int*) s->invAtomOrder, (float*) s->imageCharge);
     if (rc == CONSTV_OK) s->imageChargeValid = true;
+    s->imageBySlotValid = false;
+    return rc;
+}
+
+// Reordered slots: the per-slot image tables of the staged kernels, built when they are stale (after a re-sort or a new
+// charge snapshot) and the snapshot exists.
+static int ensureImageBySlot(constv_slab* s, cudaStream_t stream) {
+    if (!s->atomIndex || s->imageBySlotValid || !(s->cfg.flags & CONSTV_FLAG_CACHE_IMAGE_CHARGE) || !s->imageChargeValid) return CONSTV_OK;
+    const int n = s->cfg.num_atoms - s->numReal;
+    int rc;
+    if (s->cfg.precision == CONSTV_PRECISION_DOUBLE)
+        rc = launch(constv_image_by_slot_kernel<double>, gridFor(s, n, 256, 8), 256, false, stream, s->numReal, s->cfg.num_cells,
+                    (const int*) s->atomIndex, (const int*) s->invAtomOrder, (const double*) s->imageCharge, s->imageSlotBySlot, (double*) s->imageChargeBySlot);
+    else
+        rc = launch(constv_image_by_slot_kernel<float>, gridFor(s, n, 256, 8), 256, false, stream, s->numReal, s->cfg.num_cells,
+                    (const int*) s->atomIndex, (const int*) s->invAtomOrder, (const float*) s->imageCharge, s->imageSlotBySlot, (float*) s->imageChargeBySlot);
+    if (rc == CONSTV_OK) s->imageBySlotValid = true;
     return rc;
 }
 

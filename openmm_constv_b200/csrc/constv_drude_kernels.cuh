@@ -279,6 +279,40 @@ __device__ __forceinline__ void drude_emit(const SlabDev& d, const int slot, con
     }
 }
 
+// The same for the staged kernels when the per-slot image tables exist (SlabDev::imageSlotBySlot): the cell-1 image's slot
+// and charge came in with the tile (img1 < 0: the slot holds no real atom), further cells are read by slot -- no gather through
+// atomIndex -> invAtomOrder / imageCharge at the end of the tile.
+template <int PREC>
+__device__ __forceinline__ void drude_emit_tables(const SlabDev& d, const int slot, const bool moved,
+                                                  const Vec4<typename Prec<PREC>::Mixed>& v, const Vec4<typename Prec<PREC>::Real>& p,
+                                                  const Vec4<typename Prec<PREC>::Real>& c, const int img1, const typename Prec<PREC>::Real q1) {
+    using Real = typename Prec<PREC>::Real;
+    using Mixed = typename Prec<PREC>::Mixed;
+    constexpr bool kSplit = Prec<PREC>::kSplitPos;
+    const int R = d.numReal;
+    Real* __restrict__ posq = static_cast<Real*>(d.posq);
+    Real* __restrict__ corrA = static_cast<Real*>(d.corr);
+    if (moved) {
+        store4(static_cast<Mixed*>(d.velm), (size_t) slot, v);
+        store4(posq, (size_t) slot, p);
+        if (kSplit) store4(corrA, (size_t) slot, c);
+    }
+    if (p.w != -p.w && img1 >= 0) {
+        ImageCursor<PREC> cur(p, c);
+        cur.advance(1, d.zshift);
+        store4(posq, (size_t) img1, cur.posq(q1));
+        if (kSplit) store4(corrA, (size_t) img1, cur.corr());
+        for (int cell = 2; cell < d.numCells; cell++) {
+            const size_t k = (size_t) (cell - 1) * R + slot;
+            const size_t t = (size_t) d.imageSlotBySlot[k];
+            const Real qc = static_cast<const Real*>(d.imageChargeBySlot)[k];
+            cur.advance(cell, d.zshift);
+            store4(posq, t, cur.posq(qc));
+            if (kSplit) store4(corrA, t, cur.corr());
+        }
+    }
+}
+
 // The Drude step.  MODE_FUSED: the whole constraint-free step; MODE_PART1: velocities + posDelta;
 // MODE_PART2: part 2 + hard wall + image rewrite + zeroing (after the caller's constraints).
 // Gaussians: random != nullptr reads the caller's pool with the reference's addressing (ordinary
@@ -622,6 +656,7 @@ template <int PREC, int BLOCK, int SPT, bool INDEXED> struct DrudeStageB {
     Vec4<Mixed> fq[kTile];       // force components as `mixed`, w = image charge of cell 1 (identity order)
     int role[kTile];
     int orig[INDEXED ? kTile : 1];
+    int img[INDEXED ? kTile : 1];   // reordered slots: slot of the cell-1 image (per-slot tables), -1 = the slot holds no real atom
     unsigned short list[kTile];     // work items: tile-local slot of each owner, then of each ordinary particle
     unsigned short partner[kTile];  // [owner] = tile-local slot of its parent, when that parent is staged in this tile
     int warpOwners[SPT * (BLOCK / 32)], warpNormals[SPT * (BLOCK / 32)];
@@ -635,7 +670,9 @@ __device__ __forceinline__ int drude_swizzle(const int i) { return i ^ ((i >> 3)
 // Mixed precision (what the reference's example runs): 5 CTAs per SM at 96 registers measured 27.8 -> 24.5 us per step at 1M
 // atoms with six chains against 4 CTAs at 120 registers (31.6 -> 32.9 us with one launch per step;
 // profiles/r02_ab_staged_mixed_ctas_per_sm.jsonl).
-template <int PREC, int BLOCK, int SPT, bool INDEXED, bool STREAM>
+// TABLES (reordered slots): the cell-1 image's slot and charge come in with the tile from the per-slot tables
+// (SlabDev::imageSlotBySlot) instead of being gathered through atomIndex -> invAtomOrder / imageCharge at the end of the tile.
+template <int PREC, int BLOCK, int SPT, bool INDEXED, bool STREAM, bool TABLES = false>
 __global__ void __launch_bounds__(BLOCK, PREC == PREC_SINGLE ? 1024 / BLOCK : (PREC == PREC_MIXED ? 5 : 4))  // single: 64 registers, 32 warps per SM
 constv_drude_step_balanced_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ DrudeDev dd,
                                   const float4* __restrict__ random, const unsigned int randomIndex) {
@@ -679,7 +716,8 @@ constv_drude_step_balanced_kernel(const __grid_constant__ SlabDev d, const __gri
                 fr[i][0] = load_force(d.force + ls);
                 fr[i][1] = load_force(d.force + P + ls);
                 fr[i][2] = load_force(d.force + 2 * P + ls);
-                q1[i] = INDEXED ? (Real) 0 : (d.imageCharge ? static_cast<const Real*>(d.imageCharge)[ls] : posq[4 * ((size_t) R + ls) + 3]);
+                q1[i] = INDEXED ? (TABLES ? static_cast<const Real*>(d.imageChargeBySlot)[ls] : (Real) 0)
+                                : (d.imageCharge ? static_cast<const Real*>(d.imageCharge)[ls] : posq[4 * ((size_t) R + ls) + 3]);
             }
 #pragma unroll
             for (int i = 0; i < SPT; i++) {
@@ -693,6 +731,7 @@ constv_drude_step_balanced_kernel(const __grid_constant__ SlabDev d, const __gri
                     if (INDEXED) {
                         if (d.atomIndex) cp_async4(&st.orig[idx], d.atomIndex + slot);
                         else st.orig[idx] = slot;
+                        if (TABLES) cp_async4(&st.img[idx], d.imageSlotBySlot + slot);
                     }
                     emit_zero<PREC, STREAM>(d, slot);
                 } else {
@@ -856,7 +895,9 @@ constv_drude_step_balanced_kernel(const __grid_constant__ SlabDev d, const __gri
                 const Vec4<Real> c = kSplit ? st.c[at] : Vec4<Real>{0, 0, 0, 0};
                 // a pair's records are always written back (constVDrudeLangevin.cu:60-63 stores unconditionally)
                 const bool moved = role != DRUDE_ROLE_NORMAL || v.w != 0;
-                if (INDEXED) {
+                if (INDEXED && TABLES) {
+                    drude_emit_tables<PREC>(d, slot, moved, v, p, c, st.img[idx], (Real) st.fq[at].w);
+                } else if (INDEXED) {
                     DrudeAtom<PREC> rec;
                     rec.v = v; rec.p = p; rec.c = c;
                     drude_emit<PREC, true, STREAM>(d, slot, st.orig[idx], moved, rec);

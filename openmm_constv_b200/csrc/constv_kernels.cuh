@@ -52,6 +52,9 @@ struct SlabDev {
     const int* atomIndex;        // slot -> original index, nullptr = identity
     const int* invAtomOrder;     // original index -> slot
     const void* imageCharge;     // real[(numCells-1)*R] snapshot, or nullptr = re-read posq.w
+    // reordered slots, staged kernels: the same two facts per real SLOT (constv_image_by_slot_kernel), or nullptr
+    const int* imageSlotBySlot;      // int[(numCells-1)*R]: slot of the cell's image of the atom in real slot s (-1: s holds no real atom)
+    const void* imageChargeBySlot;   // real[(numCells-1)*R]: that image's charge
     DevCounters* counters;
     int numAtoms, numReal, padded, numCells;
     double zshift;               // zmax (reference mirror) or 0 (exact negation)
@@ -1020,6 +1023,22 @@ __global__ void constv_image_charge_kernel(const int numReal, const int numCells
     const int n = numReal * (numCells - 1);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
         imageCharge[k] = posq[4 * (size_t) invAtomOrder[numReal + k] + 3];
+}
+
+// Reordered slots: per real slot and image cell, where the image of the atom in that slot sits and what it is charged --
+// what the staged kernels would otherwise gather through atomIndex -> invAtomOrder / imageCharge at the end of every tile.
+// Rebuilt whenever the slot order or the charge snapshot changes.
+template <typename Real>
+__global__ void constv_image_by_slot_kernel(const int numReal, const int numCells, const int* __restrict__ atomIndex,
+                                            const int* __restrict__ invAtomOrder, const Real* __restrict__ imageCharge,
+                                            int* __restrict__ imageSlot, Real* __restrict__ imageChargeBySlot) {
+    const int n = numReal * (numCells - 1);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int cell1 = k / numReal, slot = k - cell1 * numReal, a = atomIndex[slot];
+        const bool real = a < numReal;
+        imageSlot[k] = real ? invAtomOrder[a + numReal * (cell1 + 1)] : -1;
+        imageChargeBySlot[k] = real ? imageCharge[(size_t) cell1 * numReal + a] : (Real) 0;
+    }
 }
 
 // Host-force staging -> OpenMM's force planes (constv_step_host_submit).  FROM_FLOAT converts as

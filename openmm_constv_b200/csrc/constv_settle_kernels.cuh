@@ -343,8 +343,9 @@ template <int PREC, int BLOCK, bool INDEXED> struct SettleStage {
     Vec4<Real> p[kSlots];
     Vec4<Real> c[Prec<PREC>::kSplitPos ? kSlots : 1];
     long long f[3][kSlots];
-    Real q1[INDEXED ? 1 : kSlots];   // identity order: charge of the cell-1 image, fetched with the record
+    Real q1[kSlots];                 // charge of the cell-1 image, fetched with the record (reordered slots: when the per-slot tables exist)
     int orig[INDEXED ? kSlots : 1];  // reordered slots: original index of the atom in the slot
+    int img[INDEXED ? kSlots : 1];   // reordered slots: slot of the cell-1 image (per-slot tables), -1 = the slot holds no real atom
 };
 
 // Stage in slots [base, base + slotsInTile): thread j takes slots base + j + i * BLOCK (coalesced).
@@ -512,7 +513,9 @@ __device__ __forceinline__ void settle_tiled_tile(const SlabDev& d, const Settle
 // Reordered slots: the zeroing stores of the image slots are issued in the stage-in phase, behind the tile's loads (they
 // depend on nothing): 18.7 -> 18.3 us per step at 1M atoms; in identity order they stay with the dependent stores at the
 // end of the tile (issued early: 13.7 -> 14.0 us with six chains; profiles/r02_ab_staged_zero_timing.jsonl).
-template <int PREC, int BLOCK, bool INDEXED, bool STREAM, bool ASYNC = true>
+// TABLES (reordered slots): the cell-1 image's slot and charge come in with the tile from the per-slot tables
+// (SlabDev::imageSlotBySlot) instead of being gathered through atomIndex -> invAtomOrder / imageCharge at the end of the tile.
+template <int PREC, int BLOCK, bool INDEXED, bool STREAM, bool ASYNC = true, bool TABLES = false>
 __global__ void __launch_bounds__(BLOCK, PREC == PREC_SINGLE ? 8 : (INDEXED ? 0 : 4))  // single precision: 64 registers, 8 CTAs per SM
 constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ SettleSegments seg,
                                 const float4* __restrict__ random, const unsigned int randomIndex) {
@@ -567,8 +570,14 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
                     cp_async8(&st.f[0][idx], force + slot);
                     cp_async8(&st.f[1][idx], force + P + slot);
                     cp_async8(&st.f[2][idx], force + 2 * P + slot);
-                    if (INDEXED) cp_async4(&st.orig[idx], d.atomIndex + slot);
-                    else if (sizeof(Real) == 4) cp_async4(&st.q1[idx], qbase + qstride * slot);
+                    if (INDEXED) {
+                        cp_async4(&st.orig[idx], d.atomIndex + slot);
+                        if (TABLES) {
+                            cp_async4(&st.img[idx], d.imageSlotBySlot + slot);
+                            if (sizeof(Real) == 4) cp_async4(&st.q1[idx], static_cast<const Real*>(d.imageChargeBySlot) + slot);
+                            else cp_async8(&st.q1[idx], static_cast<const Real*>(d.imageChargeBySlot) + slot);
+                        }
+                    } else if (sizeof(Real) == 4) cp_async4(&st.q1[idx], qbase + qstride * slot);
                     else cp_async8(&st.q1[idx], qbase + qstride * slot);
                 } else {
                     st.v[idx] = load4x<STREAM>(velm, slot);
@@ -577,8 +586,13 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
                     st.f[0][idx] = load_force(force + slot);
                     st.f[1][idx] = load_force(force + P + slot);
                     st.f[2][idx] = load_force(force + 2 * P + slot);
-                    if (INDEXED) st.orig[idx] = d.atomIndex[slot];
-                    else st.q1[idx] = qbase[qstride * slot];
+                    if (INDEXED) {
+                        st.orig[idx] = d.atomIndex[slot];
+                        if (TABLES) {
+                            st.img[idx] = d.imageSlotBySlot[slot];
+                            st.q1[idx] = static_cast<const Real*>(d.imageChargeBySlot)[slot];
+                        }
+                    } else st.q1[idx] = qbase[qstride * slot];
                 }
                 if (ZEARLY) emit_zero<PREC, STREAM>(d, base + idx);  // the image slots, in slot order: coalesced whatever atoms they hold
             }
@@ -639,7 +653,9 @@ constv_settle_step_tiled_kernel(const __grid_constant__ SlabDev d, const __grid_
                 const Vec4<Mixed> v = st.v[idx];
                 const Vec4<Real> p = st.p[idx];
                 const Vec4<Real> c = kSplit ? st.c[idx] : Vec4<Real>{0, 0, 0, 0};
-                if (INDEXED) {
+                if (INDEXED && TABLES) {
+                    drude_emit_tables<PREC>(d, base + idx, v.w != 0, v, p, c, st.img[idx], st.q1[idx]);
+                } else if (INDEXED) {
                     DrudeAtom<PREC> rec;
                     rec.v = v; rec.p = p; rec.c = c;
                     drude_emit<PREC, true, STREAM>(d, base + idx, st.orig[idx], v.w != 0, rec);

@@ -174,15 +174,19 @@ def role_preserving_permutation(s, rng):
 
 @pytest.mark.parametrize("precision", slabmod.PRECISIONS)
 @pytest.mark.parametrize("split,variant", [(False, 0), (False, 1), (False, 5), (True, 0)])
-def test_drude_reordered_slots(gpu, oracle, precision, split, variant):
-    """variant 0 | 5 = the staged kernels with their extra tiles zeroing the image slots, variant 1 = thread per slot."""
-    s0, normal, pairs = slabmod.make_drude_slab(2501, precision, num_cells=2, seed=13)
+@pytest.mark.parametrize("side_array,num_cells", [(False, 2), (True, 2), (True, 4)])
+def test_drude_reordered_slots(gpu, oracle, precision, split, variant, side_array, num_cells):
+    """variant 0 | 5 = the staged kernels, variant 1 = thread per slot.  side_array: with the image-charge snapshot the
+    balanced kernel reads the images' slots and charges from the per-slot tables instead of gathering them."""
+    from openmm_constv_b200 import _capi
+    s0, normal, pairs = slabmod.make_drude_slab(2501, precision, num_cells=num_cells, seed=13)
     perm = role_preserving_permutation(s0, np.random.default_rng(4))
     sp, atom_index = H.permute_slab(s0, perm)
     inv = np.empty_like(atom_index)
     inv[atom_index] = np.arange(len(atom_index), dtype=np.int32)
     pool = np.random.default_rng(8).standard_normal((2 * s0.num_real, 4)).astype(np.float32)
     ctx, it = make_drude_context(gpu, sp, pairs, 0.02, pool=pool,
+                                 flags=_capi.FLAGS_DEFAULT | (_capi.FLAG_CACHE_IMAGE_CHARGE if side_array else 0),
                                  apply_constraints=(lambda c, t: None) if split else None)
     ctx.set_atom_order(perm)
     it._kernel.set_kernel_variant(variant)

@@ -153,22 +153,71 @@ def molecule_preserving_permutation(s, rng):
 
 @pytest.mark.parametrize("precision", slabmod.PRECISIONS)
 @pytest.mark.parametrize("variant,num_cells", [(0, 2), (1, 2), (0, 4)])
-def test_fused_settle_reordered_slots(gpu, oracle, precision, variant, num_cells):
+@pytest.mark.parametrize("side_array", [False, True])
+def test_fused_settle_reordered_slots(gpu, oracle, precision, variant, num_cells, side_array):
     """OpenMM swaps whole identical molecules: slots keep their roles, images move freely.  variant 0 = the
-    staged kernel (extra tiles zero the image slots), variant 1 = the gather kernel."""
+    staged kernel, variant 1 = the gather kernel.  side_array: with the image-charge snapshot the staged kernel reads the
+    images' slots and charges from the per-slot tables (constv_image_by_slot_kernel) instead of gathering them."""
+    from openmm_constv_b200 import _capi
     s0, atoms, params, cons = slabmod.make_water_slab(2501, precision, num_cells=num_cells, seed=33)
     perm = molecule_preserving_permutation(s0, np.random.default_rng(6))
     sp, atom_index = H.permute_slab(s0, perm)
     inv = np.empty_like(atom_index)
     inv[atom_index] = np.arange(len(atom_index), dtype=np.int32)
     pool = np.random.default_rng(4).standard_normal((2 * s0.padded, 4)).astype(np.float32)
-    ctx, it = make_water_context(gpu, sp, cons, pool=pool)
+    ctx, it = make_water_context(gpu, sp, cons, pool=pool,
+                                 flags=_capi.FLAGS_DEFAULT | (_capi.FLAG_CACHE_IMAGE_CHARGE if side_array else 0))
     ctx.set_atom_order(perm)
     it._kernel.set_kernel_variant(variant)
     ref = sp.copy()
     for k in range(2):
         it.step(1)
         oracle_settle_step(oracle, ref, atoms, params, pool, random_index=k * s0.padded, inv=inv)
+        assert_slab_bits_equal(download(ctx, sp), ref)
+    ctx.close()
+
+
+@pytest.mark.parametrize("precision", ["single", "mixed"])
+def test_fused_settle_resort_between_steps(gpu, oracle, precision):
+    """A second re-sort while stepping, as OpenMM does it: the state arrays and the atomIndex array change IN PLACE and the
+    host calls constv_update_inverse_order.  The image-charge snapshot (indexed by atom) stays valid; the per-slot image
+    tables of the staged kernel must follow the new order."""
+    import torch
+    from openmm_constv_b200 import _capi
+    s0, atoms, params, cons = slabmod.make_water_slab(3001, precision, seed=35)
+    N, P = s0.num_atoms, s0.padded
+    perm1 = molecule_preserving_permutation(s0, np.random.default_rng(8))
+    sp, atom_index = H.permute_slab(s0, perm1)
+    pool = np.random.default_rng(5).standard_normal((4 * P, 4)).astype(np.float32)
+    ctx, it = make_water_context(gpu, sp, cons, pool=pool, flags=_capi.FLAGS_DEFAULT | _capi.FLAG_CACHE_IMAGE_CHARGE)
+    ctx.set_atom_order(perm1)
+    lib, slab = it._kernel._lib, it._kernel.handle
+    ref = sp.copy()
+
+    def inverse(ai):
+        inv = np.arange(P, dtype=np.int32)
+        inv[ai[:N]] = np.arange(N, dtype=np.int32)
+        return inv
+
+    order = np.arange(P, dtype=np.int32)
+    order[:N] = atom_index[:N]
+    for k in range(4):
+        if k == 2:  # slots trade places again (whole molecules, images freely): sigma[new slot] = old slot
+            sigma = np.arange(P)
+            sigma[:N] = molecule_preserving_permutation(s0, np.random.default_rng(9))
+            sig = torch.as_tensor(sigma, device="cuda")
+            for arr in (ctx.posq, ctx.velm) + ((ctx.corr,) if ctx.corr is not None else ()):
+                arr.copy_(arr[sig].clone())
+            ctx.force.copy_(ctx.force[:, sig].clone())
+            order = order[sigma]
+            ctx.atom_index.copy_(torch.as_tensor(order, device="cuda"))
+            _capi.check(lib.constv_update_inverse_order(slab, ctx.stream_ptr()))
+            ref.posq, ref.velm = ref.posq[sigma].copy(), ref.velm[sigma].copy()
+            if ref.corr is not None:
+                ref.corr = ref.corr[sigma].copy()
+            ref.force = np.ascontiguousarray(ref.force[:, sigma])
+        it.step(1)
+        oracle_settle_step(oracle, ref, atoms, params, pool, random_index=k * P, inv=inverse(order))
         assert_slab_bits_equal(download(ctx, sp), ref)
     ctx.close()
 
