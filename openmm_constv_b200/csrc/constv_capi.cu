@@ -73,6 +73,7 @@ struct constv_slab {
     int* imageSlotBySlot = nullptr;
     void* imageChargeBySlot = nullptr;
     bool imageBySlotValid = false;
+    bool imageTables = true;  // CONSTV_IMAGE_TABLES=0: never use them (comparison)
     DevCounters* counters = nullptr;
     double* kePartials = nullptr;
     double* keOut = nullptr;
@@ -172,7 +173,7 @@ SlabDev makeDev(const constv_slab* s) {
     d.atomIndex = s->atomIndex;
     d.invAtomOrder = s->invAtomOrder;
     d.imageCharge = ((s->cfg.flags & CONSTV_FLAG_CACHE_IMAGE_CHARGE) && s->imageChargeValid) ? s->imageCharge : nullptr;
-    const bool bySlot = d.imageCharge && s->atomIndex && s->imageBySlotValid;
+    const bool bySlot = d.imageCharge && s->atomIndex && s->imageBySlotValid && s->imageTables;
     d.imageSlotBySlot = bySlot ? s->imageSlotBySlot : nullptr;
     d.imageChargeBySlot = bySlot ? s->imageChargeBySlot : nullptr;
     d.counters = s->counters;
@@ -439,6 +440,7 @@ int constv_create(const constv_config* config, constv_slab** out) {
     if (const char* e = std::getenv("CONSTV_FUSED_ZERO")) s->zeroWhen = std::atoi(e);
     if (const char* e = std::getenv("CONSTV_SETTLE_WS")) s->settleWs = std::atoi(e) != 0;
     if (const char* e = std::getenv("CONSTV_INDEXED_MINB")) s->indexedMinBlocks = std::atoi(e);
+    if (const char* e = std::getenv("CONSTV_IMAGE_TABLES")) s->imageTables = std::atoi(e) != 0;
     if (const char* e = std::getenv("CONSTV_DRUDE_SPT")) s->drudeSlotsPerThread = std::min(3, std::max(1, std::atoi(e)));
     if (const char* e = std::getenv("CONSTV_WS_GROUPS")) { const int g = std::atoi(e); if (g >= 3 && g <= 5) s->wsGroups = g; }
     DeviceGuard guard(config->device);
@@ -664,6 +666,7 @@ int constv_step_fused(constv_slab* s, const void* random4, uint32_t random_index
         rc = constv_refresh_image_charges(s, stream);
         if (rc) return rc;
     }
+    if ((rc = ensureImageBySlot(s, (cudaStream_t) stream))) return rc;
     const SlabDev d = makeDev(s);
     const float4* rnd = static_cast<const float4*>(random4);
     cudaStream_t st = (cudaStream_t) stream;

@@ -759,9 +759,18 @@ constv_fused_step_indexed_kernel(const __grid_constant__ SlabDev d, const float4
     Vec4<Mixed> v{0, 0, 0, 0};
     Vec4<Real> p{0, 0, 0, 0}, c{0, 0, 0, 0};
     long long fx = 0, fy = 0, fz = 0;
+    // per-slot image tables (SlabDev::imageSlotBySlot), when the host has them: the low slot's cell-1 image slot and charge
+    // are requested with everything else instead of after atomIndex has arrived
+    const bool tables = d.imageSlotBySlot != nullptr;
+    int t1Low = -1;
+    Real q1Low = 0;
     if (inRange) {
         a0 = d.atomIndex[i];
         a1 = d.atomIndex[i + R];
+        if (tables) {
+            t1Low = d.imageSlotBySlot[i];
+            q1Low = static_cast<const Real*>(d.imageChargeBySlot)[i];
+        }
         v = load4x<true>(velm, (size_t) i);
         p = load4x<true>(posq, (size_t) i);
         if (kSplit) c = load4x<true>(corrA, (size_t) i);
@@ -784,13 +793,18 @@ constv_fused_step_indexed_kernel(const __grid_constant__ SlabDev d, const float4
     };
     // haveXi: the caller drew this atom's Philox block already (while the record was in flight)
     auto updateReal = [&](int slot, int a, Vec4<Mixed> v, Vec4<Real> p, Vec4<Real> c, long long fx, long long fy, long long fz,
-                          bool haveXi, float4 xi) {
+                          bool haveXi, float4 xi, bool low) {
         const bool charged = p.w != -p.w;
         size_t t1 = 0;
         Real q1 = 0;
         if (charged) {  // the cell-1 image's slot and charge: requested before the arithmetic
-            t1 = (size_t) d.invAtomOrder[a + R];
-            q1 = d.imageCharge ? static_cast<const Real*>(d.imageCharge)[a] : posq[4 * t1 + 3];
+            if (low && tables) {
+                t1 = (size_t) t1Low;
+                q1 = q1Low;
+            } else {
+                t1 = (size_t) d.invAtomOrder[a + R];
+                q1 = d.imageCharge ? static_cast<const Real*>(d.imageCharge)[a] : posq[4 * t1 + 3];
+            }
         }
         if (v.w != 0) {
             if (random) xi = __ldcs(random + (size_t) randomIndex + slot);
@@ -828,7 +842,7 @@ constv_fused_step_indexed_kernel(const __grid_constant__ SlabDev d, const float4
         const bool drawn = a0 < R && random == nullptr;
         if (drawn && s.noisescale != 0) xi0 = gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) a0, step);
         if (a0 >= R) zeroSlot(i);
-        else updateReal(i, a0, v, p, c, fx, fy, fz, drawn, xi0);
+        else updateReal(i, a0, v, p, c, fx, fy, fz, drawn, xi0, true);
 #pragma unroll 1
         for (int cell = 1; cell < d.numCells; cell++) {
             const int slot = i + R * cell;
@@ -840,7 +854,7 @@ constv_fused_step_indexed_kernel(const __grid_constant__ SlabDev d, const float4
                 if (kSplit) c2 = load4x<true>(corrA, (size_t) slot);
                 updateReal(slot, a, load4x<true>(velm, (size_t) slot), load4x<true>(posq, (size_t) slot), c2,
                            load_force(force + slot), load_force(force + P + slot), load_force(force + 2 * P + slot),
-                           false, make_float4(0.f, 0.f, 0.f, 0.f));
+                           false, make_float4(0.f, 0.f, 0.f, 0.f), false);
             }
         }
     }

@@ -46,7 +46,8 @@ elif which == "fused":
     kind, water = "langevin", None
     chain_counts = (1, 2)
 elif which == "reordered":
-    variants = [("indexed_40_registers", {"CONSTV_INDEXED_MINB": "0"}), ("indexed_capped_32_registers", {"CONSTV_INDEXED_MINB": "8"})]
+    # the per-slot image tables (constv_image_by_slot_kernel) against the gathers through atomIndex -> invAtomOrder / imageCharge
+    variants = [("gathers", {"CONSTV_IMAGE_TABLES": "0"}), ("per_slot_image_tables", {"CONSTV_IMAGE_TABLES": "1"})]
     shard = env.slabmod.slab_tile(R, 1, 0, PRECISION, seed=bench.SLAB_SEED)
     perm = env.slabmod.molecule_permutation(shard, shard.meta["n_ion"], 3, shard.meta["n_water"] // 3, seed=7)
     shard, _ = env.slabmod.permute_slab(shard, perm)
