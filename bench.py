@@ -832,9 +832,16 @@ def run_e2e(env, wl, args, atoms_job):
     sptr = stream.cuda_stream
     ctx0, it0 = wl.ctxs[0]
     n_e2e = max(3, args.e2e_steps)
-    host_force = [torch.from_numpy(np.ascontiguousarray(slabmod.new_forces(shard, j)[:, :R])).pin_memory() for j in range(2)]
-    esize = 4 if args.precision != "double" else 8
-    host_posq = torch.empty((shard.num_atoms, 4), dtype=torch.float32 if esize == 4 else torch.float64).pin_memory()
+    # pinned buffers on the GPU's memory node where the host says which one that is (openmm_constv_b200/hostmem.py;
+    # the pool's boxes are single-node VMs: `placement` then records that nothing was done)
+    from openmm_constv_b200 import hostmem
+    placement = {}
+    with hostmem.near_gpu(torch.cuda.current_device(), placement):
+        host_force = [torch.from_numpy(np.ascontiguousarray(slabmod.new_forces(shard, j)[:, :R])).pin_memory() for j in range(2)]
+        esize = 4 if args.precision != "double" else 8
+        host_posq = torch.empty((shard.num_atoms, 4), dtype=torch.float32 if esize == 4 else torch.float64).pin_memory()
+        host_posq2 = torch.empty_like(host_posq).pin_memory()
+        host_force32 = [(torch.randn((3, R), dtype=torch.float32) * 1000.0).pin_memory() for _ in range(2)]
     h2d = host_force[0].numel() * 8
     ke_host = C.c_double(0.0)
     h = it0._kernel.handle
@@ -856,15 +863,20 @@ def run_e2e(env, wl, args, atoms_job):
             best.append(e0.elapsed_time(e1))
         return env.max_over_ranks(float(np.median(best)))
 
-    def e2e_pipelined(buffers, code, nsteps):
+    def e2e_pipelined(buffers, code, nsteps, posq_out=None):
         """submit step k+1, then collect step k: the upload of k+1 overlaps the kernels and the read-back of
-        k.  Every step still uploads its own forces and returns its own energy."""
+        k.  Every step still uploads its own forces and returns its own energy (and, with posq_out, its own posq
+        of all atoms into one of two alternating host buffers: constv_step_host_submit_state)."""
         ticket = C.c_uint64(0)
 
         def loop(n):
             prev = None
             for j in range(n):
-                capi.check(lib.constv_step_host_submit(h, buffers[j % 2].data_ptr(), code, C.byref(ticket), sptr))
+                if posq_out is None:
+                    capi.check(lib.constv_step_host_submit(h, buffers[j % 2].data_ptr(), code, C.byref(ticket), sptr))
+                else:
+                    capi.check(lib.constv_step_host_submit_state(h, buffers[j % 2].data_ptr(), code, posq_out[j % 2].data_ptr(), None,
+                                                                 C.byref(ticket), sptr))
                 if prev is not None:
                     capi.check(lib.constv_step_host_collect(h, prev, C.byref(ke_host)))
                 prev = ticket.value
@@ -888,11 +900,12 @@ def run_e2e(env, wl, args, atoms_job):
         ms_full = e2e_sync(True)
         n_pipe = 4 * n_e2e
         ms_pipe = e2e_pipelined(host_force, capi.FORCE_FIXED64, n_pipe)
-        host_force32 = [(torch.randn((3, R), dtype=torch.float32) * 1000.0).pin_memory() for _ in range(2)]
         ms_pipe32 = e2e_pipelined(host_force32, capi.FORCE_FLOAT32, n_pipe)
+        n_state = 2 * n_e2e
+        ms_state = e2e_pipelined(host_force32, capi.FORCE_FLOAT32, n_state, posq_out=[host_posq, host_posq2])
     return {"value": atoms_job * n_pipe / (ms_pipe32 * 1e-3), "unit": "atom-steps/s",
             "h2d_bytes_per_step": int(h2d // 2), "d2h_bytes_per_step": 8, "steps": n_pipe,
-            "ms_per_step": ms_pipe32 / n_pipe,
+            "ms_per_step": ms_pipe32 / n_pipe, "host_placement": placement,
             "what": "constv_step_host_submit/_collect with HOST buffers, two tickets in flight: every step uploads the real atoms' forces "
                     "from pinned memory (float32 x, y, z planes, 12 B per real atom; converted to OpenMM's fixed point on the device as "
                     "OpenMM's force kernels do), runs the fused step and the kinetic-energy reduction and reads the energy back; "
@@ -904,7 +917,11 @@ def run_e2e(env, wl, args, atoms_job):
                             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8},
             "full_state": {"value": atoms_job * n_e2e / (ms_full * 1e-3), "ms_per_step": ms_full / n_e2e,
                            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(host_posq.numel() * esize + 8),
-                           "what": "synchronous constv_step_host, plus D2H of posq for all atoms"}}
+                           "what": "synchronous constv_step_host, plus D2H of posq for all atoms"},
+            "full_state_pipelined": {"value": atoms_job * n_state / (ms_state * 1e-3), "ms_per_step": ms_state / n_state,
+                                     "h2d_bytes_per_step": int(h2d // 2), "d2h_bytes_per_step": int(host_posq.numel() * esize + 8),
+                                     "what": "constv_step_host_submit_state/_collect: float32 forces up, posq of all atoms and the energy back "
+                                             "every step; the read-back of step k (the other PCIe direction) overlaps the upload of step k+1"}}
 
 
 def run_plugin_path(args, atoms):

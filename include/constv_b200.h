@@ -242,6 +242,18 @@ CONSTV_API int constv_step_host_submit(constv_slab* slab, const void* host_force
                                        uint64_t* ticket_out, void* stream);
 CONSTV_API int constv_step_host_collect(constv_slab* slab, uint64_t ticket, double* host_ke_out);
 
+/* constv_step_host_submit that also reads the step's state back (what a trajectory frame per step needs; the
+ * reference downloads positions only when a reporter asks, through OpenMM's getState): after the step, posq of
+ * all N atoms (host_posq_out) and / or velm (host_velm_out) are copied to pinned host memory on a second internal
+ * stream, i.e. in the other PCIe direction, while the NEXT ticket's forces upload; the next step's kernels wait
+ * for the read-back (it copies straight out of the bound arrays).  Either pointer may be NULL; with both NULL this
+ * is constv_step_host_submit.  The host buffers belong to the ticket until it is collected: alternate two.
+ * collect() returns once the kinetic energy and the requested arrays have landed.  Collect every ticket before
+ * calling any other stepping entry point on the slab. */
+CONSTV_API int constv_step_host_submit_state(constv_slab* slab, const void* host_force_real, int32_t force_format,
+                                             void* host_posq_out, void* host_velm_out, uint64_t* ticket_out,
+                                             void* stream);
+
 /* ---- chains: overlapping consecutive steps of one slab ---------------------------------------- */
 
 /* A step of the reference is a sequence of whole-slab launches on one stream (Kernels.cpp:146-166), so

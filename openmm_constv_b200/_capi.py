@@ -32,7 +32,7 @@ SYMBOLS = [
     "constv_kinetic_energy", "constv_kinetic_energy_device", "constv_generate_noise",
     "constv_get_step_count", "constv_set_step_count", "constv_get_time", "constv_set_time",
     "constv_upload_state", "constv_download_state", "constv_step_host", "constv_step_host_submit",
-    "constv_step_host_collect", "constv_last_error",
+    "constv_step_host_collect", "constv_step_host_submit_state", "constv_last_error",
     "constv_version", "constv_launch_count", "constv_set_launch_shape", "constv_set_kernel_variant",
     "constv_set_chains", "constv_get_chains", "constv_step_fused_chain", "constv_step_fused_multi",
     "constv_drude_configure", "constv_drude_random_count", "constv_drude_set_parameters",
@@ -100,6 +100,7 @@ def load() -> C.CDLL:
         "constv_step_host": [vp, vp, vp, vp, C.POINTER(dbl), vp],
         "constv_step_host_submit": [vp, vp, i32, C.POINTER(u64), vp],
         "constv_step_host_collect": [vp, u64, C.POINTER(dbl)],
+        "constv_step_host_submit_state": [vp, vp, i32, vp, vp, C.POINTER(u64), vp],
         "constv_set_launch_shape": [vp, i32, i32],
         "constv_set_kernel_variant": [vp, i32, i32, i32, i32],
         "constv_set_chains": [vp, i32],

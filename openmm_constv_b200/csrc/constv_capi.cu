@@ -137,6 +137,12 @@ struct constv_slab {
         double* keDev = nullptr;   // 2 doubles
         double* keHost = nullptr;  // 2 doubles, pinned
         uint64_t submitted = 0, collected = 0;
+        // constv_step_host_submit_state: read-back of posq / velm on its own stream (the other PCIe direction)
+        cudaStream_t readStream = nullptr;
+        cudaEvent_t stepDone[2] = {nullptr, nullptr}, readDone[2] = {nullptr, nullptr};
+        bool hasRead[2] = {false, false};
+        bool readOutstanding = false;  // a read-back of the bound arrays may still be running: the next step waits for it
+        cudaEvent_t lastRead = nullptr;
     } pipe;
 };
 
@@ -510,6 +516,14 @@ int constv_destroy(constv_slab* s) {
         cudaFree(s->pipe.keDev);
         cudaFreeHost(s->pipe.keHost);
         cudaStreamDestroy(s->pipe.copyStream);
+        if (s->pipe.readStream) {
+            cudaStreamSynchronize(s->pipe.readStream);
+            for (int k = 0; k < 2; k++) {
+                cudaEventDestroy(s->pipe.stepDone[k]);
+                cudaEventDestroy(s->pipe.readDone[k]);
+            }
+            cudaStreamDestroy(s->pipe.readStream);
+        }
     }
     if (s->keHost) cudaFreeHost(s->keHost);
     delete s;
@@ -1005,6 +1019,11 @@ int constv_step_host(constv_slab* s, const int64_t* host_force_real, void* host_
 
 int constv_step_host_submit(constv_slab* s, const void* host_force_real, int32_t force_format, uint64_t* ticket_out,
                             void* stream) {
+    return constv_step_host_submit_state(s, host_force_real, force_format, nullptr, nullptr, ticket_out, stream);
+}
+
+int constv_step_host_submit_state(constv_slab* s, const void* host_force_real, int32_t force_format, void* host_posq_out,
+                                  void* host_velm_out, uint64_t* ticket_out, void* stream) {
     GUARD(s);
     int rc = checkReady(s, false);
     if (rc) return rc;
@@ -1026,6 +1045,14 @@ int constv_step_host_submit(constv_slab* s, const void* host_force_real, int32_t
         CUDA_TRY(cudaMallocHost(&p.keHost, 2 * sizeof(double)));
         p.ready = true;
     }
+    const bool wantRead = host_posq_out != nullptr || host_velm_out != nullptr;
+    if (wantRead && !p.readStream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&p.readStream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; k++) {
+            CUDA_TRY(cudaEventCreateWithFlags(&p.stepDone[k], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&p.readDone[k], cudaEventDisableTiming));
+        }
+    }
     const int slot = (int) (p.submitted & 1);
     cudaStream_t st = (cudaStream_t) stream;
     const size_t bytes = (force_format == CONSTV_FORCE_FLOAT32 ? 12 : 24) * R;
@@ -1042,10 +1069,29 @@ int constv_step_host_submit(constv_slab* s, const void* host_force_real, int32_t
         rc = launch(constv_stage_forces_kernel<false>, grid, 256, false, st, s->numReal, s->cfg.padded_num_atoms, (const void*) p.stage[slot], (long long*) s->force);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(p.stageFree[slot], st));
+    // the previous ticket's read-back copies posq / velm straight out of the bound arrays: this step must not
+    // rewrite them before it has finished (the upload and the force staging above do not wait for it)
+    if (p.readOutstanding) {
+        CUDA_TRY(cudaStreamWaitEvent(st, p.lastRead, 0));
+        p.readOutstanding = false;
+    }
     rc = constv_step_fused(s, nullptr, 0, stream);
     if (rc) return rc;
     rc = constv_kinetic_energy_device(s, 0.5 * s->stepSize, p.keDev + slot, stream);
     if (rc) return rc;
+    p.hasRead[slot] = wantRead;
+    if (wantRead) {
+        const size_t N = (size_t) s->cfg.num_atoms;
+        CUDA_TRY(cudaEventRecord(p.stepDone[slot], st));
+        CUDA_TRY(cudaStreamWaitEvent(p.readStream, p.stepDone[slot], 0));
+        if (host_posq_out)
+            CUDA_TRY(cudaMemcpyAsync(host_posq_out, s->posq, 4 * realSize(s->cfg.precision) * N, cudaMemcpyDeviceToHost, p.readStream));
+        if (host_velm_out)
+            CUDA_TRY(cudaMemcpyAsync(host_velm_out, s->velm, 4 * mixedSize(s->cfg.precision) * N, cudaMemcpyDeviceToHost, p.readStream));
+        CUDA_TRY(cudaEventRecord(p.readDone[slot], p.readStream));
+        p.lastRead = p.readDone[slot];
+        p.readOutstanding = true;
+    }
     CUDA_TRY(cudaMemcpyAsync(p.keHost + slot, p.keDev + slot, sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaEventRecord(p.done[slot], st));
     *ticket_out = p.submitted++;
@@ -1059,6 +1105,7 @@ int constv_step_host_collect(constv_slab* s, uint64_t ticket, double* host_ke_ou
         return fail(CONSTV_ERR_STATE, "tickets are collected in submission order (next: %llu)", (unsigned long long) p.collected);
     const int slot = (int) (ticket & 1);
     CUDA_TRY(cudaEventSynchronize(p.done[slot]));
+    if (p.hasRead[slot]) CUDA_TRY(cudaEventSynchronize(p.readDone[slot]));
     if (host_ke_out) *host_ke_out = p.keHost[slot];
     p.collected++;
     return CONSTV_OK;

@@ -114,13 +114,13 @@ def prefer_node(node):
 
 
 @contextlib.contextmanager
-def near_gpu(device_index, report=None):
+def near_gpu(device_index, report=None, pci_address=None):
     """Pinned buffers allocated inside the block land on the GPU's memory node when the host allows it.
 
     Two routes, both undone on exit: the thread runs on the node's cores (first touch; only the cores the cpuset
     already allows), and the thread's memory policy prefers the node.  `report`, a dict, receives what happened."""
     report = {} if report is None else report
-    node = pci_numa_node(gpu_pci_address(device_index))
+    node = pci_numa_node(pci_address if pci_address is not None else gpu_pci_address(device_index))
     report.update({"gpu_node": node, "cpu_route": False, "policy_route": False})
     if node < 0:
         yield report

@@ -627,6 +627,75 @@ def test_pipelined_host_stepping_equals_synchronous(gpu, oracle, fmt):
     ctx_b.close()
 
 
+@pytest.mark.parametrize("which", ["posq", "posq_velm", "velm"])
+def test_pipelined_state_readback_equals_synchronous(gpu, oracle, which):
+    """constv_step_host_submit_state: every ticket's posq / velm, read back on the second copy stream while the
+    next ticket's forces upload, are the arrays the synchronous constv_step_host returns for that step -- i.e.
+    the next step's kernels really wait for the read-back of the arrays they overwrite."""
+    import ctypes as C
+    import torch
+    from openmm_constv_b200 import _capi
+    lib = _capi.load()
+    s0 = slabmod.make_slab(200003, "single", seed=29)  # large enough that a read-back outlasts the next step's kernels
+    R, N, nsteps = s0.num_real, s0.num_atoms, 6
+    rng = np.random.default_rng(9)
+    f32 = [(rng.standard_normal((3, R)) * 1000.0).astype(np.float32) for _ in range(nsteps)]
+    fixed = [np.trunc(f.astype(np.float64) * 4294967296.0).astype(np.int64) for f in f32]
+    ctx_a, it_a = make_context(gpu, s0, seed=5)
+    _capi.check(lib.constv_set_parameters(it_a._kernel.handle, T, GAMMA, DT))
+    want = []
+    for g in fixed:
+        hf = torch.from_numpy(np.ascontiguousarray(g)).pin_memory()
+        hp = torch.zeros((N, 4), dtype=torch.float32).pin_memory()
+        hv = torch.zeros((N, 4), dtype=torch.float32).pin_memory()
+        ke = C.c_double(0.0)
+        _capi.check(lib.constv_step_host(it_a._kernel.handle, hf.data_ptr(), hp.data_ptr(), hv.data_ptr(), C.byref(ke), ctx_a.stream_ptr()))
+        want.append((hp.numpy().copy(), hv.numpy().copy(), ke.value))
+    ctx_b, it_b = make_context(gpu, s0, seed=5)
+    _capi.check(lib.constv_set_parameters(it_b._kernel.handle, T, GAMMA, DT))
+    pinned = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in f32]
+    out_p = [torch.zeros((N, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    out_v = [torch.zeros((N, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    h = it_b._kernel.handle
+
+    def check(k, ke):
+        if "posq" in which:
+            assert_bits_equal(out_p[k % 2].numpy(), want[k][0])
+        if "velm" in which:
+            assert_bits_equal(out_v[k % 2].numpy(), want[k][1])
+        assert ke == want[k][2]
+
+    prev = None
+    for k in range(nsteps):
+        t = C.c_uint64(0)
+        _capi.check(lib.constv_step_host_submit_state(h, pinned[k].data_ptr(), _capi.FORCE_FLOAT32,
+                                                      out_p[k % 2].data_ptr() if "posq" in which else None,
+                                                      out_v[k % 2].data_ptr() if "velm" in which else None,
+                                                      C.byref(t), ctx_b.stream_ptr()))
+        if prev is not None:
+            ke = C.c_double(0.0)
+            _capi.check(lib.constv_step_host_collect(h, prev, C.byref(ke)))
+            check(k - 1, ke.value)
+        prev = t.value
+    ke = C.c_double(0.0)
+    _capi.check(lib.constv_step_host_collect(h, prev, C.byref(ke)))
+    check(nsteps - 1, ke.value)
+    # a plain ticket behind a state ticket still waits for the read-back before it rewrites the arrays
+    t = C.c_uint64(0)
+    _capi.check(lib.constv_step_host_submit_state(h, pinned[0].data_ptr(), _capi.FORCE_FLOAT32, out_p[0].data_ptr(), None, C.byref(t), ctx_b.stream_ptr()))
+    t2 = C.c_uint64(0)
+    _capi.check(lib.constv_step_host_submit(h, pinned[1].data_ptr(), _capi.FORCE_FLOAT32, C.byref(t2), ctx_b.stream_ptr()))
+    _capi.check(lib.constv_step_host_collect(h, t.value, None))
+    snapshot = out_p[0].numpy().copy()
+    _capi.check(lib.constv_step_host_collect(h, t2.value, None))
+    hf = torch.from_numpy(np.ascontiguousarray(fixed[0])).pin_memory()
+    hp = torch.zeros((N, 4), dtype=torch.float32).pin_memory()
+    _capi.check(lib.constv_step_host(it_a._kernel.handle, hf.data_ptr(), hp.data_ptr(), None, None, ctx_a.stream_ptr()))
+    assert_bits_equal(snapshot, hp.numpy())
+    ctx_a.close()
+    ctx_b.close()
+
+
 # ---- full-size, size-independent properties ------------------------------------------------------------
 
 def test_full_size_slab_properties_and_oracle(gpu, oracle):
