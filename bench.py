@@ -1110,6 +1110,8 @@ def main():
                    "constv_settle_step_tiled_kernel" if kind == "settle" else
                    "constv_part1_kernel + constv_settle_positions_kernel + constv_part2_mirror_kernel" if kind == "settle_split" else
                    "constv_fused_step_indexed_kernel" if args.reordered else "constv_fused_step_kernel")
+    if kind == "settle" and not args.ensemble and env.capi.last_kernel():
+        kernel_name = env.capi.last_kernel()  # the library's choice of stage-in (constv_settle_step_{bulk,tiled,ws}_kernel), as launched
 
     also = {}
     # ---- one launch per step on the same slab (what a host with other kernels between two steps gets at best)
@@ -1221,7 +1223,8 @@ def main():
         ww = Workload(env, args, shw, kind="settle", chains=6, water=(w_atoms, w_params, w_cons))
         kw_ = max(20, min(K, 1200))
         tw = time_steps(env, ww, kw_, 5, use_graph=use_graph, repeats=args.repeats)
-        also["rigid_water"] = rate_record(shw.num_atoms * world, kw_, tw, ww.algorithmic_bytes(), ww.chains, peak, "constv_settle_step_tiled_kernel",
+        also["rigid_water"] = rate_record(shw.num_atoms * world, kw_, tw, ww.algorithmic_bytes(), ww.chains, peak,
+                                          env.capi.last_kernel() or "constv_settle_step_tiled_kernel",
                                           {"atoms_per_gpu": shw.num_atoms, "n_gpus": world, "rigid_molecules_per_gpu": int(len(w_atoms)),
                                            "replicas": ww.replicas, "parity_note": "SETTLE restated from recall: CUDA == oracle bit for bit, "
                                            "oracle unpinned against OpenMM's solver (DESIGN.md 5)"})

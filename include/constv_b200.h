@@ -384,6 +384,10 @@ CONSTV_API const char* constv_last_error(void);
 CONSTV_API int constv_version(void);
 /* Kernels launched by this library in this process so far (bench.py's gpu_launches). */
 CONSTV_API uint64_t constv_launch_count(void);
+/* Name of the kernel behind the calling thread's most recent launch, where the library had a choice ("" otherwise):
+ * the rigid-molecule step's constv_settle_step_{tiled,bulk,ws,tiled_batched}_kernel, constv_fused_step_tma_kernel.
+ * Diagnostics and tests (which variant did constv_set_kernel_variant / the automatic rule pick). */
+CONSTV_API const char* constv_last_kernel(void);
 /* Tuning knobs of the fused kernel: real/image pairs per thread (1, 2 or 4) and the grid:
  * ctas_per_sm = -1 launches a one-shot grid (one tile per CTA, the default), 1..32 a persistent grid
  * of that many CTAs per SM; 0 keeps the current value. */
@@ -393,10 +397,12 @@ CONSTV_API int constv_set_launch_shape(constv_slab* slab, int32_t pairs_per_thre
  * kernel, which measured faster than the TMA ring on B200), 1 = the plain-load kernel, 2 = the
  * TMA-pipelined kernel (error unless the slab is eligible: identity order, Philox noise,
  * CONSTV_FLAG_CACHE_IMAGE_CHARGE, even P).  For the rigid-molecule step (constv_step_fused_settle*): 0 = automatic
- * (the staged kernel, its stage filled by asynchronous copies), 1 = the gather kernel, 3 = the staged kernel with its
- * stage filled through registers (round 1's), 4 = the warp-specialised TMA pipeline
- * (bulk copies in and out; identity order, Philox noise, CONSTV_FLAG_CACHE_IMAGE_CHARGE, num_cells == 2, else the
- * staged kernel runs); same results bit for bit.  For the Drude step (constv_drude_step_fused*): 0 = automatic (the
+ * (the staged kernel; its stage is filled by bulk copies issued by one thread for a chain's launch and for launches of
+ * at least two waves of CTAs, by per-thread asynchronous copies otherwise), 1 = the gather kernel, 3 = the staged
+ * kernel with its stage filled through registers (round 1's), 4 = the warp-specialised TMA pipeline, 6 = always the
+ * bulk stage-in, 7 = always the per-thread asynchronous copies (4 and 6 need identity order, Philox noise,
+ * CONSTV_FLAG_CACHE_IMAGE_CHARGE, num_cells == 2 and P a multiple of 4, else the cp.async-staged kernel runs); same
+ * results bit for bit.  For the Drude step (constv_drude_step_fused*): 0 = automatic (the
  * staged kernel whose warps draw chunks of work items), 1 = the thread-per-slot gather kernel, 5 = the staged kernel with
  * one work item per thread (round 1's); same results bit for bit.
  * (block_size, stages) in {(128,6), (256,2), (256,3), (256,4), (512,2), (512,3)} shape the TMA ring, ctas_per_sm caps the persistent

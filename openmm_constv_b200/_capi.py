@@ -33,7 +33,7 @@ SYMBOLS = [
     "constv_get_step_count", "constv_set_step_count", "constv_get_time", "constv_set_time",
     "constv_upload_state", "constv_download_state", "constv_step_host", "constv_step_host_submit",
     "constv_step_host_collect", "constv_step_host_submit_state", "constv_last_error",
-    "constv_version", "constv_launch_count", "constv_set_launch_shape", "constv_set_kernel_variant",
+    "constv_version", "constv_launch_count", "constv_last_kernel", "constv_set_launch_shape", "constv_set_kernel_variant",
     "constv_set_chains", "constv_get_chains", "constv_step_fused_chain", "constv_step_fused_multi",
     "constv_drude_configure", "constv_drude_random_count", "constv_drude_set_parameters",
     "constv_drude_get_parameters", "constv_drude_step_part1", "constv_drude_step_part2",
@@ -133,6 +133,8 @@ def load() -> C.CDLL:
     lib.constv_last_error.argtypes = []
     lib.constv_version.restype = C.c_int
     lib.constv_launch_count.restype = C.c_uint64
+    lib.constv_last_kernel.restype = C.c_char_p
+    lib.constv_last_kernel.argtypes = []
     _lib = lib
     return lib
 
@@ -144,6 +146,11 @@ def check(rc: int) -> None:
 
 def launch_count() -> int:
     return int(load().constv_launch_count())
+
+
+def last_kernel() -> str:
+    """Kernel behind this thread's most recent launch where the library had a choice ('' otherwise)."""
+    return load().constv_last_kernel().decode()
 
 
 def validate_system(masses, num_cells: int, box_z: float, cell_size: float) -> float:

@@ -24,6 +24,7 @@ using namespace constv;
 namespace {
 
 thread_local std::string g_lastError;
+thread_local const char* g_lastKernel = "";  // constv_last_kernel: which kernel the calling thread's last launch was
 std::atomic<uint64_t> g_launchCount{0};
 
 int fail(int code, const char* fmt, ...) {
@@ -244,6 +245,7 @@ int launch(K kernel, int grid, int block, bool pdl, cudaStream_t stream, Args...
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, args...));
+    g_lastKernel = "";  // launch sites that have a choice of kernels name theirs afterwards
     g_launchCount.fetch_add(1, std::memory_order_relaxed);
     return CONSTV_OK;
 }
@@ -309,6 +311,7 @@ int launchFusedTmaShape(constv_slab* s, const SlabDev& d, cudaStream_t st) {
     cfg.attrs = attr;
     cfg.numAttrs = (s->cfg.flags & CONSTV_FLAG_PDL) ? 1 : 0;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, d));
+    g_lastKernel = "constv_fused_step_tma_kernel";
     g_launchCount.fetch_add(1, std::memory_order_relaxed);
     return CONSTV_OK;
 }
@@ -407,6 +410,7 @@ extern "C" {
 const char* constv_last_error(void) { return g_lastError.c_str(); }
 int constv_version(void) { return CONSTV_VERSION; }
 uint64_t constv_launch_count(void) { return g_launchCount.load(std::memory_order_relaxed); }
+const char* constv_last_kernel(void) { return g_lastKernel; }
 
 int constv_validate_system(int32_t num_atoms, int32_t num_cells, const double* masses, double box_z,
                            double cell_size, double* zmax_out) {
@@ -1127,9 +1131,10 @@ int constv_set_launch_shape(constv_slab* s, int32_t pairs_per_thread, int32_t ct
 
 int constv_set_kernel_variant(constv_slab* s, int32_t variant, int32_t block_size, int32_t stages, int32_t ctas_per_sm) {
     if (!s) return fail(CONSTV_ERR_INVALID, "null slab");
-    if (variant < 0 || variant > 5)
+    if (variant < 0 || variant > 7)
         return fail(CONSTV_ERR_INVALID, "variant must be 0 (auto), 1 (LDG / gather), 2 (TMA ring), 3 (LDG-staged rigid-water kernel), 4 (TMA-pipelined "
-                                        "rigid-water kernel) or 5 (Drude step staged with one work item per thread)");
+                                        "rigid-water kernel), 5 (Drude step staged with one work item per thread), 6 (rigid-water kernel with a bulk "
+                                        "stage-in) or 7 (rigid-water kernel staged by cp.async)");
     s->variant = variant;
     if (block_size) s->tmaBlock = block_size;
     if (stages) s->tmaStages = stages;

@@ -71,6 +71,18 @@ elif which in ("settle_chains", "drude_chains", "settle_reordered", "drude_reord
         perm = env.slabmod.molecule_permutation(shard, shard.meta["n_ion"], per, n_mol, seed=7)
         shard, _ = env.slabmod.permute_slab(shard, perm)
     ROUNDS = 3
+elif which in ("settle_bulk", "settle_bulk_reordered"):
+    # the staged kernel (cp.async stage-in, variant 7) against the same shape with a bulk stage-in by one thread (variant 6);
+    # variant 0 = the library's rule (bulk for a chain's launch and for launches of at least two waves of CTAs)
+    variants = [("cp_async_staged", {"_variant": 7}), ("bulk_stage_in", {"_variant": 6}), ("automatic", {"_variant": 0})]
+    shard, w_atoms, w_params, w_cons = env.slabmod.slab_tile(R, 1, 0, PRECISION, seed=bench.SLAB_SEED, maker=env.slabmod.make_water_slab)
+    kind, water = "settle", (w_atoms, w_params, w_cons)
+    chain_counts = (1, 2, 3, 6)
+    if which.endswith("reordered"):
+        perm = env.slabmod.molecule_permutation(shard, shard.meta["n_ion"], 3, shard.meta["n_water"] // 3, seed=7)
+        shard, _ = env.slabmod.permute_slab(shard, perm)
+        chain_counts = (1,)
+    ROUNDS = 3
 elif which == "drude":
     # the staged Drude step: thread t <-> work item t (spt1) against the balanced kernel (csrc/constv_drude_kernels.cuh)
     variants = [("item_per_thread", {"CONSTV_DRUDE_SPT": "1"}), ("balanced_2_slots_per_thread", {"CONSTV_DRUDE_SPT": "2"}),

@@ -34,10 +34,22 @@ def gpu():
 
 
 WS = 4  # constv_set_kernel_variant: the TMA-pipelined rigid-water kernel (0 = auto = the staged kernel; 3 = the same, staged through registers)
+WS_PIPELINE = 4
+BULK = 6  # the staged kernel's shape with the pipeline's bulk stage-in (constv_settle_step_bulk_kernel)
 
 
-def make_context(gpu, s, cons, seed=77, flags=None, variant=WS):
+@pytest.fixture(params=[WS, BULK], ids=["pipeline", "bulk_stage_in"], autouse=True)
+def kernel_variant(request):
+    """Every test of this module runs once per kernel: both read the same 4-slot-aligned load windows."""
+    global WS
+    before, WS = WS, request.param
+    yield request.param
+    WS = before
+
+
+def make_context(gpu, s, cons, seed=77, flags=None, variant=None):
     from openmm_constv_b200 import _capi
+    variant = WS if variant is None else variant
     sysm = gpu.SlabSystem()
     sysm.addParticles(s.masses)
     sysm.setDefaultPeriodicBoxVectors((s.box[0], 0, 0), (0, s.box[1], 0), (0, 0, s.num_cells * s.zmax))
@@ -91,6 +103,10 @@ def run_against_oracle(gpu, oracle, s0, atoms, params, cons, nsteps=3, flags=Non
                            delta, prm, dt, xi, 0, inv, atoms, params, *(() if zero else (False, False)))
         assert_same(download(ctx, s0), ref)
     assert it._kernel.get_step_count() == nsteps
+    # which kernel ran: the variant under test needs the image-charge side array and padded % 4 == 0, else the staged kernel
+    eligible = bool((_capi.FLAGS_DEFAULT if flags is None else flags) & _capi.FLAG_CACHE_IMAGE_CHARGE) and s0.padded % 4 == 0 and s0.num_cells == 2
+    want = {WS_PIPELINE: "constv_settle_step_ws_kernel", BULK: "constv_settle_step_bulk_kernel"}[WS] if eligible else "constv_settle_step_tiled_kernel"
+    assert _capi.last_kernel() == want
     got = download(ctx, s0)
     ctx.close()
     return got
@@ -205,3 +221,74 @@ def test_ws_chains_and_graph_replay(gpu, chains):
     torch.cuda.synchronize()
     assert_same(download(ctx, s0), want)
     ctx.close()
+
+
+def _molecule_preserving_permutation(s, rng):
+    """perm[new slot] = old slot: whole water molecules trade places, images freely (what OpenMM's re-sort does)."""
+    R, N = s.num_real, s.num_atoms
+    n_ion, n_mol = s.meta["n_ion"], s.meta["n_molecules"]
+    perm = np.arange(N, dtype=np.int32)
+    order = rng.permutation(n_mol)
+    for k in range(3):
+        perm[n_ion + k: n_ion + 3 * n_mol: 3] = n_ion + 3 * order + k
+    perm[R:N] = R + rng.permutation(N - R)
+    return perm
+
+
+@pytest.mark.parametrize("precision", slabmod.PRECISIONS)
+@pytest.mark.parametrize("num_cells", [2, 4])
+@pytest.mark.parametrize("num_real", [1003, 40009])
+def test_bulk_stage_in_on_reordered_slots(gpu, precision, num_cells, num_real):
+    """Reordered slots (whole molecules swapped, images anywhere), Philox noise keyed by the original index, the per-slot image
+    tables: kernel variant 6 (bulk stage-in, three more bulk copies for atomIndex and the tables) leaves the bits of
+    variant 7 (the cp.async-staged kernel, itself pinned on the oracle in tests/test_gpu_settle.py), with a re-sort
+    between steps."""
+    import torch
+    from openmm_constv_b200 import _capi
+    s0, atoms, params, cons = slabmod.make_water_slab(num_real, precision, num_cells=num_cells, seed=51)
+    perm = _molecule_preserving_permutation(s0, np.random.default_rng(11))
+    sp, atom_index = H.permute_slab(s0, perm)
+    N, P = s0.num_atoms, s0.padded
+    out = []
+    for variant, kernel in ((BULK, "constv_settle_step_bulk_kernel"), (7, "constv_settle_step_tiled_kernel")):
+        ctx, it = make_context(gpu, sp, cons, seed=13, variant=variant, flags=_capi.FLAGS_DEFAULT | _capi.FLAG_CACHE_IMAGE_CHARGE)
+        ctx.set_atom_order(perm)
+        lib, slab = it._kernel._lib, it._kernel.handle
+        order = np.arange(P, dtype=np.int32)
+        order[:N] = atom_index[:N]
+        for k in range(4):
+            if k == 2:  # slots trade places again, in place, as OpenMM does it
+                sigma = np.arange(P)
+                sigma[:N] = _molecule_preserving_permutation(s0, np.random.default_rng(12))
+                sig = torch.as_tensor(sigma, device="cuda")
+                for arr in (ctx.posq, ctx.velm) + ((ctx.corr,) if ctx.corr is not None else ()):
+                    arr.copy_(arr[sig].clone())
+                ctx.force.copy_(ctx.force[:, sig].clone())
+                order = order[sigma]
+                ctx.atom_index.copy_(torch.as_tensor(order, device="cuda"))
+                _capi.check(lib.constv_update_inverse_order(slab, ctx.stream_ptr()))
+            ctx.force.copy_(torch.from_numpy(slabmod.new_forces(sp, k)))
+            it.step(1)
+            if k >= 1:  # the first step takes the image-charge snapshot and builds the tables behind the staged kernel
+                assert _capi.last_kernel() == kernel
+        out.append(download(ctx, sp))
+        ctx.close()
+    assert_same(out[0], out[1])
+
+
+def test_automatic_choice_of_the_stage_in(gpu):
+    """Variant 0: per-thread asynchronous copies for one launch of fewer than two waves of CTAs, the bulk stage-in for a
+    chain's launch; same bits."""
+    from openmm_constv_b200 import _capi
+    lib = _capi.load()
+    s0, atoms, params, cons = slabmod.make_water_slab(30011, "single", seed=47)
+    out = []
+    for chains, kernel in ((1, "constv_settle_step_tiled_kernel"), (3, "constv_settle_step_bulk_kernel")):
+        ctx, it = make_context(gpu, s0, cons, seed=3, variant=0, flags=_capi.FLAGS_DEFAULT | _capi.FLAG_CACHE_IMAGE_CHARGE)
+        if chains > 1:
+            _capi.check(lib.constv_set_chains(it._kernel.handle, chains))
+        it.step(3)
+        assert _capi.last_kernel() == kernel
+        out.append(download(ctx, s0))
+        ctx.close()
+    assert_same(out[0], out[1])
