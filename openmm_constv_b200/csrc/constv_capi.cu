@@ -98,6 +98,10 @@ struct constv_slab {
     // with two chains, profiles/r02_ab_drude_balanced.jsonl); 1 = thread t takes work item t (CONSTV_DRUDE_SPT)
     int drudeSlotsPerThread = 2;
     int indexedMinBlocks = 0; // reordered-slot fused kernel, single precision: 8 = capped at 32 registers (experiment: CONSTV_INDEXED_MINB=8)
+    // bulk-staged rigid-water step: a molecule's Philox draws made while the bulk copies fly.  -1 = automatic: on in mixed / double
+    // precision (128 registers: 26.8 -> 25.8 us per step at 1M atoms with one launch, 20.8 -> 20.2 with three chains), off in single
+    // (64-register cap: 24 B of stack, 12.7 -> 13.4 us with six chains; profiles/r02_ab_settle_bulk_early.jsonl).  CONSTV_SETTLE_EARLY=0|1 forces.
+    int settleEarly = -1;
     int wsGroups = 4;         // its consumer groups in single precision (CONSTV_WS_GROUPS=3..5: experiments)
     int ctasPerSM = 0;   // 0 = one-shot grid (one tile per CTA); > 0 = persistent grid of that many CTAs per SM
     int variant = 0;     // 0 auto (= the one-shot LDG kernel, the faster one as measured), 1 LDG, 2 TMA ring
@@ -449,6 +453,7 @@ int constv_create(const constv_config* config, constv_slab** out) {
     if (const char* e = std::getenv("CONSTV_FUSED_EARLY")) s->fusedEarly = std::atoi(e) != 0;
     if (const char* e = std::getenv("CONSTV_FUSED_ZERO")) s->zeroWhen = std::atoi(e);
     if (const char* e = std::getenv("CONSTV_SETTLE_WS")) s->settleWs = std::atoi(e) != 0;
+    if (const char* e = std::getenv("CONSTV_SETTLE_EARLY")) s->settleEarly = std::atoi(e) != 0 ? 1 : 0;
     if (const char* e = std::getenv("CONSTV_INDEXED_MINB")) s->indexedMinBlocks = std::atoi(e);
     if (const char* e = std::getenv("CONSTV_IMAGE_TABLES")) s->imageTables = std::atoi(e) != 0;
     if (const char* e = std::getenv("CONSTV_DRUDE_SPT")) s->drudeSlotsPerThread = std::min(3, std::max(1, std::atoi(e)));

@@ -393,7 +393,10 @@ template <int PREC, bool INDEXED> struct BulkIn : WsIn<PREC> {
     int img[INDEXED ? kWsSlots : 1];   // slot of its cell-1 image, -1 = the slot holds no real atom
 };
 
-template <int PREC, bool INDEXED>
+// EARLY: a molecule's three Philox blocks (functions of seed, atom index and step only) are drawn while the tile's bulk
+// copies are in flight -- nothing else is live in the thread at that point, and no CTA barrier lies between the draws
+// and their use (the cp.async kernel's early draws had to cross one: DESIGN.md 3c).  Runs of single atoms draw late.
+template <int PREC, bool INDEXED, bool EARLY = false>
 __global__ void __launch_bounds__(kWsItems, PREC == PREC_SINGLE ? 8 : 4)
 constv_settle_step_bulk_kernel(const __grid_constant__ SlabDev d, const __grid_constant__ SettleSegments seg) {
     using Real = typename Prec<PREC>::Real;
@@ -454,6 +457,13 @@ constv_settle_step_bulk_kernel(const __grid_constant__ SlabDev d, const __grid_c
     const unsigned long long step = box.step;
     const unsigned int ticket = take_ticket(d.counters, holders);
     const StepScalars<Mixed> s = scalars_of<Mixed>(d);
+    float4 early[3];
+    const bool drawn = EARLY && !INDEXED && t.per == 3 && s.noisescale != 0 && j < t.items;
+    if (EARLY && drawn) {
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            early[k] = gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) (t.base + 3 * j + k), step);
+    }
     mbar_wait(smem_u32(&full), 0u);
 
     // compute item j in place (the text of the staged kernel's compute phase)
@@ -474,8 +484,10 @@ constv_settle_step_bulk_kernel(const __grid_constant__ SlabDev d, const __grid_c
                 if (moved[k]) {
                     nMoved++;
                     const int a = INDEXED ? st.orig[idx] : t.base + t.per * j + k;
-                    const float4 xi = (s.noisescale != 0) ? gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) a, step)
-                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 xi;
+                    if (EARLY && drawn) xi = early[k];
+                    else xi = (s.noisescale != 0) ? gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) a, step)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
                     part1_update(v[k], delta[k], st.f[0][idx], st.f[1][idx], st.f[2][idx], xi.x, xi.y, xi.z, s);
                 }
             }

@@ -83,6 +83,14 @@ elif which in ("settle_bulk", "settle_bulk_reordered"):
         shard, _ = env.slabmod.permute_slab(shard, perm)
         chain_counts = (1,)
     ROUNDS = 3
+elif which == "settle_bulk_early":
+    # bulk stage-in: the three Philox blocks of a molecule drawn while the bulk copies are in flight (CONSTV_SETTLE_EARLY=1)
+    variants = [("bulk_draw_late", {"_variant": 6, "CONSTV_SETTLE_EARLY": "0"}), ("bulk_draw_early", {"_variant": 6, "CONSTV_SETTLE_EARLY": "1"}),
+                ("cp_async_staged", {"_variant": 7, "CONSTV_SETTLE_EARLY": "0"})]
+    shard, w_atoms, w_params, w_cons = env.slabmod.slab_tile(R, 1, 0, PRECISION, seed=bench.SLAB_SEED, maker=env.slabmod.make_water_slab)
+    kind, water = "settle", (w_atoms, w_params, w_cons)
+    chain_counts = (1, 3, 6)
+    ROUNDS = 3
 elif which == "drude":
     # the staged Drude step: thread t <-> work item t (spt1) against the balanced kernel (csrc/constv_drude_kernels.cuh)
     variants = [("item_per_thread", {"CONSTV_DRUDE_SPT": "1"}), ("balanced_2_slots_per_thread", {"CONSTV_DRUDE_SPT": "2"}),
