@@ -679,11 +679,26 @@ def time_steps_in_graph(env, wl, K, W, repeats, target_s, sample_clocks):
         replays = int(np.ceil(n_rep / per))
         events = [torch.cuda.Event(enable_timing=True, external=True) for _ in range(per + 2)]
         graph = torch.cuda.CUDAGraph()
+        # The event record nodes hang off the chain of regions as side branches (recorded on `tick`, which waits for the
+        # region's last kernel): an event is stamped when its region completes, and the next region's first kernels depend
+        # on that same completion, not on the event node -- so the node's own latency is not charged to the next region.
+        side_branch = os.environ.get("BENCH_EVENT_BRANCH", "1") != "0"
+        tick = torch.cuda.Stream() if side_branch else None
         with torch.cuda.graph(graph, stream=stream):
             events[0].record(stream)
             for r in range(per + 1):
                 wl.launch_steps(W + r * K, K)
-                events[r + 1].record(stream)
+                if side_branch:
+                    done = torch.cuda.Event()
+                    done.record(stream)
+                    tick.wait_event(done)
+                    events[r + 1].record(tick)
+                else:
+                    events[r + 1].record(stream)
+            if side_branch:
+                back = torch.cuda.Event()
+                back.record(tick)
+                stream.wait_event(back)
         graph.replay()  # untimed: uploads the graph, warms clocks and caches
         stream.synchronize()
         env.barrier()
