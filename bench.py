@@ -657,7 +657,9 @@ def time_steps_in_graph(env, wl, K, W, repeats, target_s, sample_clocks):
     """Short regions (K x launches per step <= 400 kernels, e.g. the driver's --steps 20): the timed regions AND the
     event records between them are nodes of one CUDA graph -- [event][K steps][event][K steps] ... -- so that a region
     boundary costs an event node, not the relaunch of a graph (measured: ~7 us per 20-step graph relaunch, 3 % of a
-    230 us region).  Events are created external=True (cudaEventRecordExternal), which is what makes an event recorded
+    230 us region).  The event nodes are side branches: with the node IN the chain of regions the next region's kernels
+    waited for it, and its ~5 us of latency was charged to every 20-step region (11.53 against 11.26 us per step, session 62;
+    at 200-step regions 11.03 against 11.02).  BENCH_EVENT_BRANCH=0 restores the in-line nodes.  Events are created external=True (cudaEventRecordExternal), which is what makes an event recorded
     by a graph node usable with elapsed_time.  The graph holds `per` + 1 regions; the first interval of every replay
     (the GPU was idle before it) is discarded."""
     torch, stream, capi = env.torch, env.stream, env.capi
@@ -720,8 +722,9 @@ def time_steps_in_graph(env, wl, K, W, repeats, target_s, sample_clocks):
     med = float(np.median(ms))
     return {"ms": env.max_over_ranks(med), "ms_min": env.min_over_ranks(float(ms.min())), "ms_max": env.max_over_ranks(float(ms.max())),
             "ms_this_rank": med, "repeats": int(len(ms)), "untimed_regions": per + 1 + replays, "eager_launches": int(eager),
-            "graph": f"one CUDA graph of {per + 1} regions of {K} steps with an (external) event record node between regions, replayed "
-                     f"{replays}x; the first region of every replay is untimed; PDL",
+            "graph": f"one CUDA graph of {per + 1} regions of {K} steps with an (external) event record node between regions"
+                     + (" (a side branch off the region's last kernels: the next region depends on those kernels, not on the event node)" if side_branch else "")
+                     + f", replayed {replays}x; the first region of every replay is untimed; PDL",
             "clocks": clocks}
 
 
