@@ -1308,6 +1308,28 @@ def main():
                             "UNPINNED against OpenMM (DESIGN.md 5); kernel == oracle bit for bit") if water else None,
             "also": also,
         }
+
+        def pick(d, *keys):
+            for k in keys:
+                d = d.get(k) if isinstance(d, dict) else None
+            return d
+
+        # the numbers of the line once more, compact, as its LAST key (a reader of the tail of a long line sees them)
+        line["summary"] = {
+            "us_per_step": 1e3 * ms_step, "frac_measured_peak": achieved / peak, "atom_steps_per_s": value, "n_gpus": world, "steps": K,
+            "eager_launches_in_region": int(t["eager_launches"]), "partition_parity": pick(also, "partition_parity", "result"),
+            "e2e_ms_per_step": pick(e2e, "ms_per_step"), "e2e_atom_steps_per_s": pick(e2e, "value"),
+            "e2e_full_state_ms_per_step": pick(e2e, "full_state", "ms_per_step"),
+            "e2e_full_state_pipelined_ms_per_step": pick(e2e, "full_state_pipelined", "ms_per_step"),
+            "cpu_baseline_atom_steps_per_s": pick(cpu, "value"), "reference_gpu_us_per_step": (1e3 * pick(ref_gpu, "ms_per_step")) if pick(ref_gpu, "ms_per_step") else None,
+            "single_launch_us": pick(also, "single_launch", "us_per_step"),
+            "plugin_path_identity_forces_marginal_us": pick(also, "plugin_path", "identity", "forces", "marginal_us"),
+            "plugin_path_reordered_forces_marginal_us": pick(also, "plugin_path", "reordered", "forces", "marginal_us"),
+            "slab_16M_us": pick(also, "slab_16M", "us_per_step"), "slab_16M_frac": pick(also, "slab_16M", "frac_measured_peak"),
+            "ensemble_64x100k_us": pick(also, "ensemble_64x100k", "us_per_step"), "ensemble_64x100k_frac": pick(also, "ensemble_64x100k", "frac_measured_peak"),
+            "rigid_water_us": pick(also, "rigid_water", "us_per_step"), "rigid_water_frac": pick(also, "rigid_water", "frac_measured_peak"),
+            "drude_us": pick(also, "drude", "us_per_step"), "drude_frac": pick(also, "drude", "frac_measured_peak"),
+        }
         print(json.dumps(line), flush=True)
     if world > 1:
         env.dist.destroy_process_group()
