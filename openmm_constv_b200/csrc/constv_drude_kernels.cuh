@@ -662,7 +662,11 @@ template <int PREC, int BLOCK, int SPT, bool INDEXED> struct DrudeStageB {
     int warpOwners[SPT * (BLOCK / 32)], warpNormals[SPT * (BLOCK / 32)];
     int next;                    // next chunk of 32 work items
 };
+#ifdef CONSTV_DRUDE_NO_SWIZZLE  // experiment (session 68): the stage laid out linearly, as bulk copies would leave it
+__device__ __forceinline__ int drude_swizzle(const int i) { return i; }
+#else
 __device__ __forceinline__ int drude_swizzle(const int i) { return i ^ ((i >> 3) & 7); }
+#endif
 
 // The zeroing stores of the image slots are issued in the stage-in phase, behind the loads (they depend on nothing):
 // 13.4 -> 13.0 us per step at 1M atoms with six chains, 19.4 -> 18.7 us with one launch per step

@@ -63,6 +63,8 @@ elif which in ("settle_chains", "drude_chains", "settle_reordered", "drude_reord
         shard, w_atoms, w_params, w_cons = env.slabmod.slab_tile(R, 1, 0, PRECISION, seed=bench.SLAB_SEED, maker=env.slabmod.make_water_slab)
         kind, water = "settle", (w_atoms, w_params, w_cons)
     chain_counts = (2, 3, 4, 6, 8, 12)
+    if os.environ.get("AB_CHAINS"):
+        chain_counts = tuple(int(x) for x in os.environ["AB_CHAINS"].split(","))
     if which.endswith("reordered"):
         chain_counts = (1,)
     if which.endswith("reordered"):
