@@ -243,7 +243,8 @@ CONSTV_API int constv_step_host_submit(constv_slab* slab, const void* host_force
 CONSTV_API int constv_step_host_collect(constv_slab* slab, uint64_t ticket, double* host_ke_out);
 
 /* constv_step_host_submit that also reads the step's state back (what a trajectory frame per step needs; the
- * reference downloads positions only when a reporter asks, through OpenMM's getState): after the step, posq of
+ * reference downloads positions only when a reporter asks, through OpenMM's getState: DCDReporter and
+ * context.getState(getPositions=True), example/nacl_1m_spce/nacl_constv.py:156,172,198): after the step, posq of
  * all N atoms (host_posq_out) and / or velm (host_velm_out) are copied to pinned host memory on a second internal
  * stream, i.e. in the other PCIe direction, while the NEXT ticket's forces upload; the next step's kernels wait
  * for the read-back (it copies straight out of the bound arrays).  Either pointer may be NULL; with both NULL this
