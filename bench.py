@@ -1128,8 +1128,8 @@ def main():
                    "constv_settle_step_tiled_kernel" if kind == "settle" else
                    "constv_part1_kernel + constv_settle_positions_kernel + constv_part2_mirror_kernel" if kind == "settle_split" else
                    "constv_fused_step_indexed_kernel" if args.reordered else "constv_fused_step_kernel")
-    if kind == "settle" and not args.ensemble and env.capi.last_kernel():
-        kernel_name = env.capi.last_kernel()  # the library's choice of stage-in (constv_settle_step_{bulk,tiled,ws}_kernel), as launched
+    if kind == "settle" and env.capi.last_kernel():
+        kernel_name = env.capi.last_kernel()  # the library's choice of stage-in (constv_settle_step_{bulk,tiled,ws}[_batched]_kernel), as launched
 
     also = {}
     # ---- one launch per step on the same slab (what a host with other kernels between two steps gets at best)

@@ -386,7 +386,7 @@ CONSTV_API int constv_version(void);
 /* Kernels launched by this library in this process so far (bench.py's gpu_launches). */
 CONSTV_API uint64_t constv_launch_count(void);
 /* Name of the kernel behind the calling thread's most recent launch, where the library had a choice ("" otherwise):
- * the rigid-molecule step's constv_settle_step_{tiled,bulk,ws,tiled_batched}_kernel, constv_fused_step_tma_kernel.
+ * the rigid-molecule step's constv_settle_step_{tiled,bulk,ws,tiled_batched,bulk_batched}_kernel, constv_fused_step_tma_kernel.
  * Diagnostics and tests (which variant did constv_set_kernel_variant / the automatic rule pick). */
 CONSTV_API const char* constv_last_kernel(void);
 /* Tuning knobs of the fused kernel: real/image pairs per thread (1, 2 or 4) and the grid:

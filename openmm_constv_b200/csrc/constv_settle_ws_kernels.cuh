@@ -556,4 +556,180 @@ constv_settle_step_bulk_kernel(const __grid_constant__ SlabDev d, const __grid_c
     if (j == 0 && allMoved) bulk_wait_read<0>();  // the stage must outlive the bulk stores' reads of it
 }
 
+// The same tile as a device function, for the ensemble kernel below (`full`, `box`, `counts` and the stage are the CTA's
+// own).  The single-slab kernel above keeps its own copy of this text: calling the function from it, though inlined,
+// costs 16 B of stack under the 64-register cap (as with settle_tiled_tile and the staged kernel).
+template <int PREC, bool INDEXED, bool EARLY>
+__device__ __forceinline__ void settle_bulk_tile(const SlabDev& d, const SettleSegments& seg, BulkIn<PREC, INDEXED>& st,
+                                                 unsigned long long& full, StepBox& box, unsigned int (&counts)[1], const int tileIndex) {
+    using Real = typename Prec<PREC>::Real;
+    using Mixed = typename Prec<PREC>::Mixed;
+    constexpr bool kSplit = Prec<PREC>::kSplitPos;
+
+    const int j = (int) threadIdx.x;
+    const int R = d.numReal;
+    const size_t P = (size_t) d.padded;
+    const unsigned int holders = (unsigned int) (d.rangeHi - d.rangeLo);
+    const WsTile t = ws_tile_of(seg, tileIndex);
+    const int lo = t.base & ~3;  // load window: multiples of 4 slots
+    const int off = t.base - lo;
+    Real* __restrict__ posq = static_cast<Real*>(d.posq);
+    Real* __restrict__ corrA = static_cast<Real*>(d.corr);
+    Mixed* __restrict__ velm = static_cast<Mixed*>(d.velm);
+    long long* __restrict__ force = d.force;
+
+    if (j == 0) {
+        mbar_init(smem_u32(&full), 1);
+        counts[0] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    pdl_wait();
+    pdl_launch();
+    if (j == 0) {
+        // image charges: the side array, by atom (identity order) or by slot (the host checks they are there)
+        const Real* __restrict__ charge = static_cast<const Real*>(INDEXED ? d.imageChargeBySlot : d.imageCharge);
+        const int hi = min((t.base + t.n + 3) & ~3, (int) P);
+        const unsigned int w = (unsigned int) (hi - lo);
+        const unsigned int bar = smem_u32(&full);
+        mbar_expect_tx(bar, w * (unsigned int) (sizeof(Vec4<Mixed>) + sizeof(Vec4<Real>) * (kSplit ? 2 : 1) + 24 + sizeof(Real) + (INDEXED ? 8 : 0)));
+        bulk_g2s(smem_u32(st.v), velm + 4 * (size_t) lo, w * (unsigned int) sizeof(Vec4<Mixed>), bar);
+        bulk_g2s(smem_u32(st.p), posq + 4 * (size_t) lo, w * (unsigned int) sizeof(Vec4<Real>), bar);
+        if (kSplit) bulk_g2s(smem_u32(st.c), corrA + 4 * (size_t) lo, w * (unsigned int) sizeof(Vec4<Real>), bar);
+        bulk_g2s(smem_u32(st.f[0]), force + lo, w * 8u, bar);
+        bulk_g2s(smem_u32(st.f[1]), force + P + lo, w * 8u, bar);
+        bulk_g2s(smem_u32(st.f[2]), force + 2 * P + lo, w * 8u, bar);
+        bulk_g2s(smem_u32(st.q1), charge + lo, w * (unsigned int) sizeof(Real), bar);
+        if (INDEXED) {
+            bulk_g2s(smem_u32(st.orig), d.atomIndex + lo, w * 4u, bar);
+            bulk_g2s(smem_u32(st.img), d.imageSlotBySlot + lo, w * 4u, bar);
+        }
+    }
+    if (INDEXED) {  // the image slots, in slot order: coalesced whatever atoms they hold, and dependent on nothing
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            if (j + i * kWsItems < t.n) emit_zero<PREC, true>(d, t.base + j + i * kWsItems);
+    }
+    publish_step(box, d.counters);
+    __syncthreads();  // the barrier's initialisation, the counts and the step index are visible to every thread
+    const unsigned long long step = box.step;
+    const unsigned int ticket = take_ticket(d.counters, holders);
+    const StepScalars<Mixed> s = scalars_of<Mixed>(d);
+    float4 early[3];
+    const bool drawn = EARLY && !INDEXED && t.per == 3 && s.noisescale != 0 && j < t.items;
+    if (EARLY && drawn) {
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            early[k] = gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) (t.base + 3 * j + k), step);
+    }
+    mbar_wait(smem_u32(&full), 0u);
+
+    // compute item j in place (the text of the staged kernel's compute phase)
+    unsigned int nMoved = 0;
+    if (j < t.items) {
+        Vec4<Mixed> v[3], delta[3];
+        Vec4<Real> p[3], c[3];
+        bool moved[3] = {false, false, false};
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            if (k < t.per) {
+                const int idx = off + t.per * j + k;
+                v[k] = st.v[idx];
+                p[k] = st.p[idx];
+                c[k] = kSplit ? st.c[idx] : Vec4<Real>{0, 0, 0, 0};
+                delta[k] = Vec4<Mixed>{0, 0, 0, 0};
+                moved[k] = v[k].w != 0;
+                if (moved[k]) {
+                    nMoved++;
+                    const int a = INDEXED ? st.orig[idx] : t.base + t.per * j + k;
+                    float4 xi;
+                    if (EARLY && drawn) xi = early[k];
+                    else xi = (s.noisescale != 0) ? gaussian4<false>(d.seed, d.globalAtomOffset + (unsigned long long) a, step)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                    part1_update(v[k], delta[k], st.f[0][idx], st.f[1][idx], st.f[2][idx], xi.x, xi.y, xi.z, s);
+                }
+            }
+        if (t.per == 3) {
+            Mixed pos[3][3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) drude_pos_load<PREC>(p[k], c[k], pos[k]);
+            settle_molecule<Mixed>(pos[0], pos[1], pos[2], delta[0], delta[1], delta[2], rcp_rn(v[0].w), rcp_rn(v[1].w),
+                                   rcp_rn(v[2].w), t.prm.x, t.prm.y);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            if (k < t.per && moved[k]) {
+                const int idx = off + t.per * j + k;
+                part2_update<PREC>(p[k], c[k], v[k], delta[k], s.invDt);
+                st.v[idx] = v[k];
+                st.p[idx] = p[k];
+                if (kSplit) st.c[idx] = c[k];
+            }
+    }
+    nMoved = __reduce_add_sync(0xffffffffu, nMoved);
+    if ((j & 31) == 0 && nMoved) atomicAdd(&counts[0], nMoved);
+    fence_proxy_async_smem();  // this thread's writes to the stage, before the bulk stores read them
+    __syncthreads();
+
+    // stage out.  Every atom moved (runs of ions and of water): the own records go out as they lie, two or three bulk
+    // stores by one thread; otherwise (wall atoms do not move: nothing to store; mixed tiles: legal, rare) per slot.
+    const bool allMoved = counts[0] == (unsigned int) t.n;
+    if (j == 0 && allMoved) {
+        bulk_s2g(velm + 4 * (size_t) t.base, smem_u32(&st.v[off]), (unsigned int) t.n * (unsigned int) sizeof(Vec4<Mixed>));
+        bulk_s2g(posq + 4 * (size_t) t.base, smem_u32(&st.p[off]), (unsigned int) t.n * (unsigned int) sizeof(Vec4<Real>));
+        if (kSplit) bulk_s2g(corrA + 4 * (size_t) t.base, smem_u32(&st.c[off]), (unsigned int) t.n * (unsigned int) sizeof(Vec4<Real>));
+        bulk_commit();
+    }
+    const bool someMoved = counts[0] != 0 && !allMoved;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int idx = j + i * kWsItems;
+        if (idx < t.n) {
+            const int slot = t.base + idx;
+            if (someMoved) {
+                const Vec4<Mixed> v = st.v[off + idx];
+                if (v.w != 0) {
+                    store4x<true>(velm, (size_t) slot, v);
+                    store4x<true>(posq, (size_t) slot, st.p[off + idx]);
+                    if (kSplit) store4x<true>(corrA, (size_t) slot, st.c[off + idx]);
+                }
+            }
+            const Vec4<Real> p = st.p[off + idx];
+            if (INDEXED) {
+                // the image records go where the tables say (every cell); the own record went out above
+                drude_emit_tables<PREC>(d, slot, false, Vec4<Mixed>{0, 0, 0, 0}, p, kSplit ? st.c[off + idx] : Vec4<Real>{0, 0, 0, 0},
+                                        st.img[off + idx], st.q1[off + idx]);
+            } else {
+                if (p.w != -p.w) {  // the image rewrite (constVLangevin.cu:143: neutral atoms are skipped)
+                    ImageCursor<PREC> cur(p, kSplit ? st.c[off + idx] : Vec4<Real>{0, 0, 0, 0});
+                    cur.advance(1, s.zshift);
+                    store4x<true>(posq, (size_t) slot + R, cur.posq(st.q1[off + idx]));
+                    if (kSplit) store4x<true>(corrA, (size_t) slot + R, cur.corr());
+                }
+                emit_zero<PREC, true>(d, slot);
+            }
+        }
+    }
+    close_step(d.counters, ticket, holders, step);
+    if (j == 0 && allMoved) bulk_wait_read<0>();  // the stage must outlive the bulk stores' reads of it
+}
+
+// An ensemble of slabs (identity slot order, Philox noise, image-charge side arrays) in ONE launch, one tile per CTA: the
+// CTA looks its tile up in the table of slabs (constv_settle_step_tiled_batched_kernel's table) and runs it with that
+// slab's descriptor, runs and step counter.
+template <int PREC, int CAP>
+__global__ void __launch_bounds__(kWsItems, PREC == PREC_SINGLE ? 8 : 4)
+constv_settle_step_bulk_batched_kernel(const __grid_constant__ SettleBatchParams<CAP> b) {
+    extern __shared__ unsigned char smemRawBulkB[];
+    BulkIn<PREC, false>& st = *reinterpret_cast<BulkIn<PREC, false>*>(((size_t) smemRawBulkB + 127) & ~(size_t) 127);
+    __shared__ __align__(8) unsigned long long full;
+    __shared__ StepBox box;
+    __shared__ unsigned int counts[1];
+    const int tile = (int) blockIdx.x;
+    int k = 0;
+#pragma unroll
+    for (int q = 1; q < CAP; q++)
+        if (q < b.numSlabs && tile >= b.tileBase[q]) k = q;
+    settle_bulk_tile<PREC, false, PREC != PREC_SINGLE>(b.slab[k], b.seg[k], st, full, box, counts, tile - b.tileBase[k]);
+}
+
 }  // namespace constv

@@ -360,27 +360,33 @@ def test_example_sized_rigid_water_trajectory(gpu, oracle, precision):
 
 
 @pytest.mark.parametrize("precision", ["single", "mixed"])
-def test_batched_rigid_water_ensemble(gpu, precision):
+@pytest.mark.parametrize("side_array", [False, True])
+def test_batched_rigid_water_ensemble(gpu, precision, side_array):
     """constv_step_fused_settle_batched: 11 rigid-water slabs of different sizes and seeds in one call (two
-    launches: groups of 8) == each slab stepped on its own."""
+    launches: groups of 8) == each slab stepped on its own.  side_array: with the image-charge snapshot the batch runs
+    the bulk-staged kernel (constv_settle_step_bulk_batched_kernel), else the cp.async-staged one."""
     from openmm_constv_b200 import _capi
     lib = _capi.load()
+    flags = _capi.FLAGS_DEFAULT | (_capi.FLAG_CACHE_IMAGE_CHARGE if side_array else 0)
     sizes = [37, 500, 2049, 7494, 3000, 129, 1000, 6000, 4097, 999, 2500]
     solo, batch = [], []
     for k, n in enumerate(sizes):
         s0, atoms, params, cons = slabmod.make_water_slab(n, precision, seed=60 + k)
-        ctx, it = make_water_context(gpu, s0, cons, seed=100 + k)
+        ctx, it = make_water_context(gpu, s0, cons, seed=100 + k, flags=flags)
+        it._kernel.set_kernel_variant(7)  # each slab on its own: the cp.async-staged kernel, pinned on the oracle above
         it.step(3)
         solo.append(download(ctx, s0))
         ctx.close()
-        batch.append((s0,) + make_water_context(gpu, s0, cons, seed=100 + k))
+        batch.append((s0,) + make_water_context(gpu, s0, cons, seed=100 + k, flags=flags))
     handles = (C.c_void_p * len(batch))(*[it._kernel.handle for _, _, it in batch])
     for _, _, it in batch:
         _capi.check(lib.constv_set_parameters(it._kernel.handle, T, GAMMA, DT))
     launches = _capi.launch_count()
     for _ in range(3):
         _capi.check(lib.constv_step_fused_settle_batched(handles, len(batch), None))
-    assert _capi.launch_count() - launches == 3 * 2
+    # two launches per step (groups of 8), plus one image-charge snapshot per slab before the first step
+    assert _capi.launch_count() - launches == 3 * 2 + (len(batch) if side_array else 0)
+    assert _capi.last_kernel() == ("constv_settle_step_bulk_batched_kernel" if side_array else "constv_settle_step_tiled_batched_kernel")
     for want, (s0, ctx, it) in zip(solo, batch):
         assert it._kernel.get_step_count() == 3
         assert_slab_bits_equal(download(ctx, s0), want)
